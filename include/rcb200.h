@@ -1,0 +1,129 @@
+/* rcb200.h -- C ABI of librcb200.so: the B200-native sampler hot path of RedClust.
+ *
+ * The reference (RedClust.jl v1.2.2) is pure Julia and has NO FFI/plugin boundary
+ * (SURVEY.md section 8b); the drop-in boundary is its exported Julia API
+ * (/root/reference/src/RedClust.jl:32-66).  This header is what a `ccall`-based Julia host
+ * (redclust.jl_b200/julia/RedClustB200.jl) or the Python ctypes mirror
+ * (redclust.jl_b200/host.py) binds.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative rc_status otherwise; rc_last_error()
+ *     returns a thread-local message (the host wrapper turns it into ErrorException /
+ *     ArgumentError exactly where the reference throws, src/types.jl:40-54,149-153).
+ *   - matrices are dense fp64; D is symmetric so row-/column-major are the same bytes.
+ *   - labels crossing the ABI are 1-based int64 (Julia `Vector{Int}`), Bool vectors are 1 byte.
+ *   - the caller owns every host buffer; the library keeps no host pointer after returning.
+ *   - handles are opaque, bound to one CUDA device, and not thread-safe per handle.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     RC_ERR_CUDA.
+ */
+#ifndef RCB200_H
+#define RCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCB200_VERSION 100 /* 0.1.0 */
+
+typedef enum rc_status {
+  RC_OK = 0,
+  RC_ERR_ARG = -1,       /* invalid argument (null pointer, bad size, bad option)          */
+  RC_ERR_CUDA = -2,      /* CUDA runtime failure / no device                               */
+  RC_ERR_NOTSYM = -3,    /* "D must be symmetric."              (src/types.jl:149-151)     */
+  RC_ERR_DOMAIN = -4,    /* non-finite entry or non-positive off-diagonal dissimilarity    */
+  RC_ERR_SLOTS = -5,     /* a chain needed more live cluster slots than the slot capacity  */
+  RC_ERR_STATE = -6      /* handle used out of order                                        */
+} rc_status;
+
+/* MCMCOptionsList, src/types.jl:26-58 (numsamples is derived: floor((numiters-burnin)/thin)). */
+typedef struct rc_options {
+  int64_t numiters, burnin, thin, numGibbs, numMH;
+} rc_options;
+
+/* PriorHyperparamsList, src/types.jl:93-108. */
+typedef struct rc_params {
+  double delta1, delta2, alpha, beta, zeta, gamma, eta, sigma, proposalsd_r, u, v;
+  int64_t K_initial;
+  int64_t maxK;
+  int32_t repulsion;
+  int32_t _pad;
+} rc_params;
+
+typedef struct rc_data rc_data;       /* MCMCData: device-resident D / log D   (src/types.jl:145-162) */
+typedef struct rc_sampler rc_sampler; /* chains' MCMCState + MCMCResult traces (src/types.jl:131-137,193-248) */
+
+int32_t rc_version(void);
+const char* rc_last_error(void);
+int32_t rc_device_count(void);
+
+/* ---- MCMCData -------------------------------------------------------------------------- */
+/* MCMCData(D): src/types.jl:148-156.  Validates squareness/symmetry, builds
+ * logD = log.(D - Diagonal(D) + I) and the fixed-point images the kernels stream.            */
+int32_t rc_data_from_dist(const double* D, int64_t n, int32_t device, rc_data** out);
+/* MCMCData(points): src/types.jl:159-162 = pairwise(Euclidean(), X, dims=2) with X dim x n
+ * column-major (point i = X[i*dim .. i*dim+dim-1]); also src/utils.jl:144-145, src/prior.jl:51,180. */
+int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t device, rc_data** out);
+int64_t rc_data_n(const rc_data* d);
+/* data.D and data.logD back to the host as n x n fp64. */
+int32_t rc_data_copy_dist(const rc_data* d, double* D_out);
+int32_t rc_data_copy_logdist(const rc_data* d, double* logD_out);
+void rc_data_destroy(rc_data* d);
+
+/* ---- runsampler ------------------------------------------------------------------------ */
+/* r ~ Gamma(eta, 1/sigma), p ~ Beta(u, v): src/mcmc.jl:524-525, drawn on the structured stream. */
+int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, double* r, double* p);
+
+/* Allocate `nchains` independent chains (global chain ids chain_offset .. chain_offset+nchains-1)
+ * on the data's device.  init_labels: nchains x n, 1-based, any slot ids in 1..n (src/types.jl:131-137);
+ * init_r / init_p: nchains values.  slot_cap: max simultaneously live clusters per chain
+ * (0 = default 64; at most 255) -- the reference allows up to n.             */
+int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par,
+                          int64_t nchains, int64_t chain_offset, const int64_t* init_labels,
+                          const double* init_r, const double* init_p, uint64_t seed,
+                          int32_t slot_cap, rc_sampler** out);
+/* Advance every chain by `iters` iterations of the loop at src/mcmc.jl:537-555
+ * (iters < 0: run to numiters).  One persistent kernel launch per call.                       */
+int32_t rc_sampler_run(rc_sampler* s, int64_t iters);
+/* Seconds of device time (CUDA events) spent in rc_sampler_run so far, and iterations done:
+ * MCMCResult.runtime / mean_iter_time, src/mcmc.jl:536,586-587.                                */
+int32_t rc_sampler_progress(const rc_sampler* s, int64_t* iters_done, double* device_seconds);
+int64_t rc_sampler_numsamples(const rc_sampler* s);
+/* Recorded samples of one chain (src/mcmc.jl:546-554): labels numsamples x n (sortlabels'd,
+ * 1-based), K, r, p, loglik, logposterior.  Any pointer may be NULL.                          */
+int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* labels, int64_t* K,
+                                double* r, double* p, double* loglik, double* logposterior);
+/* r_acceptances (numiters), splitmerge_acceptances / splitmerge_splits (numiters*numMH):
+ * src/mcmc.jl:538-543.                                                                         */
+int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t* r_acc,
+                                    uint8_t* sm_acc, uint8_t* sm_split);
+/* Current MCMCState of one chain: labels (n, 1-based slot ids), r, p -- the `init` argument of
+ * a resumed run (src/mcmc.jl:504,519-529).                                                     */
+int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p);
+/* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the slot capacity overflowed.           */
+int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain);
+/* Posterior co-clustering counts of the device-resident samples of chains [chain0, chain0+nch):
+ * sum(adjacencymatrix.(clusts)) (src/mcmc.jl:560, src/utils.jl:59-63) as exact int32 counts in a
+ * DEVICE buffer of n*n int32 (e.g. a torch tensor's data_ptr, so the caller can all-reduce it
+ * over NCCL before dividing).                                                                  */
+int32_t rc_sampler_psm_counts_dev(const rc_sampler* s, int64_t chain0, int64_t nch, void* counts_dev);
+/* Same, divided by the number of samples, into a host n x n fp64 matrix.                       */
+int32_t rc_sampler_psm(const rc_sampler* s, int64_t chain0, int64_t nch, double* psm_out);
+void rc_sampler_destroy(rc_sampler* s);
+
+/* ---- stand-alone pieces ------------------------------------------------------------------ */
+/* loglik(data, state, params) and logprior(state, params) for one host label vector:
+ * src/mcmc.jl:1-78.                                                                            */
+int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels, double* out);
+/* PSM of host label vectors (S x n, any positive labels): src/mcmc.jl:560.                    */
+int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, double* psm_out);
+/* MPEL search of getpointestimate (src/pointestimate.jl:34-59): loss_sums[i] = sum_j loss(c_i,c_j),
+ * *best = first argmin (0-based).  loss: 0 binder (Mirkin), 1 omARI, 2 VI, 3 ID (un-normalised). */
+int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device,
+                double* loss_sums, int64_t* best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCB200_H */
