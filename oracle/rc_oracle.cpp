@@ -296,7 +296,10 @@ void gibbs_full(const Data& d, State& s, const rc_params& P, uint64_t key, uint3
     for (int64_t kk = 0; kk < m; ++kk)                                               // :247
       lp[kk] = lpr[kk] + (L1[kk] + (P.repulsion ? L2[kk] : copysign(0.0, L2[kk])));
     std::vector<double> u(m);
-    for (int64_t kk = 0; kk < m; ++kk) u[kk] = rc_draw1(key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)kk);
+    for (int64_t kk = 0; kk < m; ++kk) {   // candidates 2q and 2q+1 share one Philox block (u0, u1)
+      rc_draw dr = rc_draw2(key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
+      u[kk] = (kk & 1) ? dr.u1 : dr.u0;
+    }
     int64_t k = sample_logweights(lp, u);                                            // :249
     int64_t cnew = cand[k];
     s.clusts[i] = cnew;                                                              // :251-252

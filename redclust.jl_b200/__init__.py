@@ -1,0 +1,15 @@
+"""redclust.jl_b200 -- B200-native sampler hot path of RedClust.jl behind the reference's API.
+
+The directory name contains a dot, so it is loaded under the module name `redclust_jl_b200`
+(see __graft_entry__.load_package()).  Only what the hot path needs lives here:
+  csrc/        hand-written sm_100a CUDA kernels + the C ABI (include/rcb200.h) -> librcb200.so
+  _lib.py      ctypes binding of the C ABI
+  host.py      host-side mirror of the reference's API (MCMCData, runsampler, getpointestimate, ...)
+  prior.py     host-side fitprior / k-medoids (caller of the hot path)
+  julia/       the `ccall` twin of host.py for a Julia host
+"""
+from .host import (MCMCOptionsList, PriorHyperparamsList, MCMCData, MCMCState, MCMCResult, Sampler, runsampler,
+                   getpointestimate, binderloss, infodist, adjacencymatrix, sortlabels, makematrix, uppertriangle,
+                   generatemixture, params_from_labels, psm, mpel_loss_sums, init_rp, ArgumentError)
+from ._lib import RCError, LIB_PATH
+from .prior import fitprior, sampledist, sampleK, kmedoids, kmeans

@@ -1,0 +1,320 @@
+// rc_api.cu -- C ABI of librcb200.so (include/rcb200.h): handles, validation, launches.
+// There is NO CPU fallback: every compute entry point needs a CUDA device.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "rc_sampler.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct rc_sampler {
+  const rc_data* d;
+  rc_options opt;
+  rc_params par;
+  int64_t nchains, chain_offset, numsamples;
+  uint64_t seed;
+  int cap, tiles, npad_max;
+  size_t smem;
+  // device
+  double *LGA, *LGZ, *LOGN;
+  uint8_t* labels; int* sizes; double *r, *p; int* status;
+  rc_i128 *WD, *WL; longlong2* T; unsigned short* Slist; double* terms;
+  uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
+  uint8_t *r_acc, *sm_acc, *sm_split;
+  // progress
+  int64_t iters_done;
+  double dev_seconds;
+  bool W_ready;
+  cudaStream_t stream;
+  cudaEvent_t e0, e1;
+};
+
+namespace {
+
+int validate_options(const rc_options* o) {
+  // messages of MCMCOptionsList's constructor, src/types.jl:40-54
+  if (o->numiters < 1) { rc_set_error("numiters must be \xe2\x89\xa5 1."); return RC_ERR_ARG; }
+  if (o->burnin > o->numiters) { rc_set_error("burnin must be < numiters"); return RC_ERR_ARG; }
+  if (o->burnin < 0) { rc_set_error("burnin must be non-negative."); return RC_ERR_ARG; }
+  if (o->thin < 1) { rc_set_error("thin must be positive."); return RC_ERR_ARG; }
+  if (o->numGibbs < 0) { rc_set_error("numGibbs must be non-negative."); return RC_ERR_ARG; }
+  if (o->numMH < 0) { rc_set_error("numMH must be non-negative."); return RC_ERR_ARG; }
+  return RC_OK;
+}
+
+template <class T>
+int dalloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * count);
+  if (e != cudaSuccess) { rc_set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e)); return RC_ERR_CUDA; }
+  return RC_OK;
+}
+
+void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
+  memset(&kp, 0, sizeof(kp));
+  kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
+  kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->d->DL;
+  kp.P = s->par;
+  kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
+  kp.zgratio = s->par.zeta * rc_log(s->par.gamma) - rc_lgamma(s->par.zeta);     // mcmc.jl:18,187,294
+  kp.lgd1 = rc_lgamma(s->par.delta1);
+  kp.lgd2 = rc_lgamma(s->par.delta2);
+  kp.LGA = s->LGA; kp.LGZ = s->LGZ; kp.LOGN = s->LOGN;
+  kp.burnin = s->opt.burnin; kp.thin = s->opt.thin; kp.numGibbs = s->opt.numGibbs; kp.numMH = s->opt.numMH;
+  kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
+  kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;
+  kp.labels = s->labels; kp.sizes = s->sizes; kp.r = s->r; kp.p = s->p; kp.status = s->status;
+  kp.WD = s->WD; kp.WL = s->WL; kp.T = s->T; kp.Slist = s->Slist; kp.terms = s->terms;
+  kp.out_labels = s->out_labels; kp.out_K = s->out_K; kp.out_r = s->out_r; kp.out_p = s->out_p;
+  kp.out_ll = s->out_ll; kp.out_lp = s->out_lp; kp.r_acc = s->r_acc; kp.sm_acc = s->sm_acc; kp.sm_split = s->sm_split;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t rc_version(void) { return RCB200_VERSION; }
+const char* rc_last_error(void) { return g_err; }
+
+int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, double* r, double* p) {
+  if (!params || !r || !p) { rc_set_error("rc_init_rp: null pointer"); return RC_ERR_ARG; }
+  rc_init_rp_draw(params->eta, params->sigma, params->u, params->v, seed, (uint64_t)chain_id, r, p);
+  return RC_OK;
+}
+
+void rc_sampler_destroy(rc_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->d->device);
+  cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
+  cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
+  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->terms);
+  cudaFree(s->out_labels); cudaFree(s->out_K); cudaFree(s->out_r); cudaFree(s->out_p); cudaFree(s->out_ll); cudaFree(s->out_lp);
+  cudaFree(s->r_acc); cudaFree(s->sm_acc); cudaFree(s->sm_split);
+  if (s->e0) cudaEventDestroy(s->e0);
+  if (s->e1) cudaEventDestroy(s->e1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par, int64_t nchains,
+                          int64_t chain_offset, const int64_t* init_labels, const double* init_r,
+                          const double* init_p, uint64_t seed, int32_t slot_cap, rc_sampler** out) {
+  if (!d || !opt || !par || !init_labels || !init_r || !init_p || !out || nchains < 1) {
+    rc_set_error("rc_sampler_create: null pointer or nchains < 1"); return RC_ERR_ARG;
+  }
+  int st = validate_options(opt);
+  if (st) return st;
+  if (opt->numMH > 1) {
+    rc_set_error("numMH > 1 is not supported yet by the device sampler (numMH must be 0 or 1)."); return RC_ERR_ARG;
+  }
+  const int64_t n = d->n;
+  if (opt->numMH > 0 && n < 2) { rc_set_error("split-merge needs at least 2 observations."); return RC_ERR_ARG; }
+  int cap = slot_cap == 0 ? RC_MAXCAP : slot_cap;
+  if (cap < 2 || cap > RC_MAXCAP) { rc_set_error("slot_cap must be in 2..%d", RC_MAXCAP); return RC_ERR_ARG; }
+  if (par->maxK < 0 || !(par->proposalsd_r > 0)) { rc_set_error("invalid hyperparameters (maxK < 0 or proposalsd_r <= 0)"); return RC_ERR_ARG; }
+  const int tiles = (int)((n + RC_W - 1) / RC_W);
+  const int64_t npad = ((n + 7) & ~7LL) + 8LL * tiles * cap;
+  if (npad > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(d->device));
+  const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad);
+  int maxsmem = 0;
+  RC_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+  if (smem > (size_t)maxsmem) {
+    rc_set_error("chain state needs %zu bytes of shared memory (> %d available): reduce n or slot_cap", smem, maxsmem);
+    return RC_ERR_ARG;
+  }
+  // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
+  std::vector<uint8_t> lab((size_t)nchains * n);
+  std::vector<int> sizes((size_t)nchains * cap, 0);
+  for (int64_t c = 0; c < nchains; ++c)
+    for (int64_t j = 0; j < n; ++j) {
+      const int64_t l = init_labels[c * n + j];
+      if (l < 1 || l > cap) {
+        rc_set_error("initial label %lld of chain %lld is outside 1..slot_cap (%d); relabel with sortlabels first",
+                     (long long)l, (long long)c, cap);
+        return RC_ERR_SLOTS;
+      }
+      lab[c * n + j] = (uint8_t)(l - 1);
+      sizes[c * cap + (l - 1)] += 1;
+    }
+  for (int64_t c = 0; c < nchains; ++c)
+    if (!(init_r[c] > 0) || !(init_p[c] > 0 && init_p[c] < 1)) {
+      rc_set_error("initial r must be > 0 and p in (0, 1) (chain %lld)", (long long)c); return RC_ERR_ARG;
+    }
+  rc_sampler* s = new rc_sampler();
+  memset(s, 0, sizeof(*s));
+  s->d = d; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
+  s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem;
+  s->numsamples = (opt->numiters - opt->burnin) / opt->thin;   // floor((numiters - burnin) / thin), types.jl:55
+  const size_t NS = (size_t)std::max<int64_t>(s->numsamples, 1);
+#define TRY(x) do { st = (x); if (st) { rc_sampler_destroy(s); return st; } } while (0)
+  TRY(dalloc(&s->LGA, n + 2)); TRY(dalloc(&s->LGZ, n + 2)); TRY(dalloc(&s->LOGN, n + 2));
+  TRY(dalloc(&s->labels, (size_t)nchains * n)); TRY(dalloc(&s->sizes, (size_t)nchains * cap));
+  TRY(dalloc(&s->r, nchains)); TRY(dalloc(&s->p, nchains)); TRY(dalloc(&s->status, nchains));
+  TRY(dalloc(&s->WD, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WL, (size_t)nchains * cap * cap));
+  TRY(dalloc(&s->T, opt->numMH > 0 ? (size_t)nchains * n * cap : 1));
+  TRY(dalloc(&s->Slist, (size_t)nchains * n)); TRY(dalloc(&s->terms, (size_t)nchains * cap * cap));
+  TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
+  TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
+  TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));
+  TRY(dalloc(&s->r_acc, (size_t)nchains * opt->numiters));
+  TRY(dalloc(&s->sm_acc, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
+  TRY(dalloc(&s->sm_split, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
+#undef TRY
+  cudaMemcpy(s->labels, lab.data(), lab.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(s->sizes, sizes.data(), sizes.size() * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(s->r, init_r, sizeof(double) * nchains, cudaMemcpyHostToDevice);
+  cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice);
+  cudaMemset(s->status, 0, sizeof(int) * nchains);
+  cudaMemset(s->r_acc, 0, (size_t)nchains * opt->numiters);
+  cudaMemset(s->sm_acc, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1));
+  cudaMemset(s->sm_split, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1));
+  cudaStreamCreate(&s->stream);
+  cudaEventCreate(&s->e0); cudaEventCreate(&s->e1);
+  rc_launch_tables(s->par, (int)n, s->LGA, s->LGZ, s->LOGN, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) { rc_set_error("sampler setup failed: %s", cudaGetErrorString(e)); rc_sampler_destroy(s); return RC_ERR_CUDA; }
+  *out = s;
+  return RC_OK;
+}
+
+int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
+  if (!s) { rc_set_error("rc_sampler_run: null handle"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(s->d->device));
+  int64_t it1 = iters < 0 ? s->opt.numiters : std::min<int64_t>(s->opt.numiters, s->iters_done + iters);
+  if (it1 <= s->iters_done && s->W_ready) return RC_OK;
+  rc_kparams kp;
+  fill_kparams(s, kp);
+  kp.it0 = s->iters_done; kp.it1 = it1;
+  kp.init_W = s->W_ready ? 0 : 1;
+  RC_CUDA(cudaEventRecord(s->e0, s->stream));
+  rc_launch_chain_kernel(kp, s->smem, s->stream);
+  RC_CUDA(cudaGetLastError());
+  RC_CUDA(cudaEventRecord(s->e1, s->stream));
+  RC_CUDA(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  RC_CUDA(cudaEventElapsedTime(&ms, s->e0, s->e1));
+  s->dev_seconds += ms * 1e-3;
+  s->iters_done = it1;
+  s->W_ready = true;
+  std::vector<int> status((size_t)s->nchains);
+  RC_CUDA(cudaMemcpy(status.data(), s->status, sizeof(int) * s->nchains, cudaMemcpyDeviceToHost));
+  for (int64_t c = 0; c < s->nchains; ++c)
+    if (status[c]) {
+      rc_set_error("chain %lld needed more than slot_cap = %d simultaneously live clusters", (long long)c, s->cap);
+      return RC_ERR_SLOTS;
+    }
+  return RC_OK;
+}
+
+int32_t rc_sampler_progress(const rc_sampler* s, int64_t* iters_done, double* device_seconds) {
+  if (!s) { rc_set_error("rc_sampler_progress: null handle"); return RC_ERR_ARG; }
+  if (iters_done) *iters_done = s->iters_done;
+  if (device_seconds) *device_seconds = s->dev_seconds;
+  return RC_OK;
+}
+
+int64_t rc_sampler_numsamples(const rc_sampler* s) { return s ? s->numsamples : 0; }
+
+int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* labels, int64_t* K, double* r, double* p,
+                                double* loglik, double* logposterior) {
+  if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_samples: bad handle or chain"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(s->d->device));
+  const int64_t n = s->d->n, S = s->numsamples;
+  if (S == 0) return RC_OK;
+  if (labels) {
+    std::vector<uint8_t> tmp((size_t)S * n);
+    RC_CUDA(cudaMemcpy(tmp.data(), s->out_labels + (size_t)chain * S * n, tmp.size(), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < tmp.size(); ++t) labels[t] = tmp[t];
+  }
+  if (K) {
+    std::vector<int> tmp((size_t)S);
+    RC_CUDA(cudaMemcpy(tmp.data(), s->out_K + (size_t)chain * S, sizeof(int) * S, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < S; ++t) K[t] = tmp[t];
+  }
+  if (r) RC_CUDA(cudaMemcpy(r, s->out_r + (size_t)chain * S, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  if (p) RC_CUDA(cudaMemcpy(p, s->out_p + (size_t)chain * S, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  if (loglik) RC_CUDA(cudaMemcpy(loglik, s->out_ll + (size_t)chain * S, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  if (logposterior) RC_CUDA(cudaMemcpy(logposterior, s->out_lp + (size_t)chain * S, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  return RC_OK;
+}
+
+int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t* r_acc, uint8_t* sm_acc, uint8_t* sm_split) {
+  if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_acceptances: bad handle or chain"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(s->d->device));
+  const size_t ni = (size_t)s->opt.numiters, nm = ni * (size_t)s->opt.numMH;
+  if (r_acc) RC_CUDA(cudaMemcpy(r_acc, s->r_acc + chain * ni, ni, cudaMemcpyDeviceToHost));
+  if (sm_acc && nm) RC_CUDA(cudaMemcpy(sm_acc, s->sm_acc + chain * nm, nm, cudaMemcpyDeviceToHost));
+  if (sm_split && nm) RC_CUDA(cudaMemcpy(sm_split, s->sm_split + chain * nm, nm, cudaMemcpyDeviceToHost));
+  return RC_OK;
+}
+
+int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p) {
+  if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_state: bad handle or chain"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(s->d->device));
+  const int64_t n = s->d->n;
+  if (labels) {
+    std::vector<uint8_t> tmp((size_t)n);
+    RC_CUDA(cudaMemcpy(tmp.data(), s->labels + (size_t)chain * n, n, cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < n; ++j) labels[j] = (int64_t)tmp[j] + 1;
+  }
+  if (r) RC_CUDA(cudaMemcpy(r, s->r + chain, sizeof(double), cudaMemcpyDeviceToHost));
+  if (p) RC_CUDA(cudaMemcpy(p, s->p + chain, sizeof(double), cudaMemcpyDeviceToHost));
+  return RC_OK;
+}
+
+int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain) {
+  if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_chain_status: bad handle or chain"); return RC_ERR_ARG; }
+  cudaSetDevice(s->d->device);
+  int st = 0;
+  if (cudaMemcpy(&st, s->status + chain, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return RC_ERR_CUDA;
+  return st;
+}
+
+// loglik(data, state, params) for one host label vector (src/mcmc.jl:1-56): block sums from scratch,
+// then the same evaluation the sampler uses.
+int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels, double* out) {
+  if (!d || !par || !labels || !out) { rc_set_error("rc_loglik: null pointer"); return RC_ERR_ARG; }
+  rc_options opt = {1, 0, 1, 0, 0};
+  const int64_t n = d->n;
+  // compact arbitrary positive labels order-preservingly (loglik visits clusters in ascending slot order)
+  std::vector<int64_t> uniq(labels, labels + n);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  if ((int64_t)uniq.size() > RC_MAXCAP) { rc_set_error("rc_loglik: more than %d clusters", RC_MAXCAP); return RC_ERR_SLOTS; }
+  std::vector<int64_t> lab((size_t)n);
+  for (int64_t j = 0; j < n; ++j) lab[j] = (std::lower_bound(uniq.begin(), uniq.end(), labels[j]) - uniq.begin()) + 1;
+  double r0 = 1.0, p0 = 0.5;
+  rc_sampler* s = nullptr;
+  int st = rc_sampler_create(d, &opt, par, 1, 0, lab.data(), &r0, &p0, 0, 0, &s);
+  if (st) return st;
+  rc_kparams kp;
+  fill_kparams(s, kp);
+  kp.it0 = 0; kp.it1 = 0; kp.init_W = 1; kp.loglik_only = 1;
+  rc_launch_chain_kernel(kp, s->smem, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out, s->out_ll, sizeof(double), cudaMemcpyDeviceToHost);
+  rc_sampler_destroy(s);
+  RC_CUDA(e);
+  return RC_OK;
+}
+
+// internal accessors used by rc_post.cu
+const uint8_t* rc_sampler_dev_labels(const rc_sampler* s, int64_t* S, int64_t* n, int64_t* nchains, int* device) {
+  if (S) *S = s->numsamples;
+  if (n) *n = s->d->n;
+  if (nchains) *nchains = s->nchains;
+  if (device) *device = s->d->device;
+  return s->out_labels;
+}
+
+}  // extern "C"

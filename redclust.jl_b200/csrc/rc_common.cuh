@@ -1,0 +1,67 @@
+// rc_common.cuh -- shared declarations of the sm_100a implementation (internal, not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/rcb200.h"
+#include "rc_math.h"
+#include "rc_rng.h"
+
+// ---- error plumbing ----------------------------------------------------------------------------
+void rc_set_error(const char* fmt, ...);
+#define RC_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      rc_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,     \
+                   cudaGetErrorString(e_));                                                    \
+      return RC_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// ---- 128-bit two's complement accumulators (block totals of the fixed-point images) ------------
+struct rc_i128 {
+  unsigned long long lo;
+  long long hi;
+};
+__host__ __device__ __forceinline__ void rc_add128(rc_i128& a, long long s) {
+  unsigned long long lo = a.lo + (unsigned long long)s;
+  a.hi += (s < 0 ? -1LL : 0LL) + (lo < a.lo ? 1LL : 0LL);
+  a.lo = lo;
+}
+__host__ __device__ __forceinline__ void rc_add128(rc_i128& a, const rc_i128& b) {
+  unsigned long long lo = a.lo + b.lo;
+  a.hi += b.hi + (lo < a.lo ? 1LL : 0LL);
+  a.lo = lo;
+}
+__host__ __device__ __forceinline__ void rc_sub128(rc_i128& a, const rc_i128& b) {
+  unsigned long long lo = a.lo - b.lo;
+  a.hi -= b.hi + (a.lo < b.lo ? 1LL : 0LL);
+  a.lo = lo;
+}
+__host__ __device__ __forceinline__ rc_i128 rc_make128(long long s) {
+  rc_i128 r; r.lo = (unsigned long long)s; r.hi = s < 0 ? -1LL : 0LL; return r;
+}
+__host__ __device__ __forceinline__ double rc_deq128(const rc_i128& a, int q) { return rc_dequant128(a.hi, a.lo, q); }
+
+// ---- MCMCData on the device (src/types.jl:145-157) ----------------------------------------------
+// D   : n x n fp64 (as given / as built by the distance kernel)
+// DL  : n x n interleaved fixed-point images {Dq, Lq} = {round(D * 2^qD), round(logD * 2^qL)}; the
+//       sampler streams ONLY this array (16 B per matrix entry = the same bytes as fp64 D + fp64 logD).
+struct rc_data {
+  int64_t n;
+  int device;
+  double* D;
+  longlong2* DL;
+  int qD, qL;
+};
+
+// geometry of the label-sorted column permutation the sampler reduces rows with
+#define RC_LOGW 11
+#define RC_W (1 << RC_LOGW)          // columns per row tile (32 KB of DL)
+#define RC_DUMMY 0xFFFFu             // padding entry of a label run
+#define RC_GROUP 8                   // columns per lane-group (runs are padded to multiples of this)
+#define RC_MAXCAP 128                // max live cluster slots per chain
+#define RC_NS (RC_MAXCAP / 32)
+#define RC_DETACHED 0xFF

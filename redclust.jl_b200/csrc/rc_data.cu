@@ -1,0 +1,242 @@
+// rc_data.cu -- MCMCData on the device: validation, log D, fixed-point images, Euclidean distance
+// matrix.  Replaces /root/reference/src/types.jl:145-162 and the pairwise(Euclidean(), X, dims=2)
+// call sites (src/types.jl:160, src/utils.jl:144-145, src/prior.jl:51,180).
+#include "rc_common.cuh"
+
+namespace {
+
+// any(D .!= D') (types.jl:149) + domain scan.  flags[0]: asymmetric, flags[1]: bad off-diagonal entry
+// (non-finite or <= 0, whose log cannot be represented), maxbits[0/1]: bit patterns of max|D|, max|logD|.
+__global__ void k_scan(const double* __restrict__ D, int64_t n, int* flags, unsigned long long* maxbits) {
+  const int64_t total = n * n;
+  double mD = 0.0, mL = 0.0;
+  int asym = 0, bad = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n, j = t - i * n;
+    const double v = D[t];
+    if (i != j) {
+      if (v != D[j * n + i]) asym = 1;
+      if (!(v > 0.0) || !(v < RC_INF)) { bad = 1; continue; }
+      const double l = rc_log(v - 0.0 + 0.0);
+      mL = fmax(mL, fabs(l));
+    } else if (!(fabs(v) < RC_INF)) { bad = 1; continue; }
+    mD = fmax(mD, fabs(v));
+  }
+  for (int off = 16; off; off >>= 1) {
+    mD = fmax(mD, __shfl_xor_sync(0xffffffffu, mD, off));
+    mL = fmax(mL, __shfl_xor_sync(0xffffffffu, mL, off));
+    asym |= __shfl_xor_sync(0xffffffffu, asym, off);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (asym) atomicOr(&flags[0], 1);
+    if (bad) atomicOr(&flags[1], 1);
+    atomicMax(&maxbits[0], (unsigned long long)__double_as_longlong(mD));   // non-negative doubles order like their bits
+    atomicMax(&maxbits[1], (unsigned long long)__double_as_longlong(mL));
+  }
+}
+
+// logD = log.(D .- Diagonal(D) .+ I) (types.jl:155) and the fixed-point images the sampler streams.
+__global__ void k_build_dl(const double* __restrict__ D, int64_t n, int qD, int qL, longlong2* __restrict__ DL) {
+  const int64_t total = n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n, j = t - i * n;
+    const double v = D[t];
+    const double arg = (i == j) ? (v - v + 1.0) : (v - 0.0 + 0.0);
+    longlong2 o;
+    o.x = rc_quantize(v, qD);
+    o.y = rc_quantize(rc_log(arg), qL);
+    DL[t] = o;
+  }
+}
+
+__global__ void k_logd(const double* __restrict__ D, int64_t n, double* __restrict__ out) {
+  const int64_t total = n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n, j = t - i * n;
+    const double v = D[t];
+    out[t] = rc_log((i == j) ? (v - v + 1.0) : (v - 0.0 + 0.0));
+  }
+}
+
+// |x_i|^2, ascending-coordinate summation (no FMA: the file is compiled with -fmad=false).
+__global__ void k_sqnorm(const double* __restrict__ X, int64_t dim, int64_t n, double* __restrict__ sq) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int64_t t = 0; t < dim; ++t) { const double x = X[i * dim + t]; a += x * x; }
+  sq[i] = a;
+}
+
+// Gram-form Euclidean distances, upper triangle mirrored, exact zero diagonal:
+// D_ij = sqrt(max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 0)).  32x32 output tile per CTA, operands staged
+// through shared memory; each dot product is accumulated in ascending coordinate order, so the result
+// is independent of the tiling (and identical to the CPU oracle's).
+#define DT 32
+__global__ void __launch_bounds__(256) k_distm(const double* __restrict__ X, const double* __restrict__ sq, int64_t dim,
+                                                int64_t n, double* __restrict__ D) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  __shared__ double Xi[DT][DT + 1], Xj[DT][DT + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t i0 = (int64_t)bi * DT, j0 = (int64_t)bj * DT;
+  for (int64_t t0 = 0; t0 < dim; t0 += DT) {
+    for (int r = ty; r < DT; r += 8) {
+      const int64_t t = t0 + tx;
+      Xi[r][tx] = (i0 + r < n && t < dim) ? X[(i0 + r) * dim + t] : 0.0;
+      Xj[r][tx] = (j0 + r < n && t < dim) ? X[(j0 + r) * dim + t] : 0.0;
+    }
+    __syncthreads();
+    const int tmax = (int)((dim - t0) < DT ? (dim - t0) : DT);
+    for (int t = 0; t < tmax; ++t) {
+      const double xj = Xj[tx][t];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += Xi[ty + 8 * q][t] * xj;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t i = i0 + ty + 8 * q, j = j0 + tx;
+    if (i >= n || j >= n) continue;
+    if (i == j) { D[i * n + i] = 0.0; continue; }
+    if (j < i) continue;                        // diagonal tile: lower half comes from the mirror
+    const double v = sq[i] + sq[j] - 2 * acc[q];
+    const double r = sqrt(v > 0.0 ? v : 0.0);
+    D[i * n + j] = r;
+    D[j * n + i] = r;
+  }
+}
+
+int finish_data(rc_data* d) {
+  const int64_t n = d->n;
+  int* flags = nullptr; unsigned long long* maxbits = nullptr;
+  RC_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+  RC_CUDA(cudaMalloc(&maxbits, 2 * sizeof(unsigned long long)));
+  RC_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
+  RC_CUDA(cudaMemset(maxbits, 0, 2 * sizeof(unsigned long long)));
+  const int grid = 148 * 8;
+  k_scan<<<grid, 256>>>(d->D, n, flags, maxbits);
+  RC_CUDA(cudaGetLastError());
+  int hflags[2]; unsigned long long hbits[2];
+  RC_CUDA(cudaMemcpy(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost));
+  RC_CUDA(cudaMemcpy(hbits, maxbits, sizeof(hbits), cudaMemcpyDeviceToHost));
+  cudaFree(flags); cudaFree(maxbits);
+  if (hflags[0]) { rc_set_error("D must be symmetric."); return RC_ERR_NOTSYM; }
+  if (hflags[1]) {
+    rc_set_error("D must have finite entries and strictly positive off-diagonal dissimilarities (log D must be finite).");
+    return RC_ERR_DOMAIN;
+  }
+  double mD, mL;
+  memcpy(&mD, &hbits[0], 8); memcpy(&mL, &hbits[1], 8);
+  d->qD = rc_choose_q(mD, n);
+  d->qL = rc_choose_q(mL, n);
+  if (d->qD < 0 || d->qL < 0) { rc_set_error("dissimilarities too large for the fixed-point image."); return RC_ERR_DOMAIN; }
+  RC_CUDA(cudaMalloc(&d->DL, sizeof(longlong2) * (size_t)n * n));
+  k_build_dl<<<grid, 256>>>(d->D, n, d->qD, d->qL, d->DL);
+  RC_CUDA(cudaGetLastError());
+  RC_CUDA(cudaDeviceSynchronize());
+  return RC_OK;
+}
+
+int select_device(int32_t device) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+    rc_set_error("no CUDA device available (librcb200 has no CPU fallback)");
+    return RC_ERR_CUDA;
+  }
+  if (device < 0 || device >= cnt) { rc_set_error("device %d out of range (0..%d)", device, cnt - 1); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(device));
+  return RC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t rc_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+
+int32_t rc_data_from_dist(const double* D, int64_t n, int32_t device, rc_data** out) {
+  if (!D || !out || n < 1) { rc_set_error("rc_data_from_dist: null pointer or n < 1"); return RC_ERR_ARG; }
+  int st = select_device(device);
+  if (st) return st;
+  rc_data* d = new rc_data();
+  d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
+  if (cudaMalloc(&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess) {
+    rc_set_error("out of device memory for D (%lld x %lld)", (long long)n, (long long)n); delete d; return RC_ERR_CUDA;
+  }
+  if (cudaMemcpy(d->D, D, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    rc_set_error("upload of D failed"); rc_data_destroy(d); return RC_ERR_CUDA;
+  }
+  st = finish_data(d);
+  if (st) { rc_data_destroy(d); return st; }
+  *out = d;
+  return RC_OK;
+}
+
+int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t device, rc_data** out) {
+  if (!X || !out || n < 1 || dim < 1) { rc_set_error("rc_data_from_points: null pointer or empty input"); return RC_ERR_ARG; }
+  int st = select_device(device);
+  if (st) return st;
+  rc_data* d = new rc_data();
+  d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
+  double *dX = nullptr, *sq = nullptr;
+  if (cudaMalloc(&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess || cudaMalloc(&dX, sizeof(double) * (size_t)n * dim) != cudaSuccess ||
+      cudaMalloc(&sq, sizeof(double) * (size_t)n) != cudaSuccess) {
+    rc_set_error("out of device memory for the distance matrix"); cudaFree(dX); cudaFree(sq); rc_data_destroy(d); return RC_ERR_CUDA;
+  }
+  cudaMemcpy(dX, X, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice);
+  k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
+  const unsigned nb = (unsigned)((n + DT - 1) / DT);
+  k_distm<<<dim3(nb, nb), 256>>>(dX, sq, dim, n, d->D);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(dX); cudaFree(sq);
+  if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); rc_data_destroy(d); return RC_ERR_CUDA; }
+  st = finish_data(d);
+  if (st) { rc_data_destroy(d); return st; }
+  *out = d;
+  return RC_OK;
+}
+
+int64_t rc_data_n(const rc_data* d) { return d ? d->n : 0; }
+
+int32_t rc_data_copy_dist(const rc_data* d, double* D_out) {
+  if (!d || !D_out) { rc_set_error("rc_data_copy_dist: null pointer"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(d->device));
+  RC_CUDA(cudaMemcpy(D_out, d->D, sizeof(double) * (size_t)d->n * d->n, cudaMemcpyDeviceToHost));
+  return RC_OK;
+}
+
+int32_t rc_data_copy_logdist(const rc_data* d, double* logD_out) {
+  if (!d || !logD_out) { rc_set_error("rc_data_copy_logdist: null pointer"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(d->device));
+  double* tmp = nullptr;
+  RC_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)d->n * d->n));
+  k_logd<<<148 * 8, 256>>>(d->D, d->n, tmp);
+  cudaError_t e = cudaMemcpy(logD_out, tmp, sizeof(double) * (size_t)d->n * d->n, cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  RC_CUDA(e);
+  return RC_OK;
+}
+
+int32_t rc_data_scales(const rc_data* d, int32_t* qD, int32_t* qL) {
+  if (!d) { rc_set_error("rc_data_scales: null pointer"); return RC_ERR_ARG; }
+  if (qD) *qD = d->qD;
+  if (qL) *qL = d->qL;
+  return RC_OK;
+}
+
+void rc_data_destroy(rc_data* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaFree(d->D);
+  cudaFree(d->DL);
+  delete d;
+}
+
+}  // extern "C"

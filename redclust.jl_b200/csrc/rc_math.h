@@ -218,9 +218,11 @@ RC_HD double rc_dequant128(int64_t hi, uint64_t lo, int q) {
   return d * rc_from_bits((uint64_t)(0x3ff - q) << 52);
 }
 
-#if !defined(__CUDA_ARCH__)
 // Fixed-point scale: the largest q <= 50 with n * maxabs * 2^q < 2^61 (host side, both the
 // library and the oracle call this so the images are identical).  Returns -1 if none exists.
+#if defined(__CUDACC__)
+__host__
+#endif
 static inline int rc_choose_q(double maxabs, int64_t n) {
   double v = maxabs * (double)n;
   if (!(v > 0.0)) return 50;
@@ -230,4 +232,3 @@ static inline int rc_choose_q(double maxabs, int64_t n) {
   if (q > 50) q = 50;
   return q < 0 ? -1 : q;
 }
-#endif

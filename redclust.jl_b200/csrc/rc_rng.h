@@ -22,7 +22,7 @@ enum rc_site {
   RC_SITE_SM_LAUNCH = 7,  // a = position in S               (mcmc.jl:404)
   RC_SITE_SM_RGIBBS = 8,  // a = scan index, b = position in S (utils.jl:4 via mcmc.jl:337)
   RC_SITE_SM_ACCEPT = 9,  //                                 (mcmc.jl:469)
-  RC_SITE_SCAN = 10,      // a = point i (0-based), b = candidate index (utils.jl:4 via mcmc.jl:249)
+  RC_SITE_SCAN = 10,      // a = point i (0-based), b = candidate index / 2 (u0: even, u1: odd candidate) (utils.jl:4 via mcmc.jl:249)
   RC_SITE_INIT = 11       // a = 0: r ~ Gamma, 1: p ~ Beta   (mcmc.jl:524-525), iteration 0
 };
 

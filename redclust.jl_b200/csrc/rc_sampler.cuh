@@ -1,0 +1,45 @@
+// rc_sampler.cuh -- kernel-side parameter block of the persistent chain kernel (internal).
+#pragma once
+#include "rc_common.cuh"
+
+#define RC_NTHR 128
+#define RC_NWARP (RC_NTHR / 32)
+
+struct rc_kparams {
+  int n, cap, tiles, npad_max;
+  int qD, qL;
+  const longlong2* DL;
+  rc_params P;
+  double abratio, zgratio, lgd1, lgd2;
+  const double* LGA;    // lgamma(alpha + delta1 * s), s = 0..n+1
+  const double* LGZ;    // lgamma(zeta + delta2 * s)
+  const double* LOGN;   // log(s)
+  long long it0, it1;   // run iterations it0+1 .. it1 (1-based, as in mcmc.jl:537)
+  long long burnin, thin, numGibbs, numMH, numiters, numsamples;
+  unsigned long long seed;
+  long long chain_offset;
+  int nchains;
+  int init_W;           // 1: (re)build the block-sum matrices from the labels before iterating
+  // per-chain state (global memory)
+  uint8_t* labels;      // [nchains][n]   0-based slot ids
+  int* sizes;           // [nchains][cap]
+  double* r;            // [nchains]
+  double* p;            // [nchains]
+  int* status;          // [nchains]
+  rc_i128* WD;          // [nchains][cap*cap]  block sums of Dq, entry (min(k,t), max(k,t))
+  rc_i128* WL;          // [nchains][cap*cap]  block sums of Lq
+  longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj
+  unsigned short* Slist;// [nchains][n]
+  double* terms;        // [nchains][cap*cap]  log-likelihood terms scratch
+  // outputs
+  uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
+  int* out_K;           // [nchains][numsamples]
+  double *out_r, *out_p, *out_ll, *out_lp;
+  uint8_t *r_acc, *sm_acc, *sm_split;
+  // standalone log-likelihood mode (rc_loglik): skip iterations, write loglik to out_ll[chain]
+  int loglik_only;
+};
+
+size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max);
+void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, cudaStream_t st);
+void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);

@@ -1,0 +1,450 @@
+"""Host-side mirror of RedClust.jl's public API for the sampler hot path (the reference is pure Julia and
+Julia is not installed in this image, so -- as the task allows -- the host side above the C ABI is written
+in Python; julia/RedClustB200.jl is the `ccall` twin of this file).
+
+Names, argument meaning and error behaviour follow the reference:
+  MCMCOptionsList        /root/reference/src/types.jl:26-58
+  PriorHyperparamsList   /root/reference/src/types.jl:93-108
+  MCMCData               /root/reference/src/types.jl:145-162
+  MCMCResult             /root/reference/src/types.jl:193-248
+  runsampler             /root/reference/src/mcmc.jl:501-590
+  getpointestimate       /root/reference/src/pointestimate.jl:17-60
+  binderloss / infodist  /root/reference/src/pointestimate.jl:68-98
+  adjacencymatrix / sortlabels / makematrix / generatemixture   /root/reference/src/utils.jl:59-156
+
+All heavy work happens in librcb200.so on the GPU.  Nothing here falls back to the CPU: without the
+library or a device the calls raise.  The extra keyword arguments (`nchains`, `seed`, `device`,
+`slot_cap`) are additions the reference has no equivalent for (it runs one chain per call on the
+task-local RNG)."""
+import ctypes as C
+import math
+import time
+import numpy as np
+
+from . import _lib
+from ._lib import RCError, rc_options, rc_params, check, ptr, lib
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError."""
+
+
+# ------------------------------------------------------------------------------------------------
+class MCMCOptionsList:
+    def __init__(self, numiters=5000, burnin=None, thin=1, numGibbs=5, numMH=1):
+        if burnin is None:
+            burnin = int(math.floor(0.2 * numiters))
+        for name, v in (("numiters", numiters), ("burnin", burnin), ("thin", thin), ("numGibbs", numGibbs), ("numMH", numMH)):
+            if not isinstance(v, (int, np.integer)):
+                raise TypeError(f"{name} must be an integer")
+        if numiters < 1:
+            raise RCError(_lib.RC_ERR_ARG, "numiters must be ≥ 1.")
+        if burnin > numiters:
+            raise RCError(_lib.RC_ERR_ARG, "burnin must be < numiters")
+        if thin < 1:
+            raise RCError(_lib.RC_ERR_ARG, "thin must be positive.")
+        if numGibbs < 0:
+            raise RCError(_lib.RC_ERR_ARG, "numGibbs must be non-negative.")
+        if numMH < 0:
+            raise RCError(_lib.RC_ERR_ARG, "numMH must be non-negative.")
+        self.numiters, self.burnin, self.thin, self.numGibbs, self.numMH = int(numiters), int(burnin), int(thin), int(numGibbs), int(numMH)
+        self.numsamples = int(math.floor((numiters - burnin) / thin))
+
+    def _c(self):
+        return rc_options(self.numiters, self.burnin, self.thin, self.numGibbs, self.numMH)
+
+    def __repr__(self):
+        return (f"MCMC Options: {self.numiters} iterations, {self.burnin} burnin, {self.numsamples} samples, "
+                f"{self.numGibbs} restricted Gibbs steps per split-merge, {self.numMH} split-merge steps per iteration")
+
+
+class PriorHyperparamsList:
+    _fields = ("delta1", "alpha", "beta", "delta2", "zeta", "gamma", "eta", "sigma", "proposalsd_r", "u", "v",
+               "K_initial", "repulsion", "maxK")
+    _greek = {"δ1": "delta1", "δ2": "delta2", "α": "alpha", "β": "beta", "ζ": "zeta", "γ": "gamma", "η": "eta", "σ": "sigma"}
+
+    def __init__(self, **kw):
+        kw = {self._greek.get(k, k): v for k, v in kw.items()}
+        d = dict(delta1=1.0, alpha=1.0, beta=1.0, delta2=1.0, zeta=1.0, gamma=1.0, eta=1.0, sigma=1.0,
+                 proposalsd_r=None, u=1.0, v=1.0, K_initial=1, repulsion=True, maxK=0)
+        for k in kw:
+            if k not in d:
+                raise TypeError(f"unknown hyperparameter {k}")
+        d.update(kw)
+        if d["proposalsd_r"] is None:
+            d["proposalsd_r"] = math.sqrt(d["eta"]) / d["sigma"]      # types.jl:102
+        for k, v in d.items():
+            setattr(self, k, v)
+
+    def _c(self):
+        return rc_params(float(self.delta1), float(self.delta2), float(self.alpha), float(self.beta), float(self.zeta),
+                         float(self.gamma), float(self.eta), float(self.sigma), float(self.proposalsd_r), float(self.u),
+                         float(self.v), int(self.K_initial), int(self.maxK), int(bool(self.repulsion)), 0)
+
+    def __repr__(self):
+        return "PriorHyperparamsList(" + ", ".join(f"{k}={getattr(self, k)!r}" for k in self._fields) + ")"
+
+
+class MCMCData:
+    """Device-resident dissimilarity matrix (D, log D and their fixed-point images)."""
+
+    def __init__(self, data, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+        if isinstance(data, np.ndarray) and data.ndim == 2 and data.dtype == np.float64 and not getattr(data, "_rc_points", False):
+            D = data
+            if D.shape[0] != D.shape[1]:
+                raise RCError(_lib.RC_ERR_ARG, "D must be a square matrix.")
+            D = np.ascontiguousarray(D)
+            check(lib().rc_data_from_dist(ptr(D), D.shape[0], device, C.byref(self._h)))
+        else:
+            X = makematrix(data)                      # dim x n, as the reference
+            Xt = np.ascontiguousarray(X.T)            # point-major for the kernel
+            check(lib().rc_data_from_points(ptr(Xt), Xt.shape[1], Xt.shape[0], device, C.byref(self._h)))
+        self.n = int(lib().rc_data_n(self._h))
+
+    @classmethod
+    def from_points(cls, points, device=0):
+        """MCMCData(points): points is a sequence of n observation vectors (or an n x dim array)."""
+        obj = cls.__new__(cls)
+        obj._h = C.c_void_p()
+        obj.device = device
+        P = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+        check(lib().rc_data_from_points(ptr(P), P.shape[1], P.shape[0], device, C.byref(obj._h)))
+        obj.n = int(lib().rc_data_n(obj._h))
+        return obj
+
+    @property
+    def D(self):
+        out = np.empty((self.n, self.n))
+        check(lib().rc_data_copy_dist(self._h, ptr(out)))
+        return out
+
+    @property
+    def logD(self):
+        out = np.empty((self.n, self.n))
+        check(lib().rc_data_copy_logdist(self._h, ptr(out)))
+        return out
+
+    def scales(self):
+        a, b = C.c_int32(), C.c_int32()
+        check(lib().rc_data_scales(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.rc_data_destroy(h)
+            self._h = None
+
+    def __repr__(self):
+        return f"MCMC data : {self.n}×{self.n} dissimilarity matrix."
+
+
+class MCMCState:
+    """clusts (1-based labels), r, p -- the `init` argument of runsampler (types.jl:131-137)."""
+
+    def __init__(self, clusts, r, p):
+        self.clusts = np.asarray(clusts, dtype=np.int64)
+        self.r, self.p = float(r), float(p)
+
+
+class MCMCResult:
+    """Fields of the reference's MCMCResult (types.jl:193-224)."""
+
+    def __repr__(self):
+        return (f"MCMC Summary: {self.options.numiters} iterations, {len(self.K)} samples, "
+                f"acceptance rate r {self.r_acceptance_rate:.3f}, split-merge {self.splitmerge_acceptance_rate:.3f}, "
+                f"runtime {self.runtime:.3f} s")
+
+
+def _autocor(x):
+    """StatsBase.autocor(x): demeaned, lags 0:min(S-1, round(10 log10 S))."""
+    x = np.asarray(x, dtype=np.float64)
+    S = x.size
+    if S == 0:
+        return np.zeros(0)
+    lags = np.arange(0, min(S - 1, int(round(10 * math.log10(S)))) + 1)
+    z = x - x.mean()
+    zz = float(z @ z)
+    return np.array([float(z[:S - l] @ z[l:]) / zz if zz != 0 else float("nan") for l in lags])
+
+
+def iac_ess_acf(x):
+    acf = _autocor(x)
+    iac = acf.sum() * 2
+    return iac, len(x) / iac if iac != 0 else float("nan"), acf
+
+
+class Sampler:
+    """Thin owner of an rc_sampler handle: `nchains` chains of one data set on one device."""
+
+    def __init__(self, data, options, params, init_labels, init_r, init_p, seed=0, chain_offset=0, slot_cap=0):
+        self.data, self.options, self.params = data, options, params
+        lab = np.ascontiguousarray(np.asarray(init_labels, dtype=np.int64).reshape(-1, data.n))
+        self.nchains = lab.shape[0]
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(init_r, dtype=np.float64), (self.nchains,)))
+        p = np.ascontiguousarray(np.broadcast_to(np.asarray(init_p, dtype=np.float64), (self.nchains,)))
+        self._h = C.c_void_p()
+        o, q = options._c(), params._c()
+        check(lib().rc_sampler_create(data._h, C.byref(o), C.byref(q), self.nchains, chain_offset, ptr(lab), ptr(r), ptr(p),
+                                      seed, slot_cap, C.byref(self._h)))
+
+    def run(self, iters=-1):
+        check(lib().rc_sampler_run(self._h, iters))
+
+    def progress(self):
+        a, b = C.c_int64(), C.c_double()
+        check(lib().rc_sampler_progress(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def samples(self, chain=0):
+        S, n = int(lib().rc_sampler_numsamples(self._h)), self.data.n
+        out = dict(labels=np.zeros((S, n), np.int64), K=np.zeros(S, np.int64), r=np.zeros(S), p=np.zeros(S),
+                   loglik=np.zeros(S), logposterior=np.zeros(S))
+        check(lib().rc_sampler_copy_samples(self._h, chain, ptr(out["labels"]), ptr(out["K"]), ptr(out["r"]), ptr(out["p"]),
+                                            ptr(out["loglik"]), ptr(out["logposterior"])))
+        ni, nm = self.options.numiters, self.options.numiters * self.options.numMH
+        out["r_acc"] = np.zeros(ni, np.uint8)
+        out["sm_acc"] = np.zeros(nm, np.uint8)
+        out["sm_split"] = np.zeros(nm, np.uint8)
+        check(lib().rc_sampler_copy_acceptances(self._h, chain, ptr(out["r_acc"]), ptr(out["sm_acc"]), ptr(out["sm_split"])))
+        return out
+
+    def state(self, chain=0):
+        lab = np.zeros(self.data.n, np.int64)
+        r, p = C.c_double(), C.c_double()
+        check(lib().rc_sampler_copy_state(self._h, chain, ptr(lab), C.byref(r), C.byref(p)))
+        return MCMCState(lab, r.value, p.value)
+
+    def psm(self, chain0=0, nch=None):
+        nch = self.nchains - chain0 if nch is None else nch
+        out = np.zeros((self.data.n, self.data.n))
+        check(lib().rc_sampler_psm(self._h, chain0, nch, ptr(out)))
+        return out
+
+    def psm_counts_dev(self, counts_ptr, chain0=0, nch=None):
+        nch = self.nchains - chain0 if nch is None else nch
+        check(lib().rc_sampler_psm_counts_dev(self._h, chain0, nch, C.c_void_p(counts_ptr)))
+
+    def close(self):
+        if self._h and _lib._lib is not None:
+            _lib._lib.rc_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def init_rp(params, seed, chain):
+    r, p = C.c_double(), C.c_double()
+    q = params._c()
+    check(lib().rc_init_rp(C.byref(q), seed, chain, C.byref(r), C.byref(p)))
+    return r.value, p.value
+
+
+def _result_from(samples, options, params, psm, runtime):
+    res = MCMCResult()
+    res.clusts = [samples["labels"][j] for j in range(samples["labels"].shape[0])]
+    res.posterior_coclustering = psm
+    for name in ("K", "r", "p"):
+        x = samples[name]
+        setattr(res, name, x)
+        iac, ess, acf = iac_ess_acf(x)                                         # mcmc.jl:564-573
+        setattr(res, name + "_iac", iac); setattr(res, name + "_ess", ess); setattr(res, name + "_acf", acf)
+        setattr(res, name + "_mean", float(np.mean(x)) if len(x) else float("nan"))
+        setattr(res, name + "_variance", float(np.var(x, ddof=1)) if len(x) > 1 else float("nan"))
+    res.splitmerge_acceptances = samples["sm_acc"].astype(bool)
+    res.splitmerge_splits = samples["sm_split"].astype(bool)
+    res.r_acceptances = samples["r_acc"].astype(bool)
+    res.splitmerge_acceptance_rate = float(res.splitmerge_acceptances.mean()) if options.numMH > 0 else 0.0   # :576-580
+    res.r_acceptance_rate = float(res.r_acceptances.mean())
+    res.loglik, res.logposterior = samples["loglik"], samples["logposterior"]
+    res.options, res.params = options, params
+    res.runtime = runtime
+    res.mean_iter_time = runtime / options.numiters
+    return res
+
+
+def runsampler(data, options=None, params=None, init=None, verbose=True, nchains=1, seed=0, slot_cap=0):
+    """runsampler(data, options, params, init; verbose) -> MCMCResult   (mcmc.jl:501-590).
+    With nchains > 1 returns a list of MCMCResult (independent chains, one persistent kernel)."""
+    if options is None:
+        options = MCMCOptionsList()
+    if params is None:
+        from .prior import fitprior
+        params = fitprior(data.D, "k-medoids", True, verbose=verbose)
+    n = data.n
+    if init is None:                                                           # mcmc.jl:519-527
+        from .prior import kmedoids
+        k0 = min(params.maxK, params.K_initial) if params.maxK > 0 else params.K_initial
+        lab0 = kmedoids(data.D, int(k0), maxiter=1000)["assignments"]
+        labs = np.tile(lab0, (nchains, 1))
+        rp = [init_rp(params, seed, c) for c in range(nchains)]
+        r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
+    else:
+        inits = init if isinstance(init, (list, tuple)) else [init] * nchains
+        labs = np.stack([sortlabels(s.clusts) if np.max(s.clusts) > (slot_cap or 128) else np.asarray(s.clusts) for s in inits])
+        r0 = np.array([s.r for s in inits]); p0 = np.array([s.p for s in inits])
+    if verbose:
+        print("Run MCMC")
+        print(f"Setup: {options.numiters} iterations, {options.numsamples} samples, {n} observations.")
+    smp = Sampler(data, options, params, labs, r0, p0, seed=seed, slot_cap=slot_cap)
+    smp.run(-1)
+    _, runtime = smp.progress()
+    if verbose:
+        print("Computing summary statistics and diagnostics.")
+    results = []
+    for c in range(nchains):
+        s = smp.samples(c)
+        psm = smp.psm(c, 1) if options.numsamples > 0 else np.full((n, n), np.nan)   # mcmc.jl:560
+        results.append(_result_from(s, options, params, psm, runtime))
+    smp.close()
+    return results[0] if nchains == 1 else results
+
+
+# ------------------------------------------------------------------------------------------------
+def makematrix(x):
+    """utils.jl:154-156: vector of vectors -> matrix whose COLUMNS are the vectors."""
+    return np.asarray([np.asarray(v, dtype=np.float64) for v in x], dtype=np.float64).T.copy()
+
+
+def adjacencymatrix(clusts):
+    c = np.asarray(clusts)
+    return c[:, None] == c[None, :]
+
+
+def sortlabels(x):
+    x = np.asarray(x)
+    _, first, inv = np.unique(x, return_index=True, return_inverse=True)
+    order = np.argsort(np.argsort(first))
+    return (order[inv] + 1).astype(np.int64)
+
+
+def uppertriangle(M):
+    M = np.asarray(M)
+    i, j = np.triu_indices(M.shape[0], 1)
+    return M[i, j]
+
+
+def psm(labels, device=0):
+    """sum(adjacencymatrix.(clusts)) ./ numsamples on the GPU (mcmc.jl:560) for host label vectors."""
+    L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    out = np.zeros((L.shape[1], L.shape[1]))
+    check(lib().rc_psm(ptr(L), L.shape[0], L.shape[1], device, ptr(out)))
+    return out
+
+
+_LOSS = {"binder": 0, "omARI": 1, "VI": 2, "ID": 3}
+
+
+def mpel_loss_sums(labels, loss, device=0):
+    L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    sums = np.zeros(L.shape[0])
+    best = C.c_int64()
+    check(lib().rc_mpel(ptr(L), L.shape[0], L.shape[1], _LOSS[loss], device, ptr(sums), C.byref(best)))
+    return sums, best.value
+
+
+def getpointestimate(samples, method="MAP", loss="VI", device=0):
+    """getpointestimate(samples; method, loss) -> (clust, i)   (pointestimate.jl:17-60); i is 0-based here."""
+    if method == "MPEL" and isinstance(loss, str) and loss not in _LOSS:
+        raise ArgumentError("Invalid loss function specifier.")
+    if method not in ("MAP", "MLE", "MPEL"):
+        raise ArgumentError("Invalid method specifier.")
+    if method == "MAP":
+        i = int(np.argmax(samples.logposterior))
+    elif method == "MLE":
+        i = int(np.argmax(samples.loglik))
+    elif isinstance(loss, str):
+        _, i = mpel_loss_sums(np.stack(samples.clusts), loss, device)
+    else:                                                   # user-supplied loss: host loop, as the reference
+        cl = samples.clusts
+        S = len(cl)
+        M = np.zeros((S, S))
+        for a in range(S):
+            for b in range(a + 1, S):
+                M[a, b] = loss(cl[a], cl[b])
+        i = int(np.argmin((M + M.T).sum(0)))
+    return samples.clusts[i], i
+
+
+def _pair_loss(a, b, loss):
+    sums, _ = mpel_loss_sums(np.stack([np.asarray(a, np.int64), np.asarray(b, np.int64)]), loss)
+    return float(sums[0])
+
+
+def binderloss(a, b, normalised=True):
+    if len(a) != len(b):
+        raise ArgumentError("Length of the input vectors must be equal.")
+    n = len(a)
+    return _pair_loss(a, b, "binder") * (1 if normalised else n * (n - 1) // 2)
+
+
+def infodist(a, b, normalised=True):
+    if len(a) != len(b):
+        raise ArgumentError("Length of the input vectors must be equal.")
+    d = _pair_loss(a, b, "ID")
+    if not normalised:
+        return d
+    n = len(a)
+    def H(x):
+        c = np.unique(x, return_counts=True)[1] / n
+        return float(-(c * np.log(c)).sum())
+    m = max(H(a), H(b))
+    return 1 - (m - d) / m if m > 0 else float("nan")
+
+
+def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None, device=0, oracle=False):
+    """generatemixture(N, K; α, dim, radius, σ, rng) (utils.jl:101-147): Dirichlet weights, sorted labels,
+    simplex-vertex centres, isotropic normal points, Euclidean distance matrix (built on the GPU).
+    The 5000-iteration oracle co-clustering matrix (utils.jl:130-143) is not consumed by the sampler and is
+    out of scope of this build: `oracle_coclustering` is None unless oracle=True is implemented later."""
+    alpha = K if alpha is None else alpha
+    dim = K if dim is None else dim
+    if N < 1:
+        raise ArgumentError("N must be greater than 1.")
+    if K < 1 or K > N:
+        raise ArgumentError("K must satisfy 1 ≤ K ≤ N.")
+    if alpha <= 0:
+        raise ArgumentError("α must be positive.")
+    if dim < K:
+        raise ArgumentError("dim must be ≥ K.")
+    if radius <= 0:
+        raise ArgumentError("radius must be positive.")
+    if sigma <= 0:
+        raise ArgumentError("σ must be positive.")
+    g = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+    probs = g.dirichlet(np.full(K, float(alpha)))
+    clusts = np.sort(g.choice(K, size=N, p=probs)) + 1
+    pts = g.normal(0.0, sigma, size=(N, dim))
+    pts[np.arange(N), clusts - 1] += radius
+    data = MCMCData.from_points(pts, device=device)
+    return dict(points=[pts[i] for i in range(N)], distancematrix=data.D, clusts=clusts.astype(np.int64), probs=probs,
+                oracle_coclustering=None, data=data)
+
+
+def params_from_labels(D, labels, eta=None, sigma=None, u=None, v=None, **kw):
+    """Hyperparameters from a notional clustering, exactly as fitprior does after its clustering step
+    (prior.jl:73-110): Gamma MLE shapes of within / between distances, alpha = |A| delta1, beta = sum(A),
+    zeta = |B| delta2, gamma = sum(B).  eta, sigma, u, v default to moment matches of (r, p) ~ NegBin fit."""
+    from .prior import gamma_mle_shape
+    D = np.asarray(D); labels = np.asarray(labels)
+    n = D.shape[0]
+    iu = np.triu_indices(n, 1)
+    same = (labels[:, None] == labels[None, :])[iu]
+    d = D[iu]
+    A, B = d[same], d[~same]
+    K = len(np.unique(labels))
+    if A.size:
+        d1 = gamma_mle_shape(A); al, be = A.size * d1, float(A.sum())
+    else:
+        d1, al, be = 1.0, 1.0, 1.0
+    if B.size:
+        d2 = gamma_mle_shape(B); ze, ga = B.size * d2, float(B.sum())
+    else:
+        d2, ze, ga = 1.0, 1.0, 1.0
+    p = dict(delta1=d1, alpha=al, beta=be, delta2=d2, zeta=ze, gamma=ga, eta=4.0 if eta is None else eta,
+             sigma=2.0 if sigma is None else sigma, u=2.0 if u is None else u, v=20.0 if v is None else v, K_initial=K)
+    p.update(kw)
+    return PriorHyperparamsList(**p)

@@ -1,0 +1,279 @@
+"""Host-side prior fitting: fitprior / sampledist / sampleK and the notional clustering helpers
+(/root/reference/src/prior.jl:22-367, src/mcmc.jl:592-636 sample_rp).  SURVEY.md section 8(f) rank 1: caller
+of the hot path, kept on the host (one-off O(K) / O(n^2) work dominated by k-means / k-medoids, which
+are third-party Clustering.jl code in the reference).  The distance matrix it needs is built by the GPU
+kernel behind MCMCData (prior.jl:51,180)."""
+import math
+import warnings
+import numpy as np
+from scipy.special import digamma, polygamma, gammaln, betaln
+
+
+class ArgumentError(ValueError):
+    pass
+
+
+# ---- third-party pieces restated (Clustering.jl kmeans / kmedoids, Distributions.fit_mle) -----------
+def kmedoids(D, k, maxiter=1000, rng=None):
+    """Clustering.kmedoids(D, k; maxiter): alternate assignment / medoid update from a random seeding."""
+    D = np.asarray(D)
+    n = D.shape[0]
+    g = np.random.default_rng(0 if rng is None else rng)
+    # k-medoids++ style seeding (Clustering.jl's default :kmpp)
+    med = [int(g.integers(n))]
+    mind = D[med[0]].copy()
+    for _ in range(1, k):
+        w = mind ** 2
+        tot = w.sum()
+        nxt = int(g.choice(n, p=w / tot)) if tot > 0 else int(g.integers(n))
+        med.append(nxt)
+        mind = np.minimum(mind, D[nxt])
+    med = np.array(med)
+    converged = False
+    assign = np.argmin(D[med], axis=0)
+    for _ in range(maxiter):
+        newmed = med.copy()
+        for c in range(k):
+            mem = np.where(assign == c)[0]
+            if mem.size:
+                newmed[c] = mem[np.argmin(D[np.ix_(mem, mem)].sum(0))]
+        newassign = np.argmin(D[newmed], axis=0)
+        if np.array_equal(newmed, med) and np.array_equal(newassign, assign):
+            converged = True
+            break
+        med, assign = newmed, newassign
+    cost = float(D[med[assign], np.arange(n)].sum())
+    return dict(assignments=(assign + 1).astype(np.int64), medoids=med, totalcost=cost, converged=converged)
+
+
+def kmeans(X, k, maxiter=1000, rng=None):
+    """Clustering.kmeans(X, k; maxiter) with X dim x n (columns are observations), k-means++ seeding."""
+    X = np.asarray(X, dtype=np.float64)
+    P = X.T
+    n = P.shape[0]
+    g = np.random.default_rng(0 if rng is None else rng)
+    cent = [P[int(g.integers(n))]]
+    d2 = ((P - cent[0]) ** 2).sum(1)
+    for _ in range(1, k):
+        tot = d2.sum()
+        nxt = int(g.choice(n, p=d2 / tot)) if tot > 0 else int(g.integers(n))
+        cent.append(P[nxt])
+        d2 = np.minimum(d2, ((P - P[nxt]) ** 2).sum(1))
+    cent = np.array(cent)
+    assign = np.zeros(n, np.int64)
+    converged = False
+    for it in range(maxiter):
+        dist = ((P[:, None, :] - cent[None, :, :]) ** 2).sum(2) if n * k <= 4_000_000 else \
+            (P ** 2).sum(1)[:, None] + (cent ** 2).sum(1)[None, :] - 2 * P @ cent.T
+        newassign = np.argmin(dist, axis=1)
+        if it > 0 and np.array_equal(newassign, assign):
+            converged = True
+            break
+        assign = newassign
+        for c in range(k):
+            mem = assign == c
+            if mem.any():
+                cent[c] = P[mem].mean(0)
+    cost = float(((P - cent[assign]) ** 2).sum())
+    return dict(assignments=(assign + 1).astype(np.int64), centers=cent.T, totalcost=cost, converged=converged)
+
+
+def gamma_mle_shape(x, w=None):
+    """shape(fit_mle(Gamma, x[, w])): Newton iteration on log(a) - digamma(a) = log(mean) - mean(log)."""
+    x = np.asarray(x, dtype=np.float64)
+    if w is None:
+        mx, mlx = x.mean(), np.log(x).mean()
+    else:
+        w = np.asarray(w, dtype=np.float64)
+        mx, mlx = (w * x).sum() / w.sum(), (w * np.log(x)).sum() / w.sum()
+    s = math.log(mx) - mlx
+    if not s > 0:
+        return 1e8
+    a = (3 - s + math.sqrt((s - 3) ** 2 + 24 * s)) / (12 * s)
+    for _ in range(1000):
+        f = math.log(a) - float(digamma(a)) - s
+        fp = 1 / a - float(polygamma(1, a))
+        an = a - f / fp
+        if an <= 0:
+            an = a / 2
+        if abs(an - a) <= 1e-16 * max(1.0, a) * 16:
+            a = an
+            break
+        a = an
+    return float(a)
+
+
+def gamma_mle(x, w=None):
+    """(shape, rate) of fit_mle(Gamma, x)."""
+    a = gamma_mle_shape(x, w)
+    x = np.asarray(x, dtype=np.float64)
+    m = x.mean() if w is None else float((np.asarray(w) * x).sum() / np.sum(w))
+    return a, a / m
+
+
+def beta_mle(x, maxiter=1000, tol=1e-14):
+    """Distributions.fit_mle(Beta, x): Newton on the digamma equations from moment-matched start."""
+    x = np.asarray(x, dtype=np.float64)
+    m, v = x.mean(), x.var()
+    t = m * (1 - m) / v - 1 if v > 0 else 1.0
+    a, b = max(m * t, 1e-3), max((1 - m) * t, 1e-3)
+    g1, g2 = np.log(x).mean(), np.log1p(-x).mean()
+    for _ in range(maxiter):
+        f = np.array([digamma(a) - digamma(a + b) - g1, digamma(b) - digamma(a + b) - g2])
+        t3 = polygamma(1, a + b)
+        J = np.array([[polygamma(1, a) - t3, -t3], [-t3, polygamma(1, b) - t3]])
+        step = np.linalg.solve(J, f)
+        an, bn = a - step[0], b - step[1]
+        if an <= 0: an = a / 2
+        if bn <= 0: bn = b / 2
+        done = abs(an - a) + abs(bn - b) < tol * (a + b)
+        a, b = float(an), float(bn)
+        if done:
+            break
+    return a, b
+
+
+def detectknee(x, y):
+    """prior.jl:340-360."""
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    ind = np.argsort(x, kind="stable")
+    x, y = x[ind], y[ind]
+    a = (y[-1] - y[0]) / (x[-1] - x[0]) if x[-1] != x[0] else float("nan")
+    b = y[0] - a * x[0]
+    dist = np.abs(a * x + b - y) / math.sqrt(a * a + 1)
+    if np.isnan(dist).all():
+        return x[0], y[0]
+    i = int(np.nanargmax(dist)) if not np.isnan(dist[0]) else 0
+    return x[i], y[i]
+
+
+def _trunc_logcdf_ratio(r, cand, sd):
+    from scipy.stats import norm
+    return norm.logcdf(r / sd) - norm.logcdf(cand / sd)
+
+
+def sample_rp(clustsizes, numiters=5000, burnin=None, thin=1, params=None, rng=None):
+    """mcmc.jl:592-636: (r, p)-only chain for fixed cluster sizes (default hyperparameters when called from
+    fitprior: eta = sigma = u = v = 1, proposalsd_r = 1)."""
+    g = np.random.default_rng(0 if rng is None else rng)
+    burnin = int(math.floor(0.2 * numiters)) if burnin is None else burnin
+    eta = sigma = u = v = sd = 1.0
+    if params is not None:
+        eta, sigma, u, v, sd = params.eta, params.sigma, params.u, params.v, params.proposalsd_r
+    C = np.asarray([c for c in clustsizes if c > 0], dtype=np.float64)
+    n, K = C.sum(), len(C)
+    r = g.gamma(eta, sigma)          # quirk Q6: scale sigma here (mcmc.jl:617)
+    p = g.beta(u, v)
+    rs, ps = [], []
+    from scipy.stats import truncnorm, norm
+    for i in range(1, numiters + 1):
+        cand = truncnorm.rvs((0 - r) / sd, np.inf, loc=r, scale=sd, random_state=g)
+        l1mp = math.log1p(-p) if p < 1 else -np.inf
+        lpc = (eta - 1) * math.log(cand) + K * (cand * l1mp - gammaln(cand)) - cand * sigma + gammaln(C - 1 + cand).sum()
+        lpr = (eta - 1) * math.log(r) + K * (r * l1mp - gammaln(r)) - r * sigma + gammaln(C - 1 + r).sum()
+        lratio = norm.logcdf(cand / sd) - norm.logcdf(r / sd)     # log pdf ratio of the two truncated normals
+        if math.log(g.random()) < min(0.0, lpc - lpr - lratio):
+            r = cand
+        p = g.beta(n - K + u, r * K + v)
+        if i > burnin and (i - burnin) % thin == 0:
+            rs.append(r); ps.append(p)
+    return dict(r=np.array(rs), p=np.array(ps))
+
+
+def _prepare(data, algo, diss, Kmin, Kmax, device):
+    from .host import MCMCData, makematrix
+    if isinstance(data, (list, tuple)):
+        if diss:
+            raise ArgumentError("diss = true but data is not a dissimilarity matrix. Assuming that the data is a vector of observations.")
+        x = makematrix(data)
+        diss = False
+    else:
+        x = np.asarray(data, dtype=np.float64)
+    N = x.shape[1]
+    if diss and x.shape[0] != x.shape[1]:
+        raise ArgumentError("Supplied dissimilarity matrix is not square.")
+    if algo == "k-means" and diss:
+        raise ArgumentError("Cannot use algorithm `k-means` with a dissimilarity matrix.")
+    if algo not in ("k-means", "k-medoids"):
+        raise ArgumentError("Algo must be 'k-means' or 'k-medoids'.")
+    Kmax = N // 2 if Kmax is None else Kmax
+    if not (1 <= Kmin <= Kmax <= N):
+        raise ArgumentError("Kmin and Kmax must satisfy 1 ≤ Kmin ≤ Kmax ≤ N")
+    dissM = x if diss else MCMCData.from_points(x.T, device=device).D      # pairwise(Euclidean(), x, dims=2)
+    return x, N, dissM, Kmax
+
+
+def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, rng=None):
+    """fitprior(data, algo, diss = false; Kmin, Kmax, verbose) -> PriorHyperparamsList   (prior.jl:22-128)."""
+    from .host import PriorHyperparamsList, uppertriangle
+    x, N, dissM, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
+    if verbose:
+        print("Fitting prior hyperparameters")
+    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dissM)
+    objective = np.zeros(Kmax - Kmin + 1)
+    for k in range(1, Kmax - Kmin + 2):            # quirk Q11: clusters with k = loop index (prior.jl:63-64)
+        t = clustfn(inp, k, maxiter=1000, rng=rng)
+        objective[k - 1] = t["totalcost"]
+        if not t["converged"]:
+            warnings.warn(f"Clustering did not converge at K = {k}")
+    K = int(detectknee(np.arange(Kmin, Kmax + 1), objective)[0])
+    notional = clustfn(inp, K, maxiter=1000, rng=rng)["assignments"]
+    adj = uppertriangle(notional[:, None] == notional[None, :])
+    ut = uppertriangle(dissM)
+    A, B = ut[adj], ut[~adj]
+    sizes = np.bincount(notional)[1:]
+    t = sample_rp(sizes, rng=rng)
+    proposalsd_r = float(np.std(t["r"], ddof=1))
+    eta, sigma = gamma_mle(t["r"])
+    u, v = beta_mle(t["p"])
+    if K == N:
+        warnings.warn("Got a notional clustering of entirely singletons. Falling back to defaults for cohesion parameters.")
+        d1, al, be = 1.0, 1.0, 1.0
+    else:
+        d1 = gamma_mle_shape(A); al = A.size * d1; be = float(A.sum())
+    if K == 1:
+        warnings.warn("Got a notional clustering with a single cluster. Falling back to defaults for repulsion parameters.")
+        d2, ze, ga = 1.0, 1.0, 1.0
+    else:
+        d2 = gamma_mle_shape(B); ze = B.size * d2; ga = float(B.sum())
+    return PriorHyperparamsList(delta1=d1, delta2=d2, alpha=al, beta=be, zeta=ze, gamma=ga, eta=eta, sigma=sigma,
+                                proposalsd_r=proposalsd_r, u=u, v=v, K_initial=K)
+
+
+def sampledist(params, type, numsamples=1, rng=None):
+    """prior.jl:284-308."""
+    if type not in ("intercluster", "intracluster"):
+        raise ArgumentError('type must be either "intercluster" or "intracluster".')
+    if numsamples < 1:
+        raise ArgumentError("numsamples must be a positive integer.")
+    g = np.random.default_rng(rng)
+    a, b, d = (params.alpha, params.beta, params.delta1) if type == "intracluster" else (params.zeta, params.gamma, params.delta2)
+    lam = g.gamma(a, 1 / b, size=numsamples)
+    return g.gamma(d, 1 / lam)
+
+
+def sampleK(params_or_eta, *args, rng=None):
+    """sampleK(params, numsamples, n) / sampleK(eta, sigma, u, v, numsamples, n)   (prior.jl:316-338)."""
+    if hasattr(params_or_eta, "eta"):
+        q = params_or_eta
+        eta, sigma, u, v = q.eta, q.sigma, q.u, q.v
+        numsamples, n = args
+    else:
+        eta = params_or_eta
+        sigma, u, v, numsamples, n = args
+    if n < 1:
+        raise ArgumentError("n must be a positive integer.")
+    if numsamples < 1:
+        raise ArgumentError("numsamples must be a positive integer.")
+    g = np.random.default_rng(rng)
+    K = np.arange(1, n)
+    out = np.zeros(numsamples, np.int64)
+    for i in range(numsamples):
+        r, p = g.gamma(eta, 1 / sigma), g.beta(u, v)
+        lp = np.zeros(n)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lp[:n - 1] = (r * K) * np.log1p(-p) + (n - K) * np.log(p) - np.log(n - K) - betaln(r * K, n - K)
+            lp[n - 1] = r * n * np.log1p(-p)
+        lp = lp - lp.min()
+        out[i] = int(np.argmax(-np.log(-np.log(g.random(n))) + lp)) + 1
+    return out

@@ -1,0 +1,137 @@
+"""GPU parity tests of the persistent chain kernel against the CPU oracle (same structured random stream):
+label trajectories, K, r, p, acceptances bit-exact; loglik / logposterior bit-exact (the block sums are
+exact integers, so the fp64 evaluation sees identical inputs) -- the north-star tolerance is 1e-10 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def oparams(orc, params):
+    return orc.make_params(**{k: getattr(params, k) for k in params._fields})
+
+
+def run_both(pkg, orc, D, labels, params, numiters, burnin, thin, numGibbs, numMH, seed, nchains=1, slot_cap=0):
+    opts = pkg.MCMCOptionsList(numiters=numiters, burnin=burnin, thin=thin, numGibbs=numGibbs, numMH=numMH)
+    data = pkg.MCMCData(np.ascontiguousarray(D))
+    labs = np.tile(np.asarray(labels, np.int64), (nchains, 1))
+    rp = [pkg.init_rp(params, seed, c) for c in range(nchains)]
+    smp = pkg.Sampler(data, opts, params, labs, [x[0] for x in rp], [x[1] for x in rp], seed=seed, slot_cap=slot_cap)
+    smp.run(-1)
+    out = []
+    for c in range(nchains):
+        got = smp.samples(c)
+        ref = orc.run_chain(D, orc.Options(numiters, burnin, thin, numGibbs, numMH), oparams(orc, params), labels,
+                            rp[c][0], rp[c][1], seed=seed, chain=c)
+        st = smp.state(c)
+        out.append((got, ref, st))
+    return out, smp
+
+
+def assert_same(got, ref, st=None):
+    assert np.array_equal(got["r_acc"], ref["r_acc"])
+    assert np.array_equal(got["sm_split"], ref["sm_split"])
+    assert np.array_equal(got["sm_acc"], ref["sm_acc"])
+    assert np.array_equal(got["K"], ref["K"])
+    assert np.array_equal(got["labels"], ref["labels"])
+    for k in ("r", "p", "loglik", "logposterior"):
+        assert np.array_equal(got[k], ref[k]), (k, got[k][:4], ref[k][:4])
+    if st is not None:
+        assert np.array_equal(st.clusts, ref["final_labels"])
+        assert st.r == ref["final_rp"][0] and st.p == ref["final_rp"][1]
+
+
+def mixture(n, K, dim, sigma, seed):
+    g = np.random.default_rng(seed)
+    w = g.dirichlet(np.full(K, float(K)))
+    lab = np.sort(g.choice(K, size=n, p=w)) + 1
+    lab = (np.unique(lab, return_inverse=True)[1] + 1).astype(np.int64)
+    X = g.normal(0, sigma, size=(n, dim))
+    X[np.arange(n), lab - 1] += 1.0
+    return X, lab
+
+
+def test_loglik_matches_oracle(pkg, orc, golden):
+    for k in (1, 2, 3):
+        D, lab = golden[k]["distance_matrix"], golden[k]["cluster_labels"]
+        params = pkg.params_from_labels(D, lab)
+        data = pkg.MCMCData(D)
+        import ctypes as C
+        out = C.c_double()
+        q = params._c()
+        from redclust_jl_b200._lib import lib, check, ptr
+        for labels in (lab, np.random.default_rng(k).integers(1, 7, size=lab.size)):
+            labels = np.ascontiguousarray(labels, dtype=np.int64)
+            check(lib().rc_loglik(data._h, C.byref(q), ptr(labels), C.byref(out)))
+            assert out.value == orc.loglik(D, oparams(orc, params), labels)
+
+
+def test_fixture_gibbs_only(pkg, orc, golden):
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab)
+    (res,), _ = run_both(pkg, orc, D, lab, params, 60, 10, 1, 5, 0, seed=11)
+    assert_same(*res)
+
+
+def test_fixture_default_options(pkg, orc, golden):
+    for k in (1, 2, 3):
+        D, lab = golden[k]["distance_matrix"], golden[k]["cluster_labels"]
+        params = pkg.params_from_labels(D, lab)
+        (res,), _ = run_both(pkg, orc, D, lab, params, 150, 30, 3, 5, 1, seed=100 + k)
+        assert_same(*res)
+        assert res[1]["sm_split"].sum() > 0 and (1 - res[1]["sm_split"]).sum() > 0      # both move types exercised
+
+
+def test_single_cluster_start_and_no_repulsion(pkg, orc, golden):
+    D = golden[3]["distance_matrix"]
+    lab = np.ones(100, np.int64)
+    params = pkg.params_from_labels(D, golden[3]["cluster_labels"], repulsion=False)
+    (res,), _ = run_both(pkg, orc, D, lab, params, 80, 0, 1, 3, 1, seed=5)
+    assert_same(*res)
+
+
+def test_maxK_and_numGibbs0(pkg, orc, golden):
+    D, lab = golden[2]["distance_matrix"], golden[2]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab, maxK=10)
+    (res,), _ = run_both(pkg, orc, D, lab, params, 80, 0, 1, 0, 1, seed=9)
+    assert_same(*res)
+    assert res[0]["K"].max() <= 10
+
+
+def test_multichain_n1000(pkg, orc):
+    X, lab = mixture(1000, 20, 50, 0.25, 3)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab)
+    res, smp = run_both(pkg, orc, D, lab, params, 12, 2, 2, 5, 1, seed=77, nchains=4)
+    for got, ref, st in res:
+        assert_same(got, ref, st)
+    # PSM counts of the device-resident samples are exact integers
+    S = res[0][1]["labels"].shape[0]
+    psm = smp.psm(0, 4)
+    cnt = sum(orc.psm_counts(r[1]["labels"]) for r in res)
+    assert np.array_equal(psm * (4 * S), cnt)
+
+
+def test_multitile_n2500_resume(pkg, orc):
+    X, lab = mixture(2500, 12, 20, 0.3, 8)     # two row tiles (RC_W = 2048)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab)
+    opts = pkg.MCMCOptionsList(numiters=6, burnin=0, thin=1)
+    r0, p0 = pkg.init_rp(params, 1, 0)
+    smp = pkg.Sampler(data, opts, params, lab, r0, p0, seed=1)
+    smp.run(2); smp.run(1); smp.run(-1)                   # resumable: three launches == one run
+    got = smp.samples(0)
+    ref = orc.run_chain(D, orc.Options(6, 0, 1, 5, 1), oparams(orc, params), lab, r0, p0, seed=1, chain=0)
+    assert_same(got, ref, smp.state(0))
+
+
+def test_slot_overflow_is_reported(pkg, golden):
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab)
+    opts = pkg.MCMCOptionsList(numiters=50, burnin=0, thin=1)
+    smp = pkg.Sampler(pkg.MCMCData(D), opts, params, lab, 1.0, 0.5, seed=2, slot_cap=10)
+    with pytest.raises(pkg.RCError) as e:
+        smp.run(-1)
+    assert e.value.status == -5
