@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sampler hot path (BASELINE.json: "Gibbs+SM sweeps/sec x chains at n=10k").
+
+One *step* = one iteration of runsampler's loop (sample_r, sample_p, one split-merge proposal with 5 restricted
+Gibbs scans, one full Gibbs scan, record) for EVERY chain on the GPU = one launch of the persistent chain
+kernel.  Workload at N=1: BASELINE configs[2] "generatemixture n=10,000 K~50 dim=100, fp64 distM (800 MB),
+256 chains"; with N GPUs every rank runs its own 256 chains (independent chains shard with no data-path
+collective -> weak scaling).  Prints ONE JSON line (see the task contract).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun ... bench.py --gpus N ...        (N > 1)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+
+def synth(n, K, dim, sigma, alpha, seed):
+    """Point generator of generatemixture (utils.jl:113-128) without the oracle co-clustering loop."""
+    g = np.random.default_rng(seed)
+    probs = g.dirichlet(np.full(K, float(alpha)))
+    lab = np.sort(g.choice(K, size=n, p=probs))
+    lab = (np.unique(lab, return_inverse=True)[1] + 1).astype(np.int64)
+    X = g.normal(0.0, sigma, size=(n, dim))
+    X[np.arange(n), lab - 1] += 1.0
+    return X, lab
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def profile_traffic(n):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this n."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(str(n))
+    except Exception:
+        return None
+
+
+def cpu_reference(args, X, lab, params_fields, steps, warmup, cores, D=None):
+    """The CPU restatement of RedClust.jl (oracle/rc_oracle.cpp) on the host cores: `cores` independent chains,
+    one per thread, each running one sweep per step.  Returns (chain-sweeps/s, ms per step, description)."""
+    orc = graft.load_oracle()
+    if D is None:
+        D = orc.distm(X)
+    P = orc.make_params(**params_fields)
+    r0 = [1.5] * cores
+    p0 = [0.9] * cores
+    if warmup > 0:
+        orc.time_chains(D, orc.Options(min(warmup, 1), 0, 1, args.numGibbs, args.numMH), P, lab, r0, p0, seed=args.seed, nthreads=cores)
+    secs, _ = orc.time_chains(D, orc.Options(steps, 0, 1, args.numGibbs, args.numMH), P, lab, r0, p0, seed=args.seed, nthreads=cores)
+    return cores * steps / secs, secs / steps * 1e3, f"{cores} independent chains x {steps} sweeps of the n={args.n} workload, one chain per host thread"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10000)
+    ap.add_argument("--K", type=int, default=50)
+    ap.add_argument("--dim", type=int, default=100)
+    ap.add_argument("--sigma", type=float, default=0.1)
+    ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--numGibbs", type=int, default=5)
+    ap.add_argument("--numMH", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=44)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 0)
+    steps = max(args.steps, 1)
+    workload = (f"generatemixture(N={args.n}, K={args.K}; alpha={args.K}, sigma={args.sigma}, dim={args.dim}) seed {args.seed}, "
+                f"{args.chains} chains per GPU, numGibbs={args.numGibbs}, numMH={args.numMH}, every sweep recorded")
+    config = {"workload": workload, "n": args.n, "chains_per_gpu": args.chains, "hyperparameters": "from true labels as prior.jl:73-110",
+              "init": "true labels, r/p from their priors", "l2": f"inputs larger than L2 (DL = {16 * args.n * args.n / 1e9:.2f} GB streamed per chain-sweep)"}
+    X, lab = synth(args.n, args.K, args.dim, args.sigma, args.K, args.seed)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pkg_fields = None
+        orc = graft.load_oracle()
+        D = orc.distm(X)
+        pkg = graft.load_package()
+        params = pkg.params_from_labels(D, lab)
+        fields = {k: getattr(params, k) for k in params._fields}
+        cores = os.cpu_count() or 1
+        val, ms, sample = cpu_reference(args, X, lab, fields, steps, W, cores, D=D)
+        line = {"impl": "reference", "metric": "Gibbs+SM chain-sweeps/sec", "value": val, "unit": "chain-sweeps/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 (exact i64 fixed-point cluster sums)", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "CPU restatement of RedClust.jl v1.2.2 (Julia is not installed; the reference itself is single-threaded)"}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = graft.load_package()
+
+    # ---- setup (untimed): distance matrix on the GPU, hyperparameters, chains ----
+    data = pkg.MCMCData.from_points(X, device=local_rank)
+    Dh = data.D
+    params = pkg.params_from_labels(Dh, lab)
+    opts = pkg.MCMCOptionsList(numiters=W + steps, burnin=0, thin=1, numGibbs=args.numGibbs, numMH=args.numMH)
+    chain0 = rank * args.chains
+    rp = [pkg.init_rp(params, args.seed, chain0 + c) for c in range(args.chains)]
+    r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
+    labs = np.tile(lab, (args.chains, 1))
+    smp = pkg.Sampler(data, opts, params, labs, r0, p0, seed=args.seed, chain_offset=chain0)
+    smp.run(0)                       # builds the block-sum matrices (setup, like MCMCData construction)
+    for _ in range(W):
+        smp.run(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clk = ClockSampler(local_rank)
+    barrier()
+    clk.start()
+    _, t0 = smp.progress()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        smp.run(1)                   # ONE launch of the persistent chain kernel per step
+    barrier()
+    w1 = time.perf_counter()
+    _, t1 = smp.progress()
+    clk.stop_flag = True
+    dev_s = t1 - t0                  # CUDA events on the launching stream, summed over the K launches
+    tt = torch.tensor([dev_s, w1 - w0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = float(tt[0]), float(tt[1])
+    value = world * args.chains * steps / dev_s
+    st = smp.samples(0)
+    Kfinal = int(st["K"][-1])
+    smp.close()
+
+    # ---- end-to-end through the public API with HOST buffers (upload D, build, run, read results back) ----
+    e2e = None
+    if not args.no_e2e:
+        Dp = torch.from_numpy(Dh).pin_memory()
+        barrier()
+        e0 = time.perf_counter()
+        d2 = pkg.MCMCData(Dp.numpy(), device=local_rank)
+        o2 = pkg.MCMCOptionsList(numiters=steps, burnin=0, thin=1, numGibbs=args.numGibbs, numMH=args.numMH)
+        s2 = pkg.Sampler(d2, o2, params, labs, r0, p0, seed=args.seed, chain_offset=chain0)
+        s2.run(-1)
+        outs = [s2.samples(c) for c in range(args.chains)]
+        barrier()
+        e1 = time.perf_counter()
+        et = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        h2d = Dh.nbytes + labs.nbytes + r0.nbytes + p0.nbytes
+        d2h = sum(sum(v.nbytes for v in o.values()) for o in outs)
+        e2e = {"value": world * args.chains * steps / float(et[0]), "unit": "chain-sweeps/s",
+               "h2d_bytes_per_step": int(h2d / steps), "d2h_bytes_per_step": int(d2h / steps),
+               "includes": "upload of D from pinned host memory, logD / fixed-point build, block-sum init, sampling, readback of all samples"}
+        s2.close()
+        del d2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    b_scan = 16.0 * args.n * (args.n - 1)                         # algorithmic bytes per chain-sweep
+    per_launch_bytes = b_scan * args.chains
+    achieved = per_launch_bytes / (dev_s / steps) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profile_traffic(args.n), "kernel": "k_chain", "peak_source": peak_src + " (of measured)",
+                "algorithmic_bytes_per_launch": per_launch_bytes,
+                "note": "algorithmic bytes = chains x 16 n (n-1) per sweep (full scan only); chains that walk the same rows share them through L2, so DRAM traffic can be far below the algorithmic bytes"}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cores = os.cpu_count() or 1
+        fields = {k: getattr(params, k) for k in params._fields}
+        v, ms, sample = cpu_reference(args, X, lab, fields, args.cpu_steps, 0, cores, D=Dh)
+        cpu = {"value": v, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample}
+    line = {"metric": "Gibbs+SM chain-sweeps/sec", "value": value, "unit": "chain-sweeps/s", "n_gpus": world, "steps": steps, "warmup": W,
+            "ms_per_step": dev_s / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (exact i64 fixed-point cluster sums)", "data": "synthetic", "config": config,
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": steps, "roofline": roofline, "cpu_baseline": cpu,
+            "wall_ms_per_step": wall_s / steps * 1e3, "K_final_chain0": Kfinal}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,7 @@ def lib():
         L.rco_run.restype = C.c_int
         L.rco_loglik.restype = C.c_double
         L.rco_logprior.restype = C.c_double
+        L.rco_time_chains.restype = C.c_double
         for f in ("rco_log", "rco_exp", "rco_log1p", "rco_lgamma", "rco_erfc", "rco_normcdf", "rco_norminv"):
             getattr(L, f).restype = C.c_double
             getattr(L, f).argtypes = [C.c_double]
@@ -97,6 +98,19 @@ def run_chain(D, options, params, init_labels, init_r, init_p, seed=0, chain=0, 
                   _p(out["r_acc"], C.c_uint8), _p(out["sm_acc"], C.c_uint8), _p(out["sm_split"], C.c_uint8),
                   _p(out["final_labels"], C.c_int64), _p(out["final_rp"], C.c_double))
     return out
+
+
+def time_chains(D, options, params, init_labels, init_r, init_p, seed=0, chain0=0, nthreads=1, sum_mode=0):
+    """Timed multi-chain run (bench.py cpu_baseline / --impl reference).  Returns (seconds in the loops, final K)."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    r = np.ascontiguousarray(init_r, dtype=np.float64); p = np.ascontiguousarray(init_p, dtype=np.float64)
+    init = np.ascontiguousarray(init_labels, dtype=np.int64)
+    K = np.zeros(r.size, np.int64)
+    secs = lib().rco_time_chains(_p(D, C.c_double), C.c_int64(n), C.byref(options), C.byref(params), _p(init, C.c_int64),
+                                 _p(r, C.c_double), _p(p, C.c_double), C.c_uint64(seed), C.c_int64(chain0),
+                                 C.c_int64(r.size), C.c_int(nthreads), C.c_int(sum_mode), _p(K, C.c_int64))
+    return secs, K
 
 
 def loglik(D, params, labels, sum_mode=0):

@@ -24,6 +24,8 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <chrono>
 #include "../include/rcb200.h"
 #include "../redclust.jl_b200/csrc/rc_math.h"
 #include "../redclust.jl_b200/csrc/rc_rng.h"
@@ -549,6 +551,37 @@ void rco_distm(const double* X, int64_t dim, int64_t n, double* D) {
       D[i * n + j] = r; D[j * n + i] = r;
     }
   }
+}
+
+// Timed multi-chain driver for bench.py's cpu_baseline / --impl reference legs: the data images are built
+// once (untimed), then `nchains` independent chains run `sweeps` iterations of the loop at mcmc.jl:537-555
+// on `nthreads` host threads (one chain per thread at a time; the reference itself is single-threaded,
+// so this is the "one independent chain per core" figure of BASELINE.md section 4).  Returns the seconds
+// spent in the iteration loops (wall clock over all threads) and each chain's final K.
+double rco_time_chains(const double* D, int64_t n, const rc_options* O, const rc_params* P, const int64_t* init_labels,
+                       const double* init_r, const double* init_p, uint64_t seed, int64_t chain0, int64_t nchains,
+                       int nthreads, int sum_mode, int64_t* final_K) {
+  Data d; build_data(d, D, n, sum_mode);
+  std::vector<std::thread> th;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      for (int64_t c = t; c < nchains; c += nthreads) {
+        State s = make_state(init_labels, n, init_r[c], init_p[c]);
+        const uint64_t key = rc_chain_key(seed, (uint64_t)(chain0 + c));
+        std::vector<uint8_t> acc((size_t)std::max<int64_t>(O->numMH, 1)), spl((size_t)std::max<int64_t>(O->numMH, 1));
+        double sink = 0;
+        for (int64_t i = 1; i <= O->numiters; ++i) {
+          sample_r(s, *P, key, (uint32_t)i);
+          sample_p(s, *P, key, (uint32_t)i);
+          sample_labels(d, s, *P, *O, key, (uint32_t)i, acc.data(), spl.data());
+          if (i > O->burnin && (i - O->burnin) % O->thin == 0) sink += loglik(d, s, *P) + logprior(s, *P);
+        }
+        if (final_K) final_K[c] = s.K + (sink != sink ? 0 : 0);
+      }
+    });
+  for (auto& x : th) x.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // probes for tests/test_math.py

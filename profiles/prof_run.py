@@ -1,0 +1,29 @@
+"""Profiling driver: the bench workload (n=10k, 256 chains) with one init launch, one warm-up sweep and
+`--steps` profiled sweeps.  Used under ncu (see profiles/README.md); numbers printed here are not bench values."""
+import argparse, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft
+import bench
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=10000)
+ap.add_argument("--K", type=int, default=50)
+ap.add_argument("--dim", type=int, default=100)
+ap.add_argument("--chains", type=int, default=256)
+ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--numMH", type=int, default=1)
+a = ap.parse_args()
+pkg = graft.load_package()
+X, lab = bench.synth(a.n, a.K, a.dim, 0.1, a.K, 44)
+data = pkg.MCMCData.from_points(X)
+params = pkg.params_from_labels(data.D, lab)
+opts = pkg.MCMCOptionsList(numiters=1 + a.steps, burnin=0, thin=1, numMH=a.numMH)
+rp = [pkg.init_rp(params, 44, c) for c in range(a.chains)]
+smp = pkg.Sampler(data, opts, params, np.tile(lab, (a.chains, 1)), [x[0] for x in rp], [x[1] for x in rp], seed=44)
+smp.run(0)
+smp.run(1)
+for _ in range(a.steps):
+    smp.run(1)
+print("iters, device seconds:", smp.progress())

@@ -428,20 +428,36 @@ def params_from_labels(D, labels, eta=None, sigma=None, u=None, v=None, **kw):
     """Hyperparameters from a notional clustering, exactly as fitprior does after its clustering step
     (prior.jl:73-110): Gamma MLE shapes of within / between distances, alpha = |A| delta1, beta = sum(A),
     zeta = |B| delta2, gamma = sum(B).  eta, sigma, u, v default to moment matches of (r, p) ~ NegBin fit."""
-    from .prior import gamma_mle_shape
+    from .prior import gamma_shape_from_stats
     D = np.asarray(D); labels = np.asarray(labels)
     n = D.shape[0]
-    iu = np.triu_indices(n, 1)
-    same = (labels[:, None] == labels[None, :])[iu]
-    d = D[iu]
-    A, B = d[same], d[~same]
     K = len(np.unique(labels))
-    if A.size:
-        d1 = gamma_mle_shape(A); al, be = A.size * d1, float(A.sum())
+    # sufficient statistics of the within-cluster (A) and between-cluster (B) upper-triangle distances
+    tot_s, tot_l = 0.0, 0.0
+    for i0 in range(0, n, 1024):
+        blk = D[i0:i0 + 1024]
+        tot_s += float(blk.sum())
+        with np.errstate(divide="ignore"):
+            lg = np.log(blk)
+        lg[np.arange(blk.shape[0]), np.arange(i0, i0 + blk.shape[0])] = 0.0
+        tot_l += float(lg.sum())
+    tot_s = (tot_s - float(np.trace(D))) / 2; tot_l /= 2
+    nA, sA, lA = 0, 0.0, 0.0
+    for k in np.unique(labels):
+        mem = np.where(labels == k)[0]
+        if mem.size < 2:
+            continue
+        sub = D[np.ix_(mem, mem)]
+        iu = np.triu_indices(mem.size, 1)
+        vals = sub[iu]
+        nA += vals.size; sA += float(vals.sum()); lA += float(np.log(vals).sum())
+    nB, sB, lB = n * (n - 1) // 2 - nA, tot_s - sA, tot_l - lA
+    if nA:
+        d1 = gamma_shape_from_stats(sA / nA, lA / nA); al, be = nA * d1, sA
     else:
         d1, al, be = 1.0, 1.0, 1.0
-    if B.size:
-        d2 = gamma_mle_shape(B); ze, ga = B.size * d2, float(B.sum())
+    if nB:
+        d2 = gamma_shape_from_stats(sB / nB, lB / nB); ze, ga = nB * d2, sB
     else:
         d2, ze, ga = 1.0, 1.0, 1.0
     p = dict(delta1=d1, alpha=al, beta=be, delta2=d2, zeta=ze, gamma=ga, eta=4.0 if eta is None else eta,

@@ -78,14 +78,8 @@ def kmeans(X, k, maxiter=1000, rng=None):
     return dict(assignments=(assign + 1).astype(np.int64), centers=cent.T, totalcost=cost, converged=converged)
 
 
-def gamma_mle_shape(x, w=None):
-    """shape(fit_mle(Gamma, x[, w])): Newton iteration on log(a) - digamma(a) = log(mean) - mean(log)."""
-    x = np.asarray(x, dtype=np.float64)
-    if w is None:
-        mx, mlx = x.mean(), np.log(x).mean()
-    else:
-        w = np.asarray(w, dtype=np.float64)
-        mx, mlx = (w * x).sum() / w.sum(), (w * np.log(x)).sum() / w.sum()
+def gamma_shape_from_stats(mx, mlx):
+    """Gamma MLE shape from the sample mean and the mean of logs (Newton on log(a) - digamma(a) = log(mx) - mlx)."""
     s = math.log(mx) - mlx
     if not s > 0:
         return 1e8
@@ -101,6 +95,17 @@ def gamma_mle_shape(x, w=None):
             break
         a = an
     return float(a)
+
+
+def gamma_mle_shape(x, w=None):
+    """shape(fit_mle(Gamma, x[, w]))."""
+    x = np.asarray(x, dtype=np.float64)
+    if w is None:
+        mx, mlx = x.mean(), np.log(x).mean()
+    else:
+        w = np.asarray(w, dtype=np.float64)
+        mx, mlx = (w * x).sum() / w.sum(), (w * np.log(x)).sum() / w.sum()
+    return gamma_shape_from_stats(mx, mlx)
 
 
 def gamma_mle(x, w=None):

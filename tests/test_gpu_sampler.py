@@ -99,7 +99,7 @@ def test_maxK_and_numGibbs0(pkg, orc, golden):
 
 
 def test_multichain_n1000(pkg, orc):
-    X, lab = mixture(1000, 20, 50, 0.25, 3)
+    X, lab = mixture(1000, 20, 50, 0.18, 3)
     data = pkg.MCMCData.from_points(X)
     D = data.D
     params = pkg.params_from_labels(D, lab)
@@ -114,7 +114,7 @@ def test_multichain_n1000(pkg, orc):
 
 
 def test_multitile_n2500_resume(pkg, orc):
-    X, lab = mixture(2500, 12, 20, 0.3, 8)     # two row tiles (RC_W = 2048)
+    X, lab = mixture(2500, 12, 20, 0.2, 8)     # two row tiles (RC_W = 2048)
     data = pkg.MCMCData.from_points(X)
     D = data.D
     params = pkg.params_from_labels(D, lab)
