@@ -2,6 +2,7 @@
 // There is NO CPU fallback: every compute entry point needs a CUDA device.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 #include "rc_sampler.cuh"
@@ -21,12 +22,12 @@ struct rc_sampler {
   rc_params par;
   int64_t nchains, chain_offset, numsamples;
   uint64_t seed;
-  int cap, tiles, npad_max;
+  int cap, tiles, npad_max, G;
   size_t smem;
   // device
   double *LGA, *LGZ, *LOGN;
   uint8_t* labels; int* sizes; double *r, *p; int* status;
-  rc_i128 *WD, *WL; longlong2* T; unsigned short* Slist; double* terms;
+  rc_i128 *WD, *WL; longlong2* T; unsigned short* Slist; uint8_t* origM; double* terms;
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
@@ -73,7 +74,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
   kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;
   kp.labels = s->labels; kp.sizes = s->sizes; kp.r = s->r; kp.p = s->p; kp.status = s->status;
-  kp.WD = s->WD; kp.WL = s->WL; kp.T = s->T; kp.Slist = s->Slist; kp.terms = s->terms;
+  kp.WD = s->WD; kp.WL = s->WL; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.terms = s->terms;
   kp.out_labels = s->out_labels; kp.out_K = s->out_K; kp.out_r = s->out_r; kp.out_p = s->out_p;
   kp.out_ll = s->out_ll; kp.out_lp = s->out_lp; kp.r_acc = s->r_acc; kp.sm_acc = s->sm_acc; kp.sm_split = s->sm_split;
 }
@@ -96,7 +97,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   cudaSetDevice(s->d->device);
   cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
   cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
-  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->terms);
+  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->terms);
   cudaFree(s->out_labels); cudaFree(s->out_K); cudaFree(s->out_r); cudaFree(s->out_p); cudaFree(s->out_ll); cudaFree(s->out_lp);
   cudaFree(s->r_acc); cudaFree(s->sm_acc); cudaFree(s->sm_split);
   if (s->e0) cudaEventDestroy(s->e0);
@@ -125,13 +126,28 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   const int64_t npad = ((n + 7) & ~7LL) + 8LL * tiles * cap;
   if (npad > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(d->device));
-  const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad);
-  int maxsmem = 0;
+  int maxsmem = 0, nsm = 0;
   RC_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
-  if (smem > (size_t)maxsmem) {
-    rc_set_error("chain state needs %zu bytes of shared memory (> %d available): reduce n or slot_cap", smem, maxsmem);
+  RC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device));
+  // chains per CTA: the chains of a CTA share every staged row tile.  Use the smallest G that lets all
+  // chains be co-resident (so they stay in rough lock step and share rows through L2 as well).
+  int G = 0, forceG = 0;
+  if (const char* e = getenv("RCB200_CHAINS_PER_CTA")) forceG = atoi(e);   // test hook
+  for (int g : {1, 2, 4}) {
+    if (forceG && g != forceG) continue;
+    const size_t sm = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, g);
+    if (sm > (size_t)maxsmem) break;
+    G = g;
+    const int64_t ctas = (nchains + g - 1) / g;
+    const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g)));
+    if (ctas <= (int64_t)nsm * per_sm) break;
+  }
+  if (G == 0) {
+    rc_set_error("chain state needs %zu bytes of shared memory (> %d available): reduce n or slot_cap",
+                 rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, 1), maxsmem);
     return RC_ERR_ARG;
   }
+  const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G);
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
   std::vector<uint8_t> lab((size_t)nchains * n);
   std::vector<int> sizes((size_t)nchains * cap, 0);
@@ -153,7 +169,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   rc_sampler* s = new rc_sampler();
   memset(s, 0, sizeof(*s));
   s->d = d; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
-  s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem;
+  s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem; s->G = G;
   s->numsamples = (opt->numiters - opt->burnin) / opt->thin;   // floor((numiters - burnin) / thin), types.jl:55
   const size_t NS = (size_t)std::max<int64_t>(s->numsamples, 1);
 #define TRY(x) do { st = (x); if (st) { rc_sampler_destroy(s); return st; } } while (0)
@@ -162,7 +178,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   TRY(dalloc(&s->r, nchains)); TRY(dalloc(&s->p, nchains)); TRY(dalloc(&s->status, nchains));
   TRY(dalloc(&s->WD, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WL, (size_t)nchains * cap * cap));
   TRY(dalloc(&s->T, opt->numMH > 0 ? (size_t)nchains * n * cap : 1));
-  TRY(dalloc(&s->Slist, (size_t)nchains * n)); TRY(dalloc(&s->terms, (size_t)nchains * cap * cap));
+  TRY(dalloc(&s->Slist, (size_t)nchains * (n + 2))); TRY(dalloc(&s->origM, (size_t)nchains * (n + 2))); TRY(dalloc(&s->terms, (size_t)nchains * cap * cap));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
   TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));
@@ -197,7 +213,7 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   kp.it0 = s->iters_done; kp.it1 = it1;
   kp.init_W = s->W_ready ? 0 : 1;
   RC_CUDA(cudaEventRecord(s->e0, s->stream));
-  rc_launch_chain_kernel(kp, s->smem, s->stream);
+  rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
   RC_CUDA(cudaGetLastError());
   RC_CUDA(cudaEventRecord(s->e1, s->stream));
   RC_CUDA(cudaStreamSynchronize(s->stream));
@@ -300,7 +316,7 @@ int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels,
   rc_kparams kp;
   fill_kparams(s, kp);
   kp.it0 = 0; kp.it1 = 0; kp.init_W = 1; kp.loglik_only = 1;
-  rc_launch_chain_kernel(kp, s->smem, s->stream);
+  rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e == cudaSuccess) e = cudaMemcpy(out, s->out_ll, sizeof(double), cudaMemcpyDeviceToHost);
   rc_sampler_destroy(s);

@@ -4,30 +4,38 @@
 //   sample_r!  (mcmc.jl:80-136)      -> update_r()
 //   sample_p!  (mcmc.jl:138-155)     -> update_p()
 //   sample_labels! (mcmc.jl:356-479) -> splitmerge_step() x numMH, then full_scan()
-//   sample_labels_Gibbs! (:158-256)  -> full_scan(): reduce_row() + scan_decide()
+//   sample_labels_Gibbs! (:158-256)  -> full_scan(): reduce_row_staged() + scan_decide()
 //   sample_labels_Gibbs_restricted! (:259-354) -> restricted_scan()
 //   loglik (:1-56), logprior (:58-78), record step (:546-554), sortlabels (utils.jl:69-74)
 //
-// Data layout / algorithm (DESIGN.md sections 2-4):
+// Organisation (DESIGN.md sections 2-4):
+//   * One CTA runs G chains (G x 128 threads).  During the full Gibbs scan all chains of a CTA visit
+//     rows 0..n-1 in lock step, so every 2048-column tile of row i of DL is staged ONCE into shared
+//     memory by a bulk async copy (cp.async.bulk -> UBLKCP, mbarrier full/empty ring) and reduced by all
+//     G chains against their own label vectors.  CTAs on other SMs walk the same rows at about the same
+//     time and hit L2, so HBM traffic per sweep is ~ n^2 x 16 B / (chains sharing a row load).
 //   * DL[i][j] = {Dq, Lq}: 64-bit fixed-point images of D and log D.  Every cluster sum is an exact
 //     integer, so results do not depend on tiling, lane count or reduction order: the kernel is
 //     bit-identical to the CPU oracle by construction.
-//   * reduce_row(x): s_k = sum_{j in k} DL[x][j] for all slots k at once.  Columns are kept in a
-//     (tile, label)-sorted permutation whose label runs are padded to groups of 8; a lane sums one
-//     group, a warp-shuffle segmented scan combines the groups of a run, run tails accumulate into
-//     per-warp bins.  No atomics, no label compares in the inner loop.
-//   * The K x K block-sum matrices W (128-bit integers) are maintained incrementally from the row
-//     sums of every accepted move, so loglik() never re-reads D: it is O(K^2) transcendentals.
+//   * Row reduction: columns are kept in a (tile, label)-sorted permutation whose label runs are padded to
+//     groups of 8; a lane sums one group (8 gathers from the staged tile), a warp-shuffle segmented scan
+//     combines the groups of a run, run tails accumulate into per-warp bins.  No atomics, no label
+//     compares in the inner loop.  A move patches the permutation in place (rebuild when a run is full).
+//   * The K x K block-sum matrices W (128-bit integers) are maintained incrementally from the row sums
+//     of every move, so loglik() never re-reads D: it is O(K^2) transcendentals.
 //   * Split-merge: row sums of the members of ci u cj are taken once (launch state); the restricted
-//     scans then only gather the |ci u cj| entries of one row per step.
+//     scans then only gather the |ci u cj| entries of one row per step, on a single warp.
 #include "rc_sampler.cuh"
 
 namespace {
 
+#define RC_NSTAGE 3
+// a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
+__host__ __device__ inline size_t stage_bytes_for(int n) { return (size_t)(n < RC_W ? ((n + 7) & ~7) : RC_W) * 16 + 128; }
+
 struct Scal {
   double r, p, logp, log1mp;
   double ltp;
-  double ll_cur, ll_fin;
   double dtmp[4];
   rc_i128 aaD, aaL, abD, abL, bbD, bbL;   // block sums of the proposed state (rows a, b)
   int K;
@@ -37,14 +45,24 @@ struct Scal {
   int itmp[8];
 };
 
+struct CtaShared {
+  unsigned long long full[RC_NSTAGE];
+  unsigned long long empty[RC_NSTAGE];
+  int active[8];
+  int nact;
+  int issuer;
+};
+
 struct Ctx {
   int n, cap, tiles;
   int qD, qL;
+  int ctid, cwarp, lane, barid;           // thread / warp index within the chain, named barrier of the chain
+  unsigned dummy;                         // permutation padding entry = index of the zero slot behind a staged tile
+  size_t stage_bytes;
   const longlong2* DL;
   const rc_kparams* kp;
-  // shared memory
+  // shared memory (per chain)
   uint8_t* lab;
-  uint8_t* labL;
   unsigned short* perm;
   uint8_t* glabel;
   unsigned short* runStart;
@@ -57,29 +75,65 @@ struct Ctx {
   uint8_t* clist;         // [cap]
   long long* red;         // [RC_NWARP * 4]
   Scal* sc;
+  // shared memory (per CTA)
+  unsigned char* stages;
+  CtaShared* cta;
   // per-chain global memory
   rc_i128* WD;
   rc_i128* WL;
   longlong2* T;
-  unsigned short* Slist;
+  unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
+  uint8_t* origM;         // their labels in the chain's state
   double* terms;
   unsigned long long key;
 };
 
-__device__ __forceinline__ int tri(int k, int t, int cap) { return k < t ? k * cap + t : t * cap + k; }
+__device__ __forceinline__ void csync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.barid), "r"(RC_NTHR) : "memory"); }
 
+__device__ __forceinline__ int tri(int k, int t, int cap) { return k < t ? k * cap + t : t * cap + k; }
 __device__ __forceinline__ long long shfl_up_ll(long long v, int off) { return __shfl_up_sync(0xffffffffu, v, off); }
 __device__ __forceinline__ long long shfl_xor_ll(long long v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+
+// ---- mbarrier / bulk-copy primitives -----------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA engine, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // (tile, label)-sorted column permutation with label runs padded to multiples of RC_GROUP.
 // ------------------------------------------------------------------------------------------------
-__device__ void build_perm(const Ctx& c, const uint8_t* lab) {
-  const int tid = threadIdx.x, E = c.tiles * c.cap;
+__device__ void build_perm(const Ctx& c) {
+  const uint8_t* lab = c.lab;
+  const int tid = c.ctid, E = c.tiles * c.cap;
   for (int t = tid; t < E; t += RC_NTHR) c.cnt[t] = 0;
-  __syncthreads();
+  csync(c);
   for (int j = tid; j < c.n; j += RC_NTHR) atomicAdd(&c.cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
-  __syncthreads();
+  csync(c);
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
     const int b = tid * chunk, e = min(E, b + chunk);
@@ -94,30 +148,30 @@ __device__ void build_perm(const Ctx& c, const uint8_t* lab) {
     for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + 7u) & ~7u; }
     if (tid == 31) c.runStart[E] = (unsigned short)incl;
   }
-  __syncthreads();
+  csync(c);
   const int total = c.runStart[E];
   for (int t = tid; t <= c.tiles; t += RC_NTHR) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
-  for (int q = tid; q < total; q += RC_NTHR) c.perm[q] = (unsigned short)RC_DUMMY;
-  __syncthreads();   // cnt is still being read above by nobody, but keep phases separate for clarity
+  for (int q = tid; q < total; q += RC_NTHR) c.perm[q] = (unsigned short)c.dummy;
   for (int t = tid; t < E; t += RC_NTHR) {
     const int g0 = c.runStart[t] >> 3, g1 = c.runStart[t + 1] >> 3;
     const uint8_t l = (uint8_t)(t % c.cap);
     for (int g = g0; g < g1; ++g) c.glabel[g] = l;
-    c.cnt[t] = 0;
   }
-  __syncthreads();
+  csync(c);
+  for (int t = tid; t < E; t += RC_NTHR) c.cnt[t] = 0;
+  csync(c);
   for (int j = tid; j < c.n; j += RC_NTHR) {
     const int e = (j >> RC_LOGW) * c.cap + lab[j];
     const unsigned pos = c.runStart[e] + atomicAdd(&c.cnt[e], 1u);
     c.perm[pos] = (unsigned short)(j & (RC_W - 1));
   }
-  __syncthreads();
+  csync(c);
 }
 
-// Point j (column) moved from slot a to slot b: patch the permutation in place (warp 0).  If the run of
-// (tile, b) has no free padding entry the caller rebuilds.
+// Point j (column) moved from slot a to slot b: patch the permutation in place (warp 0 of the chain).  If the
+// run of (tile, b) has no free padding entry the caller rebuilds.
 __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
-  const int lane = threadIdx.x & 31;
+  const int lane = c.lane;
   const int tile = j >> RC_LOGW;
   const unsigned short idx = (unsigned short)(j & (RC_W - 1));
   {
@@ -125,7 +179,7 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
     const int p0 = c.runStart[e], p1 = c.runStart[e + 1];
     for (int pb = p0; pb < p1; pb += 32) {
       const int p = pb + lane;
-      if (p < p1 && c.perm[p] == idx) c.perm[p] = (unsigned short)RC_DUMMY;
+      if (p < p1 && c.perm[p] == idx) c.perm[p] = (unsigned short)c.dummy;
     }
   }
   __syncwarp();
@@ -135,7 +189,7 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
     const int p0 = c.runStart[e], p1 = c.runStart[e + 1];
     for (int pb = p0; pb < p1 && !done; pb += 32) {
       const int p = pb + lane;
-      const unsigned m = __ballot_sync(0xffffffffu, p < p1 && c.perm[p] == (unsigned short)RC_DUMMY);
+      const unsigned m = __ballot_sync(0xffffffffu, p < p1 && c.perm[p] == (unsigned short)c.dummy);
       if (m) {
         if (lane == __ffs(m) - 1) c.perm[p] = idx;
         done = true;
@@ -147,54 +201,66 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// reduce_row: partial[warp][slot] = sums of DL[x][j] over the columns j of each label run handled by
-// the warp.  The caller __syncthreads() and adds the RC_NWARP partials.   (matsum(D,[i],clust_k) and
-// matsum(logD,[i],clust_k) for every k at once: mcmc.jl:210-213, 311-318; utils.jl:9-17.)
+// Row reduction: partial[warp][slot] += sums of DL[x][j] over the label runs handled by the warp
+// (matsum(D,[i],clust_k) and matsum(logD,[i],clust_k) for every k at once: mcmc.jl:210-213, 311-318;
+// utils.jl:9-17).  reduce_tile works on one tile of the row: `src` is either the staged tile in shared
+// memory (padding entries read the zero slot behind it) or the row in global memory.
 // ------------------------------------------------------------------------------------------------
-__device__ void reduce_row(const Ctx& c, int x) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  longlong2* part = c.partial + warp * c.cap;
-  for (int s = lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
-  __syncwarp();
-  const longlong2* row = c.DL + (size_t)x * c.n;
-  for (int tile = 0; tile < c.tiles; ++tile) {
-    const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
-    const longlong2* rt = row + tile * RC_W;
-    for (int gb = g0 + warp * 32; gb < g1; gb += RC_NWARP * 32) {
-      const int g = gb + lane;
-      const bool valid = g < g1;
-      const int lab = valid ? (int)c.glabel[g] : 0x100;
-      long long d = 0, l = 0;
-      if (valid) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(c.perm + g * RC_GROUP);
-        const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
+template <bool STAGED>
+__device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src, int tile, longlong2* part) {
+  const int lane = c.lane, warp = c.cwarp;
+  const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
+  for (int gb = g0 + warp * 32; gb < g1; gb += RC_NWARP * 32) {
+    const int g = gb + lane;
+    const bool valid = g < g1;
+    const int lab = valid ? (int)c.glabel[g] : 0x100;
+    long long d = 0, l = 0;
+    if (valid) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(c.perm + g * RC_GROUP);
+      const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-        for (int e = 0; e < RC_GROUP; ++e) {
-          const unsigned idx = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-          if (idx != RC_DUMMY) {
-            const longlong2 v = __ldg(rt + idx);
-            d += v.x; l += v.y;
-          }
+      for (int e = 0; e < RC_GROUP; ++e) {
+        const unsigned idx = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        if (STAGED) {
+          const longlong2 v = src[idx];
+          d += v.x; l += v.y;
+        } else if (idx != c.dummy) {
+          const longlong2 v = __ldg(src + idx);
+          d += v.x; l += v.y;
         }
       }
-      const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != lab);
-      const int runstart = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-      const int pos = lane - runstart;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const long long od = shfl_up_ll(d, off), ol = shfl_up_ll(l, off);
-        if (pos >= off) { d += od; l += ol; }
-      }
-      const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-      if (valid && tail) {
-        longlong2 a = part[lab];
-        a.x += d; a.y += l;
-        part[lab] = a;
-      }
-      __syncwarp();
     }
+    const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != lab);
+    const int runstart = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const int pos = lane - runstart;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const long long od = shfl_up_ll(d, off), ol = shfl_up_ll(l, off);
+      if (pos >= off) { d += od; l += ol; }
+    }
+    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+    if (valid && tail) {
+      longlong2 a = part[lab];
+      a.x += d; a.y += l;
+      part[lab] = a;
+    }
+    __syncwarp();
   }
+}
+
+__device__ __forceinline__ void zero_partial(const Ctx& c) {
+  longlong2* part = c.partial + c.cwarp * c.cap;
+  for (int s = c.lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
+  __syncwarp();
+}
+
+// Row x straight from global memory / L2 (split-merge member rows, block-sum initialisation).
+__device__ void reduce_row_global(const Ctx& c, int x) {
+  zero_partial(c);
+  const longlong2* row = c.DL + (size_t)x * c.n;
+  longlong2* part = c.partial + c.cwarp * c.cap;
+  for (int tile = 0; tile < c.tiles; ++tile) reduce_tile<false>(c, row + tile * RC_W, tile, part);
 }
 
 __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s) {
@@ -208,16 +274,15 @@ __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One step of the full Gibbs scan for point i (mcmc.jl:192-253), executed by warp 0 after reduce_row(i).
-// Lane l owns slots l, l+32, l+64, l+96.
+// One step of the full Gibbs scan for point i (mcmc.jl:192-253), executed by warp 0 of the chain after
+// the row reduction.  Lane l owns slots l, l+32, l+64, l+96.
 // ------------------------------------------------------------------------------------------------
-__device__ void scan_decide(const Ctx& c, int i, unsigned it) {
-  const int lane = threadIdx.x & 31;
+__device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
+  const int lane = c.lane;
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int cap = c.cap;
   const int li = c.lab[i];
-  const longlong2 self = __ldg(c.DL + (size_t)i * c.n + i);
   const double r = c.sc->r, logp = c.sc->logp, log1mp = c.sc->log1mp;
 
   long long bd[RC_NS], bl[RC_NS];
@@ -377,41 +442,80 @@ __device__ void scan_decide(const Ctx& c, int i, unsigned it) {
   }
 }
 
-// sample_labels_Gibbs! (mcmc.jl:158-256) on the chain's state.
-__device__ void full_scan(const Ctx& c, unsigned it) {
-  for (int i = 0; i < c.n; ++i) {
-    reduce_row(c, i);
-    __syncthreads();
-    if (threadIdx.x < 32) scan_decide(c, i, it);
-    __syncthreads();
-    if (c.sc->status) return;
-    if (c.sc->rebuild) {
-      __syncthreads();
-      if (threadIdx.x == 0) c.sc->rebuild = 0;
-      build_perm(c, c.lab);
+// sample_labels_Gibbs! (mcmc.jl:158-256).  All ACTIVE chains of the CTA run this together: the tiles of row
+// i are staged once (bulk async copy, RC_NSTAGE-deep ring) and consumed by every active chain.  A chain
+// whose slot capacity overflows keeps consuming tiles (so the ring keeps moving) but stops deciding.
+__device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
+  const int n = c.n, tiles = c.tiles;
+  const long long ntile = (long long)n * tiles;
+  const bool issuer = is_issuer_chain && c.ctid == 0;
+  CtaShared* cs = c.cta;
+  auto issue = [&](long long t) {   // stage tile t of the row stream
+    const int row = (int)(t / tiles), tile = (int)(t - (long long)row * tiles);
+    const int s = (int)(t % RC_NSTAGE);
+    const int cols = min(RC_W, n - tile * RC_W);
+    const unsigned bytes = (unsigned)cols * 16u;
+    mbar_expect_tx(&cs->full[s], bytes);
+    bulk_g2s(c.stages + (size_t)s * c.stage_bytes, c.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
+  };
+  if (issuer)
+    for (long long t = 0; t < RC_NSTAGE && t < ntile; ++t) issue(t);
+  bool dead = false;
+  long long t = 0;
+  longlong2* part = c.partial + c.cwarp * c.cap;
+  for (int i = 0; i < n; ++i) {
+    longlong2 self = make_longlong2(0, 0);
+    if (c.ctid == 0) self = __ldg(c.DL + (size_t)i * n + i);
+    zero_partial(c);
+    for (int tile = 0; tile < tiles; ++tile, ++t) {
+      const int s = (int)(t % RC_NSTAGE);
+      const unsigned ph = (unsigned)((t / RC_NSTAGE) & 1);
+      if (issuer && t >= 1 && t - 1 + RC_NSTAGE < ntile) {         // refill the stage freed by tile t-1
+        const long long tp = t - 1;
+        mbar_wait(&cs->empty[tp % RC_NSTAGE], (unsigned)((tp / RC_NSTAGE) & 1));
+        issue(tp + RC_NSTAGE);
+      }
+      __syncwarp();
+      mbar_wait(&cs->full[s], ph);
+      reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)s * c.stage_bytes), tile, part);
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&cs->empty[s]);
+    }
+    csync(c);
+    if (c.cwarp == 0 && !dead) {
+      self.x = __shfl_sync(0xffffffffu, self.x, 0);
+      self.y = __shfl_sync(0xffffffffu, self.y, 0);
+      scan_decide(c, i, it, self);
+    }
+    csync(c);
+    if (c.sc->status) dead = true;
+    if (!dead && c.sc->rebuild) {
+      csync(c);
+      if (c.ctid == 0) c.sc->rebuild = 0;
+      build_perm(c);
     }
   }
-  if (threadIdx.x < 32) {                                                    // :254
+  if (c.cwarp == 0) {                                                       // :254
     int K = 0;
-    for (int s = threadIdx.x; s < c.cap; s += 32) K += c.sizes[s] > 0;
+    for (int s = c.lane; s < c.cap; s += 32) K += c.sizes[s] > 0;
     for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
-    if (threadIdx.x == 0) c.sc->K = K;
+    if (c.lane == 0) c.sc->K = K;
   }
-  __syncthreads();
+  csync(c);
 }
 
 // Block sums from scratch: W[k][t] = sum_{x in k, y in t} DL[x][y]  (n row reductions).
 __device__ void init_W(const Ctx& c) {
-  for (int t = threadIdx.x; t < c.cap * c.cap; t += RC_NTHR) {
+  for (int t = c.ctid; t < c.cap * c.cap; t += RC_NTHR) {
     rc_i128 z; z.lo = 0; z.hi = 0;
     c.WD[t] = z; c.WL[t] = z;
   }
-  __syncthreads();
+  csync(c);
   for (int x = 0; x < c.n; ++x) {
-    reduce_row(c, x);
-    __syncthreads();
+    reduce_row_global(c, x);
+    csync(c);
     const int k = c.lab[x];
-    for (int t = k + (int)threadIdx.x; t < c.cap; t += RC_NTHR) {
+    for (int t = k + c.ctid; t < c.cap; t += RC_NTHR) {
       const longlong2 b = bin_total(c, t);
       if (b.x != 0 || b.y != 0) {
         const int ix = k * c.cap + t;
@@ -419,7 +523,7 @@ __device__ void init_W(const Ctx& c) {
         rc_i128 d = c.WL[ix]; rc_add128(d, b.y); c.WL[ix] = d;
       }
     }
-    __syncthreads();
+    csync(c);
   }
 }
 
@@ -446,21 +550,21 @@ __device__ __forceinline__ rc_i128 getW(const Ctx& c, bool logm, int k, int t) {
 __device__ double loglik_eval(const Ctx& c, const int* sz) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
-  __syncthreads();
-  if (threadIdx.x < 32) {                                                    // C = findall(clustsizes .> 0)  (:22)
+  csync(c);
+  if (c.ctid < 32) {                                                        // C = findall(clustsizes .> 0)  (:22)
     int base = 0;
     for (int w = 0; w * 32 < c.cap; ++w) {
-      const int s = w * 32 + threadIdx.x;
+      const int s = w * 32 + c.ctid;
       const bool live = s < c.cap && sz[s] > 0;
       const unsigned m = __ballot_sync(0xffffffffu, live);
-      if (live) c.clist[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (uint8_t)s;
+      if (live) c.clist[base + __popc(m & ((1u << c.ctid) - 1u))] = (uint8_t)s;
       base += __popc(m);
     }
-    if (threadIdx.x == 0) c.sc->itmp[0] = base;
+    if (c.ctid == 0) c.sc->itmp[0] = base;
   }
-  __syncthreads();
+  csync(c);
   const int K = c.sc->itmp[0];
-  for (int idx = threadIdx.x; idx < K * K; idx += RC_NTHR) {
+  for (int idx = c.ctid; idx < K * K; idx += RC_NTHR) {
     const int ki = idx / K, ti = idx - ki * K;
     if (ti < ki) continue;
     const int k = c.clist[ki], t = c.clist[ti];
@@ -481,8 +585,8 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
     }
     c.terms[idx] = term;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  csync(c);
+  if (c.ctid == 0) {
     double L1 = 0;
     for (int ki = 0; ki < K; ++ki) L1 += c.terms[ki * K + ki];
     double L2 = 0;
@@ -490,17 +594,17 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
       for (int ti = ki + 1; ti < K; ++ti) L2 += c.terms[ki * K + ti];
     c.sc->dtmp[0] = P.repulsion ? (L1 + L2) : (L1 + copysign(0.0, L2));      // :54
   }
-  __syncthreads();
+  csync(c);
   return c.sc->dtmp[0];
 }
 
 __device__ __forceinline__ double xlogy(double a, double b) { return (a == 0.0 && !rc_isnan(b)) ? 0.0 : a * rc_log(b); }
 __device__ __forceinline__ double xlog1py(double a, double b) { return (a == 0.0 && !rc_isnan(b)) ? 0.0 : a * rc_log1p(b); }
 
-// logprior (mcmc.jl:58-78); warp 0.
+// logprior (mcmc.jl:58-78); warp 0 of the chain.
 __device__ double logprior_eval(const Ctx& c) {
   const rc_params& P = c.kp->P;
-  const int lane = threadIdx.x & 31;
+  const int lane = c.lane;
   const double r = c.sc->r, p = c.sc->p;
   double* tv = c.terms;   // scratch: per-slot terms
   for (int s = lane; s < c.cap; s += 32)
@@ -524,10 +628,10 @@ __device__ double logprior_eval(const Ctx& c) {
   return __shfl_sync(0xffffffffu, L, 0);
 }
 
-// sample_r! (mcmc.jl:80-136); warp 0.  Returns accept.
+// sample_r! (mcmc.jl:80-136); warp 0 of the chain.  Returns accept.
 __device__ bool update_r(const Ctx& c, unsigned it) {
   const rc_params& P = c.kp->P;
-  const int lane = threadIdx.x & 31;
+  const int lane = c.lane;
   const double r = c.sc->r, p = c.sc->p, sd = P.proposalsd_r;
   double cand = r;
   if (lane == 0) {
@@ -558,8 +662,7 @@ __device__ bool update_r(const Ctx& c, unsigned it) {
     for (int s = 0; s < c.cap; ++s)
       if (c.sizes[s] > 0) { lpc = lpc + tc[s]; lpr = lpr + tr[s]; }
     const double log2pi = 1.8378770664093454836;
-    // logpdf(truncated(Normal(mu, sd), 0, Inf), x)
-    double lq[2];
+    double lq[2];   // logpdf(truncated(Normal(mu, sd), 0, Inf), x)
     for (int q = 0; q < 2; ++q) {
       const double mu = q == 0 ? r : cand, x = q == 0 ? cand : r;
       const double zz = (x - mu) / sd;
@@ -575,7 +678,7 @@ __device__ bool update_r(const Ctx& c, unsigned it) {
   return __shfl_sync(0xffffffffu, accept, 0) != 0;
 }
 
-// sample_p! (mcmc.jl:138-155); thread 0.
+// sample_p! (mcmc.jl:138-155); one thread.
 __device__ void update_p(const Ctx& c, unsigned it) {
   const rc_params& P = c.kp->P;
   const double a = (double)(c.n - c.sc->K) + P.u;
@@ -587,106 +690,110 @@ __device__ void update_p(const Ctx& c, unsigned it) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Restricted Gibbs scan (mcmc.jl:259-354) over Slist[0..nS) on the launch state (labL, szL).
-// forced: allocate toward the chain's current labels (c.lab) and only accumulate the probability.
-// The log transition probability is returned in c.sc->ltp.
+// Restricted Gibbs scan (mcmc.jl:259-354) over the members Slist[0..nS) on the launch state, which lives
+// IN PLACE in c.lab / c.szL (the chain's own labels of the members are kept in origM and restored by the
+// caller).  Runs on warp 0 of the chain; the log transition probability is returned in c.sc->ltp.
+// forced: allocate toward the chain's labels (origM) and only accumulate the probability.
 // ------------------------------------------------------------------------------------------------
-__device__ void restricted_scan(const Ctx& c, unsigned it, unsigned mh, unsigned scan, int nS, int pi, int pj, int ca,
-                                int cb, int c1, int c2, bool forced) {
+__device__ void restricted_scan(const Ctx& c, unsigned it, unsigned mh, unsigned scan, int nS, int ca, int cb, int c1,
+                                int c2, bool forced) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) c.sc->ltp = 0.0;
+  const int lane = c.lane;
+  const int mt = nS + 2;
+  double ltp = 0.0;
   for (int pos = 0; pos < nS; ++pos) {
     const int y = c.Slist[pos];
-    __syncthreads();
-    if (tid == 0) {                                                          // :303-304
-      c.szL[c.labL[y]] -= 1;
-      c.labL[y] = RC_DETACHED;
-    }
-    __syncthreads();
-    // sums of row y over the current members of the two candidate clusters (all live in S u {i, j})
+    const int cur = c.lab[y];
+    // static sums of row y over the first two live slots (prefetch; unused if they are the candidates)
+    longlong2 tst = make_longlong2(0, 0);
+    if (lane == 2 || lane == 3) tst = c.T[(size_t)pos * c.cap + (lane == 2 ? c1 : c2)];
+    // sums of row y over the current members of the two candidate clusters (all live in S u {i, j});
+    // y itself is detached (:303-304), so it is skipped
     long long aD = 0, aL = 0, bD = 0, bL = 0;
     const longlong2* row = c.DL + (size_t)y * c.n;
-    for (int q = tid; q < nS + 2; q += RC_NTHR) {
-      const int x = q < nS ? (int)c.Slist[q] : (q == nS ? pi : pj);
-      const int l = c.labL[x];
-      if (l == ca) { const longlong2 v = __ldg(row + x); aD += v.x; aL += v.y; }
-      else if (l == cb) { const longlong2 v = __ldg(row + x); bD += v.x; bL += v.y; }
+    for (int q0 = 0; q0 < mt; q0 += 128) {
+      int xs[4]; longlong2 vs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int q = q0 + u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vs[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (xs[u] < 0 || xs[u] == y) continue;
+        const int l = c.lab[xs[u]];
+        if (l == ca) { aD += vs[u].x; aL += vs[u].y; }
+        else if (l == cb) { bD += vs[u].x; bL += vs[u].y; }
+      }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       aD += shfl_xor_ll(aD, off); aL += shfl_xor_ll(aL, off);
       bD += shfl_xor_ll(bD, off); bL += shfl_xor_ll(bL, off);
     }
-    if (lane == 0) { c.red[warp * 4 + 0] = aD; c.red[warp * 4 + 1] = aL; c.red[warp * 4 + 2] = bD; c.red[warp * 4 + 3] = bL; }
-    __syncthreads();
-    if (warp == 0) {
-      // lanes 0..3 evaluate slots {ca, cb, c1, c2}
-      const int slot = lane == 0 ? ca : (lane == 1 ? cb : (lane == 2 ? c1 : c2));
-      double L1 = 0.0, lpr = 0.0, L2p = 0.0;
-      if (lane < 4) {
-        long long sd, sl;
-        if (slot == ca || slot == cb) {
-          const int o = slot == ca ? 0 : 2;
-          sd = 0; sl = 0;
-          for (int w = 0; w < RC_NWARP; ++w) { sd += c.red[w * 4 + o]; sl += c.red[w * 4 + o + 1]; }
-        } else {
-          const longlong2 t = c.T[(size_t)pos * c.cap + slot];
-          sd = t.x; sl = t.y;
-        }
-        const int szs = c.szL[slot];
-        const double szd = (double)szs;
-        const double sD = rc_dequant(sd, c.qD), sL = rc_dequant(sl, c.qL);
-        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;                       // :313-319
-        L2p = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;   // :327-330
-        if (lane < 2) {                                                                       // :307-312, 321-326
-          const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-          L1 = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-          lpr = kp.LOGN[szs + 1] + c.sc->logp + rc_log((double)(szs - 1) + c.sc->r) - kp.LOGN[szs];
-        }
-      }
-      const double L2i = __shfl_sync(0xffffffffu, L2p, 2) + __shfl_sync(0xffffffffu, L2p, 3);   // :331 (quirk Q2)
-      const double L2 = L2i - L2p;                                                               // :332-334
-      const double lpv = lpr + (L1 + (P.repulsion ? L2 : copysign(0.0, L2)));                    // :335
-      double lp0 = __shfl_sync(0xffffffffu, lpv, 0), lp1 = __shfl_sync(0xffffffffu, lpv, 1);
-      if (lane == 0) {
-        int k, cnew;
-        if (!forced) {                                                                           // :336-338
-          const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_RGIBBS, mh, scan, (uint32_t)pos);
-          double mn = lp0;
-          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-          lp0 -= mn; lp1 -= mn;
-          const double g0 = -rc_log(-rc_log(dr.u0)) + lp0;
-          const double g1 = -rc_log(-rc_log(dr.u1)) + lp1;
-          k = 0;
-          if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
-          cnew = k == 0 ? ca : cb;
-        } else {                                                                                 // :339-342
-          cnew = c.lab[y];
-          k = (ca == cnew) ? 0 : 1;
-        }
-        c.labL[y] = (uint8_t)cnew;                                                               // :344-345
-        c.szL[cnew] += 1;
-        double mn = lp0;                                                                         // :348 (quirk Q3)
-        if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-        lp0 += mn; lp1 += mn;
-        double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
-        const double den = p0 + p1;
-        p0 /= den; p1 /= den;
-        c.sc->ltp += rc_log(k == 0 ? p0 : p1);                                                   // :351
+    // lanes 0..3 evaluate slots {ca, cb, c1, c2}; sizes are those after detaching y
+    const int slot = lane == 0 ? ca : (lane == 1 ? cb : (lane == 2 ? c1 : c2));
+    double L1 = 0.0, lpr = 0.0, L2p = 0.0;
+    if (lane < 4) {
+      long long sd, sl;
+      if (slot == ca) { sd = aD; sl = aL; }
+      else if (slot == cb) { sd = bD; sl = bL; }
+      else { sd = tst.x; sl = tst.y; }
+      const int szs = c.szL[slot] - (slot == cur ? 1 : 0);
+      const double szd = (double)szs;
+      const double sD = rc_dequant(sd, c.qD), sL = rc_dequant(sl, c.qL);
+      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;                             // :313-319
+      L2p = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;   // :327-330
+      if (lane < 2) {                                                                             // :307-312, 321-326
+        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+        L1 = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+        lpr = kp.LOGN[szs + 1] + c.sc->logp + rc_log((double)(szs - 1) + c.sc->r) - kp.LOGN[szs];
       }
     }
+    const double L2i = __shfl_sync(0xffffffffu, L2p, 2) + __shfl_sync(0xffffffffu, L2p, 3);      // :331 (quirk Q2)
+    const double L2 = L2i - L2p;                                                                  // :332-334
+    const double lpv = lpr + (L1 + (P.repulsion ? L2 : copysign(0.0, L2)));                       // :335
+    double lp0 = __shfl_sync(0xffffffffu, lpv, 0), lp1 = __shfl_sync(0xffffffffu, lpv, 1);
+    int k, cnew;
+    if (!forced) {                                                                                // :336-338
+      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_RGIBBS, mh, scan, (uint32_t)pos);
+      double mn = lp0;
+      if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+      lp0 -= mn; lp1 -= mn;
+      const double g0 = -rc_log(-rc_log(dr.u0)) + lp0;
+      const double g1 = -rc_log(-rc_log(dr.u1)) + lp1;
+      k = 0;
+      if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
+      cnew = k == 0 ? ca : cb;
+    } else {                                                                                      // :339-342
+      cnew = c.origM[pos];
+      k = (ca == cnew) ? 0 : 1;
+    }
+    if (lane == 0 && cnew != cur) {                                                               // :344-345
+      c.lab[y] = (uint8_t)cnew;
+      c.szL[cur] -= 1;
+      c.szL[cnew] += 1;
+    }
+    double mn = lp0;                                                                              // :348 (quirk Q3)
+    if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+    lp0 += mn; lp1 += mn;
+    double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
+    const double den = p0 + p1;
+    p0 /= den; p1 /= den;
+    ltp += rc_log(k == 0 ? p0 : p1);                                                              // :351
+    __syncwarp();
   }
-  __syncthreads();
+  if (lane == 0) c.sc->ltp = ltp;
+  __syncwarp();
 }
 
 // One split-merge proposal (mcmc.jl:372-474) on the chain's current state.  Returns accept through
-// c.sc->itmp[1], split through itmp[2].
+// c.sc->itmp[1], split through itmp[2].  The chain's labels / sizes are unchanged on return (quirk Q1:
+// an accepted proposal never reaches the caller's state).
 __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = c.ctid, lane = c.lane, warp = c.cwarp;
   const int n = c.n, cap = c.cap;
   const double r = c.sc->r, p = c.sc->p;
   const int K = c.sc->K;
@@ -696,9 +803,9 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
   if (i2 == i1) i2 = n;
   const int pi = (int)i1 - 1, pj = (int)i2 - 1;
   const int ci = c.lab[pi], cj = c.lab[pj];
-  __syncthreads();
+  csync(c);
   if (tid == 0) { c.sc->itmp[1] = 0; c.sc->itmp[2] = 0; }
-  if (P.maxK > 0 && ci == cj && K >= P.maxK) { __syncthreads(); return; }   // :384-386
+  if (P.maxK > 0 && ci == cj && K >= P.maxK) { csync(c); return; }          // :384-386
   // S = members of ci or cj except i, j, ascending (:389-390): ordered compaction
   {
     const int chunk = (n + RC_NTHR - 1) / RC_NTHR;
@@ -708,20 +815,19 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     int incl = cntm;
     for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
     if (lane == 31) c.itmp[warp] = incl;
-    __syncthreads();
+    csync(c);
     int woff = 0;
     for (int w = 0; w < warp; ++w) woff += c.itmp[w];
     int o = woff + incl - cntm;
     for (int k = b; k < e; ++k)
-      if ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj) c.Slist[o++] = (unsigned short)k;
+      if ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj) { c.Slist[o] = (unsigned short)k; c.origM[o] = c.lab[k]; ++o; }
     if (tid == RC_NTHR - 1) c.sc->itmp[3] = woff + incl;
-    __syncthreads();
+    csync(c);
   }
   const int nS = c.sc->itmp[3];
-  // launch state (:393-408)
-  for (int k = tid; k < n; k += RC_NTHR) c.labL[k] = c.lab[k];
+  if (tid == 0) { c.Slist[nS] = (unsigned short)pi; c.origM[nS] = (uint8_t)ci; c.Slist[nS + 1] = (unsigned short)pj; c.origM[nS + 1] = (uint8_t)cj; }
+  // launch state (:393-408), in place in c.lab / c.szL
   for (int s = tid; s < cap; s += RC_NTHR) c.szL[s] = c.sizes[s];
-  __syncthreads();
   const bool split = ci == cj;
   int ca = ci;
   if (split) {
@@ -734,90 +840,88 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
       }
       if (lane == 0) c.sc->itmp[4] = e;
     }
-    __syncthreads();
+    csync(c);
     ca = c.sc->itmp[4];
-    if (ca < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; __syncthreads(); return; }
-    if (tid == 0) { c.labL[pi] = (uint8_t)ca; c.szL[ci] -= 1; c.szL[ca] += 1; }
+    if (ca < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; csync(c); return; }
+    if (tid == 0) c.lab[pi] = (uint8_t)ca;
   }
   const int cb = cj;
-  __syncthreads();
+  csync(c);
   {
     int na = 0, nb = 0;   // launch allocation of S (:402-407)
     for (int pos = tid; pos < nS; pos += RC_NTHR) {
       const int k = c.Slist[pos];
       const double u = rc_draw1(c.key, it, RC_SITE_SM_LAUNCH, mh, (uint32_t)pos, 0);
       const int cn = rc_randint(u, 2) == 1 ? ca : cb;
-      c.labL[k] = (uint8_t)cn;
+      c.lab[k] = (uint8_t)cn;
       na += cn == ca; nb += cn == cb;
     }
     for (int off = 16; off; off >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, off); nb += __shfl_xor_sync(0xffffffffu, nb, off); }
     if (lane == 0) { c.itmp[warp * 2] = na; c.itmp[warp * 2 + 1] = nb; }
-    __syncthreads();
+    csync(c);
     if (tid == 0) {
       int ta = 0, tb = 0;
       for (int w = 0; w < RC_NWARP; ++w) { ta += c.itmp[w * 2]; tb += c.itmp[w * 2 + 1]; }
+      if (split) c.szL[ci] = 0;
       c.szL[ca] = 1 + ta;
       c.szL[cb] = 1 + tb;
+      int c1 = -1, c2 = -1;                   // first two live slots of the launch state (C[1], C[2] of :273, :331)
+      for (int s = 0; s < cap && c2 < 0; ++s)
+        if (c.szL[s] > 0) { if (c1 < 0) c1 = s; else c2 = s; }
+      c.sc->itmp[5] = c1; c.sc->itmp[6] = c2;
     }
-    __syncthreads();
-  }
-  // first two live slots of the launch state (C[1], C[2] of :273, :331)
-  if (tid == 0) {
-    int c1 = -1, c2 = -1;
-    for (int s = 0; s < cap && c2 < 0; ++s)
-      if (c.szL[s] > 0) { if (c1 < 0) c1 = s; else c2 = s; }
-    c.sc->itmp[5] = c1; c.sc->itmp[6] = c2;
+    csync(c);
   }
   // row sums by slot of every member of S u {i, j} under the launch labels
-  build_perm(c, c.labL);
+  build_perm(c);
   for (int pos = 0; pos < nS + 2; ++pos) {
-    const int x = pos < nS ? (int)c.Slist[pos] : (pos == nS ? pi : pj);
-    reduce_row(c, x);
-    __syncthreads();
+    reduce_row_global(c, c.Slist[pos]);
+    csync(c);
     for (int s = tid; s < cap; s += RC_NTHR) c.T[(size_t)pos * cap + s] = bin_total(c, s);
-    __syncthreads();
+    csync(c);
   }
   const int c1 = c.sc->itmp[5], c2 = c.sc->itmp[6];
-  for (unsigned g = 0; g < (unsigned)kp.numGibbs; ++g)                       // :411-414
-    restricted_scan(c, it, mh, g, nS, pi, pj, ca, cb, c1, c2, false);
-  double log_prior_ratio, log_proposal_ratio;
+  if (warp == 0) {
+    for (unsigned g = 0; g < (unsigned)kp.numGibbs; ++g)                     // :411-414
+      restricted_scan(c, it, mh, g, nS, ca, cb, c1, c2, false);
+    restricted_scan(c, it, mh, (unsigned)kp.numGibbs, nS, ca, cb, c1, c2, !split);   // :419 / :454-455
+  }
+  csync(c);
+  double log_prior_ratio = 0.0, log_proposal_ratio = 0.0;
   if (split) {                                                              // :416-434
-    restricted_scan(c, it, mh, (unsigned)kp.numGibbs, nS, pi, pj, ca, cb, c1, c2, false);
     const int sza = c.szL[ca], szb = c.szL[cb];   // szfinal[cfinal[i]], szfinal[cfinal[j]]
-    log_prior_ratio = rc_log((double)(K + 1)) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r) +
-                      rc_lgamma((double)(sza - 1) + r) + rc_lgamma((double)(szb - 1) + r) +
-                      rc_log((double)sza) + rc_log((double)szb) +
-                      -(rc_lgamma((double)(c.sizes[ci] - 1) + r) + rc_log((double)c.sizes[ci]));
-    log_proposal_ratio = c.sc->ltp;
+    if (tid == 0) {
+      log_prior_ratio = rc_log((double)(K + 1)) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r) +
+                        rc_lgamma((double)(sza - 1) + r) + rc_lgamma((double)(szb - 1) + r) +
+                        rc_log((double)sza) + rc_log((double)szb) +
+                        -(rc_lgamma((double)(c.sizes[ci] - 1) + r) + rc_log((double)c.sizes[ci]));
+      log_proposal_ratio = c.sc->ltp;
+    }
     // block sums of the proposed state: rows a (= new slot ca) and b (= cb)
     rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);   // [rowA_D | rowA_L | rowB_D | rowB_L] x cap
-    __syncthreads();
     for (int t = tid; t < cap; t += RC_NTHR) {
       rc_i128 sd, sl; sd.lo = 0; sd.hi = 0; sl.lo = 0; sl.hi = 0;
-      for (int q = 0; q < nS + 2; ++q) {
-        const int x = q < nS ? (int)c.Slist[q] : (q == nS ? pi : pj);
-        if (c.labL[x] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
-      }
+      for (int q = 0; q < nS + 2; ++q)
+        if (c.lab[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
       rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
     }
-    __syncthreads();
     // cross = sum_{x in a_F, y in b_F} DL[x][y]: one warp per row x, lanes over the members
     rc_i128 crD, crL; crD.lo = 0; crD.hi = 0; crL.lo = 0; crL.hi = 0;
     for (int q = warp; q < nS + 2; q += RC_NWARP) {
-      const int x = q < nS ? (int)c.Slist[q] : (q == nS ? pi : pj);
-      if (c.labL[x] != ca) continue;
+      const int x = c.Slist[q];
+      if (c.lab[x] != ca) continue;
       const longlong2* row = c.DL + (size_t)x * n;
       long long sd = 0, sl = 0;
       for (int q2 = lane; q2 < nS + 2; q2 += 32) {
-        const int y = q2 < nS ? (int)c.Slist[q2] : (q2 == nS ? pi : pj);
-        if (c.labL[y] == cb) { const longlong2 v = __ldg(row + y); sd += v.x; sl += v.y; }
+        const int y = c.Slist[q2];
+        if (c.lab[y] == cb) { const longlong2 v = __ldg(row + y); sd += v.x; sl += v.y; }
       }
       for (int off = 16; off; off >>= 1) { sd += shfl_xor_ll(sd, off); sl += shfl_xor_ll(sl, off); }
       rc_add128(crD, sd); rc_add128(crL, sl);
     }
     rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch
     if (lane == 0) { red128[warp * 2] = crD; red128[warp * 2 + 1] = crL; }
-    __syncthreads();
+    csync(c);
     if (tid == 0) {
       rc_i128 xD = red128[0], xL = red128[1];
       for (int w = 1; w < RC_NWARP; ++w) { rc_add128(xD, red128[w * 2]); rc_add128(xL, red128[w * 2 + 1]); }
@@ -831,24 +935,24 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
       rc_sub128(bbL, aaL); rc_sub128(bbL, xL); rc_sub128(bbL, xL);
       c.sc->aaD = aaD; c.sc->aaL = aaL; c.sc->abD = xD; c.sc->abL = xL; c.sc->bbD = bbD; c.sc->bbL = bbL;
     }
-    __syncthreads();
+    csync(c);
     for (int t = tid; t < cap; t += RC_NTHR) {                               // row b = row ci of the current state - row a
       rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
       rc_sub128(bD, rows[0 * cap + t]); rc_sub128(bL, rows[1 * cap + t]);
       rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
     }
     if (tid == 0) { c.sc->fslotA = ca; c.sc->fslotB = cb; c.sc->itmp[2] = 1; }
-    __syncthreads();
+    csync(c);
   } else {                                                                  // merge (:435-459)
     const int szf = c.sizes[ci] + c.sizes[cj];
-    log_prior_ratio = -(rc_log((double)K) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r)) +
-                      rc_lgamma((double)(szf - 1) + r) + rc_log((double)szf) +
-                      -(rc_lgamma((double)(c.sizes[ci] - 1) + r) + rc_lgamma((double)(c.sizes[cj] - 1) + r) +
-                        rc_log((double)c.sizes[ci]) + rc_log((double)c.sizes[cj]));
-    restricted_scan(c, it, mh, (unsigned)kp.numGibbs, nS, pi, pj, ca, cb, c1, c2, true);   // :454-455
-    log_proposal_ratio = -c.sc->ltp;
+    if (tid == 0) {
+      log_prior_ratio = -(rc_log((double)K) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r)) +
+                        rc_lgamma((double)(szf - 1) + r) + rc_log((double)szf) +
+                        -(rc_lgamma((double)(c.sizes[ci] - 1) + r) + rc_lgamma((double)(c.sizes[cj] - 1) + r) +
+                          rc_log((double)c.sizes[ci]) + rc_log((double)c.sizes[cj]));
+      log_proposal_ratio = -c.sc->ltp;
+    }
     rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);
-    __syncthreads();
     for (int t = tid; t < cap; t += RC_NTHR) {                               // row cj of the merged state
       rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
       rc_add128(bD, c.WD[tri(cj, t, cap)]); rc_add128(bL, c.WL[tri(cj, t, cap)]);
@@ -865,17 +969,11 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
       c.sc->aaD = z; c.sc->aaL = z; c.sc->abD = z; c.sc->abL = z; c.sc->bbD = bbD; c.sc->bbL = bbL;
       c.sc->fslotA = ci; c.sc->fslotB = cj;
     }
-    __syncthreads();
-    // sizes of the merged state
-    for (int s = tid; s < cap; s += RC_NTHR) c.szL[s] = c.sizes[s];
-    __syncthreads();
-    if (tid == 0) { c.szL[ci] = 0; c.szL[cj] = szf; }
-    __syncthreads();
+    for (int s = tid; s < cap; s += RC_NTHR) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
+    csync(c);
   }
   const double ll_fin = loglik_eval(c, c.szL);                              // :462-464
-  __syncthreads();
   if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; }
-  __syncthreads();
   const double ll_cur = loglik_eval(c, c.sizes);
   if (tid == 0) {
     const double log_lik_ratio = ll_fin - ll_cur;
@@ -883,120 +981,178 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     const double lu = rc_log(rc_draw1(c.key, it, RC_SITE_SM_ACCEPT, mh, 0, 0));
     c.sc->itmp[1] = lu < lar ? 1 : 0;                                                   // :469-472
   }
-  __syncthreads();
+  // restore the chain's own labels of the members (the proposal lived in place)
+  for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+  csync(c);
 }
 
 // sortlabels (utils.jl:69-74): first-appearance relabelling to 1..K.
 __device__ void record_labels(const Ctx& c, uint8_t* out) {
-  const int tid = threadIdx.x;
+  const int tid = c.ctid;
   for (int s = tid; s < c.cap; s += RC_NTHR) c.itmp[s] = 0x7fffffff;
-  __syncthreads();
+  csync(c);
   for (int j = tid; j < c.n; j += RC_NTHR) atomicMin(&c.itmp[c.lab[j]], j);
-  __syncthreads();
+  csync(c);
   for (int s = tid; s < c.cap; s += RC_NTHR) {
     const int f = c.itmp[s];
     int id = 1;
     for (int t = 0; t < c.cap; ++t) id += c.itmp[t] < f;
     c.clist[s] = (uint8_t)id;
   }
-  __syncthreads();
+  csync(c);
   for (int j = tid; j < c.n; j += RC_NTHR) out[j] = c.clist[c.lab[j]];
-  __syncthreads();
+  csync(c);
 }
 
-__global__ void __launch_bounds__(RC_NTHR) k_chain(const __grid_constant__ rc_kparams kp) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int chain = blockIdx.x;
-  const int tid = threadIdx.x;
+struct ChainLayout {
+  size_t partial, sc, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, glabel, lab, total;
+};
+__host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, int npad_max) {
+  ChainLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
+  L.partial = take(sizeof(longlong2) * RC_NWARP * cap);
+  L.sc = take(sizeof(Scal));
+  L.red = take(sizeof(long long) * RC_NWARP * 4);
+  L.perm = take(sizeof(unsigned short) * npad_max);
+  L.runStart = take(sizeof(unsigned short) * (tiles * cap + 1));
+  L.cnt = take(sizeof(unsigned int) * tiles * cap);
+  L.tileStart = take(sizeof(int) * (tiles + 1));
+  L.sizes = take(sizeof(int) * cap);
+  L.szL = take(sizeof(int) * cap);
+  L.itmp = take(sizeof(int) * cap);
+  L.clist = take(cap);
+  L.glabel = take(npad_max / RC_GROUP);
+  L.lab = take(n);
+  L.total = (o + 127) & ~(size_t)127;
+  return L;
+}
+__host__ __device__ inline size_t cta_header_bytes() { return (sizeof(CtaShared) + 127) & ~(size_t)127; }
+
+template <int G>
+__global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ rc_kparams kp) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int cl = threadIdx.x / RC_NTHR;               // chain slot within the CTA
+  const int chain = blockIdx.x * G + cl;
+  const bool valid = chain < kp.nchains;
   const int n = kp.n, cap = kp.cap, tiles = kp.tiles;
   Ctx c;
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
+  c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl;
   {
-    size_t o = 0;
-    auto take = [&](size_t bytes) { unsigned char* p = smem + o; o += (bytes + 15) & ~(size_t)15; return p; };
-    c.partial = reinterpret_cast<longlong2*>(take(sizeof(longlong2) * RC_NWARP * cap));
-    c.sc = reinterpret_cast<Scal*>(take(sizeof(Scal)));
-    c.red = reinterpret_cast<long long*>(take(sizeof(long long) * RC_NWARP * 4));
-    c.perm = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * kp.npad_max));
-    c.runStart = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * (tiles * cap + 1)));
-    c.cnt = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * tiles * cap));
-    c.tileStart = reinterpret_cast<int*>(take(sizeof(int) * (tiles + 1)));
-    c.sizes = reinterpret_cast<int*>(take(sizeof(int) * cap));
-    c.szL = reinterpret_cast<int*>(take(sizeof(int) * cap));
-    c.itmp = reinterpret_cast<int*>(take(sizeof(int) * cap));
-    c.clist = reinterpret_cast<uint8_t*>(take(cap));
-    c.glabel = reinterpret_cast<uint8_t*>(take(kp.npad_max / RC_GROUP));
-    c.lab = reinterpret_cast<uint8_t*>(take(n));
-    c.labL = reinterpret_cast<uint8_t*>(take(n));
+    const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
+    c.stage_bytes = stage_bytes_for(n);
+    c.dummy = (unsigned)((c.stage_bytes - 128) / 16);
+    c.cta = reinterpret_cast<CtaShared*>(smem);
+    c.stages = smem + cta_header_bytes();
+    unsigned char* base = c.stages + (size_t)RC_NSTAGE * c.stage_bytes + (size_t)cl * L.total;
+    c.partial = reinterpret_cast<longlong2*>(base + L.partial);
+    c.sc = reinterpret_cast<Scal*>(base + L.sc);
+    c.red = reinterpret_cast<long long*>(base + L.red);
+    c.perm = reinterpret_cast<unsigned short*>(base + L.perm);
+    c.runStart = reinterpret_cast<unsigned short*>(base + L.runStart);
+    c.cnt = reinterpret_cast<unsigned int*>(base + L.cnt);
+    c.tileStart = reinterpret_cast<int*>(base + L.tileStart);
+    c.sizes = reinterpret_cast<int*>(base + L.sizes);
+    c.szL = reinterpret_cast<int*>(base + L.szL);
+    c.itmp = reinterpret_cast<int*>(base + L.itmp);
+    c.clist = base + L.clist;
+    c.glabel = base + L.glabel;
+    c.lab = base + L.lab;
   }
-  c.WD = kp.WD + (size_t)chain * cap * cap;
-  c.WL = kp.WL + (size_t)chain * cap * cap;
-  c.T = kp.T + (size_t)chain * n * cap;
-  c.Slist = kp.Slist + (size_t)chain * n;
-  c.terms = kp.terms + (size_t)chain * cap * cap;
-  c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + chain));
+  const int ch = valid ? chain : 0;
+  c.WD = kp.WD + (size_t)ch * cap * cap;
+  c.WL = kp.WL + (size_t)ch * cap * cap;
+  c.T = kp.T + (size_t)ch * n * cap;
+  c.Slist = kp.Slist + (size_t)ch * (n + 2);
+  c.origM = kp.origM + (size_t)ch * (n + 2);
+  c.terms = kp.terms + (size_t)ch * cap * cap;
+  c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
+  const int tid = c.ctid;
 
-  // load the chain's state
-  for (int j = tid; j < n; j += RC_NTHR) c.lab[j] = kp.labels[(size_t)chain * n + j];
-  for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
-  if (tid == 0) {
-    Scal& s = *c.sc;
-    s.r = kp.r[chain]; s.p = kp.p[chain];
-    s.logp = rc_log(s.p); s.log1mp = rc_log(1 - s.p);
-    s.status = kp.status[chain]; s.rebuild = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0;
-    int K = 0;
-    for (int q = 0; q < cap; ++q) K += kp.sizes[(size_t)chain * cap + q] > 0;
-    s.K = K;
+  // zero slots behind every stage (padding entries of the permutation point there)
+  for (int t = threadIdx.x; t < RC_NSTAGE * 8; t += blockDim.x)
+    reinterpret_cast<longlong2*>(c.stages + (size_t)(t / 8) * c.stage_bytes + (size_t)c.dummy * 16)[t % 8] = make_longlong2(0, 0);
+  if (valid) {   // load the chain's state
+    for (int j = tid; j < n; j += RC_NTHR) c.lab[j] = kp.labels[(size_t)chain * n + j];
+    for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
+    if (tid == 0) {
+      Scal& s = *c.sc;
+      s.r = kp.r[chain]; s.p = kp.p[chain];
+      s.logp = rc_log(s.p); s.log1mp = rc_log(1 - s.p);
+      s.status = kp.status[chain]; s.rebuild = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0;
+      int K = 0;
+      for (int q = 0; q < cap; ++q) K += kp.sizes[(size_t)chain * cap + q] > 0;
+      s.K = K;
+    }
+    csync(c);
+    build_perm(c);
+    if (kp.init_W) init_W(c);
+    if (kp.loglik_only) {
+      const double ll = loglik_eval(c, c.sizes);
+      if (tid == 0) kp.out_ll[chain] = ll;
+    }
   }
+  if (kp.loglik_only) return;
   __syncthreads();
-  build_perm(c, c.lab);
-  if (kp.init_W) init_W(c);
-  if (kp.loglik_only) {
-    const double ll = loglik_eval(c, c.sizes);
-    if (tid == 0) kp.out_ll[chain] = ll;
-    return;
-  }
 
   for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
-    if (c.sc->status) break;
     const unsigned it = (unsigned)iter;
-    if (tid < 32) {
-      const bool ra = update_r(c, it);                                       // mcmc.jl:538
-      if (tid == 0) {
-        kp.r_acc[(size_t)chain * kp.numiters + (iter - 1)] = ra ? 1 : 0;
-        update_p(c, it);                                                     // :539
+    bool alive = valid;
+    if (alive) { csync(c); alive = c.sc->status == 0; }
+    bool do_scan = alive;
+    if (alive) {
+      if (c.cwarp == 0) {
+        const bool ra = update_r(c, it);                                     // mcmc.jl:538
+        if (tid == 0) {
+          kp.r_acc[(size_t)chain * kp.numiters + (iter - 1)] = ra ? 1 : 0;
+          update_p(c, it);                                                   // :539
+        }
       }
+      csync(c);
+      // sample_labels! (:540)
+      bool perm_dirty = false;
+      for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
+        splitmerge_step(c, it, mh);
+        perm_dirty = true;
+        if (c.sc->status) { do_scan = false; break; }
+        const int acc = c.sc->itmp[1], spl = c.sc->itmp[2];
+        if (tid == 0) {
+          kp.sm_acc[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)acc;
+          kp.sm_split[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)spl;
+        }
+        csync(c);
+        // Quirk Q1: an accepted proposal rebinds sample_labels!'s LOCAL state; the final
+        // scan (:477) then runs on that local object and the caller's labels are untouched this iteration.
+        // Its draws are independent of everything kept (structured stream), so the scan is skipped.
+        if (acc) { do_scan = false; break; }
+      }
+      if (perm_dirty && do_scan) build_perm(c);
+    }
+    // ---- CTA level: agree on the chains that scan, (re)arm the tile ring ----
+    if (tid == 0) c.cta->active[cl] = do_scan ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int nact = 0, issuer = -1;
+      for (int q = 0; q < G; ++q)
+        if (c.cta->active[q]) { if (issuer < 0) issuer = q; ++nact; }
+      c.cta->nact = nact; c.cta->issuer = issuer;
+      if (iter != kp.it0 + 1)
+        for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_NWARP); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    // sample_labels! (:540)
-    bool accepted_any = false;
-    bool perm_dirty = false;
-    for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
-      splitmerge_step(c, it, mh);
-      if (c.sc->status) break;
-      const int acc = c.sc->itmp[1], spl = c.sc->itmp[2];
-      if (tid == 0) {
-        kp.sm_acc[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)acc;
-        kp.sm_split[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)spl;
-      }
-      perm_dirty = true;
-      if (acc) { accepted_any = true; break; }   // numMH == 1: the accepted state never reaches the caller (quirk Q1)
-      __syncthreads();
-    }
+    if (do_scan) full_scan(c, it, c.cta->issuer == cl);
     __syncthreads();
-    if (c.sc->status) break;
-    if (perm_dirty) build_perm(c, c.lab);
-    // Quirk Q1: an accepted proposal rebinds sample_labels!'s LOCAL state; the final scan
-    // (:477) then runs on that local object and the caller's labels are untouched this iteration.  The
-    // draws of that discarded scan are independent of everything kept (structured stream), so it is skipped.
-    if (!accepted_any) full_scan(c, it);
-    if (c.sc->status) break;
-    if (iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0) {             // :546-554
+    if (alive) alive = c.sc->status == 0;
+    if (alive && iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0) {    // :546-554
       const long long j = (iter - kp.burnin) / kp.thin - 1;
       if (j < kp.numsamples) {
         record_labels(c, kp.out_labels + ((size_t)chain * kp.numsamples + j) * n);
         const double ll = loglik_eval(c, c.sizes);
-        if (tid < 32) {
+        if (c.cwarp == 0) {
           const double lpv = logprior_eval(c);
           if (tid == 0) {
             const size_t o = (size_t)chain * kp.numsamples + j;
@@ -1004,15 +1160,16 @@ __global__ void __launch_bounds__(RC_NTHR) k_chain(const __grid_constant__ rc_kp
             kp.out_ll[o] = ll; kp.out_lp[o] = ll + lpv;
           }
         }
-        __syncthreads();
+        csync(c);
       }
     }
   }
-  __syncthreads();
-  // store the chain's state
-  for (int j = tid; j < n; j += RC_NTHR) kp.labels[(size_t)chain * n + j] = c.lab[j];
-  for (int s = tid; s < cap; s += RC_NTHR) kp.sizes[(size_t)chain * cap + s] = c.sizes[s];
-  if (tid == 0) { kp.r[chain] = c.sc->r; kp.p[chain] = c.sc->p; kp.status[chain] = c.sc->status; }
+  if (valid) {   // store the chain's state
+    csync(c);
+    for (int j = tid; j < n; j += RC_NTHR) kp.labels[(size_t)chain * n + j] = c.lab[j];
+    for (int s = tid; s < cap; s += RC_NTHR) kp.sizes[(size_t)chain * cap + s] = c.sizes[s];
+    if (tid == 0) { kp.r[chain] = c.sc->r; kp.p[chain] = c.sc->p; kp.status[chain] = c.sc->status; }
+  }
 }
 
 __global__ void k_tables(rc_params P, int n, double* LGA, double* LGZ, double* LOGN) {
@@ -1026,29 +1183,22 @@ __global__ void k_tables(rc_params P, int n, double* LGA, double* LGZ, double* L
 
 }  // namespace
 
-size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max) {
-  size_t o = 0;
-  auto take = [&](size_t bytes) { o += (bytes + 15) & ~(size_t)15; };
-  take(sizeof(longlong2) * RC_NWARP * cap);
-  take(sizeof(Scal));
-  take(sizeof(long long) * RC_NWARP * 4);
-  take(sizeof(unsigned short) * npad_max);
-  take(sizeof(unsigned short) * (tiles * cap + 1));
-  take(sizeof(unsigned int) * tiles * cap);
-  take(sizeof(int) * (tiles + 1));
-  take(sizeof(int) * cap);
-  take(sizeof(int) * cap);
-  take(sizeof(int) * cap);
-  take(cap);
-  take(npad_max / RC_GROUP);
-  take(n);
-  take(n);
-  return o;
+size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G) {
+  return cta_header_bytes() + (size_t)RC_NSTAGE * stage_bytes_for(n) + (size_t)G * chain_layout(n, cap, tiles, npad_max).total;
 }
 
-void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_chain<<<kp.nchains, RC_NTHR, smem, st>>>(kp);
+void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st) {
+  const int grid = (kp.nchains + G - 1) / G;
+  if (G == 4) {
+    cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_chain<4><<<grid, RC_NTHR * 4, smem, st>>>(kp);
+  } else if (G == 2) {
+    cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_chain<2><<<grid, RC_NTHR * 2, smem, st>>>(kp);
+  } else {
+    cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_chain<1><<<grid, RC_NTHR, smem, st>>>(kp);
+  }
 }
 
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st) {

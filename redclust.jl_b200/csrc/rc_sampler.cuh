@@ -29,7 +29,8 @@ struct rc_kparams {
   rc_i128* WD;          // [nchains][cap*cap]  block sums of Dq, entry (min(k,t), max(k,t))
   rc_i128* WL;          // [nchains][cap*cap]  block sums of Lq
   longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj
-  unsigned short* Slist;// [nchains][n]
+  unsigned short* Slist;// [nchains][n+2]  members of ci u cj of the current split-merge step
+  uint8_t* origM;       // [nchains][n+2]  their labels in the chain's state
   double* terms;        // [nchains][cap*cap]  log-likelihood terms scratch
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
@@ -40,6 +41,6 @@ struct rc_kparams {
   int loglik_only;
 };
 
-size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max);
-void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, cudaStream_t st);
+size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
+void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);

@@ -135,3 +135,25 @@ def test_slot_overflow_is_reported(pkg, golden):
     with pytest.raises(pkg.RCError) as e:
         smp.run(-1)
     assert e.value.status == -5
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_chains_per_cta_share_rows(pkg, orc, golden, monkeypatch, G):
+    """G chains of a CTA consume the same staged row tiles; 3 chains leave a ragged last CTA for G = 2, 4."""
+    monkeypatch.setenv("RCB200_CHAINS_PER_CTA", str(G))
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab)
+    res, _ = run_both(pkg, orc, D, lab, params, 60, 0, 2, 5, 1, seed=31 + G, nchains=3)
+    for got, ref, st in res:
+        assert_same(got, ref, st)
+
+
+def test_multitile_two_chains_per_cta(pkg, orc, monkeypatch):
+    monkeypatch.setenv("RCB200_CHAINS_PER_CTA", "2")
+    X, lab = mixture(2500, 12, 20, 0.2, 8)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab)
+    res, _ = run_both(pkg, orc, D, lab, params, 4, 0, 1, 5, 1, seed=2, nchains=2)
+    for got, ref, st in res:
+        assert_same(got, ref, st)
