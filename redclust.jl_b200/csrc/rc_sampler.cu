@@ -84,6 +84,10 @@ struct Ctx {
   longlong2* T;
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
+  longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
+  double2* L2s;           // [n]   static repulsion terms of the first two live slots, per item
+  double2* NZ;            // [(numGibbs+1) * n] Gumbel noise of the free restricted scans
+  double* LPR;            // [n+2] prior term of joining a cluster of size s, for this iteration's (r, p)
   double* terms;
   unsigned long long key;
 };
@@ -283,7 +287,7 @@ __device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
   const rc_params& P = kp.P;
   const int cap = c.cap;
   const int li = c.lab[i];
-  const double r = c.sc->r, logp = c.sc->logp, log1mp = c.sc->log1mp;
+  const double r = c.sc->r, log1mp = c.sc->log1mp;
 
   long long bd[RC_NS], bl[RC_NS];
   int sz[RC_NS];
@@ -325,7 +329,7 @@ __device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
       const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
       const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
       L1[w] = kp.LGA[sz[w]] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-      lpr[w] = kp.LOGN[sz[w] + 1] + logp + rc_log((double)(sz[w] - 1) + r) - kp.LOGN[sz[w]];
+      lpr[w] = c.LPR[sz[w]];
       L2p[w] = kp.LGZ[sz[w]] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
       acc += L2p[w];                                                        // vecsum: lane-wise ascending slots
     }
@@ -690,98 +694,130 @@ __device__ void update_p(const Ctx& c, unsigned it) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Restricted Gibbs scan (mcmc.jl:259-354) over the members Slist[0..nS) on the launch state, which lives
-// IN PLACE in c.lab / c.szL (the chain's own labels of the members are kept in origM and restored by the
-// caller).  Runs on warp 0 of the chain; the log transition probability is returned in c.sc->ltp.
-// forced: allocate toward the chain's labels (origM) and only accumulate the probability.
+// Prior term of joining an existing cluster of size s (mcmc.jl:226, 324) for this iteration's (r, p):
+// LPR[s] = log(s+1) + log p + log(s-1+r) - log(s), evaluated in the reference's order.
 // ------------------------------------------------------------------------------------------------
-__device__ void restricted_scan(const Ctx& c, unsigned it, unsigned mh, unsigned scan, int nS, int ca, int cb, int c1,
-                                int c2, bool forced) {
+__device__ void build_lpr(const Ctx& c) {
+  const rc_kparams& kp = *c.kp;
+  const double r = c.sc->r, logp = c.sc->logp;
+  for (int s = 1 + c.ctid; s <= c.n; s += RC_NTHR)
+    c.LPR[s] = kp.LOGN[s + 1] + logp + rc_log((double)(s - 1) + r) - kp.LOGN[s];
+  csync(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// All restricted Gibbs scans of one split-merge step (mcmc.jl:259-354, called at :411-414, :419, :454)
+// over the items Slist[0..nS) on the launch state, which lives IN PLACE in c.lab / c.szL (the chain's own
+// labels of the members are kept in origM and restored by the caller).  Runs on warp 0 of the chain.
+//   * AB[q] holds the sums of member q's row over the current members of the two candidate clusters; a
+//     move of item y updates all of them from row y (exact integers), so a step that does not move reads
+//     nothing but its own entry.  Row y is gathered speculatively at the start of the step.
+//   * the Gumbel noise and the repulsion terms of non-candidate slots do not depend on the evolving state
+//     and are precomputed (NZ, L2s).
+//   * the transition probability (:347-351) is only evaluated in the last scan -- the reference discards
+//     the return value of the intermediate scans (:411-414).
+// Returns the log transition probability of the last scan in c.sc->ltp.
+// ------------------------------------------------------------------------------------------------
+#define RC_RS_NU 16
+__device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int lane = c.lane;
   const int mt = nS + 2;
+  const int numGibbs = (int)kp.numGibbs;
+  int xs[RC_RS_NU];
+#pragma unroll
+  for (int u = 0; u < RC_RS_NU; ++u) { const int q = u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
+  const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
   double ltp = 0.0;
-  for (int pos = 0; pos < nS; ++pos) {
-    const int y = c.Slist[pos];
-    const int cur = c.lab[y];
-    // static sums of row y over the first two live slots (prefetch; unused if they are the candidates)
-    longlong2 tst = make_longlong2(0, 0);
-    if (lane == 2 || lane == 3) tst = c.T[(size_t)pos * c.cap + (lane == 2 ? c1 : c2)];
-    // sums of row y over the current members of the two candidate clusters (all live in S u {i, j});
-    // y itself is detached (:303-304), so it is skipped
-    long long aD = 0, aL = 0, bD = 0, bL = 0;
-    const longlong2* row = c.DL + (size_t)y * c.n;
-    for (int q0 = 0; q0 < mt; q0 += 128) {
-      int xs[4]; longlong2 vs[4];
+  for (int g = 0; g <= numGibbs; ++g) {
+    const bool last = g == numGibbs;
+    const bool forced = last && !split;
+    for (int pos = 0; pos < nS; ++pos) {
+      const int y = c.Slist[pos];
+      const longlong2* row = c.DL + (size_t)y * c.n;
+      longlong2 ev[RC_RS_NU];                                   // speculative: row y at the member columns
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int q = q0 + u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) vs[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (xs[u] < 0 || xs[u] == y) continue;
-        const int l = c.lab[xs[u]];
-        if (l == ca) { aD += vs[u].x; aL += vs[u].y; }
-        else if (l == cb) { bD += vs[u].x; bL += vs[u].y; }
+      for (int u = 0; u < RC_RS_NU; ++u) ev[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
+      const longlong2 self = __ldg(row + y);
+      const longlong4 ab = c.AB[pos];
+      const double2 l2s = c.L2s[pos];
+      double2 nz = make_double2(0.0, 0.0);
+      if (!forced) nz = c.NZ[(size_t)g * nS + pos];
+      const int cur = c.lab[y];
+      // sums over the candidates with y detached (:303-304)
+      const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
+      const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
+      const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
+      // lanes 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
+      double X = 0.0;
+      {
+        const bool isA = (lane & 1) == 0;
+        const int szs = isA ? szA : szB;
+        const double szd = (double)szs;
+        const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
+        if ((lane & 2) == 0) {                                                                      // :313-319, 327-330
+          const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+          X = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+        } else {                                                                                    // :307-312, 321-326
+          const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+          X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+        }
       }
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      aD += shfl_xor_ll(aD, off); aL += shfl_xor_ll(aL, off);
-      bD += shfl_xor_ll(bD, off); bL += shfl_xor_ll(bL, off);
-    }
-    // lanes 0..3 evaluate slots {ca, cb, c1, c2}; sizes are those after detaching y
-    const int slot = lane == 0 ? ca : (lane == 1 ? cb : (lane == 2 ? c1 : c2));
-    double L1 = 0.0, lpr = 0.0, L2p = 0.0;
-    if (lane < 4) {
-      long long sd, sl;
-      if (slot == ca) { sd = aD; sl = aL; }
-      else if (slot == cb) { sd = bD; sl = bL; }
-      else { sd = tst.x; sl = tst.y; }
-      const int szs = c.szL[slot] - (slot == cur ? 1 : 0);
-      const double szd = (double)szs;
-      const double sD = rc_dequant(sd, c.qD), sL = rc_dequant(sl, c.qL);
-      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;                             // :313-319
-      L2p = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;   // :327-330
-      if (lane < 2) {                                                                             // :307-312, 321-326
-        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-        L1 = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-        lpr = kp.LOGN[szs + 1] + c.sc->logp + rc_log((double)(szs - 1) + c.sc->r) - kp.LOGN[szs];
+      const double L2pA = __shfl_sync(0xffffffffu, X, 0), L2pB = __shfl_sync(0xffffffffu, X, 1);
+      const double L1A = __shfl_sync(0xffffffffu, X, 2), L1B = __shfl_sync(0xffffffffu, X, 3);
+      const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
+      const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
+      const double L2i = L2p1 + L2p2;                                                               // :331 (quirk Q2)
+      const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                              // :332-334
+      double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                   // :335
+      double lp1 = c.LPR[szB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
+      int k, cnew;
+      if (!forced) {                                                                                // :336-338
+        double mn = lp0;
+        if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+        lp0 -= mn; lp1 -= mn;
+        const double g0 = nz.x + lp0, g1 = nz.y + lp1;
+        k = 0;
+        if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
+        cnew = k == 0 ? ca : cb;
+      } else {                                                                                      // :339-342
+        cnew = c.origM[pos];
+        k = (ca == cnew) ? 0 : 1;
       }
+      if (last) {                                                                                   // :347-351
+        double mn = lp0;                                                                            // quirk Q3
+        if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+        lp0 += mn; lp1 += mn;
+        double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
+        const double den = p0 + p1;
+        p0 /= den; p1 /= den;
+        ltp += rc_log(k == 0 ? p0 : p1);
+      }
+      if (cnew != cur) {                                                                            // :344-345
+        if (lane == 0) { c.lab[y] = (uint8_t)cnew; c.szL[cur] -= 1; c.szL[cnew] += 1; }
+        // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
+        const bool a2b = cur == ca;
+#pragma unroll
+        for (int u = 0; u < RC_RS_NU; ++u) {
+          const int q = u * 32 + lane;
+          if (q < mt) {
+            longlong4 t = c.AB[q];
+            if (a2b) { t.x -= ev[u].x; t.y -= ev[u].y; t.z += ev[u].x; t.w += ev[u].y; }
+            else { t.x += ev[u].x; t.y += ev[u].y; t.z -= ev[u].x; t.w -= ev[u].y; }
+            c.AB[q] = t;
+          }
+        }
+        for (int q = RC_RS_NU * 32 + lane; q < mt; q += 32) {   // members beyond the speculative window
+          const longlong2 e = __ldg(row + c.Slist[q]);
+          longlong4 t = c.AB[q];
+          if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
+          else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
+          c.AB[q] = t;
+        }
+      }
+      __syncwarp();
     }
-    const double L2i = __shfl_sync(0xffffffffu, L2p, 2) + __shfl_sync(0xffffffffu, L2p, 3);      // :331 (quirk Q2)
-    const double L2 = L2i - L2p;                                                                  // :332-334
-    const double lpv = lpr + (L1 + (P.repulsion ? L2 : copysign(0.0, L2)));                       // :335
-    double lp0 = __shfl_sync(0xffffffffu, lpv, 0), lp1 = __shfl_sync(0xffffffffu, lpv, 1);
-    int k, cnew;
-    if (!forced) {                                                                                // :336-338
-      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_RGIBBS, mh, scan, (uint32_t)pos);
-      double mn = lp0;
-      if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-      lp0 -= mn; lp1 -= mn;
-      const double g0 = -rc_log(-rc_log(dr.u0)) + lp0;
-      const double g1 = -rc_log(-rc_log(dr.u1)) + lp1;
-      k = 0;
-      if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
-      cnew = k == 0 ? ca : cb;
-    } else {                                                                                      // :339-342
-      cnew = c.origM[pos];
-      k = (ca == cnew) ? 0 : 1;
-    }
-    if (lane == 0 && cnew != cur) {                                                               // :344-345
-      c.lab[y] = (uint8_t)cnew;
-      c.szL[cur] -= 1;
-      c.szL[cnew] += 1;
-    }
-    double mn = lp0;                                                                              // :348 (quirk Q3)
-    if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-    lp0 += mn; lp1 += mn;
-    double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
-    const double den = p0 + p1;
-    p0 /= den; p1 /= den;
-    ltp += rc_log(k == 0 ? p0 : p1);                                                              // :351
-    __syncwarp();
   }
   if (lane == 0) c.sc->ltp = ltp;
   __syncwarp();
@@ -881,11 +917,37 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     csync(c);
   }
   const int c1 = c.sc->itmp[5], c2 = c.sc->itmp[6];
-  if (warp == 0) {
-    for (unsigned g = 0; g < (unsigned)kp.numGibbs; ++g)                     // :411-414
-      restricted_scan(c, it, mh, g, nS, ca, cb, c1, c2, false);
-    restricted_scan(c, it, mh, (unsigned)kp.numGibbs, nS, ca, cb, c1, c2, !split);   // :419 / :454-455
+  // state-independent inputs of the restricted scans: candidate sums under the launch labels, repulsion
+  // terms of the first two live slots when they are not candidates, Gumbel noise of the free scans
+  for (int q = tid; q < nS + 2; q += RC_NTHR) {
+    const longlong2 ta = c.T[(size_t)q * cap + ca], tb = c.T[(size_t)q * cap + cb];
+    longlong4 ab; ab.x = ta.x; ab.y = ta.y; ab.z = tb.x; ab.w = tb.y;
+    c.AB[q] = ab;
   }
+  for (int pos = tid; pos < nS; pos += RC_NTHR) {
+    double v[2] = {0.0, 0.0};
+    for (int h = 0; h < 2; ++h) {
+      const int t = h == 0 ? c1 : c2;
+      if (t == ca || t == cb) continue;
+      const longlong2 tt = c.T[(size_t)pos * cap + t];
+      const int szs = c.szL[t];
+      const double szd = (double)szs;
+      const double sD = rc_dequant(tt.x, c.qD), sL = rc_dequant(tt.y, c.qL);
+      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+      v[h] = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+    }
+    c.L2s[pos] = make_double2(v[0], v[1]);
+  }
+  {
+    const int nfree = (int)kp.numGibbs + (split ? 1 : 0);
+    for (int e = tid; e < nfree * nS; e += RC_NTHR) {
+      const int g = e / nS, pos = e - g * nS;
+      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_RGIBBS, mh, (uint32_t)g, (uint32_t)pos);
+      c.NZ[e] = make_double2(-rc_log(-rc_log(dr.u0)), -rc_log(-rc_log(dr.u1)));
+    }
+  }
+  csync(c);
+  if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
   csync(c);
   double log_prior_ratio = 0.0, log_proposal_ratio = 0.0;
   if (split) {                                                              // :416-434
@@ -905,31 +967,24 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
         if (c.lab[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
       rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
     }
-    // cross = sum_{x in a_F, y in b_F} DL[x][y]: one warp per row x, lanes over the members
-    rc_i128 crD, crL; crD.lo = 0; crD.hi = 0; crL.lo = 0; crL.hi = 0;
-    for (int q = warp; q < nS + 2; q += RC_NWARP) {
-      const int x = c.Slist[q];
-      if (c.lab[x] != ca) continue;
-      const longlong2* row = c.DL + (size_t)x * n;
-      long long sd = 0, sl = 0;
-      for (int q2 = lane; q2 < nS + 2; q2 += 32) {
-        const int y = c.Slist[q2];
-        if (c.lab[y] == cb) { const longlong2 v = __ldg(row + y); sd += v.x; sl += v.y; }
+    // within / cross sums from the running candidate sums of the final state:
+    //   aa = sum_{x in a_F} sum_{y in a_F} DL[x][y],  ab = sum_{x in a_F} sum_{y in b_F} DL[x][y]
+    rc_i128 acc[4];
+    for (int h = 0; h < 4; ++h) { acc[h].lo = 0; acc[h].hi = 0; }
+    for (int q = tid; q < nS + 2; q += RC_NTHR)
+      if (c.lab[c.Slist[q]] == ca) {
+        const longlong4 ab = c.AB[q];
+        rc_add128(acc[0], ab.x); rc_add128(acc[1], ab.y); rc_add128(acc[2], ab.z); rc_add128(acc[3], ab.w);
       }
-      for (int off = 16; off; off >>= 1) { sd += shfl_xor_ll(sd, off); sl += shfl_xor_ll(sl, off); }
-      rc_add128(crD, sd); rc_add128(crL, sl);
-    }
-    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch
-    if (lane == 0) { red128[warp * 2] = crD; red128[warp * 2 + 1] = crL; }
+    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch [RC_NTHR][4]
+    for (int h = 0; h < 4; ++h) red128[tid * 4 + h] = acc[h];
     csync(c);
     if (tid == 0) {
-      rc_i128 xD = red128[0], xL = red128[1];
-      for (int w = 1; w < RC_NWARP; ++w) { rc_add128(xD, red128[w * 2]); rc_add128(xL, red128[w * 2 + 1]); }
-      // sum_{x in a_F} R[x], R[x] = launch-state row sum over all of ci: columns ca + cb of rowA
-      rc_i128 totD = rows[0 * cap + ca], totL = rows[1 * cap + ca];
-      rc_add128(totD, rows[0 * cap + cb]); rc_add128(totL, rows[1 * cap + cb]);
-      rc_i128 aaD = totD, aaL = totL;
-      rc_sub128(aaD, xD); rc_sub128(aaL, xL);
+      rc_i128 tot[4];
+      for (int h = 0; h < 4; ++h) { tot[h].lo = 0; tot[h].hi = 0; }
+      for (int w = 0; w < RC_NTHR; ++w)
+        for (int h = 0; h < 4; ++h) rc_add128(tot[h], red128[w * 4 + h]);
+      const rc_i128 aaD = tot[0], aaL = tot[1], xD = tot[2], xL = tot[3];
       rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
       rc_sub128(bbD, aaD); rc_sub128(bbD, xD); rc_sub128(bbD, xD);
       rc_sub128(bbL, aaL); rc_sub128(bbL, xL); rc_sub128(bbL, xL);
@@ -1066,7 +1121,11 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
   c.T = kp.T + (size_t)ch * n * cap;
   c.Slist = kp.Slist + (size_t)ch * (n + 2);
   c.origM = kp.origM + (size_t)ch * (n + 2);
-  c.terms = kp.terms + (size_t)ch * cap * cap;
+  c.AB = kp.AB + (size_t)ch * (n + 2);
+  c.L2s = kp.L2s + (size_t)ch * n;
+  c.NZ = kp.NZ + (size_t)ch * (kp.numGibbs + 1) * n;
+  c.LPR = kp.LPR + (size_t)ch * (n + 2);
+  c.terms = kp.terms + (size_t)ch * (cap * cap > 1024 ? cap * cap : 1024);
   c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
   const int tid = c.ctid;
 
@@ -1110,6 +1169,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
         }
       }
       csync(c);
+      build_lpr(c);
       // sample_labels! (:540)
       bool perm_dirty = false;
       for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {

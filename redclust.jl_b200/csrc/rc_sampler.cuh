@@ -31,7 +31,11 @@ struct rc_kparams {
   longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj
   unsigned short* Slist;// [nchains][n+2]  members of ci u cj of the current split-merge step
   uint8_t* origM;       // [nchains][n+2]  their labels in the chain's state
-  double* terms;        // [nchains][cap*cap]  log-likelihood terms scratch
+  longlong4* AB;        // [nchains][n+2]  running candidate sums of the members (restricted scans)
+  double2* L2s;         // [nchains][n]    static repulsion terms per item
+  double2* NZ;          // [nchains][(numGibbs+1)*n] Gumbel noise of the free restricted scans
+  double* LPR;          // [nchains][n+2]  prior term by cluster size for the current (r, p)
+  double* terms;        // [nchains][max(cap*cap, 1024)]  log-likelihood terms / reduction scratch
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
   int* out_K;           // [nchains][numsamples]
