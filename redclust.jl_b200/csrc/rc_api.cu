@@ -123,7 +123,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   if (cap < 2 || cap > RC_MAXCAP) { rc_set_error("slot_cap must be in 2..%d", RC_MAXCAP); return RC_ERR_ARG; }
   if (par->maxK < 0 || !(par->proposalsd_r > 0)) { rc_set_error("invalid hyperparameters (maxK < 0 or proposalsd_r <= 0)"); return RC_ERR_ARG; }
   const int tiles = (int)((n + RC_W - 1) / RC_W);
-  const int64_t npad = ((n + 7) & ~7LL) + 8LL * tiles * cap;
+  const int64_t npad = (((n + 7) & ~7LL) + 7LL * tiles * cap + 7) & ~7LL;   // every (tile, slot) run is padded by at most 7
   if (npad > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(d->device));
   int maxsmem = 0, nsm = 0;
@@ -133,7 +133,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   // chains be co-resident (so they stay in rough lock step and share rows through L2 as well).
   int G = 0, forceG = 0;
   if (const char* e = getenv("RCB200_CHAINS_PER_CTA")) forceG = atoi(e);   // test hook
-  for (int g : {1, 2, 4}) {
+  for (int g : {1, 2}) {
     if (forceG && g != forceG) continue;
     const size_t sm = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, g);
     if (sm > (size_t)maxsmem) break;
@@ -180,7 +180,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   TRY(dalloc(&s->T, opt->numMH > 0 ? (size_t)nchains * n * cap : 1));
   TRY(dalloc(&s->Slist, (size_t)nchains * (n + 2))); TRY(dalloc(&s->origM, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->AB, (size_t)nchains * (n + 2))); TRY(dalloc(&s->L2s, (size_t)nchains * n));
-  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 1024)));
+  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
   TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));

@@ -45,6 +45,20 @@ struct Scal {
   int itmp[8];
 };
 
+#define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
+#define RC_NOISE 64                  // precomputed Gumbel noise entries per row
+struct ScanShared {                  // per chain: hand-off between the bulk warps and the decision warp
+  unsigned long long ready[2];       // row sums of buffer b are complete       (count RC_BW)
+  unsigned long long consumed[2];    // the decision warp has read buffer b     (count 1)
+  volatile int M;                    // moves published by the decision warp
+  volatile int decided;              // rows decided
+  int rowP[2];                       // moves already patched into the permutation when the row was reduced
+  int inited;
+  unsigned short mq_j[RC_MQ];
+  unsigned char mq_a[RC_MQ], mq_b[RC_MQ];
+  double noise[2][RC_NOISE];
+};
+
 struct CtaShared {
   unsigned long long full[RC_NSTAGE];
   unsigned long long empty[RC_NSTAGE];
@@ -57,6 +71,7 @@ struct Ctx {
   int n, cap, tiles;
   int qD, qL;
   int ctid, cwarp, lane, barid;           // thread / warp index within the chain, named barrier of the chain
+  int bbarid;                             // named barrier of the chain's bulk warps
   unsigned dummy;                         // permutation padding entry = index of the zero slot behind a staged tile
   size_t stage_bytes;
   const longlong2* DL;
@@ -68,7 +83,8 @@ struct Ctx {
   unsigned short* runStart;
   unsigned int* cnt;
   int* tileStart;
-  longlong2* partial;     // [RC_NWARP][cap]; aliased by rowA/rowB during loglik of a proposed state
+  longlong2* partial;     // [2][RC_BW][cap]; aliased by rowA/rowB during loglik of a proposed state
+  ScanShared* ss;
   int* sizes;
   int* szL;
   int* itmp;              // [cap]
@@ -93,6 +109,9 @@ struct Ctx {
 };
 
 __device__ __forceinline__ void csync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.barid), "r"(RC_NTHR) : "memory"); }
+__device__ __forceinline__ void bsync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bbarid), "r"(RC_BW * 32) : "memory"); }
+// a team is either the whole chain (RC_NTHR threads, csync) or its bulk warps (RC_BW*32 threads, bsync)
+template <bool BULK> __device__ __forceinline__ void tsync(const Ctx& c) { if (BULK) bsync(c); else csync(c); }
 
 __device__ __forceinline__ int tri(int k, int t, int cap) { return k < t ? k * cap + t : t * cap + k; }
 __device__ __forceinline__ long long shfl_up_ll(long long v, int off) { return __shfl_up_sync(0xffffffffu, v, off); }
@@ -131,13 +150,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // ------------------------------------------------------------------------------------------------
 // (tile, label)-sorted column permutation with label runs padded to multiples of RC_GROUP.
 // ------------------------------------------------------------------------------------------------
+template <bool BULK>
 __device__ void build_perm(const Ctx& c) {
+  constexpr int NT = BULK ? RC_BW * 32 : RC_NTHR;
   const uint8_t* lab = c.lab;
   const int tid = c.ctid, E = c.tiles * c.cap;
-  for (int t = tid; t < E; t += RC_NTHR) c.cnt[t] = 0;
-  csync(c);
-  for (int j = tid; j < c.n; j += RC_NTHR) atomicAdd(&c.cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
-  csync(c);
+  for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
+  tsync<BULK>(c);
+  for (int j = tid; j < c.n; j += NT) atomicAdd(&c.cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
+  tsync<BULK>(c);
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
     const int b = tid * chunk, e = min(E, b + chunk);
@@ -152,24 +173,24 @@ __device__ void build_perm(const Ctx& c) {
     for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + 7u) & ~7u; }
     if (tid == 31) c.runStart[E] = (unsigned short)incl;
   }
-  csync(c);
+  tsync<BULK>(c);
   const int total = c.runStart[E];
-  for (int t = tid; t <= c.tiles; t += RC_NTHR) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
-  for (int q = tid; q < total; q += RC_NTHR) c.perm[q] = (unsigned short)c.dummy;
-  for (int t = tid; t < E; t += RC_NTHR) {
+  for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
+  for (int q = tid; q < total; q += NT) c.perm[q] = (unsigned short)c.dummy;
+  for (int t = tid; t < E; t += NT) {
     const int g0 = c.runStart[t] >> 3, g1 = c.runStart[t + 1] >> 3;
     const uint8_t l = (uint8_t)(t % c.cap);
     for (int g = g0; g < g1; ++g) c.glabel[g] = l;
   }
-  csync(c);
-  for (int t = tid; t < E; t += RC_NTHR) c.cnt[t] = 0;
-  csync(c);
-  for (int j = tid; j < c.n; j += RC_NTHR) {
+  tsync<BULK>(c);
+  for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
+  tsync<BULK>(c);
+  for (int j = tid; j < c.n; j += NT) {
     const int e = (j >> RC_LOGW) * c.cap + lab[j];
     const unsigned pos = c.runStart[e] + atomicAdd(&c.cnt[e], 1u);
     c.perm[pos] = (unsigned short)(j & (RC_W - 1));
   }
-  csync(c);
+  tsync<BULK>(c);
 }
 
 // Point j (column) moved from slot a to slot b: patch the permutation in place (warp 0 of the chain).  If the
@@ -214,7 +235,7 @@ template <bool STAGED>
 __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src, int tile, longlong2* part) {
   const int lane = c.lane, warp = c.cwarp;
   const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
-  for (int gb = g0 + warp * 32; gb < g1; gb += RC_NWARP * 32) {
+  for (int gb = g0 + warp * 32; gb < g1; gb += RC_BW * 32) {
     const int g = gb + lane;
     const bool valid = g < g1;
     const int lab = valid ? (int)c.glabel[g] : 0x100;
@@ -253,165 +274,236 @@ __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src, 
   }
 }
 
-__device__ __forceinline__ void zero_partial(const Ctx& c) {
-  longlong2* part = c.partial + c.cwarp * c.cap;
+__device__ __forceinline__ void zero_partial(const Ctx& c, int buf) {   // bulk warps
+  longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
   for (int s = c.lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
   __syncwarp();
 }
 
-// Row x straight from global memory / L2 (split-merge member rows, block-sum initialisation).
+// Row x straight from global memory / L2 (split-merge member rows, block-sum initialisation); buffer 0.
 __device__ void reduce_row_global(const Ctx& c, int x) {
-  zero_partial(c);
+  if (c.cwarp >= RC_BW) return;
+  zero_partial(c, 0);
   const longlong2* row = c.DL + (size_t)x * c.n;
   longlong2* part = c.partial + c.cwarp * c.cap;
   for (int tile = 0; tile < c.tiles; ++tile) reduce_tile<false>(c, row + tile * RC_W, tile, part);
 }
 
-__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s) {
-  longlong2 a = c.partial[s];
+__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0) {
+  const longlong2* p = c.partial + (size_t)buf * RC_BW * c.cap;
+  longlong2 a = p[s];
 #pragma unroll
-  for (int w = 1; w < RC_NWARP; ++w) {
-    const longlong2 b = c.partial[w * c.cap + s];
+  for (int w = 1; w < RC_BW; ++w) {
+    const longlong2 b = p[w * c.cap + s];
     a.x += b.x; a.y += b.y;
   }
   return a;
 }
 
 // ------------------------------------------------------------------------------------------------
-// One step of the full Gibbs scan for point i (mcmc.jl:192-253), executed by warp 0 of the chain after
-// the row reduction.  Lane l owns slots l, l+32, l+64, l+96.
+// The full Gibbs scan (mcmc.jl:158-256) is a two-stage pipeline per chain:
+//   bulk warps (0..RC_BW-1): reduce row i against the label permutation into partial[i & 1] and signal
+//       ready[i & 1]; they run up to two rows ahead of the decisions.
+//   decision warp (RC_BW): for i = 0..n-1 (mcmc.jl:192-253) waits for row i's sums, corrects them for the
+//       moves the permutation did not contain yet (exact integers), evaluates the candidates (lane l owns
+//       slots l, l+32, l+64, l+96), draws by Gumbel-max, and publishes the move.
+// Moves are applied to the permutation by the bulk warps between two rows (patch in place; rebuild from
+// the labels once the decisions have caught up when a run is full).
 // ------------------------------------------------------------------------------------------------
-__device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
+__device__ void decide_loop(const Ctx& c, unsigned it) {
   const int lane = c.lane;
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
-  const int cap = c.cap;
-  const int li = c.lab[i];
+  const int cap = c.cap, n = c.n;
+  ScanShared* ss = c.ss;
   const double r = c.sc->r, log1mp = c.sc->log1mp;
-
-  long long bd[RC_NS], bl[RC_NS];
+  // register-resident per-slot state: size and the size-dependent table terms
   int sz[RC_NS];
-  unsigned occ[RC_NS];
+  double tA[RC_NS], tZ[RC_NS], tP[RC_NS];
 #pragma unroll
   for (int w = 0; w < RC_NS; ++w) {
     const int s = w * 32 + lane;
-    bd[w] = 0; bl[w] = 0; sz[w] = 0;
-    if (s < cap) {
-      const longlong2 t = bin_total(c, s);
-      bd[w] = t.x; bl[w] = t.y; sz[w] = c.sizes[s];
-      if (s == li) { bd[w] -= self.x; bl[w] -= self.y; sz[w] -= 1; }       // :193-194 detach i
+    sz[w] = s < cap ? c.sizes[s] : 0;
+    tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1];
+  }
+  int M = 0;
+  bool dead = false;
+  for (int i = 0; i < n; ++i) {
+    const int buf = i & 1;
+    const int li = c.lab[i];
+    const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
+    // occupancy with i detached (:193-202) -- independent of the row sums
+    unsigned occ[RC_NS];
+    double dA = 0.0, dZ = 0.0, dP = 0.0;       // table terms of li's slot at its detached size
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      const int s = w * 32 + lane;
+      const int szd = sz[w] - (s == li ? 1 : 0);
+      if (s == li) { dA = kp.LGA[szd]; dZ = kp.LGZ[szd]; dP = c.LPR[szd > 0 ? szd : 1]; }
+      occ[w] = __ballot_sync(0xffffffffu, szd > 0);
     }
-    occ[w] = __ballot_sync(0xffffffffu, sz[w] > 0);
-  }
-  int Ki = 0, e = -1;
+    int Ki = 0, e = -1;
 #pragma unroll
-  for (int w = 0; w < RC_NS; ++w) {
-    Ki += __popc(occ[w]);
-    const int lim = cap - w * 32;
-    const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
-    const unsigned emp = ~occ[w] & capmask;
-    if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                          // findfirst(clustsizes .== 0)
-  }
-  const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < c.n;             // :198
-  if (hasnew && e < 0) {                                                    // slot capacity exhausted
-    if (lane == 0) c.sc->status = RC_ERR_SLOTS;
-    return;
-  }
-  // per-slot terms (:206-242)
-  double L1[RC_NS], lpr[RC_NS], L2p[RC_NS];
-  double acc = 0.0;
-#pragma unroll
-  for (int w = 0; w < RC_NS; ++w) {
-    L1[w] = 0.0; lpr[w] = 0.0; L2p[w] = 0.0;
-    if (sz[w] > 0) {
-      const double szd = (double)sz[w];
-      const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
-      const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-      L1[w] = kp.LGA[sz[w]] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-      lpr[w] = c.LPR[sz[w]];
-      L2p[w] = kp.LGZ[sz[w]] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-      acc += L2p[w];                                                        // vecsum: lane-wise ascending slots
+    for (int w = 0; w < RC_NS; ++w) {
+      Ki += __popc(occ[w]);
+      const int lim = cap - w * 32;
+      const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+      const unsigned emp = ~occ[w] & capmask;
+      if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                        // findfirst(clustsizes .== 0)
     }
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
-  const double L2i = acc;
-  // log-probabilities, Gumbel-max (utils.jl:2-6)
-  double lp[RC_NS];
-  int kk[RC_NS];
-  bool have[RC_NS];
-  int base = 0;
-  bool anynan = false;
-  double mn = RC_INF;
-#pragma unroll
-  for (int w = 0; w < RC_NS; ++w) {
-    have[w] = false; lp[w] = 0.0; kk[w] = 0;
-    const int s = w * 32 + lane;
-    if (sz[w] > 0) {
-      const double L2 = L2i - L2p[w];
-      lp[w] = lpr[w] + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
-      kk[w] = base + __popc(occ[w] & ((1u << lane) - 1u));
-      have[w] = true;
-    } else if (hasnew && s == e) {                                          // :228-230 new cluster
-      const double L2 = L2i - 0.0;
-      lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
-      kk[w] = Ki;
-      have[w] = true;
+    const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;             // :198
+    if (!dead && hasnew && e < 0) {                                         // slot capacity exhausted
+      if (lane == 0) c.sc->status = RC_ERR_SLOTS;
+      dead = true;
     }
-    if (have[w]) {
-      if (rc_isnan(lp[w])) anynan = true;
-      else if (lp[w] < mn) mn = lp[w];
+    int kk[RC_NS];
+    bool have[RC_NS];
+    {
+      int base = 0;
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w) {
+        const int s = w * 32 + lane;
+        const bool live = (occ[w] >> lane) & 1u;
+        have[w] = live || (hasnew && s == e);
+        kk[w] = live ? base + __popc(occ[w] & ((1u << lane) - 1u)) : Ki;
+        base += __popc(occ[w]);
+      }
     }
-    base += __popc(occ[w]);
-  }
+    // ---- row sums of row i ----
+    mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
+    const int Prow = ss->rowP[buf];
+    long long bd[RC_NS], bl[RC_NS];
+    double nzv[RC_NS];
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double o = __shfl_xor_sync(0xffffffffu, mn, off);
-    if (o < mn) mn = o;
-  }
-  anynan = __any_sync(0xffffffffu, anynan);
-  if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
-  // argmax of gumbel + shifted logprob; NaN is maximal, first index wins ties
-  double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+    for (int w = 0; w < RC_NS; ++w) {
+      const int s = w * 32 + lane;
+      bd[w] = 0; bl[w] = 0; nzv[w] = 0.0;
+      if (s < cap && ((occ[w] >> lane) & 1u)) {
+        const longlong2 t = bin_total(c, s, buf);
+        bd[w] = t.x; bl[w] = t.y;
+      }
+      if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[buf][kk[w]];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ss->consumed[buf]);
+    if (dead) { if (lane == 0) { __threadfence_block(); ss->decided = i + 1; } continue; }
+    // moves of earlier steps that the permutation did not contain when row i was reduced
+    for (int m = Prow; m < M; ++m) {
+      const int j = ss->mq_j[m % RC_MQ], a = ss->mq_a[m % RC_MQ], b = ss->mq_b[m % RC_MQ];
+      const longlong2 ev = __ldg(c.DL + (size_t)i * n + j);
 #pragma unroll
-  for (int w = 0; w < RC_NS; ++w) {
-    if (!have[w]) continue;
-    const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
-    const double u = (kk[w] & 1) ? dr.u1 : dr.u0;
-    const double g = -rc_log(-rc_log(u)) + (lp[w] - mn);
-    const bool gn = rc_isnan(g);
-    bool better;
-    if (bs < 0) better = true;
-    else if (gn) better = !bnan || kk[w] < bk;
-    else if (bnan) better = false;
-    else better = g > bg || (g == bg && kk[w] < bk);
-    if (better) { bg = g; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
-  }
+      for (int w = 0; w < RC_NS; ++w) {
+        const int s = w * 32 + lane;
+        const bool live = (occ[w] >> lane) & 1u;
+        if (s == a && live) { bd[w] -= ev.x; bl[w] -= ev.y; }
+        if (s == b && live) { bd[w] += ev.x; bl[w] += ev.y; }
+      }
+    }
+    // per-slot terms (:206-242)
+    double L1[RC_NS], L2p[RC_NS];
+    double acc = 0.0;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double og = __shfl_xor_sync(0xffffffffu, bg, off);
-    const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
-    const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-    const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
-    bool better;
-    if (os < 0) better = false;
-    else if (bs < 0) better = true;
-    else if (on) better = !bnan || ok < bk;
-    else if (bnan) better = false;
-    else better = og > bg || (og == bg && ok < bk);
-    if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
-  }
-  const int cnew = bs;
-  if (lane == 0) {                                                          // :250-252
-    c.lab[i] = (uint8_t)cnew;
-    c.sizes[li] -= 1;
-    c.sizes[cnew] += 1;
-  }
-  if (cnew == li) return;
-  // the point moved: update the block-sum matrices from its row sums (exact integers)
-  {
+    for (int w = 0; w < RC_NS; ++w) {
+      L1[w] = 0.0; L2p[w] = 0.0;
+      const int s = w * 32 + lane;
+      if ((occ[w] >> lane) & 1u) {
+        if (s == li) { bd[w] -= self.x; bl[w] -= self.y; }                  // :193-194 detach i
+        const int szs = sz[w] - (s == li ? 1 : 0);
+        const double szd = (double)szs;
+        const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
+        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+        L1[w] = (s == li ? dA : tA[w]) + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+        L2p[w] = (s == li ? dZ : tZ[w]) - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+        acc += L2p[w];                                                      // vecsum: lane-wise ascending slots
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
+    const double L2i = acc;
+    // log-probabilities, Gumbel-max (utils.jl:2-6)
+    double lp[RC_NS];
+    bool anynan = false;
+    double mn = RC_INF;
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      lp[w] = 0.0;
+      const int s = w * 32 + lane;
+      if ((occ[w] >> lane) & 1u) {
+        const double L2 = L2i - L2p[w];
+        lp[w] = (s == li ? dP : tP[w]) + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
+      } else if (have[w]) {                                                 // :228-230 new cluster
+        const double L2 = L2i - 0.0;
+        lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+      }
+      if (have[w]) {
+        if (rc_isnan(lp[w])) anynan = true;
+        else if (lp[w] < mn) mn = lp[w];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, mn, off);
+      if (o < mn) mn = o;
+    }
+    anynan = __any_sync(0xffffffffu, anynan);
+    if (anynan) mn = RC_NAN;                                                // Julia minimum propagates NaN
+    // argmax of gumbel + shifted logprob; NaN is maximal, first index wins ties
+    double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      if (!have[w]) continue;
+      double nz = nzv[w];
+      if (kk[w] >= RC_NOISE) {
+        const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
+        nz = -rc_log(-rc_log((kk[w] & 1) ? dr.u1 : dr.u0));
+      }
+      const double g = nz + (lp[w] - mn);
+      const bool gn = rc_isnan(g);
+      bool better;
+      if (bs < 0) better = true;
+      else if (gn) better = !bnan || kk[w] < bk;
+      else if (bnan) better = false;
+      else better = g > bg || (g == bg && kk[w] < bk);
+      if (better) { bg = g; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, bg, off);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
+      bool better;
+      if (os < 0) better = false;
+      else if (bs < 0) better = true;
+      else if (on) better = !bnan || ok < bk;
+      else if (bnan) better = false;
+      else better = og > bg || (og == bg && ok < bk);
+      if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
+    }
+    const int cnew = bs;
+    if (cnew == li) {
+      if (lane == 0) { __threadfence_block(); ss->decided = i + 1; }
+      continue;
+    }
+    // ---- the point moved (:250-252): publish, then update sizes, cached terms and the block sums ----
+    if (lane == 0) {
+      c.lab[i] = (uint8_t)cnew;
+      c.sizes[li] -= 1;
+      c.sizes[cnew] += 1;
+      ss->mq_j[M % RC_MQ] = (unsigned short)i; ss->mq_a[M % RC_MQ] = (unsigned char)li; ss->mq_b[M % RC_MQ] = (unsigned char)cnew;
+      __threadfence_block();
+      ss->M = M + 1;
+      ss->decided = i + 1;
+    }
+    M += 1;
     const int a = li, b = cnew;
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      const int s = w * 32 + lane;
+      if (s == a) { sz[w] -= 1; tA[w] = dA; tZ[w] = dZ; tP[w] = dP; }
+      if (s == b) { sz[w] += 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]]; }
+    }
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       const int s = w * 32 + lane;
@@ -420,7 +512,7 @@ __device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
         const int ix = tri(a, a, cap);
         rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
         rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
-      } else if (bd[w] != 0 || bl[w] != 0) {
+      } else if ((occ[w] >> lane) & 1u) {
         const int ix = tri(a, s, cap);
         rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(bd[w])); c.WD[ix] = x;
         rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(bl[w])); c.WL[ix] = y;
@@ -435,25 +527,22 @@ __device__ void scan_decide(const Ctx& c, int i, unsigned it, longlong2 self) {
         const int ix = tri(b, b, cap);
         rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
         rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
-      } else if (bd[w] != 0 || bl[w] != 0) {
+      } else if ((occ[w] >> lane) & 1u) {
         const int ix = tri(b, s, cap);
         rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(bd[w])); c.WD[ix] = x;
         rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(bl[w])); c.WL[ix] = y;
       }
     }
     __syncwarp();
-    patch_perm(c, i, a, b);
   }
 }
 
-// sample_labels_Gibbs! (mcmc.jl:158-256).  All ACTIVE chains of the CTA run this together: the tiles of row
-// i are staged once (bulk async copy, RC_NSTAGE-deep ring) and consumed by every active chain.  A chain
-// whose slot capacity overflows keeps consuming tiles (so the ring keeps moving) but stops deciding.
-__device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
+__device__ void bulk_loop(const Ctx& c, unsigned it, bool is_issuer_chain) {
   const int n = c.n, tiles = c.tiles;
   const long long ntile = (long long)n * tiles;
   const bool issuer = is_issuer_chain && c.ctid == 0;
   CtaShared* cs = c.cta;
+  ScanShared* ss = c.ss;
   auto issue = [&](long long t) {   // stage tile t of the row stream
     const int row = (int)(t / tiles), tile = (int)(t - (long long)row * tiles);
     const int s = (int)(t % RC_NSTAGE);
@@ -464,13 +553,36 @@ __device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
   };
   if (issuer)
     for (long long t = 0; t < RC_NSTAGE && t < ntile; ++t) issue(t);
-  bool dead = false;
   long long t = 0;
-  longlong2* part = c.partial + c.cwarp * c.cap;
+  int Papplied = 0;
   for (int i = 0; i < n; ++i) {
-    longlong2 self = make_longlong2(0, 0);
-    if (c.ctid == 0) self = __ldg(c.DL + (size_t)i * n + i);
-    zero_partial(c);
+    const int buf = i & 1;
+    if (i >= 2) mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1));
+    bsync(c);                                   // every bulk warp is done with row i-1: the permutation may change
+    if (c.cwarp == 0) {
+      const int Mnow = ss->M;
+      __threadfence_block();
+      for (int m = Papplied; m < Mnow; ++m) patch_perm(c, ss->mq_j[m % RC_MQ], ss->mq_a[m % RC_MQ], ss->mq_b[m % RC_MQ]);
+      if (c.lane == 0) ss->rowP[buf] = Mnow;
+    }
+    bsync(c);
+    Papplied = ss->rowP[buf];
+    if (c.sc->rebuild) {                        // a label run was full: rebuild from the labels once they are final up to row i-1
+      while (ss->decided < i) __nanosleep(64);
+      __threadfence_block();
+      bsync(c);
+      build_perm<true>(c);
+      if (c.ctid == 0) { c.sc->rebuild = 0; ss->rowP[buf] = ss->M; }
+      bsync(c);
+      Papplied = ss->rowP[buf];
+    }
+    zero_partial(c, buf);
+    if (c.cwarp == RC_BW - 1) {                 // Gumbel noise of row i's candidates 2*lane, 2*lane+1 (utils.jl:4-5)
+      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);
+      ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
+      ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
+    }
+    longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
     for (int tile = 0; tile < tiles; ++tile, ++t) {
       const int s = (int)(t % RC_NSTAGE);
       const unsigned ph = (unsigned)((t / RC_NSTAGE) & 1);
@@ -485,20 +597,29 @@ __device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
       __syncwarp();
       if (c.lane == 0) mbar_arrive(&cs->empty[s]);
     }
-    csync(c);
-    if (c.cwarp == 0 && !dead) {
-      self.x = __shfl_sync(0xffffffffu, self.x, 0);
-      self.y = __shfl_sync(0xffffffffu, self.y, 0);
-      scan_decide(c, i, it, self);
-    }
-    csync(c);
-    if (c.sc->status) dead = true;
-    if (!dead && c.sc->rebuild) {
-      csync(c);
-      if (c.ctid == 0) c.sc->rebuild = 0;
-      build_perm(c);
-    }
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&ss->ready[buf]);
   }
+}
+
+// sample_labels_Gibbs! (mcmc.jl:158-256).  All ACTIVE chains of the CTA run this together: the tiles of row
+// i are staged once (bulk async copy, RC_NSTAGE-deep ring) and consumed by every active chain.  A chain
+// whose slot capacity overflows keeps consuming tiles (so the ring keeps moving) but stops deciding.
+__device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
+  ScanShared* ss = c.ss;
+  if (c.ctid == 0) {
+    if (ss->inited)
+      for (int b = 0; b < 2; ++b) { mbar_inval(&ss->ready[b]); mbar_inval(&ss->consumed[b]); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ss->ready[b], RC_BW); mbar_init(&ss->consumed[b], 1); }
+    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP[0] = 0; ss->rowP[1] = 0;
+    c.sc->rebuild = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  csync(c);
+  if (c.cwarp < RC_BW) bulk_loop(c, it, is_issuer_chain);
+  else decide_loop(c, it);
+  csync(c);
+  // moves published after the last patch pass are not in the permutation: the next user rebuilds it
   if (c.cwarp == 0) {                                                       // :254
     int K = 0;
     for (int s = c.lane; s < c.cap; s += 32) K += c.sizes[s] > 0;
@@ -909,7 +1030,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     csync(c);
   }
   // row sums by slot of every member of S u {i, j} under the launch labels
-  build_perm(c);
+  build_perm<false>(c);
   for (int pos = 0; pos < nS + 2; ++pos) {
     reduce_row_global(c, c.Slist[pos]);
     csync(c);
@@ -1060,14 +1181,15 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 }
 
 struct ChainLayout {
-  size_t partial, sc, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, glabel, lab, total;
+  size_t partial, sc, ss, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, glabel, lab, total;
 };
 __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, int npad_max) {
   ChainLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
-  L.partial = take(sizeof(longlong2) * RC_NWARP * cap);
+  L.partial = take(sizeof(longlong2) * 2 * RC_BW * cap);
   L.sc = take(sizeof(Scal));
+  L.ss = take(sizeof(ScanShared));
   L.red = take(sizeof(long long) * RC_NWARP * 4);
   L.perm = take(sizeof(unsigned short) * npad_max);
   L.runStart = take(sizeof(unsigned short) * (tiles * cap + 1));
@@ -1093,7 +1215,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
   const int n = kp.n, cap = kp.cap, tiles = kp.tiles;
   Ctx c;
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
-  c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl;
+  c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
@@ -1103,6 +1225,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
     unsigned char* base = c.stages + (size_t)RC_NSTAGE * c.stage_bytes + (size_t)cl * L.total;
     c.partial = reinterpret_cast<longlong2*>(base + L.partial);
     c.sc = reinterpret_cast<Scal*>(base + L.sc);
+    c.ss = reinterpret_cast<ScanShared*>(base + L.ss);
     c.red = reinterpret_cast<long long*>(base + L.red);
     c.perm = reinterpret_cast<unsigned short*>(base + L.perm);
     c.runStart = reinterpret_cast<unsigned short*>(base + L.runStart);
@@ -1125,7 +1248,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
   c.L2s = kp.L2s + (size_t)ch * n;
   c.NZ = kp.NZ + (size_t)ch * (kp.numGibbs + 1) * n;
   c.LPR = kp.LPR + (size_t)ch * (n + 2);
-  c.terms = kp.terms + (size_t)ch * (cap * cap > 1024 ? cap * cap : 1024);
+  c.terms = kp.terms + (size_t)ch * (cap * cap > 2048 ? cap * cap : 2048);
   c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
   const int tid = c.ctid;
 
@@ -1139,13 +1262,13 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
       Scal& s = *c.sc;
       s.r = kp.r[chain]; s.p = kp.p[chain];
       s.logp = rc_log(s.p); s.log1mp = rc_log(1 - s.p);
-      s.status = kp.status[chain]; s.rebuild = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0;
+      s.status = kp.status[chain]; s.rebuild = 0; c.ss->inited = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0;
       int K = 0;
       for (int q = 0; q < cap; ++q) K += kp.sizes[(size_t)chain * cap + q] > 0;
       s.K = K;
     }
     csync(c);
-    build_perm(c);
+    build_perm<false>(c);
     if (kp.init_W) init_W(c);
     if (kp.loglik_only) {
       const double ll = loglik_eval(c, c.sizes);
@@ -1171,10 +1294,8 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
       csync(c);
       build_lpr(c);
       // sample_labels! (:540)
-      bool perm_dirty = false;
       for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
         splitmerge_step(c, it, mh);
-        perm_dirty = true;
         if (c.sc->status) { do_scan = false; break; }
         const int acc = c.sc->itmp[1], spl = c.sc->itmp[2];
         if (tid == 0) {
@@ -1187,7 +1308,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
         // Its draws are independent of everything kept (structured stream), so the scan is skipped.
         if (acc) { do_scan = false; break; }
       }
-      if (perm_dirty && do_scan) build_perm(c);
+      if (do_scan) build_perm<false>(c);   // the scan's last moves / the proposal's launch labels are not in it
     }
     // ---- CTA level: agree on the chains that scan, (re)arm the tile ring ----
     if (tid == 0) c.cta->active[cl] = do_scan ? 1 : 0;
@@ -1199,7 +1320,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
       c.cta->nact = nact; c.cta->issuer = issuer;
       if (iter != kp.it0 + 1)
         for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
-      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_NWARP); }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_BW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1249,10 +1370,7 @@ size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G) {
 
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st) {
   const int grid = (kp.nchains + G - 1) / G;
-  if (G == 4) {
-    cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chain<4><<<grid, RC_NTHR * 4, smem, st>>>(kp);
-  } else if (G == 2) {
+  if (G == 2) {
     cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_chain<2><<<grid, RC_NTHR * 2, smem, st>>>(kp);
   } else {

@@ -2,8 +2,9 @@
 #pragma once
 #include "rc_common.cuh"
 
-#define RC_NTHR 128
-#define RC_NWARP (RC_NTHR / 32)
+#define RC_BW 4                      // bulk (row-reduction) warps per chain
+#define RC_NWARP (RC_BW + 1)         // + one decision warp
+#define RC_NTHR (RC_NWARP * 32)      // threads per chain
 
 struct rc_kparams {
   int n, cap, tiles, npad_max;

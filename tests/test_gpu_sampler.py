@@ -137,9 +137,9 @@ def test_slot_overflow_is_reported(pkg, golden):
     assert e.value.status == -5
 
 
-@pytest.mark.parametrize("G", [1, 2, 4])
+@pytest.mark.parametrize("G", [1, 2])
 def test_chains_per_cta_share_rows(pkg, orc, golden, monkeypatch, G):
-    """G chains of a CTA consume the same staged row tiles; 3 chains leave a ragged last CTA for G = 2, 4."""
+    """G chains of a CTA consume the same staged row tiles; 3 chains leave a ragged last CTA for G = 2."""
     monkeypatch.setenv("RCB200_CHAINS_PER_CTA", str(G))
     D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
     params = pkg.params_from_labels(D, lab)
