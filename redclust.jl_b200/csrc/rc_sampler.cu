@@ -53,6 +53,8 @@ struct ScanShared {                  // per chain: hand-off between the bulk war
   volatile int M;                    // moves published by the decision warp
   volatile int decided;              // rows decided
   int rowP[2];                       // moves already patched into the permutation when the row was reduced
+  int msnap[2];                      // moves published when the decision warp released buffer b
+  int prebuilt;                      // moves contained in the permutation after a rebuild
   int inited;
   unsigned short mq_j[RC_MQ];
   unsigned char mq_a[RC_MQ], mq_b[RC_MQ];
@@ -104,6 +106,7 @@ struct Ctx {
   double2* L2s;           // [n]   static repulsion terms of the first two live slots, per item
   double2* NZ;            // [(numGibbs+1) * n] Gumbel noise of the free restricted scans
   double* LPR;            // [n+2] prior term of joining a cluster of size s, for this iteration's (r, p)
+  longlong2* DG;          // [n+2] DL[x][x] of the members
   double* terms;
   unsigned long long key;
 };
@@ -384,6 +387,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       }
       if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[buf][kk[w]];
     }
+    if (lane == 0) ss->msnap[buf] = M;
     __syncwarp();
     if (lane == 0) mbar_arrive(&ss->consumed[buf]);
     if (dead) { if (lane == 0) { __threadfence_block(); ss->decided = i + 1; } continue; }
@@ -557,27 +561,27 @@ __device__ void bulk_loop(const Ctx& c, unsigned it, bool is_issuer_chain) {
   int Papplied = 0;
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
-    if (i >= 2) mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1));
-    bsync(c);                                   // every bulk warp is done with row i-1: the permutation may change
-    if (c.cwarp == 0) {
-      const int Mnow = ss->M;
-      __threadfence_block();
-      for (int m = Papplied; m < Mnow; ++m) patch_perm(c, ss->mq_j[m % RC_MQ], ss->mq_a[m % RC_MQ], ss->mq_b[m % RC_MQ]);
-      if (c.lane == 0) ss->rowP[buf] = Mnow;
-    }
-    bsync(c);
-    Papplied = ss->rowP[buf];
-    if (c.sc->rebuild) {                        // a label run was full: rebuild from the labels once they are final up to row i-1
-      while (ss->decided < i) __nanosleep(64);
-      __threadfence_block();
+    int Msnap = 0;
+    if (i >= 2) { mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1)); Msnap = ss->msnap[buf]; }
+    if (Msnap > Papplied) {                     // uniform over the chain's bulk warps: patch the permutation
+      bsync(c);                                 // every bulk warp is between two rows
+      if (c.cwarp == 0)
+        for (int m = Papplied; m < Msnap; ++m) patch_perm(c, ss->mq_j[m % RC_MQ], ss->mq_a[m % RC_MQ], ss->mq_b[m % RC_MQ]);
       bsync(c);
-      build_perm<true>(c);
-      if (c.ctid == 0) { c.sc->rebuild = 0; ss->rowP[buf] = ss->M; }
-      bsync(c);
-      Papplied = ss->rowP[buf];
+      Papplied = Msnap;
+      if (c.sc->rebuild) {                      // a label run was full: rebuild from the labels once they are final up to row i-1
+        while (ss->decided < i) __nanosleep(64);
+        __threadfence_block();
+        bsync(c);
+        build_perm<true>(c);
+        if (c.ctid == 0) { c.sc->rebuild = 0; ss->prebuilt = ss->M; }
+        bsync(c);
+        Papplied = ss->prebuilt;
+      }
     }
+    if (c.ctid == 0) ss->rowP[buf] = Papplied;
     zero_partial(c, buf);
-    if (c.cwarp == RC_BW - 1) {                 // Gumbel noise of row i's candidates 2*lane, 2*lane+1 (utils.jl:4-5)
+    if (c.cwarp == (i & (RC_BW - 1))) {         // Gumbel noise of row i's candidates 2*lane, 2*lane+1 (utils.jl:4-5)
       const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);
       ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
       ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
@@ -611,7 +615,7 @@ __device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
     if (ss->inited)
       for (int b = 0; b < 2; ++b) { mbar_inval(&ss->ready[b]); mbar_inval(&ss->consumed[b]); }
     for (int b = 0; b < 2; ++b) { mbar_init(&ss->ready[b], RC_BW); mbar_init(&ss->consumed[b], 1); }
-    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP[0] = 0; ss->rowP[1] = 0;
+    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP[0] = 0; ss->rowP[1] = 0; ss->msnap[0] = 0; ss->msnap[1] = 0; ss->prebuilt = 0;
     c.sc->rebuild = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -840,35 +844,52 @@ __device__ void build_lpr(const Ctx& c) {
 // Returns the log transition probability of the last scan in c.sc->ltp.
 // ------------------------------------------------------------------------------------------------
 #define RC_RS_NU 16
+struct RsItem {          // everything a restricted step needs that does not depend on the evolving state
+  int y;
+  longlong2 self;
+  longlong4 ab;
+  double2 l2s, nz;
+};
+__device__ __forceinline__ RsItem rs_load(const Ctx& c, int g, int pos, int nS, bool forced) {
+  RsItem t;
+  t.y = c.Slist[pos];
+  t.self = c.DG[pos];
+  t.ab = c.AB[pos];
+  t.l2s = c.L2s[pos];
+  t.nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
+  return t;
+}
 __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int lane = c.lane;
   const int mt = nS + 2;
   const int numGibbs = (int)kp.numGibbs;
+  if (nS == 0) { if (lane == 0) c.sc->ltp = 0.0; __syncwarp(); return; }
   int xs[RC_RS_NU];
 #pragma unroll
   for (int u = 0; u < RC_RS_NU; ++u) { const int q = u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
   const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
   double ltp = 0.0;
+  RsItem nx = rs_load(c, 0, 0, nS, numGibbs == 0 && !split);
   for (int g = 0; g <= numGibbs; ++g) {
     const bool last = g == numGibbs;
     const bool forced = last && !split;
     for (int pos = 0; pos < nS; ++pos) {
-      const int y = c.Slist[pos];
+      const RsItem cu = nx;
+      const int y = cu.y;
       const longlong2* row = c.DL + (size_t)y * c.n;
-      longlong2 ev[RC_RS_NU];                                   // speculative: row y at the member columns
+      longlong2 ev[RC_RS_NU];                                   // speculative: row y at the member columns (used if y moves)
 #pragma unroll
       for (int u = 0; u < RC_RS_NU; ++u) ev[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
-      const longlong2 self = __ldg(row + y);
-      const longlong4 ab = c.AB[pos];
-      const double2 l2s = c.L2s[pos];
-      double2 nz = make_double2(0.0, 0.0);
-      if (!forced) nz = c.NZ[(size_t)g * nS + pos];
+      // inputs of the next step (its AB entry is re-read below if this step moves)
+      const int npos = pos + 1 < nS ? pos + 1 : 0, ng = pos + 1 < nS ? g : g + 1;
+      const bool more = ng <= numGibbs;
+      if (more) nx = rs_load(c, ng, npos, nS, ng == numGibbs && !split);
       const int cur = c.lab[y];
       // sums over the candidates with y detached (:303-304)
-      const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
-      const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
+      const long long sAd = cu.ab.x - (cur == ca ? cu.self.x : 0), sAl = cu.ab.y - (cur == ca ? cu.self.y : 0);
+      const long long sBd = cu.ab.z - (cur == cb ? cu.self.x : 0), sBl = cu.ab.w - (cur == cb ? cu.self.y : 0);
       const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
       // lanes 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
       double X = 0.0;
@@ -887,8 +908,8 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
       }
       const double L2pA = __shfl_sync(0xffffffffu, X, 0), L2pB = __shfl_sync(0xffffffffu, X, 1);
       const double L1A = __shfl_sync(0xffffffffu, X, 2), L1B = __shfl_sync(0xffffffffu, X, 3);
-      const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
-      const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
+      const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : cu.l2s.x;
+      const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : cu.l2s.y;
       const double L2i = L2p1 + L2p2;                                                               // :331 (quirk Q2)
       const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                              // :332-334
       double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                   // :335
@@ -898,7 +919,7 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
         double mn = lp0;
         if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
         lp0 -= mn; lp1 -= mn;
-        const double g0 = nz.x + lp0, g1 = nz.y + lp1;
+        const double g0 = cu.nz.x + lp0, g1 = cu.nz.y + lp1;
         k = 0;
         if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
         cnew = k == 0 ? ca : cb;
@@ -936,12 +957,62 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
           else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
           c.AB[q] = t;
         }
+        __syncwarp();
+        if (more) nx.ab = c.AB[npos];
       }
       __syncwarp();
     }
   }
   if (lane == 0) c.sc->ltp = ltp;
   __syncwarp();
+}
+
+// Split-merge setup for a MERGE proposal: the restricted scans need, for every member x of ci u cj, only the
+// sums of its row over the members by launch label (AB) and -- when they are not candidates -- over the
+// first two live slots (L2s).  One warp per member row gathers exactly those entries instead of reducing the
+// whole row.  CL1 / CL2 hold the members of the first two live slots (n1, n2 entries).
+__device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1, int c2, const unsigned short* CL1, int n1,
+                                   const unsigned short* CL2, int n2) {
+  const rc_kparams& kp = *c.kp;
+  const rc_params& P = kp.P;
+  const int lane = c.lane, mt = nS + 2;
+  for (int q = c.cwarp; q < mt; q += RC_NWARP) {
+    const int x = c.Slist[q];
+    const longlong2* row = c.DL + (size_t)x * c.n;
+    long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // aD aL bD bL c1D c1L c2D c2L
+    for (int q2 = lane; q2 < mt; q2 += 32) {
+      const int y = c.Slist[q2];
+      const longlong2 e = __ldg(row + y);
+      const int l = c.lab[y];
+      if (l == ca) { v[0] += e.x; v[1] += e.y; } else if (l == cb) { v[2] += e.x; v[3] += e.y; }
+    }
+    for (int t = lane; t < n1; t += 32) { const longlong2 e = __ldg(row + CL1[t]); v[4] += e.x; v[5] += e.y; }
+    for (int t = lane; t < n2; t += 32) { const longlong2 e = __ldg(row + CL2[t]); v[6] += e.x; v[7] += e.y; }
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      for (int off = 16; off; off >>= 1) v[h] += shfl_xor_ll(v[h], off);
+    if (lane == 0) {
+      longlong4 ab; ab.x = v[0]; ab.y = v[1]; ab.z = v[2]; ab.w = v[3];
+      c.AB[q] = ab;
+      c.DG[q] = __ldg(row + x);
+    }
+    if (q < nS) {
+      double val = 0.0;
+      if (lane < 2) {
+        const int t = lane == 0 ? c1 : c2;
+        if (t != ca && t != cb) {
+          const int szs = c.szL[t];
+          const double szd = (double)szs;
+          const double sD = rc_dequant(lane == 0 ? v[4] : v[6], c.qD), sL = rc_dequant(lane == 0 ? v[5] : v[7], c.qL);
+          const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+          val = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+        }
+      }
+      const double other = __shfl_sync(0xffffffffu, val, 1);
+      if (lane == 0) c.L2s[q] = make_double2(val, other);
+    }
+    __syncwarp();
+  }
 }
 
 // One split-merge proposal (mcmc.jl:372-474) on the chain's current state.  Returns accept through
@@ -1029,35 +1100,55 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     }
     csync(c);
   }
-  // row sums by slot of every member of S u {i, j} under the launch labels
-  build_perm<false>(c);
-  for (int pos = 0; pos < nS + 2; ++pos) {
-    reduce_row_global(c, c.Slist[pos]);
-    csync(c);
-    for (int s = tid; s < cap; s += RC_NTHR) c.T[(size_t)pos * cap + s] = bin_total(c, s);
-    csync(c);
-  }
   const int c1 = c.sc->itmp[5], c2 = c.sc->itmp[6];
-  // state-independent inputs of the restricted scans: candidate sums under the launch labels, repulsion
-  // terms of the first two live slots when they are not candidates, Gumbel noise of the free scans
-  for (int q = tid; q < nS + 2; q += RC_NTHR) {
-    const longlong2 ta = c.T[(size_t)q * cap + ca], tb = c.T[(size_t)q * cap + cb];
-    longlong4 ab; ab.x = ta.x; ab.y = ta.y; ab.z = tb.x; ab.w = tb.y;
-    c.AB[q] = ab;
-  }
-  for (int pos = tid; pos < nS; pos += RC_NTHR) {
-    double v[2] = {0.0, 0.0};
-    for (int h = 0; h < 2; ++h) {
-      const int t = h == 0 ? c1 : c2;
-      if (t == ca || t == cb) continue;
-      const longlong2 tt = c.T[(size_t)pos * cap + t];
-      const int szs = c.szL[t];
-      const double szd = (double)szs;
-      const double sD = rc_dequant(tt.x, c.qD), sL = rc_dequant(tt.y, c.qL);
-      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-      v[h] = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+  if (split) {
+    // row sums by slot of every member of S u {i, j} under the launch labels (all slots are needed for the
+    // block sums of the proposed state)
+    build_perm<false>(c);
+    for (int pos = 0; pos < nS + 2; ++pos) {
+      reduce_row_global(c, c.Slist[pos]);
+      csync(c);
+      for (int s = tid; s < cap; s += RC_NTHR) c.T[(size_t)pos * cap + s] = bin_total(c, s);
+      csync(c);
     }
-    c.L2s[pos] = make_double2(v[0], v[1]);
+    // state-independent inputs of the restricted scans: candidate sums under the launch labels, diagonal
+    // entries, repulsion terms of the first two live slots when they are not candidates
+    for (int q = tid; q < nS + 2; q += RC_NTHR) {
+      const longlong2 ta = c.T[(size_t)q * cap + ca], tb = c.T[(size_t)q * cap + cb];
+      longlong4 ab; ab.x = ta.x; ab.y = ta.y; ab.z = tb.x; ab.w = tb.y;
+      c.AB[q] = ab;
+      const int x = c.Slist[q];
+      c.DG[q] = __ldg(c.DL + (size_t)x * n + x);
+    }
+    for (int pos = tid; pos < nS; pos += RC_NTHR) {
+      double v[2] = {0.0, 0.0};
+      for (int h = 0; h < 2; ++h) {
+        const int t = h == 0 ? c1 : c2;
+        if (t == ca || t == cb) continue;
+        const longlong2 tt = c.T[(size_t)pos * cap + t];
+        const int szs = c.szL[t];
+        const double szd = (double)szs;
+        const double sD = rc_dequant(tt.x, c.qD), sL = rc_dequant(tt.y, c.qL);
+        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+        v[h] = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+      }
+      c.L2s[pos] = make_double2(v[0], v[1]);
+    }
+  } else {
+    // merge: only member-restricted sums are needed; T's memory serves as scratch for the member lists of the
+    // first two live slots (unordered: integer sums do not depend on the order)
+    unsigned short* CL1 = reinterpret_cast<unsigned short*>(c.T);
+    unsigned short* CL2 = CL1 + n;
+    if (tid == 0) { c.itmp[8] = 0; c.itmp[9] = 0; }
+    csync(c);
+    const bool need1 = c1 != ca && c1 != cb, need2 = c2 != ca && c2 != cb;
+    for (int k = tid; k < n; k += RC_NTHR) {
+      const int l = c.lab[k];
+      if (need1 && l == c1) CL1[atomicAdd(&c.itmp[8], 1)] = (unsigned short)k;
+      else if (need2 && l == c2) CL2[atomicAdd(&c.itmp[9], 1)] = (unsigned short)k;
+    }
+    csync(c);
+    member_sums_gather(c, nS, ca, cb, c1, c2, CL1, c.itmp[8], CL2, c.itmp[9]);
   }
   {
     const int nfree = (int)kp.numGibbs + (split ? 1 : 0);
@@ -1197,7 +1288,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   L.tileStart = take(sizeof(int) * (tiles + 1));
   L.sizes = take(sizeof(int) * cap);
   L.szL = take(sizeof(int) * cap);
-  L.itmp = take(sizeof(int) * cap);
+  L.itmp = take(sizeof(int) * (cap > 16 ? cap : 16));
   L.clist = take(cap);
   L.glabel = take(npad_max / RC_GROUP);
   L.lab = take(n);
@@ -1207,7 +1298,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
 __host__ __device__ inline size_t cta_header_bytes() { return (sizeof(CtaShared) + 127) & ~(size_t)127; }
 
 template <int G>
-__global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ rc_kparams kp) {
+__global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant__ rc_kparams kp) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int cl = threadIdx.x / RC_NTHR;               // chain slot within the CTA
   const int chain = blockIdx.x * G + cl;
@@ -1248,6 +1339,7 @@ __global__ void __launch_bounds__(RC_NTHR * G) k_chain(const __grid_constant__ r
   c.L2s = kp.L2s + (size_t)ch * n;
   c.NZ = kp.NZ + (size_t)ch * (kp.numGibbs + 1) * n;
   c.LPR = kp.LPR + (size_t)ch * (n + 2);
+  c.DG = kp.DG + (size_t)ch * (n + 2);
   c.terms = kp.terms + (size_t)ch * (cap * cap > 2048 ? cap * cap : 2048);
   c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
   const int tid = c.ctid;

@@ -36,6 +36,7 @@ struct rc_kparams {
   double2* L2s;         // [nchains][n]    static repulsion terms per item
   double2* NZ;          // [nchains][(numGibbs+1)*n] Gumbel noise of the free restricted scans
   double* LPR;          // [nchains][n+2]  prior term by cluster size for the current (r, p)
+  longlong2* DG;        // [nchains][n+2]  diagonal entries DL[x][x] of the split-merge members
   double* terms;        // [nchains][max(cap*cap, 1024)]  log-likelihood terms / reduction scratch
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
