@@ -190,8 +190,13 @@ __device__ void build_perm(const Ctx& c) {
   tsync<BULK>(c);
   for (int j = tid; j < c.n; j += NT) {
     const int e = (j >> RC_LOGW) * c.cap + lab[j];
-    const unsigned pos = c.runStart[e] + atomicAdd(&c.cnt[e], 1u);
-    c.perm[pos] = (unsigned short)(j & (RC_W - 1));
+    // Column-major fill of the run's (groups x 8) slots: the element of rank rk goes to group rk % Gr, slot
+    // rk / Gr, so lanes (= consecutive groups) read consecutive ranks with the same load instruction.  Ranks
+    // follow the column order closely, and cluster members tend to be contiguous columns (generatemixture
+    // sorts the labels), which makes the shared-memory gather close to conflict-free instead of 8-group strided.
+    const unsigned r0 = c.runStart[e], Gr = (c.runStart[e + 1] - r0) >> 3;
+    const unsigned rk = atomicAdd(&c.cnt[e], 1u);
+    c.perm[r0 + (rk % Gr) * RC_GROUP + rk / Gr] = (unsigned short)(j & (RC_W - 1));
   }
   tsync<BULK>(c);
 }
