@@ -101,6 +101,9 @@ int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t*
 /* Current MCMCState of one chain: labels (n, 1-based slot ids), r, p -- the `init` argument of
  * a resumed run (src/mcmc.jl:504,519-529).                                                     */
 int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p);
+/* Profiling aid (no reference equivalent): 16 SM-cycle counters per chain accumulated by the chain kernel.
+ * out: nchains x 16 int64. */
+int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out);
 /* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the slot capacity overflowed.           */
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain);
 /* Posterior co-clustering counts of the device-resident samples of chains [chain0, chain0+nch):

@@ -27,3 +27,9 @@ smp.run(1)
 for _ in range(a.steps):
     smp.run(1)
 print("iters, device seconds:", smp.progress())
+st = smp.stats()
+its = 1 + a.steps
+print("per-iteration mean cycles over chains (SM clock):")
+for k, v in st.items():
+    if k != "-":
+        print(f"  {k:20s} {v.mean() / its:14.0f}   min {v.min() / its:14.0f}   max {v.max() / its:14.0f}")

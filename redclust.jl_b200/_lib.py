@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librcb200.so")
+LIB_PATH = os.environ.get("RCB200_LIB") or os.path.join(_HERE, "librcb200.so")   # RCB200_LIB: experiment builds
 
 RC_OK, RC_ERR_ARG, RC_ERR_CUDA, RC_ERR_NOTSYM, RC_ERR_DOMAIN, RC_ERR_SLOTS, RC_ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
@@ -54,6 +54,7 @@ SIGNATURES = {
     "rc_sampler_copy_acceptances": (C.c_int32, [_vp, C.c_int64, _vp, _vp, _vp]),
     "rc_sampler_copy_state": (C.c_int32, [_vp, C.c_int64, _vp, _P(C.c_double), _P(C.c_double)]),
     "rc_sampler_chain_status": (C.c_int32, [_vp, C.c_int64]),
+    "rc_sampler_copy_stats": (C.c_int32, [_vp, _vp]),
     "rc_sampler_psm_counts_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, _vp]),
     "rc_sampler_psm": (C.c_int32, [_vp, C.c_int64, C.c_int64, _vp]),
     "rc_sampler_destroy": (None, [_vp]),

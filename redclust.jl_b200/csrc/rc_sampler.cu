@@ -29,7 +29,9 @@
 
 namespace {
 
+#ifndef RC_NSTAGE
 #define RC_NSTAGE 3
+#endif
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
 __host__ __device__ inline size_t stage_bytes_for(int n) { return (size_t)(n < RC_W ? ((n + 7) & ~7) : RC_W) * 16 + 128; }
 
@@ -41,6 +43,7 @@ struct Scal {
   int K;
   int status;
   int rebuild;
+  int gshift;                             // lane-group size of the permutation = 8 << gshift columns
   int fslotA, fslotB;                     // slots whose W rows come from the scratch rows (-1: none)
   int itmp[8];
 };
@@ -74,7 +77,7 @@ struct Ctx {
   int qD, qL;
   int ctid, cwarp, lane, barid;           // thread / warp index within the chain, named barrier of the chain
   int bbarid;                             // named barrier of the chain's bulk warps
-  unsigned dummy;                         // permutation padding entry = index of the zero slot behind a staged tile
+  unsigned dummy;                         // permutation padding entry = byte offset of the zero slots behind a staged tile
   size_t stage_bytes;
   const longlong2* DL;
   const rc_kparams* kp;
@@ -108,8 +111,13 @@ struct Ctx {
   double* LPR;            // [n+2] prior term of joining a cluster of size s, for this iteration's (r, p)
   longlong2* DG;          // [n+2] DL[x][x] of the members
   double* terms;
+  long long* stats;       // [16] cycle counters of this chain (see rc_sampler_copy_stats)
   unsigned long long key;
 };
+// stats slots
+enum { ST_DEC_WAIT = 0, ST_DEC_WORK, ST_BULK_WAIT_CONSUMED, ST_BULK_WAIT_FULL, ST_BULK_ROWS, ST_BULK_PATCH, ST_MOVES, ST_REBUILDS,
+       ST_MH_SETUP, ST_MH_RSCAN, ST_MH_LOGLIK, ST_SCAN_TOTAL, ST_RECORD, ST_ITER_TOTAL, ST_RP, ST_BULK_REDUCE };
+__device__ __forceinline__ void st_add(const Ctx& c, int slot, long long v) { c.stats[slot] += v; }
 
 __device__ __forceinline__ void csync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.barid), "r"(RC_NTHR) : "memory"); }
 __device__ __forceinline__ void bsync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bbarid), "r"(RC_BW * 32) : "memory"); }
@@ -151,7 +159,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // ------------------------------------------------------------------------------------------------
-// (tile, label)-sorted column permutation with label runs padded to multiples of RC_GROUP.
+// (tile, label)-sorted column permutation.  Every (tile, label) run is padded to a multiple of the lane-group
+// size GS = 8 << gshift columns; GS is chosen per build as the largest of {32, 16, 8} whose padding stays
+// below ~6% of n (long runs -- e.g. sorted labels -- take 32: four times fewer segmented scans per row).
 // ------------------------------------------------------------------------------------------------
 template <bool BULK>
 __device__ void build_perm(const Ctx& c) {
@@ -165,23 +175,30 @@ __device__ void build_perm(const Ctx& c) {
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
     const int b = tid * chunk, e = min(E, b + chunk);
-    unsigned s = 0;
-    for (int t = b; t < e; ++t) s += (c.cnt[t] + 7u) & ~7u;
+    unsigned s8 = 0, s16 = 0, s32 = 0;
+    for (int t = b; t < e; ++t) { const unsigned v = c.cnt[t]; s8 += (v + 7u) & ~7u; s16 += (v + 15u) & ~15u; s32 += (v + 31u) & ~31u; }
+    unsigned t16 = s16, t32 = s32;
+    for (int off = 16; off; off >>= 1) { t16 += __shfl_xor_sync(0xffffffffu, t16, off); t32 += __shfl_xor_sync(0xffffffffu, t32, off); }
+    const unsigned budget = min((unsigned)c.kp->npad_max, (unsigned)c.n + (unsigned)c.n / 16u + 64u);
+    const int gshift = t32 <= budget ? 2 : (t16 <= budget ? 1 : 0);
+    const unsigned gm = (8u << gshift) - 1u;
+    unsigned s = gshift == 2 ? s32 : (gshift == 1 ? s16 : s8);
     unsigned incl = s;
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
       if (tid >= off) incl += o;
     }
     unsigned run = incl - s;
-    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + 7u) & ~7u; }
-    if (tid == 31) c.runStart[E] = (unsigned short)incl;
+    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + gm) & ~gm; }
+    if (tid == 31) { c.runStart[E] = (unsigned short)incl; c.sc->gshift = gshift; }
   }
   tsync<BULK>(c);
   const int total = c.runStart[E];
-  for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
+  const int gsh = 3 + c.sc->gshift;
+  for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> gsh;
   for (int q = tid; q < total; q += NT) c.perm[q] = (unsigned short)c.dummy;
   for (int t = tid; t < E; t += NT) {
-    const int g0 = c.runStart[t] >> 3, g1 = c.runStart[t + 1] >> 3;
+    const int g0 = c.runStart[t] >> gsh, g1 = c.runStart[t + 1] >> gsh;
     const uint8_t l = (uint8_t)(t % c.cap);
     for (int g = g0; g < g1; ++g) c.glabel[g] = l;
   }
@@ -190,13 +207,13 @@ __device__ void build_perm(const Ctx& c) {
   tsync<BULK>(c);
   for (int j = tid; j < c.n; j += NT) {
     const int e = (j >> RC_LOGW) * c.cap + lab[j];
-    // Column-major fill of the run's (groups x 8) slots: the element of rank rk goes to group rk % Gr, slot
+    // Column-major fill of the run's (groups x GS) slots: the element of rank rk goes to group rk % Gr, slot
     // rk / Gr, so lanes (= consecutive groups) read consecutive ranks with the same load instruction.  Ranks
     // follow the column order closely, and cluster members tend to be contiguous columns (generatemixture
-    // sorts the labels), which makes the shared-memory gather close to conflict-free instead of 8-group strided.
-    const unsigned r0 = c.runStart[e], Gr = (c.runStart[e + 1] - r0) >> 3;
+    // sorts the labels), which makes the shared-memory gather close to conflict-free instead of group-strided.
+    const unsigned r0 = c.runStart[e], Gr = (c.runStart[e + 1] - r0) >> gsh;
     const unsigned rk = atomicAdd(&c.cnt[e], 1u);
-    c.perm[r0 + (rk % Gr) * RC_GROUP + rk / Gr] = (unsigned short)(j & (RC_W - 1));
+    c.perm[r0 + ((rk % Gr) << gsh) + rk / Gr] = (unsigned short)((j & (RC_W - 1)) << 4);
   }
   tsync<BULK>(c);
 }
@@ -206,7 +223,7 @@ __device__ void build_perm(const Ctx& c) {
 __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
   const int lane = c.lane;
   const int tile = j >> RC_LOGW;
-  const unsigned short idx = (unsigned short)(j & (RC_W - 1));
+  const unsigned short idx = (unsigned short)((j & (RC_W - 1)) << 4);
   {
     const int e = tile * c.cap + a;
     const int p0 = c.runStart[e], p1 = c.runStart[e + 1];
@@ -239,44 +256,74 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
 // utils.jl:9-17).  reduce_tile works on one tile of the row: `src` is either the staged tile in shared
 // memory (padding entries read the zero slot behind it) or the row in global memory.
 // ------------------------------------------------------------------------------------------------
+// One lane-group: (8 << gshift) gathers + sums.  The permutation stores BYTE offsets (column index * 16) so a
+// gather is one LDS.128 at [tile base + offset].
 template <bool STAGED>
-__device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src, int tile, longlong2* part) {
-  const int lane = c.lane, warp = c.cwarp;
-  const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
-  for (int gb = g0 + warp * 32; gb < g1; gb += RC_BW * 32) {
-    const int g = gb + lane;
-    const bool valid = g < g1;
-    const int lab = valid ? (int)c.glabel[g] : 0x100;
-    long long d = 0, l = 0;
-    if (valid) {
-      const uint4 pk = *reinterpret_cast<const uint4*>(c.perm + g * RC_GROUP);
+__device__ __forceinline__ void gather_group(const Ctx& c, const char* src, int g, bool valid, int gshift, long long& d, long long& l) {
+  d = 0; l = 0;
+  if (valid) {
+    const uint4* pp = reinterpret_cast<const uint4*>(c.perm + ((size_t)g << (3 + gshift)));
+    const int nch = 1 << gshift;
+    for (int ch = 0; ch < nch; ++ch) {
+      const uint4 pk = pp[ch];
       const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-      for (int e = 0; e < RC_GROUP; ++e) {
-        const unsigned idx = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+      for (int e = 0; e < 8; ++e) {
+        const unsigned off = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
         if (STAGED) {
-          const longlong2 v = src[idx];
+          const longlong2 v = *reinterpret_cast<const longlong2*>(src + off);
           d += v.x; l += v.y;
-        } else if (idx != c.dummy) {
-          const longlong2 v = __ldg(src + idx);
+        } else if (off != c.dummy) {
+          const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src + off));
           d += v.x; l += v.y;
         }
       }
     }
-    const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != lab);
-    const int runstart = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-    const int pos = lane - runstart;
+  }
+}
+// segmented inclusive scan of (d, l) over lanes with equal labels (labels are sorted along the lanes);
+// returns true in the last lane of each run
+__device__ __forceinline__ bool seg_scan(int lane, int lab, long long& d, long long& l) {
+  const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != lab);
+  const int runstart = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const int pos = lane - runstart;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const long long od = shfl_up_ll(d, off), ol = shfl_up_ll(l, off);
-      if (pos >= off) { d += od; l += ol; }
+  for (int off = 1; off < 32; off <<= 1) {
+    const long long od = shfl_up_ll(d, off), ol = shfl_up_ll(l, off);
+    if (pos >= off) { d += od; l += ol; }
+  }
+  return (lane == 31) || ((heads >> (lane + 1)) & 1u);
+}
+// Two blocks of 32 groups are in flight per iteration (independent gather / scan chains) to hide the
+// shared-memory and shuffle latencies with only RC_BW warps per chain.
+template <bool STAGED>
+__device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_, int tile, longlong2* part) {
+  const int lane = c.lane, warp = c.cwarp;
+  const char* src = reinterpret_cast<const char*>(src_);
+  const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
+  const int gshift = c.sc->gshift;
+  // the tile's blocks of 32 groups go round-robin to the warps, starting at a different warp in every tile so
+  // that the odd block of a tile does not always land on the same warp
+  for (int gb = g0 + ((warp + tile) & (RC_BW - 1)) * 32; gb < g1; gb += 2 * RC_BW * 32) {
+    const int gA = gb + lane, gB = gA + RC_BW * 32;
+    const bool vA = gA < g1, vB = gB < g1;
+    const int labA = vA ? (int)c.glabel[gA] : 0x100, labB = vB ? (int)c.glabel[gB] : 0x100;
+    long long dA, lA, dB, lB;
+    gather_group<STAGED>(c, src, gA, vA, gshift, dA, lA);
+    gather_group<STAGED>(c, src, gB, vB, gshift, dB, lB);
+    const bool tA = seg_scan(lane, labA, dA, lA);
+    const bool tB = seg_scan(lane, labB, dB, lB);
+    if (vA && tA) {
+      longlong2 a = part[labA];
+      a.x += dA; a.y += lA;
+      part[labA] = a;
     }
-    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-    if (valid && tail) {
-      longlong2 a = part[lab];
-      a.x += d; a.y += l;
-      part[lab] = a;
+    __syncwarp();
+    if (vB && tB) {
+      longlong2 a = part[labB];
+      a.x += dB; a.y += lB;
+      part[labB] = a;
     }
     __syncwarp();
   }
@@ -336,6 +383,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
   }
   int M = 0;
   bool dead = false;
+  long long tlast = clock64();
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
     const int li = c.lab[i];
@@ -378,7 +426,11 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       }
     }
     // ---- row sums of row i ----
+    const long long tw0 = clock64();
     mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
+    const long long tw1 = clock64();
+    if (lane == 0) { st_add(c, ST_DEC_WAIT, tw1 - tw0); st_add(c, ST_DEC_WORK, tw0 - tlast); }
+    tlast = tw1;
     const int Prow = ss->rowP[buf];
     long long bd[RC_NS], bl[RC_NS];
     double nzv[RC_NS];
@@ -506,6 +558,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       ss->decided = i + 1;
     }
     M += 1;
+    if (lane == 0) st_add(c, ST_MOVES, 1);
     const int a = li, b = cnew;
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
@@ -546,28 +599,20 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
   }
 }
 
-__device__ void bulk_loop(const Ctx& c, unsigned it, bool is_issuer_chain) {
+// The row tiles are staged by the CTA's producer warp (produce_rows); the bulk warps only consume them.
+__device__ void bulk_loop(const Ctx& c, unsigned it) {
   const int n = c.n, tiles = c.tiles;
-  const long long ntile = (long long)n * tiles;
-  const bool issuer = is_issuer_chain && c.ctid == 0;
   CtaShared* cs = c.cta;
   ScanShared* ss = c.ss;
-  auto issue = [&](long long t) {   // stage tile t of the row stream
-    const int row = (int)(t / tiles), tile = (int)(t - (long long)row * tiles);
-    const int s = (int)(t % RC_NSTAGE);
-    const int cols = min(RC_W, n - tile * RC_W);
-    const unsigned bytes = (unsigned)cols * 16u;
-    mbar_expect_tx(&cs->full[s], bytes);
-    bulk_g2s(c.stages + (size_t)s * c.stage_bytes, c.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
-  };
-  if (issuer)
-    for (long long t = 0; t < RC_NSTAGE && t < ntile; ++t) issue(t);
   long long t = 0;
   int Papplied = 0;
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
     int Msnap = 0;
+    const long long tb0 = clock64();
     if (i >= 2) { mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1)); Msnap = ss->msnap[buf]; }
+    const long long tb1 = clock64();
+    if (c.ctid == 0) st_add(c, ST_BULK_WAIT_CONSUMED, tb1 - tb0);
     if (Msnap > Papplied) {                     // uniform over the chain's bulk warps: patch the permutation
       bsync(c);                                 // every bulk warp is between two rows
       if (c.cwarp == 0)
@@ -579,10 +624,11 @@ __device__ void bulk_loop(const Ctx& c, unsigned it, bool is_issuer_chain) {
         __threadfence_block();
         bsync(c);
         build_perm<true>(c);
-        if (c.ctid == 0) { c.sc->rebuild = 0; ss->prebuilt = ss->M; }
+        if (c.ctid == 0) { c.sc->rebuild = 0; ss->prebuilt = ss->M; st_add(c, ST_REBUILDS, 1); }
         bsync(c);
         Papplied = ss->prebuilt;
       }
+      if (c.ctid == 0) st_add(c, ST_BULK_PATCH, clock64() - tb1);
     }
     if (c.ctid == 0) ss->rowP[buf] = Papplied;
     zero_partial(c, buf);
@@ -595,26 +641,42 @@ __device__ void bulk_loop(const Ctx& c, unsigned it, bool is_issuer_chain) {
     for (int tile = 0; tile < tiles; ++tile, ++t) {
       const int s = (int)(t % RC_NSTAGE);
       const unsigned ph = (unsigned)((t / RC_NSTAGE) & 1);
-      if (issuer && t >= 1 && t - 1 + RC_NSTAGE < ntile) {         // refill the stage freed by tile t-1
-        const long long tp = t - 1;
-        mbar_wait(&cs->empty[tp % RC_NSTAGE], (unsigned)((tp / RC_NSTAGE) & 1));
-        issue(tp + RC_NSTAGE);
-      }
-      __syncwarp();
+      const long long tf0 = clock64();
       mbar_wait(&cs->full[s], ph);
+      const long long tf1 = clock64();
       reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)s * c.stage_bytes), tile, part);
       __syncwarp();
+      if (c.ctid == 0) { st_add(c, ST_BULK_WAIT_FULL, tf1 - tf0); st_add(c, ST_BULK_REDUCE, clock64() - tf1); }
       if (c.lane == 0) mbar_arrive(&cs->empty[s]);
     }
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&ss->ready[buf]);
+    if (c.ctid == 0) st_add(c, ST_BULK_ROWS, clock64() - tb0);
   }
 }
 
 // sample_labels_Gibbs! (mcmc.jl:158-256).  All ACTIVE chains of the CTA run this together: the tiles of row
 // i are staged once (bulk async copy, RC_NSTAGE-deep ring) and consumed by every active chain.  A chain
 // whose slot capacity overflows keeps consuming tiles (so the ring keeps moving) but stops deciding.
-__device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
+// Producer warp of the CTA: stages every tile of rows 0..n-1 into the RC_NSTAGE-deep ring, one bulk async copy
+// (cp.async.bulk, completion on full[s]) per tile, as soon as all consumers released the stage (empty[s]).
+__device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t stage_bytes, CtaShared* cs) {
+  if ((threadIdx.x & 31) != 0) return;
+  const int n = kp.n, tiles = kp.tiles;
+  const long long ntile = (long long)n * tiles;
+  int row = 0, tile = 0;
+  for (long long t = 0; t < ntile; ++t) {
+    const int s = (int)(t % RC_NSTAGE);
+    if (t >= RC_NSTAGE) mbar_wait(&cs->empty[s], (unsigned)(((t / RC_NSTAGE) - 1) & 1));
+    const int cols = min(RC_W, n - tile * RC_W);
+    const unsigned bytes = (unsigned)cols * 16u;
+    mbar_expect_tx(&cs->full[s], bytes);
+    bulk_g2s(stages + (size_t)s * stage_bytes, kp.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
+    if (++tile == tiles) { tile = 0; ++row; }
+  }
+}
+
+__device__ void full_scan(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   if (c.ctid == 0) {
     if (ss->inited)
@@ -625,7 +687,7 @@ __device__ void full_scan(const Ctx& c, unsigned it, bool is_issuer_chain) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   csync(c);
-  if (c.cwarp < RC_BW) bulk_loop(c, it, is_issuer_chain);
+  if (c.cwarp < RC_BW) bulk_loop(c, it);
   else decide_loop(c, it);
   csync(c);
   // moves published after the last patch pass are not in the permutation: the next user rebuilds it
@@ -1030,6 +1092,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
   const int n = c.n, cap = c.cap;
   const double r = c.sc->r, p = c.sc->p;
   const int K = c.sc->K;
+  const long long tm0 = clock64();
   // (i, j) = sample(1:n, 2, replace = false)  (:379)
   const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_PAIR, mh, 0, 0);
   long long i1 = rc_randint(dr.u0, n), i2 = rc_randint(dr.u1, n - 1);
@@ -1164,8 +1227,11 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     }
   }
   csync(c);
+  const long long tm1 = clock64();
   if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
   csync(c);
+  const long long tm2 = clock64();
+  if (tid == 0) { st_add(c, ST_MH_SETUP, tm1 - tm0); st_add(c, ST_MH_RSCAN, tm2 - tm1); }
   double log_prior_ratio = 0.0, log_proposal_ratio = 0.0;
   if (split) {                                                              // :416-434
     const int sza = c.szL[ca], szb = c.szL[cb];   // szfinal[cfinal[i]], szfinal[cfinal[j]]
@@ -1256,6 +1322,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
   // restore the chain's own labels of the members (the proposal lived in place)
   for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
   csync(c);
+  if (tid == 0) st_add(c, ST_MH_LOGLIK, clock64() - tm2);
 }
 
 // sortlabels (utils.jl:69-74): first-appearance relabelling to 1..K.
@@ -1295,7 +1362,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   L.szL = take(sizeof(int) * cap);
   L.itmp = take(sizeof(int) * (cap > 16 ? cap : 16));
   L.clist = take(cap);
-  L.glabel = take(npad_max / RC_GROUP);
+  L.glabel = take(npad_max / 8);
   L.lab = take(n);
   L.total = (o + 127) & ~(size_t)127;
   return L;
@@ -1303,11 +1370,12 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
 __host__ __device__ inline size_t cta_header_bytes() { return (sizeof(CtaShared) + 127) & ~(size_t)127; }
 
 template <int G>
-__global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant__ rc_kparams kp) {
+__global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_constant__ rc_kparams kp) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int cl = threadIdx.x / RC_NTHR;               // chain slot within the CTA
+  const bool is_producer = threadIdx.x >= RC_NTHR * G;   // last warp: stages the row tiles during the scans
+  const int cl = is_producer ? 0 : threadIdx.x / RC_NTHR;   // chain slot within the CTA
   const int chain = blockIdx.x * G + cl;
-  const bool valid = chain < kp.nchains;
+  const bool valid = !is_producer && chain < kp.nchains;
   const int n = kp.n, cap = kp.cap, tiles = kp.tiles;
   Ctx c;
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
@@ -1315,7 +1383,7 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
-    c.dummy = (unsigned)((c.stage_bytes - 128) / 16);
+    c.dummy = (unsigned)(c.stage_bytes - 128);   // byte offset of the zero slots
     c.cta = reinterpret_cast<CtaShared*>(smem);
     c.stages = smem + cta_header_bytes();
     unsigned char* base = c.stages + (size_t)RC_NSTAGE * c.stage_bytes + (size_t)cl * L.total;
@@ -1345,13 +1413,25 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
   c.NZ = kp.NZ + (size_t)ch * (kp.numGibbs + 1) * n;
   c.LPR = kp.LPR + (size_t)ch * (n + 2);
   c.DG = kp.DG + (size_t)ch * (n + 2);
+  c.stats = kp.stats + (size_t)ch * 16;
   c.terms = kp.terms + (size_t)ch * (cap * cap > 2048 ? cap * cap : 2048);
   c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
   const int tid = c.ctid;
 
   // zero slots behind every stage (padding entries of the permutation point there)
-  for (int t = threadIdx.x; t < RC_NSTAGE * 8; t += blockDim.x)
-    reinterpret_cast<longlong2*>(c.stages + (size_t)(t / 8) * c.stage_bytes + (size_t)c.dummy * 16)[t % 8] = make_longlong2(0, 0);
+  if (is_producer) {   // mirrors the CTA-level barrier sequence of the chain warps below
+    if (kp.loglik_only) return;
+    for (int t = threadIdx.x & 31; t < RC_NSTAGE * 8; t += 32)
+      reinterpret_cast<longlong2*>(c.stages + (size_t)(t / 8) * c.stage_bytes + (size_t)c.dummy)[t % 8] = make_longlong2(0, 0);
+    __syncthreads();
+    for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
+      __syncthreads();
+      __syncthreads();
+      if (c.cta->nact > 0) produce_rows(kp, c.stages, c.stage_bytes, c.cta);
+      __syncthreads();
+    }
+    return;
+  }
   if (valid) {   // load the chain's state
     for (int j = tid; j < n; j += RC_NTHR) c.lab[j] = kp.labels[(size_t)chain * n + j];
     for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
@@ -1377,6 +1457,7 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
 
   for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
     const unsigned it = (unsigned)iter;
+    const long long ti0 = clock64();
     bool alive = valid;
     if (alive) { csync(c); alive = c.sc->status == 0; }
     bool do_scan = alive;
@@ -1390,6 +1471,7 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
       }
       csync(c);
       build_lpr(c);
+      if (tid == 0) st_add(c, ST_RP, clock64() - ti0);
       // sample_labels! (:540)
       for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
         splitmerge_step(c, it, mh);
@@ -1422,8 +1504,11 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (do_scan) full_scan(c, it, c.cta->issuer == cl);
+    const long long ts0 = clock64();
+    if (do_scan) full_scan(c, it);
     __syncthreads();
+    const long long ts1 = clock64();
+    if (valid && tid == 0) st_add(c, ST_SCAN_TOTAL, ts1 - ts0);
     if (alive) alive = c.sc->status == 0;
     if (alive && iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0) {    // :546-554
       const long long j = (iter - kp.burnin) / kp.thin - 1;
@@ -1441,6 +1526,7 @@ __global__ void __launch_bounds__(RC_NTHR * G, 1) k_chain(const __grid_constant_
         csync(c);
       }
     }
+    if (valid && tid == 0) { st_add(c, ST_RECORD, clock64() - ts1); st_add(c, ST_ITER_TOTAL, clock64() - ti0); }
   }
   if (valid) {   // store the chain's state
     csync(c);
@@ -1469,10 +1555,10 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
   const int grid = (kp.nchains + G - 1) / G;
   if (G == 2) {
     cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chain<2><<<grid, RC_NTHR * 2, smem, st>>>(kp);
+    k_chain<2><<<grid, RC_NTHR * 2 + 32, smem, st>>>(kp);
   } else {
     cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chain<1><<<grid, RC_NTHR, smem, st>>>(kp);
+    k_chain<1><<<grid, RC_NTHR + 32, smem, st>>>(kp);
   }
 }
 

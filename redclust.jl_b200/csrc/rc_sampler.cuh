@@ -43,6 +43,7 @@ struct rc_kparams {
   int* out_K;           // [nchains][numsamples]
   double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
+  long long* stats;     // [nchains][16] cycle counters (debug / profiling aid)
   // standalone log-likelihood mode (rc_loglik): skip iterations, write loglik to out_ll[chain]
   int loglik_only;
 };

@@ -217,6 +217,15 @@ class Sampler:
         check(lib().rc_sampler_copy_state(self._h, chain, ptr(lab), C.byref(r), C.byref(p)))
         return MCMCState(lab, r.value, p.value)
 
+    STAT_NAMES = ("dec_wait", "dec_work", "bulk_wait_consumed", "bulk_wait_full", "bulk_rows", "bulk_patch", "moves", "rebuilds",
+                  "mh_setup", "mh_rscan", "mh_loglik", "scan_total", "record", "iter_total", "rp", "bulk_reduce")
+
+    def stats(self):
+        """Cycle counters of the chain kernel (profiling aid): dict name -> array over chains."""
+        out = np.zeros((self.nchains, 16), np.int64)
+        check(lib().rc_sampler_copy_stats(self._h, ptr(out)))
+        return {k: out[:, i] for i, k in enumerate(self.STAT_NAMES)}
+
     def psm(self, chain0=0, nch=None):
         nch = self.nchains - chain0 if nch is None else nch
         out = np.zeros((self.data.n, self.data.n))
