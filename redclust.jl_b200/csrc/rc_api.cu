@@ -148,6 +148,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
     return RC_ERR_ARG;
   }
   const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G);
+  if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles, (long long)npad, G, smem, maxsmem, (long long)nchains);
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
   std::vector<uint8_t> lab((size_t)nchains * n);
   std::vector<int> sizes((size_t)nchains * cap, 0);

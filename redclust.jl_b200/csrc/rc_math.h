@@ -42,21 +42,20 @@ RC_HD double rc_scalbn(double x, int k) {
 }
 
 // Natural logarithm, fdlibm-style argument reduction + degree-14 odd polynomial in s=f/(2+f).
+// Straight-line: the main path is always evaluated (subnormals are pre-scaled by a select) and the special
+// cases (NaN, negative, zero, +Inf) override the result at the end, so two independent calls can be
+// interleaved by the compiler.  For every input the value is the one the branching formulation returns.
 RC_HD double rc_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
   const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
                Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
                Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
                Lg7 = 1.479819860511658591e-01;
-  uint64_t ix = rc_to_bits(x);
-  int k = 0;
-  if (rc_isnan(x)) return x;
-  if ((int64_t)ix < 0) { if ((ix << 1) == 0) return -RC_INF; return RC_NAN; }
-  if (ix == 0) return -RC_INF;
-  if (ix >= 0x7ff0000000000000ULL) return x;            // +Inf
-  if (ix < 0x0010000000000000ULL) {                     // subnormal
-    x *= 0x1p54; ix = rc_to_bits(x); k -= 54;
-  }
+  const uint64_t ix0 = rc_to_bits(x);
+  const bool sub = ix0 < 0x0010000000000000ULL;          // subnormal (or +0): pre-scale
+  const double xs = sub ? x * 0x1p54 : x;
+  uint64_t ix = rc_to_bits(xs);
+  int k = sub ? -54 : 0;
   // bring mantissa into [sqrt(1/2), sqrt(2))
   uint32_t hx = (uint32_t)(ix >> 32);
   hx += 0x3ff00000 - 0x3fe6a09e;
@@ -73,7 +72,12 @@ RC_HD double rc_log(double x) {
   double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
   double R = t2 + t1;
   double dk = (double)k;
-  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  double res = s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  if (ix0 >= 0x7ff0000000000000ULL) res = x;              // +Inf, and every negative / NaN pattern lands here too
+  if ((int64_t)ix0 < 0) res = ((ix0 << 1) == 0) ? -RC_INF : RC_NAN;   // -0 -> -Inf, negative -> NaN
+  if (ix0 == 0) res = -RC_INF;
+  if (rc_isnan(x)) res = x;
+  return res;
 }
 
 // log(1+x), Kahan's compensated form on top of rc_log.

@@ -51,17 +51,17 @@ struct Scal {
 #define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
 #define RC_NOISE 64                  // precomputed Gumbel noise entries per row
 struct ScanShared {                  // per chain: hand-off between the bulk warps and the decision warp
-  unsigned long long ready[2];       // row sums of buffer b are complete       (count RC_BW)
-  unsigned long long consumed[2];    // the decision warp has read buffer b     (count 1)
+  unsigned long long ready;          // the row sums in `partial` are complete           (count RC_BW)
+  unsigned long long consumed;       // the decision warp has copied them to registers  (count 1)
   volatile int M;                    // moves published by the decision warp
   volatile int decided;              // rows decided
-  int rowP[2];                       // moves already patched into the permutation when the row was reduced
-  int msnap[2];                      // moves published when the decision warp released buffer b
+  int rowP;                          // moves already patched into the permutation when the row was reduced
+  int msnap;                         // moves published when the decision warp released the row sums
   int prebuilt;                      // moves contained in the permutation after a rebuild
   int inited;
   unsigned short mq_j[RC_MQ];
   unsigned char mq_a[RC_MQ], mq_b[RC_MQ];
-  double noise[2][RC_NOISE];
+  double noise[RC_NOISE];
 };
 
 struct CtaShared {
@@ -88,7 +88,7 @@ struct Ctx {
   unsigned short* runStart;
   unsigned int* cnt;
   int* tileStart;
-  longlong2* partial;     // [2][RC_BW][cap]; aliased by rowA/rowB during loglik of a proposed state
+  longlong2* partial;     // [RC_BW][cap]; aliased by rowA/rowB during loglik of a proposed state
   ScanShared* ss;
   int* sizes;
   int* szL;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // ------------------------------------------------------------------------------------------------
 // (tile, label)-sorted column permutation.  Every (tile, label) run is padded to a multiple of the lane-group
 // size GS = 8 << gshift columns; GS is chosen per build as the largest of {32, 16, 8} whose padding stays
-// below ~6% of n (long runs -- e.g. sorted labels -- take 32: four times fewer segmented scans per row).
+// below ~12% of n (long runs -- e.g. sorted labels -- take 32: four times fewer segmented scans per row).
 // ------------------------------------------------------------------------------------------------
 template <bool BULK>
 __device__ void build_perm(const Ctx& c) {
@@ -179,7 +179,7 @@ __device__ void build_perm(const Ctx& c) {
     for (int t = b; t < e; ++t) { const unsigned v = c.cnt[t]; s8 += (v + 7u) & ~7u; s16 += (v + 15u) & ~15u; s32 += (v + 31u) & ~31u; }
     unsigned t16 = s16, t32 = s32;
     for (int off = 16; off; off >>= 1) { t16 += __shfl_xor_sync(0xffffffffu, t16, off); t32 += __shfl_xor_sync(0xffffffffu, t32, off); }
-    const unsigned budget = min((unsigned)c.kp->npad_max, (unsigned)c.n + (unsigned)c.n / 16u + 64u);
+    const unsigned budget = min((unsigned)c.kp->npad_max, (unsigned)c.n + (unsigned)c.n / 8u + 64u);
     const int gshift = t32 <= budget ? 2 : (t16 <= budget ? 1 : 0);
     const unsigned gm = (8u << gshift) - 1u;
     unsigned s = gshift == 2 ? s32 : (gshift == 1 ? s16 : s8);
@@ -259,25 +259,36 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
 // One lane-group: (8 << gshift) gathers + sums.  The permutation stores BYTE offsets (column index * 16) so a
 // gather is one LDS.128 at [tile base + offset].
 template <bool STAGED>
+__device__ __forceinline__ void gather8(const Ctx& c, const char* src, const uint4 pk, long long& d, long long& l) {
+  const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const unsigned off = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+    if (STAGED) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(src + off);
+      d += v.x; l += v.y;
+    } else if (off != c.dummy) {
+      const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src + off));
+      d += v.x; l += v.y;
+    }
+  }
+}
+template <bool STAGED>
 __device__ __forceinline__ void gather_group(const Ctx& c, const char* src, int g, bool valid, int gshift, long long& d, long long& l) {
   d = 0; l = 0;
   if (valid) {
     const uint4* pp = reinterpret_cast<const uint4*>(c.perm + ((size_t)g << (3 + gshift)));
-    const int nch = 1 << gshift;
-    for (int ch = 0; ch < nch; ++ch) {
-      const uint4 pk = pp[ch];
-      const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const unsigned off = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
-        if (STAGED) {
-          const longlong2 v = *reinterpret_cast<const longlong2*>(src + off);
-          d += v.x; l += v.y;
-        } else if (off != c.dummy) {
-          const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src + off));
-          d += v.x; l += v.y;
-        }
+    if (gshift == 0) {
+      gather8<STAGED>(c, src, pp[0], d, l);
+    } else {
+      long long d2 = 0, l2 = 0;                      // two independent accumulation chains, 16 gathers in flight
+      const int nch = 1 << gshift;
+      for (int ch = 0; ch < nch; ch += 2) {
+        const uint4 pa = pp[ch], pb = pp[ch + 1];
+        gather8<STAGED>(c, src, pa, d, l);
+        gather8<STAGED>(c, src, pb, d2, l2);
       }
+      d += d2; l += l2;
     }
   }
 }
@@ -295,42 +306,34 @@ __device__ __forceinline__ bool seg_scan(int lane, int lab, long long& d, long l
   }
   return (lane == 31) || ((heads >> (lane + 1)) & 1u);
 }
-// Two blocks of 32 groups are in flight per iteration (independent gather / scan chains) to hide the
-// shared-memory and shuffle latencies with only RC_BW warps per chain.
+// The groups of the tile are split evenly over the RC_BW bulk warps (one lane per group, 32 groups per pass), so
+// that every warp finishes a tile at about the same time and a stage of the ring is released promptly.
 template <bool STAGED>
 __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_, int tile, longlong2* part) {
   const int lane = c.lane, warp = c.cwarp;
   const char* src = reinterpret_cast<const char*>(src_);
   const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
   const int gshift = c.sc->gshift;
-  // the tile's blocks of 32 groups go round-robin to the warps, starting at a different warp in every tile so
-  // that the odd block of a tile does not always land on the same warp
-  for (int gb = g0 + ((warp + tile) & (RC_BW - 1)) * 32; gb < g1; gb += 2 * RC_BW * 32) {
-    const int gA = gb + lane, gB = gA + RC_BW * 32;
-    const bool vA = gA < g1, vB = gB < g1;
-    const int labA = vA ? (int)c.glabel[gA] : 0x100, labB = vB ? (int)c.glabel[gB] : 0x100;
-    long long dA, lA, dB, lB;
-    gather_group<STAGED>(c, src, gA, vA, gshift, dA, lA);
-    gather_group<STAGED>(c, src, gB, vB, gshift, dB, lB);
-    const bool tA = seg_scan(lane, labA, dA, lA);
-    const bool tB = seg_scan(lane, labB, dB, lB);
-    if (vA && tA) {
-      longlong2 a = part[labA];
-      a.x += dA; a.y += lA;
-      part[labA] = a;
-    }
-    __syncwarp();
-    if (vB && tB) {
-      longlong2 a = part[labB];
-      a.x += dB; a.y += lB;
-      part[labB] = a;
+  const int per = (g1 - g0 + RC_BW - 1) / RC_BW;
+  const int wb = g0 + warp * per, we = min(g1, wb + per);
+  for (int gb = wb; gb < we; gb += 32) {
+    const int g = gb + lane;
+    const bool valid = g < we;
+    const int lab = valid ? (int)c.glabel[g] : 0x100;
+    long long d, l;
+    gather_group<STAGED>(c, src, g, valid, gshift, d, l);
+    const bool tail = seg_scan(lane, lab, d, l);
+    if (valid && tail) {
+      longlong2 a = part[lab];
+      a.x += d; a.y += l;
+      part[lab] = a;
     }
     __syncwarp();
   }
 }
 
-__device__ __forceinline__ void zero_partial(const Ctx& c, int buf) {   // bulk warps
-  longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
+__device__ __forceinline__ void zero_partial(const Ctx& c) {   // bulk warps
+  longlong2* part = c.partial + c.cwarp * c.cap;
   for (int s = c.lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
   __syncwarp();
 }
@@ -338,14 +341,14 @@ __device__ __forceinline__ void zero_partial(const Ctx& c, int buf) {   // bulk 
 // Row x straight from global memory / L2 (split-merge member rows, block-sum initialisation); buffer 0.
 __device__ void reduce_row_global(const Ctx& c, int x) {
   if (c.cwarp >= RC_BW) return;
-  zero_partial(c, 0);
+  zero_partial(c);
   const longlong2* row = c.DL + (size_t)x * c.n;
   longlong2* part = c.partial + c.cwarp * c.cap;
   for (int tile = 0; tile < c.tiles; ++tile) reduce_tile<false>(c, row + tile * RC_W, tile, part);
 }
 
-__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0) {
-  const longlong2* p = c.partial + (size_t)buf * RC_BW * c.cap;
+__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s) {
+  const longlong2* p = c.partial;
   longlong2 a = p[s];
 #pragma unroll
   for (int w = 1; w < RC_BW; ++w) {
@@ -372,36 +375,42 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
   const int cap = c.cap, n = c.n;
   ScanShared* ss = c.ss;
   const double r = c.sc->r, log1mp = c.sc->log1mp;
-  // register-resident per-slot state: size and the size-dependent table terms
+  const unsigned ltmask = (1u << lane) - 1u;
+  // register-resident per-slot state: size, and the size-dependent table terms at the current size (t*) and
+  // at size - 1 (u*: used for the slot the visited point is detached from).  Tables are only touched on moves.
   int sz[RC_NS];
-  double tA[RC_NS], tZ[RC_NS], tP[RC_NS];
+  double tA[RC_NS], tZ[RC_NS], tP[RC_NS], uA[RC_NS], uZ[RC_NS], uP[RC_NS];
 #pragma unroll
   for (int w = 0; w < RC_NS; ++w) {
     const int s = w * 32 + lane;
     sz[w] = s < cap ? c.sizes[s] : 0;
-    tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1];
+    const int s1 = sz[w] > 0 ? sz[w] : 1, s0 = sz[w] > 1 ? sz[w] - 1 : 1;
+    tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[s1];
+    uA[w] = kp.LGA[sz[w] > 0 ? sz[w] - 1 : 0]; uZ[w] = kp.LGZ[sz[w] > 0 ? sz[w] - 1 : 0]; uP[w] = c.LPR[s0];
   }
   int M = 0;
   bool dead = false;
-  long long tlast = clock64();
+  long long tlast = clock64(), acc_wait = 0, acc_work = 0;
+  int nmoves = 0;
+  longlong2 self1 = __ldg(c.DL);                                            // diagonal entry of row i (prefetched two rows ahead)
+  longlong2 self2 = n > 1 ? __ldg(c.DL + (size_t)n + 1) : make_longlong2(0, 0);
   for (int i = 0; i < n; ++i) {
-    const int buf = i & 1;
     const int li = c.lab[i];
-    const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
+    const longlong2 self = self1;
+    self1 = self2;
+    if (i + 2 < n) self2 = __ldg(c.DL + (size_t)(i + 2) * n + (i + 2));
     // occupancy with i detached (:193-202) -- independent of the row sums
     unsigned occ[RC_NS];
-    double dA = 0.0, dZ = 0.0, dP = 0.0;       // table terms of li's slot at its detached size
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       const int s = w * 32 + lane;
-      const int szd = sz[w] - (s == li ? 1 : 0);
-      if (s == li) { dA = kp.LGA[szd]; dZ = kp.LGZ[szd]; dP = c.LPR[szd > 0 ? szd : 1]; }
-      occ[w] = __ballot_sync(0xffffffffu, szd > 0);
+      occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);
     }
-    int Ki = 0, e = -1;
+    int Ki = 0, e = -1, nw = 0;
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       Ki += __popc(occ[w]);
+      if (occ[w]) nw = w + 1;
       const int lim = cap - w * 32;
       const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
       const unsigned emp = ~occ[w] & capmask;
@@ -412,6 +421,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       if (lane == 0) c.sc->status = RC_ERR_SLOTS;
       dead = true;
     }
+    if (hasnew && e >= 0 && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;           // rounds of 32 slots that hold a candidate
     int kk[RC_NS];
     bool have[RC_NS];
     {
@@ -421,33 +431,35 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
         const int s = w * 32 + lane;
         const bool live = (occ[w] >> lane) & 1u;
         have[w] = live || (hasnew && s == e);
-        kk[w] = live ? base + __popc(occ[w] & ((1u << lane) - 1u)) : Ki;
+        kk[w] = live ? base + __popc(occ[w] & ltmask) : Ki;
         base += __popc(occ[w]);
       }
     }
     // ---- row sums of row i ----
     const long long tw0 = clock64();
-    mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
+    mbar_wait(&ss->ready, (unsigned)(i & 1));
     const long long tw1 = clock64();
-    if (lane == 0) { st_add(c, ST_DEC_WAIT, tw1 - tw0); st_add(c, ST_DEC_WORK, tw0 - tlast); }
+    acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
-    const int Prow = ss->rowP[buf];
+    const int Prow = ss->rowP;
     long long bd[RC_NS], bl[RC_NS];
     double nzv[RC_NS];
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
-      const int s = w * 32 + lane;
       bd[w] = 0; bl[w] = 0; nzv[w] = 0.0;
-      if (s < cap && ((occ[w] >> lane) & 1u)) {
-        const longlong2 t = bin_total(c, s, buf);
-        bd[w] = t.x; bl[w] = t.y;
+      if (w < nw) {
+        const int s = w * 32 + lane;
+        if ((occ[w] >> lane) & 1u) {
+          const longlong2 t = bin_total(c, s);
+          bd[w] = t.x; bl[w] = t.y;
+        }
+        if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[kk[w]];
       }
-      if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[buf][kk[w]];
     }
-    if (lane == 0) ss->msnap[buf] = M;
+    if (lane == 0) ss->msnap = M;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ss->consumed[buf]);
-    if (dead) { if (lane == 0) { __threadfence_block(); ss->decided = i + 1; } continue; }
+    if (lane == 0) mbar_arrive(&ss->consumed);
+    if (dead) { if (lane == 0) ss->decided = i + 1; continue; }
     // moves of earlier steps that the permutation did not contain when row i was reduced
     for (int m = Prow; m < M; ++m) {
       const int j = ss->mq_j[m % RC_MQ], a = ss->mq_a[m % RC_MQ], b = ss->mq_b[m % RC_MQ];
@@ -466,40 +478,44 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       L1[w] = 0.0; L2p[w] = 0.0;
-      const int s = w * 32 + lane;
-      if ((occ[w] >> lane) & 1u) {
-        if (s == li) { bd[w] -= self.x; bl[w] -= self.y; }                  // :193-194 detach i
-        const int szs = sz[w] - (s == li ? 1 : 0);
-        const double szd = (double)szs;
-        const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
-        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-        L1[w] = (s == li ? dA : tA[w]) + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-        L2p[w] = (s == li ? dZ : tZ[w]) - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-        acc += L2p[w];                                                      // vecsum: lane-wise ascending slots
+      if (w < nw) {
+        const int s = w * 32 + lane;
+        if ((occ[w] >> lane) & 1u) {
+          if (s == li) { bd[w] -= self.x; bl[w] -= self.y; }                // :193-194 detach i
+          const int szs = sz[w] - (s == li ? 1 : 0);
+          const double szd = (double)szs;
+          const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
+          const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+          const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+          L1[w] = (s == li ? uA[w] : tA[w]) + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+          L2p[w] = (s == li ? uZ[w] : tZ[w]) - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+          acc += L2p[w];                                                    // vecsum: lane-wise ascending slots
+        }
       }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
     const double L2i = acc;
-    // log-probabilities, Gumbel-max (utils.jl:2-6)
+    // log-probabilities (:244-247)
     double lp[RC_NS];
     bool anynan = false;
     double mn = RC_INF;
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       lp[w] = 0.0;
-      const int s = w * 32 + lane;
-      if ((occ[w] >> lane) & 1u) {
-        const double L2 = L2i - L2p[w];
-        lp[w] = (s == li ? dP : tP[w]) + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
-      } else if (have[w]) {                                                 // :228-230 new cluster
-        const double L2 = L2i - 0.0;
-        lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
-      }
-      if (have[w]) {
-        if (rc_isnan(lp[w])) anynan = true;
-        else if (lp[w] < mn) mn = lp[w];
+      if (w < nw) {
+        const int s = w * 32 + lane;
+        if ((occ[w] >> lane) & 1u) {
+          const double L2 = L2i - L2p[w];
+          lp[w] = (s == li ? uP[w] : tP[w]) + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
+        } else if (have[w]) {                                               // :228-230 new cluster
+          const double L2 = L2i - 0.0;
+          lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+        }
+        if (have[w]) {
+          if (rc_isnan(lp[w])) anynan = true;
+          else if (lp[w] < mn) mn = lp[w];
+        }
       }
     }
 #pragma unroll
@@ -509,42 +525,71 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     }
     anynan = __any_sync(0xffffffffu, anynan);
     if (anynan) mn = RC_NAN;                                                // Julia minimum propagates NaN
-    // argmax of gumbel + shifted logprob; NaN is maximal, first index wins ties
-    double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+    // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
+    double g[RC_NS];
+    double gbest = -RC_INF;
+    bool gnan = false;
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
-      if (!have[w]) continue;
-      double nz = nzv[w];
-      if (kk[w] >= RC_NOISE) {
-        const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
-        nz = -rc_log(-rc_log((kk[w] & 1) ? dr.u1 : dr.u0));
+      g[w] = -RC_INF;
+      if (w < nw && have[w]) {
+        double nz = nzv[w];
+        if (kk[w] >= RC_NOISE) {
+          const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
+          nz = -rc_log(-rc_log((kk[w] & 1) ? dr.u1 : dr.u0));
+        }
+        g[w] = nz + (lp[w] - mn);
+        if (rc_isnan(g[w])) gnan = true;
+        else if (g[w] > gbest) gbest = g[w];
       }
-      const double g = nz + (lp[w] - mn);
-      const bool gn = rc_isnan(g);
-      bool better;
-      if (bs < 0) better = true;
-      else if (gn) better = !bnan || kk[w] < bk;
-      else if (bnan) better = false;
-      else better = g > bg || (g == bg && kk[w] < bk);
-      if (better) { bg = g; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
     }
+    int cnew;
+    if (!__any_sync(0xffffffffu, gnan)) {
+      // fast path: maximum value, then the smallest candidate index that attains it
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const double og = __shfl_xor_sync(0xffffffffu, bg, off);
-      const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
-      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-      const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
-      bool better;
-      if (os < 0) better = false;
-      else if (bs < 0) better = true;
-      else if (on) better = !bnan || ok < bk;
-      else if (bnan) better = false;
-      else better = og > bg || (og == bg && ok < bk);
-      if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, gbest, off);
+        if (o > gbest) gbest = o;
+      }
+      int kbest = 0x7fffffff, sbest = -1;
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w)
+        if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
+      const int kmin = __reduce_min_sync(0xffffffffu, kbest);
+      const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
+      cnew = __shfl_sync(0xffffffffu, sbest, __ffs(who) - 1);
+    } else {
+      // NaN is maximal for argmax and the first NaN wins
+      double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w) {
+        if (!(w < nw && have[w])) continue;
+        const bool gn = rc_isnan(g[w]);
+        bool better;
+        if (bs < 0) better = true;
+        else if (gn) better = !bnan || kk[w] < bk;
+        else if (bnan) better = false;
+        else better = g[w] > bg || (g[w] == bg && kk[w] < bk);
+        if (better) { bg = g[w]; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double og = __shfl_xor_sync(0xffffffffu, bg, off);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+        const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
+        bool better;
+        if (os < 0) better = false;
+        else if (bs < 0) better = true;
+        else if (on) better = !bnan || ok < bk;
+        else if (bnan) better = false;
+        else better = og > bg || (og == bg && ok < bk);
+        if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
+      }
+      cnew = bs;
     }
-    const int cnew = bs;
     if (cnew == li) {
-      if (lane == 0) { __threadfence_block(); ss->decided = i + 1; }
+      if (lane == 0) ss->decided = i + 1;
       continue;
     }
     // ---- the point moved (:250-252): publish, then update sizes, cached terms and the block sums ----
@@ -557,14 +602,19 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       ss->M = M + 1;
       ss->decided = i + 1;
     }
-    M += 1;
-    if (lane == 0) st_add(c, ST_MOVES, 1);
+    M += 1; nmoves += 1;
     const int a = li, b = cnew;
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
       const int s = w * 32 + lane;
-      if (s == a) { sz[w] -= 1; tA[w] = dA; tZ[w] = dZ; tP[w] = dP; }
-      if (s == b) { sz[w] += 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]]; }
+      if (s == a) {
+        sz[w] -= 1; tA[w] = uA[w]; tZ[w] = uZ[w]; tP[w] = uP[w];
+        uA[w] = kp.LGA[sz[w] > 0 ? sz[w] - 1 : 0]; uZ[w] = kp.LGZ[sz[w] > 0 ? sz[w] - 1 : 0]; uP[w] = c.LPR[sz[w] > 1 ? sz[w] - 1 : 1];
+      }
+      if (s == b) {
+        sz[w] += 1; uA[w] = tA[w]; uZ[w] = tZ[w]; uP[w] = tP[w];
+        tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]];
+      }
     }
 #pragma unroll
     for (int w = 0; w < RC_NS; ++w) {
@@ -597,6 +647,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     }
     __syncwarp();
   }
+  if (lane == 0) { st_add(c, ST_DEC_WAIT, acc_wait); st_add(c, ST_DEC_WORK, acc_work); st_add(c, ST_MOVES, nmoves); }
 }
 
 // The row tiles are staged by the CTA's producer warp (produce_rows); the bulk warps only consume them.
@@ -606,13 +657,13 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   long long t = 0;
   int Papplied = 0;
+  long long a_cons = 0, a_full = 0, a_red = 0, a_rows = 0, a_patch = 0;
   for (int i = 0; i < n; ++i) {
-    const int buf = i & 1;
     int Msnap = 0;
     const long long tb0 = clock64();
-    if (i >= 2) { mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1)); Msnap = ss->msnap[buf]; }
+    if (i >= 1) { mbar_wait(&ss->consumed, (unsigned)((i - 1) & 1)); Msnap = ss->msnap; }
     const long long tb1 = clock64();
-    if (c.ctid == 0) st_add(c, ST_BULK_WAIT_CONSUMED, tb1 - tb0);
+    a_cons += tb1 - tb0;
     if (Msnap > Papplied) {                     // uniform over the chain's bulk warps: patch the permutation
       bsync(c);                                 // every bulk warp is between two rows
       if (c.cwarp == 0)
@@ -628,16 +679,16 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
         bsync(c);
         Papplied = ss->prebuilt;
       }
-      if (c.ctid == 0) st_add(c, ST_BULK_PATCH, clock64() - tb1);
+      a_patch += clock64() - tb1;
     }
-    if (c.ctid == 0) ss->rowP[buf] = Papplied;
-    zero_partial(c, buf);
+    if (c.ctid == 0) ss->rowP = Papplied;
+    zero_partial(c);
     if (c.cwarp == (i & (RC_BW - 1))) {         // Gumbel noise of row i's candidates 2*lane, 2*lane+1 (utils.jl:4-5)
       const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);
-      ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
-      ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
+      ss->noise[2 * c.lane] = -rc_log(-rc_log(dr.u0));
+      ss->noise[2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
     }
-    longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
+    longlong2* part = c.partial + c.cwarp * c.cap;
     for (int tile = 0; tile < tiles; ++tile, ++t) {
       const int s = (int)(t % RC_NSTAGE);
       const unsigned ph = (unsigned)((t / RC_NSTAGE) & 1);
@@ -646,12 +697,16 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
       const long long tf1 = clock64();
       reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)s * c.stage_bytes), tile, part);
       __syncwarp();
-      if (c.ctid == 0) { st_add(c, ST_BULK_WAIT_FULL, tf1 - tf0); st_add(c, ST_BULK_REDUCE, clock64() - tf1); }
+      a_full += tf1 - tf0; a_red += clock64() - tf1;
       if (c.lane == 0) mbar_arrive(&cs->empty[s]);
     }
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&ss->ready[buf]);
-    if (c.ctid == 0) st_add(c, ST_BULK_ROWS, clock64() - tb0);
+    if (c.lane == 0) mbar_arrive(&ss->ready);
+    a_rows += clock64() - tb0;
+  }
+  if (c.ctid == 0) {
+    st_add(c, ST_BULK_WAIT_CONSUMED, a_cons); st_add(c, ST_BULK_WAIT_FULL, a_full); st_add(c, ST_BULK_REDUCE, a_red);
+    st_add(c, ST_BULK_ROWS, a_rows); st_add(c, ST_BULK_PATCH, a_patch);
   }
 }
 
@@ -679,10 +734,9 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
 __device__ void full_scan(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   if (c.ctid == 0) {
-    if (ss->inited)
-      for (int b = 0; b < 2; ++b) { mbar_inval(&ss->ready[b]); mbar_inval(&ss->consumed[b]); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&ss->ready[b], RC_BW); mbar_init(&ss->consumed[b], 1); }
-    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP[0] = 0; ss->rowP[1] = 0; ss->msnap[0] = 0; ss->msnap[1] = 0; ss->prebuilt = 0;
+    if (ss->inited) { mbar_inval(&ss->ready); mbar_inval(&ss->consumed); }
+    mbar_init(&ss->ready, RC_BW); mbar_init(&ss->consumed, 1);
+    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP = 0; ss->msnap = 0; ss->prebuilt = 0;
     c.sc->rebuild = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1350,7 +1404,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   ChainLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
-  L.partial = take(sizeof(longlong2) * 2 * RC_BW * cap);
+  L.partial = take(sizeof(longlong2) * RC_BW * cap);
   L.sc = take(sizeof(Scal));
   L.ss = take(sizeof(ScanShared));
   L.red = take(sizeof(long long) * RC_NWARP * 4);
