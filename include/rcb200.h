@@ -69,6 +69,9 @@ int64_t rc_data_n(const rc_data* d);
 /* data.D and data.logD back to the host as n x n fp64. */
 int32_t rc_data_copy_dist(const rc_data* d, double* D_out);
 int32_t rc_data_copy_logdist(const rc_data* d, double* logD_out);
+/* Fixed-point scales of the images the sampler streams: Dq = round(D * 2^qD), Lq = round(logD * 2^qL)
+ * (largest q <= 50 with n * max|.| * 2^q < 2^61, so that every cluster sum is an exact 64-bit integer). */
+int32_t rc_data_scales(const rc_data* d, int32_t* qD, int32_t* qL);
 void rc_data_destroy(rc_data* d);
 
 /* ---- runsampler ------------------------------------------------------------------------ */
@@ -78,7 +81,8 @@ int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, dou
 /* Allocate `nchains` independent chains (global chain ids chain_offset .. chain_offset+nchains-1)
  * on the data's device.  init_labels: nchains x n, 1-based, any slot ids in 1..n (src/types.jl:131-137);
  * init_r / init_p: nchains values.  slot_cap: max simultaneously live clusters per chain
- * (0 = default 64; at most 255) -- the reference allows up to n.             */
+ * (0 = default = maximum 128) -- the reference allows up to n; initial labels must lie in
+ * 1..slot_cap (relabel with sortlabels first).  numMH must be 0 or 1 in this build.             */
 int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par,
                           int64_t nchains, int64_t chain_offset, const int64_t* init_labels,
                           const double* init_r, const double* init_p, uint64_t seed,

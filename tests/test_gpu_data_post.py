@@ -1,0 +1,117 @@
+"""GPU tests of the data kernels (distance matrix, log D, validation), the PSM and the MPEL search, through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_distance_matrix_golden_and_oracle(pkg, orc, golden):
+    for k in (1, 2, 3):
+        pts, ref = golden[k]["points"], golden[k]["distance_matrix"]
+        data = pkg.MCMCData.from_points(pts)
+        D = data.D
+        assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)               # exact symmetry, zero diagonal
+        off = ~np.eye(100, dtype=bool)
+        assert (np.abs(D[off] - ref[off]) / ref[off]).max() < 1e-10            # reference fixture (Julia / Distances.jl)
+        assert np.array_equal(D, orc.distm(pts))                               # same operation order as the oracle
+        assert np.array_equal(data.logD, orc.logdist(D))
+        import ctypes as C
+        qd, ql = C.c_int(), C.c_int()
+        orc.lib().rco_fixedpoint_scales(D.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(100), C.byref(qd), C.byref(ql))
+        assert data.scales() == (qd.value, ql.value)
+    # vector-of-vectors constructor (MCMCData(points), types.jl:159-162) and a ragged dimension / size
+    data = pkg.MCMCData([list(p) for p in golden[1]["points"]])
+    assert np.array_equal(data.D, orc.distm(golden[1]["points"]))
+    X = np.random.default_rng(0).normal(size=(333, 37))
+    assert np.array_equal(pkg.MCMCData.from_points(X).D, orc.distm(X))
+
+
+def test_data_validation_errors(pkg, golden):
+    D = golden[1]["distance_matrix"].copy()
+    D[3, 7] += 1e-9
+    with pytest.raises(pkg.RCError, match="D must be symmetric."):              # types.jl:149-151
+        pkg.MCMCData(D)
+    with pytest.raises(pkg.RCError, match="D must be a square matrix."):        # types.jl:152-154
+        pkg.MCMCData(np.zeros((3, 4)))
+    D = golden[1]["distance_matrix"].copy()
+    D[2, 5] = D[5, 2] = 0.0
+    with pytest.raises(pkg.RCError) as e:
+        pkg.MCMCData(D)
+    assert e.value.status == -4
+    assert pkg.MCMCData(np.zeros((1, 1))).n == 1
+
+
+def test_psm_exact_counts(pkg, orc):
+    rng = np.random.default_rng(2)
+    for S, n, K in ((1, 5, 2), (37, 130, 6), (200, 257, 40)):
+        L = rng.integers(1, K + 1, size=(S, n))
+        got = pkg.psm(L)
+        assert np.array_equal(got * S, orc.psm_counts(L))
+        assert np.array_equal(got, got.T) and np.all(np.diag(got) == 1.0)
+    # labels need not be compact (any positive ids)
+    L = rng.integers(1, 5, size=(9, 40)) * 1000 + 7
+    assert np.array_equal(pkg.psm(L) * 9, orc.psm_counts(L))
+
+
+def test_mpel_losses_match_oracle(pkg, orc):
+    rng = np.random.default_rng(5)
+    L = np.stack([orc.sortlabels(rng.integers(1, rng.integers(2, 9), size=80)) for _ in range(24)])
+    L[7] = L[3]                                                                # a duplicate sample
+    for loss in ("binder", "omARI", "VI", "ID"):
+        sums, best = pkg.mpel_loss_sums(L, loss)
+        ref = orc.mpel_loss_sums(L, loss)
+        assert np.allclose(sums, ref, rtol=1e-10, atol=1e-12), loss
+        # ties between duplicate samples are broken by fp noise in the reference: compare the attained loss
+        assert abs(ref[best] - ref.min()) <= 1e-10 * max(1.0, abs(ref.min()))
+    a, b = L[0], L[1]
+    assert abs(pkg.binderloss(a, b) - orc.binderloss(a, b)) < 1e-12
+    assert abs(pkg.binderloss(a, b, normalised=False) - orc.binderloss(a, b, normalised=False)) < 1e-9
+    assert abs(pkg.infodist(a, b) - orc.infodist(a, b)) < 1e-12
+    assert abs(pkg.infodist(a, b, normalised=False) - orc.infodist(a, b, normalised=False)) < 1e-12
+    assert abs(pkg.binderloss(a, a)) < 1e-9 and abs(pkg.infodist(a, a)) < 1e-9   # test/test_pointestimates.jl:3-8
+
+
+def test_runsampler_and_pointestimate_api(pkg, golden):
+    """The README flow: MCMCData(points) -> runsampler(data, options, params) -> getpointestimate, all 7 method / loss
+    combinations of test/test_pointestimates.jl:10-16 (here with explicit params / init: fitprior is host code)."""
+    pts, lab = golden[1]["points"], golden[1]["cluster_labels"]
+    data = pkg.MCMCData.from_points(pts)
+    params = pkg.params_from_labels(data.D, lab)
+    opts = pkg.MCMCOptionsList(numiters=120, burnin=20, thin=2)
+    init = pkg.MCMCState(lab, 1.5, 0.5)
+    res = pkg.runsampler(data, opts, params, init, verbose=False)
+    assert len(res.clusts) == 50 and res.posterior_coclustering.shape == (100, 100)
+    assert np.all(np.diag(res.posterior_coclustering) == 1.0)
+    assert res.K.shape == (50,) and res.r_acceptances.shape == (120,) and res.splitmerge_splits.shape == (120,)
+    assert 0 <= res.splitmerge_acceptance_rate <= 1 and res.runtime > 0 and abs(res.mean_iter_time - res.runtime / 120) < 1e-12
+    assert len(res.K_acf) == min(49, round(10 * np.log10(50))) + 1 and res.K_acf[0] == pytest.approx(1.0)
+    for kw in (dict(method="MAP"), dict(method="MLE"), dict(method="MPEL", loss="VI"), dict(method="MPEL", loss="binder"),
+               dict(method="MPEL", loss="omARI"), dict(method="MPEL", loss="ID"),
+               dict(method="MPEL", loss=lambda x, y: float(np.mean(np.asarray(x) != np.asarray(y))))):
+        clust, i = pkg.getpointestimate(res, **kw)
+        assert 0 <= i < 50 and np.array_equal(clust, res.clusts[i])
+    # numMH = 0 (pure Gibbs, test/test_sampler.jl:7-10) and multi-chain
+    rs = pkg.runsampler(data, pkg.MCMCOptionsList(numiters=30, numMH=0), params, init, verbose=False, nchains=3, seed=4)
+    assert len(rs) == 3 and not np.array_equal(rs[0].K, rs[1].K) or not np.array_equal(rs[0].r, rs[1].r)
+    assert rs[0].splitmerge_acceptance_rate == 0
+
+
+def test_statistical_agreement_with_independent_streams(pkg, orc, golden):
+    """Second check of the north star: with INDEPENDENT random streams the posterior K distribution and the PSM of the
+    GPU chains agree with the oracle's within Monte Carlo error."""
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab)
+    P = orc.make_params(**{k: getattr(params, k) for k in params._fields})
+    nch, iters, burn = 16, 400, 100
+    opts = pkg.MCMCOptionsList(numiters=iters, burnin=burn, thin=1)
+    smp = pkg.Sampler(pkg.MCMCData(D), opts, params, np.tile(lab, (nch, 1)), [1.5] * nch, [0.5] * nch, seed=1234)
+    smp.run(-1)
+    gK = np.concatenate([smp.samples(c)["K"] for c in range(nch)])
+    gpsm = smp.psm(0, nch)
+    oK, ocnt = [], np.zeros((100, 100))
+    for c in range(nch):
+        o = orc.run_chain(D, orc.Options(iters, burn, 1, 5, 1), P, lab, 1.5, 0.5, seed=99, chain=c)
+        oK.append(o["K"]); ocnt += orc.psm_counts(o["labels"])
+    oK = np.concatenate(oK); opsm = ocnt / (nch * (iters - burn))
+    assert abs(gK.mean() - oK.mean()) < 0.6
+    assert np.abs(gpsm - opsm).mean() < 0.03
