@@ -1,0 +1,169 @@
+# RedClustB200.jl -- `ccall` host layer over librcb200.so (include/rcb200.h).
+#
+# This is the Julia twin of redclust.jl_b200/host.py: it keeps RedClust.jl's API surface
+# (MCMCData / MCMCOptionsList / PriorHyperparamsList / runsampler / MCMCResult / getpointestimate,
+# /root/reference/src/RedClust.jl:32-66) and replaces the bodies of the hot-path functions by calls into the
+# sm_100a library.  Julia is not installed in the build image, so this file is exercised only where Julia exists;
+# the same ABI is exercised by the Python mirror in the test-suite.  Drop it next to RedClust.jl's src/ and
+# `include` it after types.jl (it reuses RedClust's own MCMCOptionsList / PriorHyperparamsList / MCMCResult).
+module RedClustB200
+
+using RedClust: MCMCOptionsList, PriorHyperparamsList, MCMCResult, MCMCState, ClustLabelVector, fitprior
+using RedClust: iac_ess_acf, sortlabels
+using Clustering: kmedoids
+using StatsBase: mean_and_var, mean
+import Libdl
+
+const LIB = Ref{String}(get(ENV, "RCB200_LIB", joinpath(@__DIR__, "..", "librcb200.so")))
+
+struct rc_options
+    numiters::Int64; burnin::Int64; thin::Int64; numGibbs::Int64; numMH::Int64
+end
+struct rc_params
+    delta1::Float64; delta2::Float64; alpha::Float64; beta::Float64; zeta::Float64; gamma::Float64
+    eta::Float64; sigma::Float64; proposalsd_r::Float64; u::Float64; v::Float64
+    K_initial::Int64; maxK::Int64; repulsion::Int32; _pad::Int32
+end
+rc_options(o::MCMCOptionsList) = rc_options(o.numiters, o.burnin, o.thin, o.numGibbs, o.numMH)
+rc_params(p::PriorHyperparamsList) = rc_params(p.δ1, p.δ2, p.α, p.β, p.ζ, p.γ, p.η, p.σ, p.proposalsd_r, p.u, p.v,
+                                               p.K_initial, p.maxK, Int32(p.repulsion), Int32(0))
+
+lasterror() = unsafe_string(ccall((:rc_last_error, LIB[]), Cstring, ()))
+check(st::Integer) = st == 0 ? nothing : error(lasterror())      # ErrorException, as error(...) in src/types.jl
+
+"Device-resident MCMCData (src/types.jl:145-162)."
+mutable struct MCMCData
+    handle::Ptr{Cvoid}
+    n::Int
+    function MCMCData(D::AbstractMatrix{Float64}; device::Integer = 0)
+        size(D, 1) == size(D, 2) || error("D must be a square matrix.")
+        Dm = Matrix(D)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve Dm check(ccall((:rc_data_from_dist, LIB[]), Int32, (Ptr{Float64}, Int64, Int32, Ref{Ptr{Cvoid}}),
+                                    Dm, size(Dm, 1), device, h))
+        x = new(h[], size(Dm, 1))
+        finalizer(d -> ccall((:rc_data_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.handle), x)
+    end
+    function MCMCData(pnts::AbstractVector{<:AbstractVector{<:Float64}}; device::Integer = 0)
+        X = [pnts[i][j] for j in 1:length(pnts[1]), i in 1:length(pnts)]      # dim x n, makematrix (src/utils.jl:154-156)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve X check(ccall((:rc_data_from_points, LIB[]), Int32, (Ptr{Float64}, Int64, Int64, Int32, Ref{Ptr{Cvoid}}),
+                                   X, size(X, 1), size(X, 2), device, h))
+        x = new(h[], size(X, 2))
+        finalizer(d -> ccall((:rc_data_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.handle), x)
+    end
+end
+function Base.getproperty(d::MCMCData, s::Symbol)
+    if s === :D || s === :logD
+        out = Matrix{Float64}(undef, d.n, d.n)
+        f = s === :D ? :rc_data_copy_dist : :rc_data_copy_logdist
+        check(s === :D ? ccall((:rc_data_copy_dist, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(d, :handle), out) :
+                         ccall((:rc_data_copy_logdist, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(d, :handle), out))
+        return out
+    end
+    return getfield(d, s)
+end
+
+"""
+    runsampler(data, options = MCMCOptionsList(), params = nothing, init = nothing; verbose = true,
+               nchains = 1, seed = rand(UInt64), slot_cap = 0) -> MCMCResult (or Vector{MCMCResult})
+
+Same contract as RedClust.runsampler (src/mcmc.jl:501-590); the iteration loop runs in one persistent CUDA kernel.
+"""
+function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList(),
+                    params::Union{PriorHyperparamsList,Nothing} = nothing, init::Union{MCMCState,Nothing} = nothing;
+                    verbose = true, nchains::Integer = 1, seed::UInt64 = rand(UInt64), slot_cap::Integer = 0)
+    if isnothing(params)
+        params = fitprior(data.D, "k-medoids", true; verbose = verbose)                      # :516-518
+    end
+    n = data.n
+    cp = rc_params(params)
+    labels = Matrix{Int64}(undef, n, nchains); r0 = Vector{Float64}(undef, nchains); p0 = similar(r0)
+    if isnothing(init)                                                                       # :519-527
+        k0 = params.maxK > 0 ? min(params.maxK, params.K_initial) : params.K_initial
+        lab0 = kmedoids(data.D, k0; maxiter = 1000).assignments
+        for c in 1:nchains
+            labels[:, c] .= lab0
+            r = Ref(0.0); p = Ref(0.0)
+            check(ccall((:rc_init_rp, LIB[]), Int32, (Ref{rc_params}, UInt64, Int64, Ref{Float64}, Ref{Float64}), cp, seed, c - 1, r, p))
+            r0[c] = r[]; p0[c] = p[]
+        end
+    else
+        for c in 1:nchains
+            labels[:, c] .= sortlabels(init.clusts); r0[c] = init.r; p0[c] = init.p
+        end
+    end
+    co = rc_options(options)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve labels r0 p0 check(ccall((:rc_sampler_create, LIB[]), Int32,
+        (Ptr{Cvoid}, Ref{rc_options}, Ref{rc_params}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, UInt64, Int32, Ref{Ptr{Cvoid}}),
+        data.handle, co, cp, nchains, 0, labels, r0, p0, seed, slot_cap, h))
+    s = h[]
+    try
+        check(ccall((:rc_sampler_run, LIB[]), Int32, (Ptr{Cvoid}, Int64), s, -1))
+        iters = Ref{Int64}(0); secs = Ref(0.0)
+        check(ccall((:rc_sampler_progress, LIB[]), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Float64}), s, iters, secs))
+        S = options.numsamples
+        results = MCMCResult[]
+        for c in 0:(nchains - 1)
+            res = MCMCResult(RedClustDataShim(n), options, params)
+            lab = Matrix{Int64}(undef, n, S)
+            racc = Vector{UInt8}(undef, options.numiters); sacc = Vector{UInt8}(undef, options.numiters * options.numMH); sspl = similar(sacc)
+            GC.@preserve lab check(ccall((:rc_sampler_copy_samples, LIB[]), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s, c, lab, res.K, res.r, res.p, res.loglik, res.logposterior))
+            check(ccall((:rc_sampler_copy_acceptances, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{UInt8}, Ptr{UInt8}, Ptr{UInt8}), s, c, racc, sacc, sspl))
+            for j in 1:S
+                res.clusts[j] .= @view lab[:, j]
+            end
+            res.r_acceptances .= racc .!= 0; res.splitmerge_acceptances .= sacc .!= 0; res.splitmerge_splits .= sspl .!= 0
+            psm = Matrix{Float64}(undef, n, n)
+            check(ccall((:rc_sampler_psm, LIB[]), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), s, c, 1, psm))   # :560
+            res.posterior_coclustering = psm
+            res.K_iac, res.K_ess, res.K_acf = iac_ess_acf(res.K); res.K_mean, res.K_variance = mean_and_var(res.K)   # :564-573
+            res.r_iac, res.r_ess, res.r_acf = iac_ess_acf(res.r); res.r_mean, res.r_variance = mean_and_var(res.r)
+            res.p_iac, res.p_ess, res.p_acf = iac_ess_acf(res.p); res.p_mean, res.p_variance = mean_and_var(res.p)
+            res.splitmerge_acceptance_rate = options.numMH > 0 ? mean(res.splitmerge_acceptances) : 0
+            res.r_acceptance_rate = mean(res.r_acceptances)
+            res.runtime = secs[]; res.mean_iter_time = secs[] / options.numiters
+            push!(results, res)
+        end
+        return nchains == 1 ? results[1] : results
+    finally
+        ccall((:rc_sampler_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), s)
+    end
+end
+
+# MCMCResult's constructor only reads size(data.D, 1) (src/types.jl:225-227)
+struct RedClustDataShim; n::Int; end
+Base.getproperty(d::RedClustDataShim, s::Symbol) = s === :D ? zeros(getfield(d, :n), 0) : getfield(d, s)
+
+"MPEL search of getpointestimate (src/pointestimate.jl:34-59) on the GPU; loss in (\"binder\", \"omARI\", \"VI\", \"ID\")."
+function mpel(clusts::Vector{ClustLabelVector}, loss::String; device::Integer = 0)
+    code = Dict("binder" => 0, "omARI" => 1, "VI" => 2, "ID" => 3)[loss]
+    S = length(clusts); n = length(clusts[1])
+    L = Matrix{Int64}(undef, n, S)
+    for j in 1:S; L[:, j] .= clusts[j]; end
+    sums = Vector{Float64}(undef, S); best = Ref{Int64}(0)
+    GC.@preserve L check(ccall((:rc_mpel, LIB[]), Int32, (Ptr{Int64}, Int64, Int64, Int32, Int32, Ptr{Float64}, Ref{Int64}), L, S, n, code, device, sums, best))
+    return sums, best[] + 1
+end
+
+function getpointestimate(samples::MCMCResult; method::String = "MAP", loss::Union{String,Function} = "VI")
+    if method == "MPEL" && loss isa String && loss ∉ ["binder", "omARI", "VI", "ID"]
+        throw(ArgumentError("Invalid loss function specifier."))
+    end
+    method ∉ ["MAP", "MLE", "MPEL"] && throw(ArgumentError("Invalid method specifier."))
+    if method == "MAP"
+        i = argmax(samples.logposterior)
+    elseif method == "MLE"
+        i = argmax(samples.loglik)
+    elseif loss isa String
+        _, i = mpel(samples.clusts, loss)
+    else
+        return RedClust.getpointestimate(samples; method = method, loss = loss)   # user-supplied loss: host loop
+    end
+    return (samples.clusts[i], i)
+end
+
+end # module
