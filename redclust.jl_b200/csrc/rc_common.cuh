@@ -59,9 +59,9 @@ struct rc_data {
 
 // geometry of the label-sorted column permutation the sampler reduces rows with
 #ifndef RC_LOGW
-#define RC_LOGW 11
+#define RC_LOGW 10
 #endif
-#define RC_W (1 << RC_LOGW)          // columns per row tile (32 KB of DL)
+#define RC_W (1 << RC_LOGW)          // columns per row tile (16 KB of DL)
 #define RC_DUMMY ((unsigned)RC_W)     // padding entry of a label run: index of the zero slot behind a staged tile
 #define RC_GROUP 8                   // columns per lane-group (runs are padded to multiples of this)
 #define RC_MAXCAP 128                // max live cluster slots per chain

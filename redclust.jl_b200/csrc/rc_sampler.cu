@@ -29,9 +29,9 @@
 
 namespace {
 
-#ifndef RC_NSTAGE
-#define RC_NSTAGE 3
-#endif
+// One ring stage per bulk warp: tile T of the row stream lives in stage T % RC_NSTAGE and is reduced by bulk warp
+// T % RC_BW, so a warp only ever waits on consecutive phases of its own stage (no mbarrier phase aliasing).
+#define RC_NSTAGE RC_BW
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
 __host__ __device__ inline size_t stage_bytes_for(int n) { return (size_t)(n < RC_W ? ((n + 7) & ~7) : RC_W) * 16 + 128; }
 
@@ -43,7 +43,6 @@ struct Scal {
   int K;
   int status;
   int rebuild;
-  int gshift;                             // lane-group size of the permutation = 8 << gshift columns
   int fslotA, fslotB;                     // slots whose W rows come from the scratch rows (-1: none)
   int itmp[8];
 };
@@ -51,17 +50,17 @@ struct Scal {
 #define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
 #define RC_NOISE 64                  // precomputed Gumbel noise entries per row
 struct ScanShared {                  // per chain: hand-off between the bulk warps and the decision warp
-  unsigned long long ready;          // the row sums in `partial` are complete           (count RC_BW)
-  unsigned long long consumed;       // the decision warp has copied them to registers  (count 1)
+  unsigned long long ready[2];       // the row sums of parity b are complete             (count RC_BW)
+  unsigned long long consumed[2];    // the decision warp has copied them to registers   (count 1)
   volatile int M;                    // moves published by the decision warp
   volatile int decided;              // rows decided
-  int rowP;                          // moves already patched into the permutation when the row was reduced
-  int msnap;                         // moves published when the decision warp released the row sums
+  int rowP[2];                       // moves already patched into the permutation when the row was reduced
+  int msnap[2];                      // moves published when the decision warp released the row sums of parity b
   int prebuilt;                      // moves contained in the permutation after a rebuild
   int inited;
   unsigned short mq_j[RC_MQ];
   unsigned char mq_a[RC_MQ], mq_b[RC_MQ];
-  double noise[RC_NOISE];
+  double noise[2][RC_NOISE];
 };
 
 struct CtaShared {
@@ -88,7 +87,7 @@ struct Ctx {
   unsigned short* runStart;
   unsigned int* cnt;
   int* tileStart;
-  longlong2* partial;     // [RC_BW][cap]; aliased by rowA/rowB during loglik of a proposed state
+  longlong2* partial;     // [2][RC_BW][cap] (row parity x bulk warp); aliased by rowA/rowB during loglik of a proposed state
   ScanShared* ss;
   int* sizes;
   int* szL;
@@ -159,9 +158,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // ------------------------------------------------------------------------------------------------
-// (tile, label)-sorted column permutation.  Every (tile, label) run is padded to a multiple of the lane-group
-// size GS = 8 << gshift columns; GS is chosen per build as the largest of {32, 16, 8} whose padding stays
-// below ~12% of n (long runs -- e.g. sorted labels -- take 32: four times fewer segmented scans per row).
+// (tile, label)-sorted column permutation in chunks of 8 columns: every (tile, label) run is padded to a multiple
+// of 8, so a chunk has one label (glabel[chunk]).  A tile is reduced by ONE warp whose lane l owns the contiguous
+// chunks [l*cc, (l+1)*cc) of the tile (cc = ceil(chunks / 32)); inside a chunk the 8 entries are rotated by the
+// owning lane so that, when cluster members are contiguous columns (generatemixture sorts the labels), the 8 lanes
+// of a shared-memory wavefront hit 8 different 16-byte bank groups.
 // ------------------------------------------------------------------------------------------------
 template <bool BULK>
 __device__ void build_perm(const Ctx& c) {
@@ -175,30 +176,23 @@ __device__ void build_perm(const Ctx& c) {
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
     const int b = tid * chunk, e = min(E, b + chunk);
-    unsigned s8 = 0, s16 = 0, s32 = 0;
-    for (int t = b; t < e; ++t) { const unsigned v = c.cnt[t]; s8 += (v + 7u) & ~7u; s16 += (v + 15u) & ~15u; s32 += (v + 31u) & ~31u; }
-    unsigned t16 = s16, t32 = s32;
-    for (int off = 16; off; off >>= 1) { t16 += __shfl_xor_sync(0xffffffffu, t16, off); t32 += __shfl_xor_sync(0xffffffffu, t32, off); }
-    const unsigned budget = min((unsigned)c.kp->npad_max, (unsigned)c.n + (unsigned)c.n / 8u + 64u);
-    const int gshift = t32 <= budget ? 2 : (t16 <= budget ? 1 : 0);
-    const unsigned gm = (8u << gshift) - 1u;
-    unsigned s = gshift == 2 ? s32 : (gshift == 1 ? s16 : s8);
+    unsigned s = 0;
+    for (int t = b; t < e; ++t) s += (c.cnt[t] + 7u) & ~7u;
     unsigned incl = s;
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
       if (tid >= off) incl += o;
     }
     unsigned run = incl - s;
-    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + gm) & ~gm; }
-    if (tid == 31) { c.runStart[E] = (unsigned short)incl; c.sc->gshift = gshift; }
+    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + 7u) & ~7u; }
+    if (tid == 31) c.runStart[E] = (unsigned short)incl;
   }
   tsync<BULK>(c);
   const int total = c.runStart[E];
-  const int gsh = 3 + c.sc->gshift;
-  for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> gsh;
+  for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
   for (int q = tid; q < total; q += NT) c.perm[q] = (unsigned short)c.dummy;
   for (int t = tid; t < E; t += NT) {
-    const int g0 = c.runStart[t] >> gsh, g1 = c.runStart[t + 1] >> gsh;
+    const int g0 = c.runStart[t] >> 3, g1 = c.runStart[t + 1] >> 3;
     const uint8_t l = (uint8_t)(t % c.cap);
     for (int g = g0; g < g1; ++g) c.glabel[g] = l;
   }
@@ -206,14 +200,13 @@ __device__ void build_perm(const Ctx& c) {
   for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
   tsync<BULK>(c);
   for (int j = tid; j < c.n; j += NT) {
-    const int e = (j >> RC_LOGW) * c.cap + lab[j];
-    // Column-major fill of the run's (groups x GS) slots: the element of rank rk goes to group rk % Gr, slot
-    // rk / Gr, so lanes (= consecutive groups) read consecutive ranks with the same load instruction.  Ranks
-    // follow the column order closely, and cluster members tend to be contiguous columns (generatemixture
-    // sorts the labels), which makes the shared-memory gather close to conflict-free instead of group-strided.
-    const unsigned r0 = c.runStart[e], Gr = (c.runStart[e + 1] - r0) >> gsh;
+    const int tile = j >> RC_LOGW;
+    const int e = tile * c.cap + lab[j];
     const unsigned rk = atomicAdd(&c.cnt[e], 1u);
-    c.perm[r0 + ((rk % Gr) << gsh) + rk / Gr] = (unsigned short)((j & (RC_W - 1)) << 4);
+    const int g = (c.runStart[e] >> 3) + (int)(rk >> 3);                 // chunk of the run that takes the element
+    const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 31) >> 5;
+    const int owner = (g - g0) / cc;                                     // lane that will read this chunk
+    c.perm[g * 8 + ((rk - owner) & 7u)] = (unsigned short)((j & (RC_W - 1)) << 4);
   }
   tsync<BULK>(c);
 }
@@ -256,8 +249,8 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
 // utils.jl:9-17).  reduce_tile works on one tile of the row: `src` is either the staged tile in shared
 // memory (padding entries read the zero slot behind it) or the row in global memory.
 // ------------------------------------------------------------------------------------------------
-// One lane-group: (8 << gshift) gathers + sums.  The permutation stores BYTE offsets (column index * 16) so a
-// gather is one LDS.128 at [tile base + offset].
+// 8 gathers + sums of one chunk.  The permutation stores BYTE offsets (column index * 16) so a gather is one
+// LDS.128 at [tile base + offset]; padding entries point at the zero slots behind the staged tile.
 template <bool STAGED>
 __device__ __forceinline__ void gather8(const Ctx& c, const char* src, const uint4 pk, long long& d, long long& l) {
   const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
@@ -270,25 +263,6 @@ __device__ __forceinline__ void gather8(const Ctx& c, const char* src, const uin
     } else if (off != c.dummy) {
       const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src + off));
       d += v.x; l += v.y;
-    }
-  }
-}
-template <bool STAGED>
-__device__ __forceinline__ void gather_group(const Ctx& c, const char* src, int g, bool valid, int gshift, long long& d, long long& l) {
-  d = 0; l = 0;
-  if (valid) {
-    const uint4* pp = reinterpret_cast<const uint4*>(c.perm + ((size_t)g << (3 + gshift)));
-    if (gshift == 0) {
-      gather8<STAGED>(c, src, pp[0], d, l);
-    } else {
-      long long d2 = 0, l2 = 0;                      // two independent accumulation chains, 16 gathers in flight
-      const int nch = 1 << gshift;
-      for (int ch = 0; ch < nch; ch += 2) {
-        const uint4 pa = pp[ch], pb = pp[ch + 1];
-        gather8<STAGED>(c, src, pa, d, l);
-        gather8<STAGED>(c, src, pb, d2, l2);
-      }
-      d += d2; l += l2;
     }
   }
 }
@@ -306,34 +280,46 @@ __device__ __forceinline__ bool seg_scan(int lane, int lab, long long& d, long l
   }
   return (lane == 31) || ((heads >> (lane + 1)) & 1u);
 }
-// The groups of the tile are split evenly over the RC_BW bulk warps (one lane per group, 32 groups per pass), so
-// that every warp finishes a tile at about the same time and a stage of the ring is released promptly.
+// One tile of one row, reduced by ONE warp into its bins `part`: lane l walks its contiguous chunks keeping a
+// running sum while the label stays the same; when the label changes the finished run segment is added to its
+// bin (the run of a label ends in exactly one lane, so these read-modify-writes never collide); the open
+// segments of the 32 lanes are combined by one segmented scan at the end of the tile.
 template <bool STAGED>
 __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_, int tile, longlong2* part) {
-  const int lane = c.lane, warp = c.cwarp;
+  const int lane = c.lane;
   const char* src = reinterpret_cast<const char*>(src_);
   const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
-  const int gshift = c.sc->gshift;
-  const int per = (g1 - g0 + RC_BW - 1) / RC_BW;
-  const int wb = g0 + warp * per, we = min(g1, wb + per);
-  for (int gb = wb; gb < we; gb += 32) {
-    const int g = gb + lane;
-    const bool valid = g < we;
-    const int lab = valid ? (int)c.glabel[g] : 0x100;
-    long long d, l;
-    gather_group<STAGED>(c, src, g, valid, gshift, d, l);
-    const bool tail = seg_scan(lane, lab, d, l);
-    if (valid && tail) {
-      longlong2 a = part[lab];
-      a.x += d; a.y += l;
-      part[lab] = a;
+  const int cc = (g1 - g0 + 31) >> 5;
+  int g = g0 + lane * cc;
+  const int ge = min(g1, g + cc);
+  int cur = 0x100;
+  long long d = 0, l = 0;
+  const uint4* pp = reinterpret_cast<const uint4*>(c.perm);
+  for (; g < ge; ++g) {
+    const int lab = c.glabel[g];
+    const uint4 pk = pp[g];
+    if (lab != cur) {
+      if (cur != 0x100) {
+        longlong2 a = part[cur];
+        a.x += d; a.y += l;
+        part[cur] = a;
+      }
+      cur = lab; d = 0; l = 0;
     }
-    __syncwarp();
+    gather8<STAGED>(c, src, pk, d, l);
   }
+  __syncwarp();
+  const bool tail = seg_scan(lane, cur, d, l);
+  if (cur != 0x100 && tail) {
+    longlong2 a = part[cur];
+    a.x += d; a.y += l;
+    part[cur] = a;
+  }
+  __syncwarp();
 }
 
-__device__ __forceinline__ void zero_partial(const Ctx& c) {   // bulk warps
-  longlong2* part = c.partial + c.cwarp * c.cap;
+__device__ __forceinline__ void zero_partial(const Ctx& c, int buf) {   // bulk warps
+  longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
   for (int s = c.lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
   __syncwarp();
 }
@@ -341,14 +327,14 @@ __device__ __forceinline__ void zero_partial(const Ctx& c) {   // bulk warps
 // Row x straight from global memory / L2 (split-merge member rows, block-sum initialisation); buffer 0.
 __device__ void reduce_row_global(const Ctx& c, int x) {
   if (c.cwarp >= RC_BW) return;
-  zero_partial(c);
+  zero_partial(c, 0);
   const longlong2* row = c.DL + (size_t)x * c.n;
   longlong2* part = c.partial + c.cwarp * c.cap;
-  for (int tile = 0; tile < c.tiles; ++tile) reduce_tile<false>(c, row + tile * RC_W, tile, part);
+  for (int tile = c.cwarp; tile < c.tiles; tile += RC_BW) reduce_tile<false>(c, row + (size_t)tile * RC_W, tile, part);
 }
 
-__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s) {
-  const longlong2* p = c.partial;
+__device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0) {
+  const longlong2* p = c.partial + (size_t)buf * RC_BW * c.cap;
   longlong2 a = p[s];
 #pragma unroll
   for (int w = 1; w < RC_BW; ++w) {
@@ -437,11 +423,12 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     }
     // ---- row sums of row i ----
     const long long tw0 = clock64();
-    mbar_wait(&ss->ready, (unsigned)(i & 1));
+    const int buf = i & 1;
+    mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
     const long long tw1 = clock64();
     acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
-    const int Prow = ss->rowP;
+    const int Prow = ss->rowP[buf];
     long long bd[RC_NS], bl[RC_NS];
     double nzv[RC_NS];
 #pragma unroll
@@ -450,15 +437,15 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       if (w < nw) {
         const int s = w * 32 + lane;
         if ((occ[w] >> lane) & 1u) {
-          const longlong2 t = bin_total(c, s);
+          const longlong2 t = bin_total(c, s, buf);
           bd[w] = t.x; bl[w] = t.y;
         }
-        if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[kk[w]];
+        if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[buf][kk[w]];
       }
     }
-    if (lane == 0) ss->msnap = M;
+    if (lane == 0) ss->msnap[buf] = M;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ss->consumed);
+    if (lane == 0) mbar_arrive(&ss->consumed[buf]);
     if (dead) { if (lane == 0) ss->decided = i + 1; continue; }
     // moves of earlier steps that the permutation did not contain when row i was reduced
     for (int m = Prow; m < M; ++m) {
@@ -650,23 +637,25 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
   if (lane == 0) { st_add(c, ST_DEC_WAIT, acc_wait); st_add(c, ST_DEC_WORK, acc_work); st_add(c, ST_MOVES, nmoves); }
 }
 
-// The row tiles are staged by the CTA's producer warp (produce_rows); the bulk warps only consume them.
+// The row tiles are staged by the CTA's producer warp (produce_rows).  Tile T = row * tiles + tile of the stream is
+// reduced by bulk warp T % RC_BW of every chain, so up to RC_NSTAGE tiles are in flight on different warps.
 __device__ void bulk_loop(const Ctx& c, unsigned it) {
-  const int n = c.n, tiles = c.tiles;
+  const int n = c.n, tiles = c.tiles, w = c.cwarp;
   CtaShared* cs = c.cta;
   ScanShared* ss = c.ss;
-  long long t = 0;
   int Papplied = 0;
   long long a_cons = 0, a_full = 0, a_red = 0, a_rows = 0, a_patch = 0;
+  long long T = 0;
   for (int i = 0; i < n; ++i) {
+    const int buf = i & 1;
     int Msnap = 0;
     const long long tb0 = clock64();
-    if (i >= 1) { mbar_wait(&ss->consumed, (unsigned)((i - 1) & 1)); Msnap = ss->msnap; }
+    if (i >= 2) { mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1)); Msnap = ss->msnap[buf]; }
     const long long tb1 = clock64();
     a_cons += tb1 - tb0;
     if (Msnap > Papplied) {                     // uniform over the chain's bulk warps: patch the permutation
       bsync(c);                                 // every bulk warp is between two rows
-      if (c.cwarp == 0)
+      if (w == 0)
         for (int m = Papplied; m < Msnap; ++m) patch_perm(c, ss->mq_j[m % RC_MQ], ss->mq_a[m % RC_MQ], ss->mq_b[m % RC_MQ]);
       bsync(c);
       Papplied = Msnap;
@@ -681,38 +670,38 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
       }
       a_patch += clock64() - tb1;
     }
-    if (c.ctid == 0) ss->rowP = Papplied;
-    zero_partial(c);
-    if (c.cwarp == (i & (RC_BW - 1))) {         // Gumbel noise of row i's candidates 2*lane, 2*lane+1 (utils.jl:4-5)
-      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);
-      ss->noise[2 * c.lane] = -rc_log(-rc_log(dr.u0));
-      ss->noise[2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
-    }
-    longlong2* part = c.partial + c.cwarp * c.cap;
-    for (int tile = 0; tile < tiles; ++tile, ++t) {
-      const int s = (int)(t % RC_NSTAGE);
-      const unsigned ph = (unsigned)((t / RC_NSTAGE) & 1);
+    zero_partial(c, buf);
+    longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
+    for (int tile = 0; tile < tiles; ++tile, ++T) {
+      if ((int)(T & (RC_BW - 1)) != w) continue;
+      if (tile == 0) {                          // this warp opens row i: noise of its candidates, patch level
+        const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);   // utils.jl:4-5
+        ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
+        ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
+        if (c.lane == 0) ss->rowP[buf] = Papplied;
+      }
+      const int s = (int)(T % RC_NSTAGE);
+      const unsigned ph = (unsigned)((T / RC_NSTAGE) & 1);
       const long long tf0 = clock64();
       mbar_wait(&cs->full[s], ph);
       const long long tf1 = clock64();
       reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)s * c.stage_bytes), tile, part);
-      __syncwarp();
-      a_full += tf1 - tf0; a_red += clock64() - tf1;
       if (c.lane == 0) mbar_arrive(&cs->empty[s]);
+      a_full += tf1 - tf0; a_red += clock64() - tf1;
     }
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&ss->ready);
+    if (c.lane == 0) mbar_arrive(&ss->ready[buf]);
     a_rows += clock64() - tb0;
   }
-  if (c.ctid == 0) {
-    st_add(c, ST_BULK_WAIT_CONSUMED, a_cons); st_add(c, ST_BULK_WAIT_FULL, a_full); st_add(c, ST_BULK_REDUCE, a_red);
-    st_add(c, ST_BULK_ROWS, a_rows); st_add(c, ST_BULK_PATCH, a_patch);
+  if (c.lane == 0) {   // per-warp counters are summed over the chain's bulk warps
+    atomicAdd((unsigned long long*)&c.stats[ST_BULK_WAIT_CONSUMED], (unsigned long long)a_cons);
+    atomicAdd((unsigned long long*)&c.stats[ST_BULK_WAIT_FULL], (unsigned long long)a_full);
+    atomicAdd((unsigned long long*)&c.stats[ST_BULK_REDUCE], (unsigned long long)a_red);
+    atomicAdd((unsigned long long*)&c.stats[ST_BULK_ROWS], (unsigned long long)a_rows);
+    atomicAdd((unsigned long long*)&c.stats[ST_BULK_PATCH], (unsigned long long)a_patch);
   }
 }
 
-// sample_labels_Gibbs! (mcmc.jl:158-256).  All ACTIVE chains of the CTA run this together: the tiles of row
-// i are staged once (bulk async copy, RC_NSTAGE-deep ring) and consumed by every active chain.  A chain
-// whose slot capacity overflows keeps consuming tiles (so the ring keeps moving) but stops deciding.
 // Producer warp of the CTA: stages every tile of rows 0..n-1 into the RC_NSTAGE-deep ring, one bulk async copy
 // (cp.async.bulk, completion on full[s]) per tile, as soon as all consumers released the stage (empty[s]).
 __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t stage_bytes, CtaShared* cs) {
@@ -734,9 +723,10 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
 __device__ void full_scan(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   if (c.ctid == 0) {
-    if (ss->inited) { mbar_inval(&ss->ready); mbar_inval(&ss->consumed); }
-    mbar_init(&ss->ready, RC_BW); mbar_init(&ss->consumed, 1);
-    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP = 0; ss->msnap = 0; ss->prebuilt = 0;
+    if (ss->inited)
+      for (int b = 0; b < 2; ++b) { mbar_inval(&ss->ready[b]); mbar_inval(&ss->consumed[b]); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ss->ready[b], RC_BW); mbar_init(&ss->consumed[b], 1); }
+    ss->inited = 1; ss->M = 0; ss->decided = 0; ss->rowP[0] = 0; ss->rowP[1] = 0; ss->msnap[0] = 0; ss->msnap[1] = 0; ss->prebuilt = 0;
     c.sc->rebuild = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1404,7 +1394,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   ChainLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
-  L.partial = take(sizeof(longlong2) * RC_BW * cap);
+  L.partial = take(sizeof(longlong2) * 2 * RC_BW * cap);
   L.sc = take(sizeof(Scal));
   L.ss = take(sizeof(ScanShared));
   L.red = take(sizeof(long long) * RC_NWARP * 4);
@@ -1553,7 +1543,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
       c.cta->nact = nact; c.cta->issuer = issuer;
       if (iter != kp.it0 + 1)
         for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
-      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_BW); }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1)); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
