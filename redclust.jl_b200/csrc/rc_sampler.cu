@@ -83,7 +83,7 @@ struct Ctx {
   // shared memory (per chain)
   uint8_t* lab;
   unsigned short* perm;
-  uint8_t* glabel;
+  uint8_t* cmask;         // build scratch: occupied slots of each chunk
   unsigned short* runStart;
   unsigned int* cnt;
   int* tileStart;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 // ------------------------------------------------------------------------------------------------
 // (tile, label)-sorted column permutation in chunks of 8 columns: every (tile, label) run is padded to a multiple
-// of 8, so a chunk has one label (glabel[chunk]).  A tile is reduced by ONE warp whose lane l owns the contiguous
+// of 8, so a chunk has one label (carried in the low nibbles of its entries).  A tile is reduced by ONE warp whose lane l owns the contiguous
 // chunks [l*cc, (l+1)*cc) of the tile (cc = ceil(chunks / 32)); inside a chunk the 8 entries are rotated by the
 // owning lane so that, when cluster members are contiguous columns (generatemixture sorts the labels), the 8 lanes
 // of a shared-memory wavefront hit 8 different 16-byte bank groups.
@@ -190,11 +190,18 @@ __device__ void build_perm(const Ctx& c) {
   tsync<BULK>(c);
   const int total = c.runStart[E];
   for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
-  for (int q = tid; q < total; q += NT) c.perm[q] = (unsigned short)c.dummy;
+  // Every entry is a byte offset (column * 16, low 4 bits free); the chunk's label rides in the low nibbles of its
+  // entries 0 (low 4 bits of the label) and 1 (high 4 bits).  Padding entries point at the zero slots.
   for (int t = tid; t < E; t += NT) {
     const int g0 = c.runStart[t] >> 3, g1 = c.runStart[t + 1] >> 3;
-    const uint8_t l = (uint8_t)(t % c.cap);
-    for (int g = g0; g < g1; ++g) c.glabel[g] = l;
+    const unsigned l = (unsigned)(t % c.cap);
+    for (int g = g0; g < g1; ++g) {
+      uint4 v;
+      v.x = (c.dummy | (l & 15u)) | ((c.dummy | (l >> 4)) << 16);
+      v.y = v.z = v.w = c.dummy | (c.dummy << 16);
+      reinterpret_cast<uint4*>(c.perm)[g] = v;
+      c.cmask[g] = 0;
+    }
   }
   tsync<BULK>(c);
   for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
@@ -206,7 +213,20 @@ __device__ void build_perm(const Ctx& c) {
     const int g = (c.runStart[e] >> 3) + (int)(rk >> 3);                 // chunk of the run that takes the element
     const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 31) >> 5;
     const int owner = (g - g0) / cc;                                     // lane that will read this chunk
-    c.perm[g * 8 + ((rk - owner) & 7u)] = (unsigned short)((j & (RC_W - 1)) << 4);
+    // Slot inside the chunk: the lane reads slot s with its s-th gather; putting the column with residue r (mod 8)
+    // at slot (r - owner) mod 8 makes the 8 lanes of a shared-memory wavefront hit 8 different 16-byte bank groups.
+    // If that slot is taken (the chunk's columns are not 8 consecutive ones) any free slot will do.
+    unsigned slot = ((unsigned)j - (unsigned)owner) & 7u;
+    unsigned char* cm = &c.cmask[g];
+    unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<size_t>(cm) & ~(size_t)3);
+    const unsigned sh = (unsigned)(reinterpret_cast<size_t>(cm) & 3) * 8u;
+    for (int tries = 0; tries < 8; ++tries) {
+      const unsigned bit = (1u << slot) << sh;
+      if (!(atomicOr(word, bit) & bit)) break;
+      slot = (slot + 1u) & 7u;
+    }
+    unsigned short* pe = c.perm + g * 8 + slot;
+    *pe = (unsigned short)((((unsigned)j & (RC_W - 1)) << 4) | (*pe & 15u));
   }
   tsync<BULK>(c);
 }
@@ -216,13 +236,13 @@ __device__ void build_perm(const Ctx& c) {
 __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
   const int lane = c.lane;
   const int tile = j >> RC_LOGW;
-  const unsigned short idx = (unsigned short)((j & (RC_W - 1)) << 4);
+  const unsigned idx = ((unsigned)j & (RC_W - 1)) << 4;
   {
     const int e = tile * c.cap + a;
     const int p0 = c.runStart[e], p1 = c.runStart[e + 1];
     for (int pb = p0; pb < p1; pb += 32) {
       const int p = pb + lane;
-      if (p < p1 && c.perm[p] == idx) c.perm[p] = (unsigned short)c.dummy;
+      if (p < p1 && (c.perm[p] & 0xfff0u) == idx) c.perm[p] = (unsigned short)(c.dummy | (c.perm[p] & 15u));
     }
   }
   __syncwarp();
@@ -232,9 +252,9 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
     const int p0 = c.runStart[e], p1 = c.runStart[e + 1];
     for (int pb = p0; pb < p1 && !done; pb += 32) {
       const int p = pb + lane;
-      const unsigned m = __ballot_sync(0xffffffffu, p < p1 && c.perm[p] == (unsigned short)c.dummy);
+      const unsigned m = __ballot_sync(0xffffffffu, p < p1 && (c.perm[p] & 0xfff0u) == c.dummy);
       if (m) {
-        if (lane == __ffs(m) - 1) c.perm[p] = idx;
+        if (lane == __ffs(m) - 1) c.perm[p] = (unsigned short)(idx | (c.perm[p] & 15u));
         done = true;
       }
     }
@@ -243,12 +263,6 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Row reduction: partial[warp][slot] += sums of DL[x][j] over the label runs handled by the warp
-// (matsum(D,[i],clust_k) and matsum(logD,[i],clust_k) for every k at once: mcmc.jl:210-213, 311-318;
-// utils.jl:9-17).  reduce_tile works on one tile of the row: `src` is either the staged tile in shared
-// memory (padding entries read the zero slot behind it) or the row in global memory.
-// ------------------------------------------------------------------------------------------------
 // 8 gathers + sums of one chunk.  The permutation stores BYTE offsets (column index * 16) so a gather is one
 // LDS.128 at [tile base + offset]; padding entries point at the zero slots behind the staged tile.
 template <bool STAGED>
@@ -256,7 +270,7 @@ __device__ __forceinline__ void gather8(const Ctx& c, const char* src, const uin
   const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const unsigned off = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+    const unsigned off = (e & 1) ? ((w[e >> 1] >> 16) & 0xfff0u) : (w[e >> 1] & 0xfff0u);
     if (STAGED) {
       const longlong2 v = *reinterpret_cast<const longlong2*>(src + off);
       d += v.x; l += v.y;
@@ -295,9 +309,12 @@ __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_,
   int cur = 0x100;
   long long d = 0, l = 0;
   const uint4* pp = reinterpret_cast<const uint4*>(c.perm);
+  uint4 pkn = make_uint4(0, 0, 0, 0);
+  if (g < ge) pkn = pp[g];                                 // the next chunk's offsets (+ label nibbles) are loaded one step ahead
   for (; g < ge; ++g) {
-    const int lab = c.glabel[g];
-    const uint4 pk = pp[g];
+    const uint4 pk = pkn;
+    const int lab = (int)((pk.x & 15u) | ((pk.x >> 12) & 0xf0u));
+    if (g + 1 < ge) pkn = pp[g + 1];
     if (lab != cur) {
       if (cur != 0x100) {
         longlong2 a = part[cur];
@@ -354,7 +371,12 @@ __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0)
 // Moves are applied to the permutation by the bulk warps between two rows (patch in place; rebuild from
 // the labels once the decisions have caught up when a run is full).
 // ------------------------------------------------------------------------------------------------
-__device__ void decide_loop(const Ctx& c, unsigned it) {
+// NSR = rounds of 32 slots held in registers.  decide_rows<2> serves chains whose live slots (and next free slot)
+// are all below 64 -- half the register state, no spills -- and returns the row at which a slot >= 64 is needed;
+// decide_rows<NSR> continues from there.  `M` (moves published) and the counters carry over.
+struct DecCarry { int M, nmoves; bool dead; long long acc_wait, acc_work, tlast; };
+template <int NSR>
+__device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) {
   const int lane = c.lane;
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
@@ -364,37 +386,38 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
   const unsigned ltmask = (1u << lane) - 1u;
   // register-resident per-slot state: size, and the size-dependent table terms at the current size (t*) and
   // at size - 1 (u*: used for the slot the visited point is detached from).  Tables are only touched on moves.
-  int sz[RC_NS];
-  double tA[RC_NS], tZ[RC_NS], tP[RC_NS], uA[RC_NS], uZ[RC_NS], uP[RC_NS];
+  int sz[NSR];
+  double tA[NSR], tZ[NSR], tP[NSR], uA[NSR], uZ[NSR], uP[NSR];
 #pragma unroll
-  for (int w = 0; w < RC_NS; ++w) {
+  for (int w = 0; w < NSR; ++w) {
     const int s = w * 32 + lane;
     sz[w] = s < cap ? c.sizes[s] : 0;
     const int s1 = sz[w] > 0 ? sz[w] : 1, s0 = sz[w] > 1 ? sz[w] - 1 : 1;
     tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[s1];
     uA[w] = kp.LGA[sz[w] > 0 ? sz[w] - 1 : 0]; uZ[w] = kp.LGZ[sz[w] > 0 ? sz[w] - 1 : 0]; uP[w] = c.LPR[s0];
   }
-  int M = 0;
-  bool dead = false;
-  long long tlast = clock64(), acc_wait = 0, acc_work = 0;
-  int nmoves = 0;
-  longlong2 self1 = __ldg(c.DL);                                            // diagonal entry of row i (prefetched two rows ahead)
-  longlong2 self2 = n > 1 ? __ldg(c.DL + (size_t)n + 1) : make_longlong2(0, 0);
-  for (int i = 0; i < n; ++i) {
+  int M = cy.M;
+  bool dead = cy.dead;
+  long long tlast = cy.tlast, acc_wait = cy.acc_wait, acc_work = cy.acc_work;
+  int nmoves = cy.nmoves;
+  int istop = n;
+  longlong2 self1 = __ldg(c.DL + (size_t)istart * n + istart);              // diagonal entry of row i (prefetched two rows ahead)
+  longlong2 self2 = istart + 1 < n ? __ldg(c.DL + (size_t)(istart + 1) * n + (istart + 1)) : make_longlong2(0, 0);
+  for (int i = istart; i < n; ++i) {
     const int li = c.lab[i];
     const longlong2 self = self1;
     self1 = self2;
     if (i + 2 < n) self2 = __ldg(c.DL + (size_t)(i + 2) * n + (i + 2));
     // occupancy with i detached (:193-202) -- independent of the row sums
-    unsigned occ[RC_NS];
+    unsigned occ[NSR];
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       const int s = w * 32 + lane;
       occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);
     }
     int Ki = 0, e = -1, nw = 0;
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       Ki += __popc(occ[w]);
       if (occ[w]) nw = w + 1;
       const int lim = cap - w * 32;
@@ -403,17 +426,18 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                        // findfirst(clustsizes .== 0)
     }
     const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;             // :198
+    if (NSR * 32 < RC_MAXCAP && hasnew && e < 0 && cap > NSR * 32) { istop = i; break; }   // needs a slot beyond this instantiation
     if (!dead && hasnew && e < 0) {                                         // slot capacity exhausted
       if (lane == 0) c.sc->status = RC_ERR_SLOTS;
       dead = true;
     }
     if (hasnew && e >= 0 && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;           // rounds of 32 slots that hold a candidate
-    int kk[RC_NS];
-    bool have[RC_NS];
+    int kk[NSR];
+    bool have[NSR];
     {
       int base = 0;
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < NSR; ++w) {
         const int s = w * 32 + lane;
         const bool live = (occ[w] >> lane) & 1u;
         have[w] = live || (hasnew && s == e);
@@ -429,10 +453,10 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
     const int Prow = ss->rowP[buf];
-    long long bd[RC_NS], bl[RC_NS];
-    double nzv[RC_NS];
+    long long bd[NSR], bl[NSR];
+    double nzv[NSR];
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       bd[w] = 0; bl[w] = 0; nzv[w] = 0.0;
       if (w < nw) {
         const int s = w * 32 + lane;
@@ -452,7 +476,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       const int j = ss->mq_j[m % RC_MQ], a = ss->mq_a[m % RC_MQ], b = ss->mq_b[m % RC_MQ];
       const longlong2 ev = __ldg(c.DL + (size_t)i * n + j);
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < NSR; ++w) {
         const int s = w * 32 + lane;
         const bool live = (occ[w] >> lane) & 1u;
         if (s == a && live) { bd[w] -= ev.x; bl[w] -= ev.y; }
@@ -460,10 +484,10 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       }
     }
     // per-slot terms (:206-242)
-    double L1[RC_NS], L2p[RC_NS];
+    double L1[NSR], L2p[NSR];
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       L1[w] = 0.0; L2p[w] = 0.0;
       if (w < nw) {
         const int s = w * 32 + lane;
@@ -484,11 +508,11 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
     const double L2i = acc;
     // log-probabilities (:244-247)
-    double lp[RC_NS];
+    double lp[NSR];
     bool anynan = false;
     double mn = RC_INF;
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       lp[w] = 0.0;
       if (w < nw) {
         const int s = w * 32 + lane;
@@ -513,11 +537,11 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     anynan = __any_sync(0xffffffffu, anynan);
     if (anynan) mn = RC_NAN;                                                // Julia minimum propagates NaN
     // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
-    double g[RC_NS];
+    double g[NSR];
     double gbest = -RC_INF;
     bool gnan = false;
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       g[w] = -RC_INF;
       if (w < nw && have[w]) {
         double nz = nzv[w];
@@ -540,7 +564,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       }
       int kbest = 0x7fffffff, sbest = -1;
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w)
+      for (int w = 0; w < NSR; ++w)
         if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
       const int kmin = __reduce_min_sync(0xffffffffu, kbest);
       const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
@@ -549,7 +573,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       // NaN is maximal for argmax and the first NaN wins
       double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < NSR; ++w) {
         if (!(w < nw && have[w])) continue;
         const bool gn = rc_isnan(g[w]);
         bool better;
@@ -592,7 +616,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     M += 1; nmoves += 1;
     const int a = li, b = cnew;
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       const int s = w * 32 + lane;
       if (s == a) {
         sz[w] -= 1; tA[w] = uA[w]; tZ[w] = uZ[w]; tP[w] = uP[w];
@@ -604,7 +628,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
       }
     }
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       const int s = w * 32 + lane;
       if (s >= cap) continue;
       if (s == a) {
@@ -619,7 +643,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     }
     __syncwarp();
 #pragma unroll
-    for (int w = 0; w < RC_NS; ++w) {
+    for (int w = 0; w < NSR; ++w) {
       const int s = w * 32 + lane;
       if (s >= cap) continue;
       if (s == b) {
@@ -634,7 +658,20 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
     }
     __syncwarp();
   }
-  if (lane == 0) { st_add(c, ST_DEC_WAIT, acc_wait); st_add(c, ST_DEC_WORK, acc_work); st_add(c, ST_MOVES, nmoves); }
+  cy.M = M; cy.dead = dead; cy.tlast = tlast; cy.acc_wait = acc_wait; cy.acc_work = acc_work; cy.nmoves = nmoves;
+  return istop;
+}
+
+__device__ void decide_loop(const Ctx& c, unsigned it) {
+  DecCarry cy;
+  cy.M = 0; cy.nmoves = 0; cy.dead = false; cy.acc_wait = 0; cy.acc_work = 0; cy.tlast = clock64();
+  bool low = true;                                                          // every live slot below 64?
+  for (int s = 64 + c.lane; s < c.cap; s += 32) low = low && c.sizes[s] == 0;
+  low = __all_sync(0xffffffffu, low);
+  int i = 0;
+  if (low) i = decide_rows<2>(c, it, 0, cy);
+  if (i < c.n) decide_rows<RC_NS>(c, it, i, cy);
+  if (c.lane == 0) { st_add(c, ST_DEC_WAIT, cy.acc_wait); st_add(c, ST_DEC_WORK, cy.acc_work); st_add(c, ST_MOVES, cy.nmoves); }
 }
 
 // The row tiles are staged by the CTA's producer warp (produce_rows).  Tile T = row * tiles + tile of the stream is
@@ -645,7 +682,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   int Papplied = 0;
   long long a_cons = 0, a_full = 0, a_red = 0, a_rows = 0, a_patch = 0;
-  long long T = 0;
+  unsigned fullph = 0;                          // phase parity of this warp's stage
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
     int Msnap = 0;
@@ -672,21 +709,22 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
     }
     zero_partial(c, buf);
     longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
-    for (int tile = 0; tile < tiles; ++tile, ++T) {
-      if ((int)(T & (RC_BW - 1)) != w) continue;
-      if (tile == 0) {                          // this warp opens row i: noise of its candidates, patch level
-        const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);   // utils.jl:4-5
-        ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
-        ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
-        if (c.lane == 0) ss->rowP[buf] = Papplied;
-      }
-      const int s = (int)(T % RC_NSTAGE);
-      const unsigned ph = (unsigned)((T / RC_NSTAGE) & 1);
+    // tiles of this row owned by this warp: T = i * tiles + tile with T % RC_BW == w; stage = w
+    const int first = (w - (int)(((long long)i * tiles) & (RC_BW - 1))) & (RC_BW - 1);
+    if (first == 0) {                           // this warp opens row i: noise of its candidates, patch level
+      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);   // utils.jl:4-5
+      ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
+      ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
+      if (c.lane == 0) ss->rowP[buf] = Papplied;
+    }
+    const longlong2* stage = reinterpret_cast<const longlong2*>(c.stages + (size_t)w * c.stage_bytes);
+    for (int tile = first; tile < tiles; tile += RC_BW) {
       const long long tf0 = clock64();
-      mbar_wait(&cs->full[s], ph);
+      mbar_wait(&cs->full[w], fullph);
+      fullph ^= 1u;
       const long long tf1 = clock64();
-      reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)s * c.stage_bytes), tile, part);
-      if (c.lane == 0) mbar_arrive(&cs->empty[s]);
+      reduce_tile<true>(c, stage, tile, part);
+      if (c.lane == 0) mbar_arrive(&cs->empty[w]);
       a_full += tf1 - tf0; a_red += clock64() - tf1;
     }
     __syncwarp();
@@ -1388,7 +1426,7 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 }
 
 struct ChainLayout {
-  size_t partial, sc, ss, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, glabel, lab, total;
+  size_t partial, sc, ss, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, cmask, lab, total;
 };
 __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, int npad_max) {
   ChainLayout L;
@@ -1406,7 +1444,7 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   L.szL = take(sizeof(int) * cap);
   L.itmp = take(sizeof(int) * (cap > 16 ? cap : 16));
   L.clist = take(cap);
-  L.glabel = take(npad_max / 8);
+  L.cmask = take(npad_max / 8 + 4);
   L.lab = take(n);
   L.total = (o + 127) & ~(size_t)127;
   return L;
@@ -1443,7 +1481,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     c.szL = reinterpret_cast<int*>(base + L.szL);
     c.itmp = reinterpret_cast<int*>(base + L.itmp);
     c.clist = base + L.clist;
-    c.glabel = base + L.glabel;
+    c.cmask = base + L.cmask;
     c.lab = base + L.lab;
   }
   const int ch = valid ? chain : 0;
