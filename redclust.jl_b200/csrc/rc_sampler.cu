@@ -29,9 +29,11 @@
 
 namespace {
 
-// One ring stage per bulk warp: tile T of the row stream lives in stage T % RC_NSTAGE and is reduced by bulk warp
-// T % RC_BW, so a warp only ever waits on consecutive phases of its own stage (no mbarrier phase aliasing).
-#define RC_NSTAGE RC_BW
+// Tile T of the row stream lives in stage T % RC_NSTAGE and is reduced by bulk warp T % RC_BW of every chain: RC_BW
+// tiles are being reduced while one more is in flight.  A warp revisits a stage only every RC_NSTAGE * RC_BW tiles and
+// mbarrier parity waits are only unambiguous one phase ahead, so the producer publishes the tile it issues into a stage
+// (CtaShared::issued) and a consumer waits for that to reach its tile before it waits on the stage's `full` barrier.
+#define RC_NSTAGE (RC_BW + 1)
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
 __host__ __device__ inline size_t stage_bytes_for(int n) { return (size_t)(n < RC_W ? ((n + 7) & ~7) : RC_W) * 16 + 128; }
 
@@ -66,6 +68,7 @@ struct ScanShared {                  // per chain: hand-off between the bulk war
 struct CtaShared {
   unsigned long long full[RC_NSTAGE];
   unsigned long long empty[RC_NSTAGE];
+  volatile long long issued[RC_NSTAGE];   // tile of the row stream last issued into each stage (-1: none)
   int active[8];
   int nact;
   int issuer;
@@ -83,9 +86,8 @@ struct Ctx {
   // shared memory (per chain)
   uint8_t* lab;
   unsigned short* perm;
-  uint8_t* cmask;         // build scratch: occupied slots of each chunk
   unsigned short* runStart;
-  unsigned int* cnt;
+  unsigned char* bscratch[2];   // build_perm scratch (run counters + chunk slot masks): aliases the row-sum buffers
   int* tileStart;
   longlong2* partial;     // [2][RC_BW][cap] (row parity x bulk warp); aliased by rowA/rowB during loglik of a proposed state
   ScanShared* ss;
@@ -129,6 +131,21 @@ __device__ __forceinline__ long long shfl_xor_ll(long long v, int off) { return 
 
 // ---- mbarrier / bulk-copy primitives -----------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Explicit shared-space accesses (32-bit shared addresses): the hot loops must not fall back to generic LD/ST,
+// which the compiler emits when it cannot prove that a pointer carried in Ctx points to shared memory.
+__device__ __forceinline__ longlong2 lds_ll2(unsigned a) {
+  longlong2 v;
+  asm volatile("ld.shared.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_ll2(unsigned a, longlong2 v) {
+  asm volatile("st.shared.v2.s64 [%0], {%1, %2};" ::"r"(a), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -165,26 +182,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // of a shared-memory wavefront hit 8 different 16-byte bank groups.
 // ------------------------------------------------------------------------------------------------
 template <bool BULK>
-__device__ void build_perm(const Ctx& c) {
+__device__ void build_perm(const Ctx& c, int buf = 0) {
   constexpr int NT = BULK ? RC_BW * 32 : RC_NTHR;
   const uint8_t* lab = c.lab;
   const int tid = c.ctid, E = c.tiles * c.cap;
-  for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
+  unsigned int* const cnt = reinterpret_cast<unsigned int*>(c.bscratch[buf]);      // [tiles * cap] run sizes / cursors
+  unsigned char* const cmask = c.bscratch[buf] + sizeof(unsigned int) * E;          // [chunks] occupied slots
+  for (int t = tid; t < E; t += NT) cnt[t] = 0;
   tsync<BULK>(c);
-  for (int j = tid; j < c.n; j += NT) atomicAdd(&c.cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
+  for (int j = tid; j < c.n; j += NT) atomicAdd(&cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
   tsync<BULK>(c);
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
     const int b = tid * chunk, e = min(E, b + chunk);
     unsigned s = 0;
-    for (int t = b; t < e; ++t) s += (c.cnt[t] + 7u) & ~7u;
+    for (int t = b; t < e; ++t) s += (cnt[t] + 7u) & ~7u;
     unsigned incl = s;
     for (int off = 1; off < 32; off <<= 1) {
       const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
       if (tid >= off) incl += o;
     }
     unsigned run = incl - s;
-    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (c.cnt[t] + 7u) & ~7u; }
+    for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (cnt[t] + 7u) & ~7u; }
     if (tid == 31) c.runStart[E] = (unsigned short)incl;
   }
   tsync<BULK>(c);
@@ -200,16 +219,16 @@ __device__ void build_perm(const Ctx& c) {
       v.x = (c.dummy | (l & 15u)) | ((c.dummy | (l >> 4)) << 16);
       v.y = v.z = v.w = c.dummy | (c.dummy << 16);
       reinterpret_cast<uint4*>(c.perm)[g] = v;
-      c.cmask[g] = 0;
+      cmask[g] = 0;
     }
   }
   tsync<BULK>(c);
-  for (int t = tid; t < E; t += NT) c.cnt[t] = 0;
+  for (int t = tid; t < E; t += NT) cnt[t] = 0;
   tsync<BULK>(c);
   for (int j = tid; j < c.n; j += NT) {
     const int tile = j >> RC_LOGW;
     const int e = tile * c.cap + lab[j];
-    const unsigned rk = atomicAdd(&c.cnt[e], 1u);
+    const unsigned rk = atomicAdd(&cnt[e], 1u);
     const int g = (c.runStart[e] >> 3) + (int)(rk >> 3);                 // chunk of the run that takes the element
     const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 31) >> 5;
     const int owner = (g - g0) / cc;                                     // lane that will read this chunk
@@ -217,7 +236,7 @@ __device__ void build_perm(const Ctx& c) {
     // at slot (r - owner) mod 8 makes the 8 lanes of a shared-memory wavefront hit 8 different 16-byte bank groups.
     // If that slot is taken (the chunk's columns are not 8 consecutive ones) any free slot will do.
     unsigned slot = ((unsigned)j - (unsigned)owner) & 7u;
-    unsigned char* cm = &c.cmask[g];
+    unsigned char* cm = &cmask[g];
     unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<size_t>(cm) & ~(size_t)3);
     const unsigned sh = (unsigned)(reinterpret_cast<size_t>(cm) & 3) * 8u;
     for (int tries = 0; tries < 8; ++tries) {
@@ -263,18 +282,26 @@ __device__ void patch_perm(const Ctx& c, int j, int a, int b) {
   __syncwarp();
 }
 
-// 8 gathers + sums of one chunk.  The permutation stores BYTE offsets (column index * 16) so a gather is one
-// LDS.128 at [tile base + offset]; padding entries point at the zero slots behind the staged tile.
-template <bool STAGED>
-__device__ __forceinline__ void gather8(const Ctx& c, const char* src, const uint4 pk, long long& d, long long& l) {
+// 8 gathers + sums of one chunk.  The permutation stores BYTE offsets (column index * 16; the low nibbles of entries
+// 0 and 1 carry the chunk's label) so a gather is one LDS.128 at [tile base + offset]; padding entries point at the
+// zero slots behind the staged tile.
+__device__ __forceinline__ void gather8_staged(unsigned tile_addr, const uint4 pk, long long& d, long long& l) {
+  const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
+  longlong2 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const unsigned off = (e & 1) ? ((w[e >> 1] >> 16) & 0xfff0u) : (w[e >> 1] & 0xfff0u);
+    v[e] = lds_ll2(tile_addr + off);
+  }
+  d += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+  l += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+}
+__device__ __forceinline__ void gather8_global(const Ctx& c, const char* src, const uint4 pk, long long& d, long long& l) {
   const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const unsigned off = (e & 1) ? ((w[e >> 1] >> 16) & 0xfff0u) : (w[e >> 1] & 0xfff0u);
-    if (STAGED) {
-      const longlong2 v = *reinterpret_cast<const longlong2*>(src + off);
-      d += v.x; l += v.y;
-    } else if (off != c.dummy) {
+    if (off != c.dummy) {
       const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(src + off));
       d += v.x; l += v.y;
     }
@@ -298,46 +325,49 @@ __device__ __forceinline__ bool seg_scan(int lane, int lab, long long& d, long l
 // running sum while the label stays the same; when the label changes the finished run segment is added to its
 // bin (the run of a label ends in exactly one lane, so these read-modify-writes never collide); the open
 // segments of the 32 lanes are combined by one segmented scan at the end of the tile.
+// STAGED: `src_` is the staged tile in shared memory, otherwise the row in global memory.
 template <bool STAGED>
 __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_, int tile, longlong2* part) {
   const int lane = c.lane;
   const char* src = reinterpret_cast<const char*>(src_);
+  const unsigned tile_addr = STAGED ? smem_u32(src_) : 0u;
+  const unsigned part_addr = smem_u32(part), perm_addr = smem_u32(c.perm);
   const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
   const int cc = (g1 - g0 + 31) >> 5;
   int g = g0 + lane * cc;
   const int ge = min(g1, g + cc);
   int cur = 0x100;
   long long d = 0, l = 0;
-  const uint4* pp = reinterpret_cast<const uint4*>(c.perm);
   uint4 pkn = make_uint4(0, 0, 0, 0);
-  if (g < ge) pkn = pp[g];                                 // the next chunk's offsets (+ label nibbles) are loaded one step ahead
+  if (g < ge) pkn = lds_u4(perm_addr + (unsigned)g * 16u);  // the next chunk's offsets (+ label nibbles) are loaded one step ahead
   for (; g < ge; ++g) {
     const uint4 pk = pkn;
     const int lab = (int)((pk.x & 15u) | ((pk.x >> 12) & 0xf0u));
-    if (g + 1 < ge) pkn = pp[g + 1];
+    if (g + 1 < ge) pkn = lds_u4(perm_addr + (unsigned)(g + 1) * 16u);
     if (lab != cur) {
       if (cur != 0x100) {
-        longlong2 a = part[cur];
+        longlong2 a = lds_ll2(part_addr + (unsigned)cur * 16u);
         a.x += d; a.y += l;
-        part[cur] = a;
+        sts_ll2(part_addr + (unsigned)cur * 16u, a);
       }
       cur = lab; d = 0; l = 0;
     }
-    gather8<STAGED>(c, src, pk, d, l);
+    if (STAGED) gather8_staged(tile_addr, pk, d, l);
+    else gather8_global(c, src, pk, d, l);
   }
   __syncwarp();
   const bool tail = seg_scan(lane, cur, d, l);
   if (cur != 0x100 && tail) {
-    longlong2 a = part[cur];
+    longlong2 a = lds_ll2(part_addr + (unsigned)cur * 16u);
     a.x += d; a.y += l;
-    part[cur] = a;
+    sts_ll2(part_addr + (unsigned)cur * 16u, a);
   }
   __syncwarp();
 }
 
 __device__ __forceinline__ void zero_partial(const Ctx& c, int buf) {   // bulk warps
-  longlong2* part = c.partial + (buf * RC_BW + c.cwarp) * c.cap;
-  for (int s = c.lane; s < c.cap; s += 32) part[s] = make_longlong2(0, 0);
+  const unsigned part = smem_u32(c.partial + (buf * RC_BW + c.cwarp) * c.cap);
+  for (int s = c.lane; s < c.cap; s += 32) sts_ll2(part + (unsigned)s * 16u, make_longlong2(0, 0));
   __syncwarp();
 }
 
@@ -351,11 +381,11 @@ __device__ void reduce_row_global(const Ctx& c, int x) {
 }
 
 __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0) {
-  const longlong2* p = c.partial + (size_t)buf * RC_BW * c.cap;
-  longlong2 a = p[s];
+  const unsigned p = smem_u32(c.partial + (size_t)buf * RC_BW * c.cap) + (unsigned)s * 16u;
+  longlong2 a = lds_ll2(p);
 #pragma unroll
   for (int w = 1; w < RC_BW; ++w) {
-    const longlong2 b = p[w * c.cap + s];
+    const longlong2 b = lds_ll2(p + (unsigned)(w * c.cap) * 16u);
     a.x += b.x; a.y += b.y;
   }
   return a;
@@ -682,7 +712,6 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
   ScanShared* ss = c.ss;
   int Papplied = 0;
   long long a_cons = 0, a_full = 0, a_red = 0, a_rows = 0, a_patch = 0;
-  unsigned fullph = 0;                          // phase parity of this warp's stage
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
     int Msnap = 0;
@@ -700,7 +729,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
         while (ss->decided < i) __nanosleep(64);
         __threadfence_block();
         bsync(c);
-        build_perm<true>(c);
+        build_perm<true>(c, buf);
         if (c.ctid == 0) { c.sc->rebuild = 0; ss->prebuilt = ss->M; st_add(c, ST_REBUILDS, 1); }
         bsync(c);
         Papplied = ss->prebuilt;
@@ -717,14 +746,16 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
       ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
       if (c.lane == 0) ss->rowP[buf] = Papplied;
     }
-    const longlong2* stage = reinterpret_cast<const longlong2*>(c.stages + (size_t)w * c.stage_bytes);
     for (int tile = first; tile < tiles; tile += RC_BW) {
+      const long long T = (long long)i * tiles + tile;
+      const int st = (int)(T % RC_NSTAGE);
+      const unsigned k = (unsigned)(T / RC_NSTAGE);
       const long long tf0 = clock64();
-      mbar_wait(&cs->full[w], fullph);
-      fullph ^= 1u;
+      while (cs->issued[st] != T) __nanosleep(20);           // the stage has moved on to tile T (see RC_NSTAGE)
+      mbar_wait(&cs->full[st], k & 1u);
       const long long tf1 = clock64();
-      reduce_tile<true>(c, stage, tile, part);
-      if (c.lane == 0) mbar_arrive(&cs->empty[w]);
+      reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)st * c.stage_bytes), tile, part);
+      if (c.lane == 0) mbar_arrive(&cs->empty[st]);
       a_full += tf1 - tf0; a_red += clock64() - tf1;
     }
     __syncwarp();
@@ -752,6 +783,8 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
     if (t >= RC_NSTAGE) mbar_wait(&cs->empty[s], (unsigned)(((t / RC_NSTAGE) - 1) & 1));
     const int cols = min(RC_W, n - tile * RC_W);
     const unsigned bytes = (unsigned)cols * 16u;
+    cs->issued[s] = t;
+    __threadfence_block();
     mbar_expect_tx(&cs->full[s], bytes);
     bulk_g2s(stages + (size_t)s * stage_bytes, kp.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
     if (++tile == tiles) { tile = 0; ++row; }
@@ -1426,7 +1459,8 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 }
 
 struct ChainLayout {
-  size_t partial, sc, ss, red, perm, runStart, cnt, tileStart, sizes, szL, itmp, clist, cmask, lab, total;
+  size_t partial, sc, ss, red, perm, runStart, bscratch, tileStart, sizes, szL, itmp, clist, lab, total;
+  int scratch_aliased;
 };
 __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, int npad_max) {
   ChainLayout L;
@@ -1438,13 +1472,16 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
   L.red = take(sizeof(long long) * RC_NWARP * 4);
   L.perm = take(sizeof(unsigned short) * npad_max);
   L.runStart = take(sizeof(unsigned short) * (tiles * cap + 1));
-  L.cnt = take(sizeof(unsigned int) * tiles * cap);
+  {
+    const size_t need = sizeof(unsigned int) * tiles * cap + npad_max / 8 + 8;
+    L.scratch_aliased = need <= sizeof(longlong2) * RC_BW * cap;
+    L.bscratch = L.scratch_aliased ? L.partial : take(need);
+  }
   L.tileStart = take(sizeof(int) * (tiles + 1));
   L.sizes = take(sizeof(int) * cap);
   L.szL = take(sizeof(int) * cap);
   L.itmp = take(sizeof(int) * (cap > 16 ? cap : 16));
   L.clist = take(cap);
-  L.cmask = take(npad_max / 8 + 4);
   L.lab = take(n);
   L.total = (o + 127) & ~(size_t)127;
   return L;
@@ -1475,13 +1512,13 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     c.red = reinterpret_cast<long long*>(base + L.red);
     c.perm = reinterpret_cast<unsigned short*>(base + L.perm);
     c.runStart = reinterpret_cast<unsigned short*>(base + L.runStart);
-    c.cnt = reinterpret_cast<unsigned int*>(base + L.cnt);
+    c.bscratch[0] = base + L.bscratch;
+    c.bscratch[1] = base + L.bscratch + (L.scratch_aliased ? sizeof(longlong2) * RC_BW * cap : 0);
     c.tileStart = reinterpret_cast<int*>(base + L.tileStart);
     c.sizes = reinterpret_cast<int*>(base + L.sizes);
     c.szL = reinterpret_cast<int*>(base + L.szL);
     c.itmp = reinterpret_cast<int*>(base + L.itmp);
     c.clist = base + L.clist;
-    c.cmask = base + L.cmask;
     c.lab = base + L.lab;
   }
   const int ch = valid ? chain : 0;
@@ -1581,7 +1618,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
       c.cta->nact = nact; c.cta->issuer = issuer;
       if (iter != kp.it0 + 1)
         for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
-      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1)); }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1)); c.cta->issued[s] = -1; }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
