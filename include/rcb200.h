@@ -82,7 +82,7 @@ int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, dou
  * on the data's device.  init_labels: nchains x n, 1-based, any slot ids in 1..n (src/types.jl:131-137);
  * init_r / init_p: nchains values.  slot_cap: max simultaneously live clusters per chain
  * (0 = default = maximum 128) -- the reference allows up to n; initial labels must lie in
- * 1..slot_cap (relabel with sortlabels first).  numMH must be 0 or 1 in this build.             */
+ * 1..slot_cap (relabel with sortlabels first).             */
 int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par,
                           int64_t nchains, int64_t chain_offset, const int64_t* init_labels,
                           const double* init_r, const double* init_p, uint64_t seed,

@@ -27,7 +27,7 @@ struct rc_sampler {
   // device
   double *LGA, *LGZ, *LOGN;
   uint8_t* labels; int* sizes; double *r, *p; int* status;
-  rc_i128 *WD, *WL; longlong2* T; unsigned short* Slist; uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms; long long* stats;
+  rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist; uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms; long long* stats;
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
@@ -74,7 +74,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
   kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;
   kp.labels = s->labels; kp.sizes = s->sizes; kp.r = s->r; kp.p = s->p; kp.status = s->status;
-  kp.WD = s->WD; kp.WL = s->WL; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s; kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats;
+  kp.WD = s->WD; kp.WL = s->WL; kp.WDbak = s->WDbak; kp.WLbak = s->WLbak; kp.labbak = s->labbak; kp.szbak = s->szbak; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s; kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats;
   kp.out_labels = s->out_labels; kp.out_K = s->out_K; kp.out_r = s->out_r; kp.out_p = s->out_p;
   kp.out_ll = s->out_ll; kp.out_lp = s->out_lp; kp.r_acc = s->r_acc; kp.sm_acc = s->sm_acc; kp.sm_split = s->sm_split;
 }
@@ -97,7 +97,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   cudaSetDevice(s->d->device);
   cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
   cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
-  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats);
+  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->WDbak); cudaFree(s->WLbak); cudaFree(s->labbak); cudaFree(s->szbak); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats);
   cudaFree(s->out_labels); cudaFree(s->out_K); cudaFree(s->out_r); cudaFree(s->out_p); cudaFree(s->out_ll); cudaFree(s->out_lp);
   cudaFree(s->r_acc); cudaFree(s->sm_acc); cudaFree(s->sm_split);
   if (s->e0) cudaEventDestroy(s->e0);
@@ -114,9 +114,6 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   }
   int st = validate_options(opt);
   if (st) return st;
-  if (opt->numMH > 1) {
-    rc_set_error("numMH > 1 is not supported yet by the device sampler (numMH must be 0 or 1)."); return RC_ERR_ARG;
-  }
   const int64_t n = d->n;
   if (opt->numMH > 0 && n < 2) { rc_set_error("split-merge needs at least 2 observations."); return RC_ERR_ARG; }
   int cap = slot_cap == 0 ? RC_MAXCAP : slot_cap;
@@ -179,6 +176,10 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   TRY(dalloc(&s->r, nchains)); TRY(dalloc(&s->p, nchains)); TRY(dalloc(&s->status, nchains));
   TRY(dalloc(&s->WD, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WL, (size_t)nchains * cap * cap));
   TRY(dalloc(&s->T, opt->numMH > 0 ? (size_t)nchains * n * cap : 1));
+  if (opt->numMH > 1) {
+    TRY(dalloc(&s->WDbak, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WLbak, (size_t)nchains * cap * cap));
+    TRY(dalloc(&s->labbak, (size_t)nchains * n)); TRY(dalloc(&s->szbak, (size_t)nchains * (cap + 1)));
+  }
   TRY(dalloc(&s->Slist, (size_t)nchains * (n + 2))); TRY(dalloc(&s->origM, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->AB, (size_t)nchains * (n + 2))); TRY(dalloc(&s->L2s, (size_t)nchains * n));
   TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2))); TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));

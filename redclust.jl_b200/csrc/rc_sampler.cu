@@ -45,6 +45,7 @@ struct Scal {
   int K;
   int status;
   int rebuild;
+  int forked;                             // numMH > 1: an accepted proposal replaced the local state this iteration
   int fslotA, fslotB;                     // slots whose W rows come from the scratch rows (-1: none)
   int itmp[8];
 };
@@ -103,6 +104,10 @@ struct Ctx {
   // per-chain global memory
   rc_i128* WD;
   rc_i128* WL;
+  rc_i128* WDbak;         // numMH > 1: the chain's own block sums / labels / sizes while an accepted proposal is the local state
+  rc_i128* WLbak;
+  uint8_t* labbak;
+  int* szbak;
   longlong2* T;
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
@@ -1197,10 +1202,12 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
   }
 }
 
-// One split-merge proposal (mcmc.jl:372-474) on the chain's current state.  Returns accept through
-// c.sc->itmp[1], split through itmp[2].  The chain's labels / sizes are unchanged on return (quirk Q1:
-// an accepted proposal never reaches the caller's state).
-__device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
+// One split-merge proposal (mcmc.jl:372-474) on the current LOCAL state of sample_labels!.  Returns accept through
+// c.sc->itmp[1], split through itmp[2].  With commit == false the state is unchanged on return.  With commit == true
+// (more proposals follow in this iteration, numMH > 1) an accepted proposal becomes the local state (:470): labels,
+// sizes, K and the block sums W are replaced -- the caller backs the chain's own state up first and restores it
+// after the last proposal (quirk Q1: the accepted state never reaches runsampler's state).
+__device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool commit) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int tid = c.ctid, lane = c.lane, warp = c.cwarp;
@@ -1434,8 +1441,35 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh) {
     const double lu = rc_log(rc_draw1(c.key, it, RC_SITE_SM_ACCEPT, mh, 0, 0));
     c.sc->itmp[1] = lu < lar ? 1 : 0;                                                   // :469-472
   }
-  // restore the chain's own labels of the members (the proposal lived in place)
-  for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+  csync(c);
+  if (commit && c.sc->itmp[1]) {
+    // the proposed state becomes the local state of the remaining proposals of this iteration
+    if (!c.sc->forked) {                                   // first accepted proposal: keep the chain's own block sums
+      for (int t = tid; t < cap * cap; t += RC_NTHR) { c.WDbak[t] = c.WD[t]; c.WLbak[t] = c.WL[t]; }
+      csync(c);
+      if (tid == 0) c.sc->forked = 1;
+    }
+    const rc_i128* rows = reinterpret_cast<const rc_i128*>(c.partial);   // [rowA_D | rowA_L | rowB_D | rowB_L] x cap
+    const int A = split ? ca : ci, B = split ? cb : cj;
+    for (int t = tid; t < cap; t += RC_NTHR) {
+      if (t != A && t != B) {
+        c.WD[tri(A, t, cap)] = rows[0 * cap + t]; c.WL[tri(A, t, cap)] = rows[1 * cap + t];
+        c.WD[tri(B, t, cap)] = rows[2 * cap + t]; c.WL[tri(B, t, cap)] = rows[3 * cap + t];
+      }
+    }
+    if (tid == 0) {
+      c.WD[tri(A, A, cap)] = c.sc->aaD; c.WL[tri(A, A, cap)] = c.sc->aaL;
+      c.WD[tri(A, B, cap)] = c.sc->abD; c.WL[tri(A, B, cap)] = c.sc->abL;
+      c.WD[tri(B, B, cap)] = c.sc->bbD; c.WL[tri(B, B, cap)] = c.sc->bbL;
+      c.sc->K = split ? K + 1 : K - 1;
+    }
+    if (!split)
+      for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = (uint8_t)cj;     // :436-445 (split: labels are final in place)
+    for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = c.szL[s];
+  } else {
+    // restore the labels of the members (the proposal lived in place)
+    for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+  }
   csync(c);
   if (tid == 0) st_add(c, ST_MH_LOGLIK, clock64() - tm2);
 }
@@ -1525,6 +1559,10 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
   c.WD = kp.WD + (size_t)ch * cap * cap;
   c.WL = kp.WL + (size_t)ch * cap * cap;
   c.T = kp.T + (size_t)ch * n * cap;
+  c.WDbak = kp.WDbak ? kp.WDbak + (size_t)ch * cap * cap : nullptr;
+  c.WLbak = kp.WLbak ? kp.WLbak + (size_t)ch * cap * cap : nullptr;
+  c.labbak = kp.labbak ? kp.labbak + (size_t)ch * n : nullptr;
+  c.szbak = kp.szbak ? kp.szbak + (size_t)ch * (cap + 1) : nullptr;
   c.Slist = kp.Slist + (size_t)ch * (n + 2);
   c.origM = kp.origM + (size_t)ch * (n + 2);
   c.AB = kp.AB + (size_t)ch * (n + 2);
@@ -1592,8 +1630,15 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
       build_lpr(c);
       if (tid == 0) st_add(c, ST_RP, clock64() - ti0);
       // sample_labels! (:540)
+      const bool multi = kp.numMH > 1;
+      if (multi) {                                           // the chain's own state, in case a proposal is accepted and committed
+        for (int j = tid; j < n; j += RC_NTHR) c.labbak[j] = c.lab[j];
+        for (int s = tid; s < cap; s += RC_NTHR) c.szbak[s] = c.sizes[s];
+        if (tid == 0) { c.szbak[cap] = c.sc->K; c.sc->forked = 0; }
+        csync(c);
+      }
       for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
-        splitmerge_step(c, it, mh);
+        splitmerge_step(c, it, mh, mh + 1 < (unsigned)kp.numMH);
         if (c.sc->status) { do_scan = false; break; }
         const int acc = c.sc->itmp[1], spl = c.sc->itmp[2];
         if (tid == 0) {
@@ -1601,10 +1646,19 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
           kp.sm_split[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)spl;
         }
         csync(c);
-        // Quirk Q1: an accepted proposal rebinds sample_labels!'s LOCAL state; the final
-        // scan (:477) then runs on that local object and the caller's labels are untouched this iteration.
-        // Its draws are independent of everything kept (structured stream), so the scan is skipped.
-        if (acc) { do_scan = false; break; }
+        // Quirk Q1: an accepted proposal rebinds sample_labels!'s LOCAL state; the remaining
+        // proposals and the final scan (:477) run on that local object and the caller's labels are untouched this
+        // iteration.  The scan's draws are independent of everything kept (structured stream), so it is skipped.
+        if (acc) do_scan = false;
+      }
+      if (multi && c.sc->status == 0) {                      // back to the chain's own state
+        if (c.sc->forked) {
+          for (int t = tid; t < cap * cap; t += RC_NTHR) { c.WD[t] = c.WDbak[t]; c.WL[t] = c.WLbak[t]; }
+          for (int j = tid; j < n; j += RC_NTHR) c.lab[j] = c.labbak[j];
+          for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = c.szbak[s];
+          if (tid == 0) c.sc->K = c.szbak[cap];
+        }
+        csync(c);
       }
       if (do_scan) build_perm<false>(c);   // the scan's last moves / the proposal's launch labels are not in it
     }

@@ -29,6 +29,9 @@ struct rc_kparams {
   int* status;          // [nchains]
   rc_i128* WD;          // [nchains][cap*cap]  block sums of Dq, entry (min(k,t), max(k,t))
   rc_i128* WL;          // [nchains][cap*cap]  block sums of Lq
+  rc_i128 *WDbak, *WLbak; // [nchains][cap*cap]  numMH > 1 only: the chain's own block sums while a proposal is committed
+  uint8_t* labbak;      // [nchains][n]
+  int* szbak;           // [nchains][cap+1]
   longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj
   unsigned short* Slist;// [nchains][n+2]  members of ci u cj of the current split-merge step
   uint8_t* origM;       // [nchains][n+2]  their labels in the chain's state

@@ -157,3 +157,18 @@ def test_multitile_two_chains_per_cta(pkg, orc, monkeypatch):
     res, _ = run_both(pkg, orc, D, lab, params, 4, 0, 1, 5, 1, seed=2, nchains=2)
     for got, ref, st in res:
         assert_same(got, ref, st)
+
+
+def test_several_proposals_per_iteration(pkg, orc, golden):
+    """numMH > 1: an accepted proposal becomes the local state of the remaining proposals of the iteration (and, by
+    quirk Q1, never reaches the chain's own state)."""
+    D = golden[3]["distance_matrix"]
+    params = pkg.params_from_labels(D, golden[3]["cluster_labels"], repulsion=False)
+    (res,), _ = run_both(pkg, orc, D, np.ones(100, np.int64), params, 60, 0, 1, 3, 4, seed=5)   # splits accepted often
+    assert_same(*res)
+    assert res[1]["sm_acc"].sum() > 10
+    for k in (1, 2):
+        D, lab = golden[k]["distance_matrix"], golden[k]["cluster_labels"]
+        params = pkg.params_from_labels(D, lab)
+        (res,), _ = run_both(pkg, orc, D, lab, params, 80, 10, 2, 5, 3, seed=60 + k)
+        assert_same(*res)
