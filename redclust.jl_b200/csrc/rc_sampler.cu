@@ -1023,7 +1023,7 @@ __device__ void build_lpr(const Ctx& c) {
 // labels of the members are kept in origM and restored by the caller).  Runs on warp 0 of the chain.
 //   * AB[q] holds the sums of member q's row over the current members of the two candidate clusters; a
 //     move of item y updates all of them from row y (exact integers), so a step that does not move reads
-//     nothing but its own entry.  Row y is gathered speculatively at the start of the step.
+//     nothing but its own entry.
 //   * the Gumbel noise and the repulsion terms of non-candidate slots do not depend on the evolving state
 //     and are precomputed (NZ, L2s).
 //   * the transition probability (:347-351) is only evaluated in the last scan -- the reference discards
@@ -1066,9 +1066,6 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
       const RsItem cu = nx;
       const int y = cu.y;
       const longlong2* row = c.DL + (size_t)y * c.n;
-      longlong2 ev[RC_RS_NU];                                   // speculative: row y at the member columns (used if y moves)
-#pragma unroll
-      for (int u = 0; u < RC_RS_NU; ++u) ev[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
       // inputs of the next step (its AB entry is re-read below if this step moves)
       const int npos = pos + 1 < nS ? pos + 1 : 0, ng = pos + 1 < nS ? g : g + 1;
       const bool more = ng <= numGibbs;
@@ -1127,6 +1124,9 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
         if (lane == 0) { c.lab[y] = (uint8_t)cnew; c.szL[cur] -= 1; c.szL[cnew] += 1; }
         // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
         const bool a2b = cur == ca;
+        longlong2 ev[RC_RS_NU];                                 // row y at the member columns (only read when y moves)
+#pragma unroll
+        for (int u = 0; u < RC_RS_NU; ++u) ev[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
 #pragma unroll
         for (int u = 0; u < RC_RS_NU; ++u) {
           const int q = u * 32 + lane;
