@@ -27,7 +27,7 @@ struct rc_sampler {
   // device
   double *LGA, *LGZ, *LOGN;
   uint8_t* labels; int* sizes; double *r, *p; int* status;
-  rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist; uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms; long long* stats;
+  rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist; uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms; long long* stats; unsigned* gridbar; bool coresident;
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
@@ -74,7 +74,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
   kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;
   kp.labels = s->labels; kp.sizes = s->sizes; kp.r = s->r; kp.p = s->p; kp.status = s->status;
-  kp.WD = s->WD; kp.WL = s->WL; kp.WDbak = s->WDbak; kp.WLbak = s->WLbak; kp.labbak = s->labbak; kp.szbak = s->szbak; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s; kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats;
+  kp.WD = s->WD; kp.WL = s->WL; kp.WDbak = s->WDbak; kp.WLbak = s->WLbak; kp.labbak = s->labbak; kp.szbak = s->szbak; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s; kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats; kp.gridbar = (s->coresident && getenv("RCB200_GRIDBAR")) ? s->gridbar : nullptr;   // experiment: align the scans of all CTAs (no gain measured)
   kp.out_labels = s->out_labels; kp.out_K = s->out_K; kp.out_r = s->out_r; kp.out_p = s->out_p;
   kp.out_ll = s->out_ll; kp.out_lp = s->out_lp; kp.r_acc = s->r_acc; kp.sm_acc = s->sm_acc; kp.sm_split = s->sm_split;
 }
@@ -97,7 +97,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   cudaSetDevice(s->d->device);
   cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
   cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
-  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->WDbak); cudaFree(s->WLbak); cudaFree(s->labbak); cudaFree(s->szbak); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats);
+  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->WDbak); cudaFree(s->WLbak); cudaFree(s->labbak); cudaFree(s->szbak); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats); cudaFree(s->gridbar);
   cudaFree(s->out_labels); cudaFree(s->out_K); cudaFree(s->out_r); cudaFree(s->out_p); cudaFree(s->out_ll); cudaFree(s->out_lp);
   cudaFree(s->r_acc); cudaFree(s->sm_acc); cudaFree(s->sm_split);
   if (s->e0) cudaEventDestroy(s->e0);
@@ -182,7 +182,8 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   }
   TRY(dalloc(&s->Slist, (size_t)nchains * (n + 2))); TRY(dalloc(&s->origM, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->AB, (size_t)nchains * (n + 2))); TRY(dalloc(&s->L2s, (size_t)nchains * n));
-  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2))); TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));
+  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2))); TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->gridbar, 1));
+  s->coresident = rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
   TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));
@@ -217,6 +218,7 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   fill_kparams(s, kp);
   kp.it0 = s->iters_done; kp.it1 = it1;
   kp.init_W = s->W_ready ? 0 : 1;
+  RC_CUDA(cudaMemsetAsync(s->gridbar, 0, sizeof(unsigned), s->stream));
   RC_CUDA(cudaEventRecord(s->e0, s->stream));
   rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
   RC_CUDA(cudaGetLastError());

@@ -34,6 +34,8 @@ namespace {
 // mbarrier parity waits are only unambiguous one phase ahead, so the producer publishes the tile it issues into a stage
 // (CtaShared::issued) and a consumer waits for that to reach its tile before it waits on the stage's `full` barrier.
 #define RC_NSTAGE (RC_BW + 1)
+#define RC_PAIR 1                    // bulk warps that reduce one tile together (RC_BW / RC_PAIR tiles are reduced at a time)
+#define RC_NPAIR (RC_BW / RC_PAIR)
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
 __host__ __device__ inline size_t stage_bytes_for(int n) { return (size_t)(n < RC_W ? ((n + 7) & ~7) : RC_W) * 16 + 128; }
 
@@ -235,8 +237,8 @@ __device__ void build_perm(const Ctx& c, int buf = 0) {
     const int e = tile * c.cap + lab[j];
     const unsigned rk = atomicAdd(&cnt[e], 1u);
     const int g = (c.runStart[e] >> 3) + (int)(rk >> 3);                 // chunk of the run that takes the element
-    const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 31) >> 5;
-    const int owner = (g - g0) / cc;                                     // lane that will read this chunk
+    const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 32 * RC_PAIR - 1) / (32 * RC_PAIR);
+    const int owner = (g - g0) / cc;                                     // (virtual) lane that will read this chunk
     // Slot inside the chunk: the lane reads slot s with its s-th gather; putting the column with residue r (mod 8)
     // at slot (r - owner) mod 8 makes the 8 lanes of a shared-memory wavefront hit 8 different 16-byte bank groups.
     // If that slot is taken (the chunk's columns are not 8 consecutive ones) any free slot will do.
@@ -326,7 +328,7 @@ __device__ __forceinline__ bool seg_scan(int lane, int lab, long long& d, long l
   }
   return (lane == 31) || ((heads >> (lane + 1)) & 1u);
 }
-// One tile of one row, reduced by ONE warp into its bins `part`: lane l walks its contiguous chunks keeping a
+// One tile of one row, reduced by RC_PAIR warps (each into its own bins `part`): a lane walks its contiguous chunks keeping a
 // running sum while the label stays the same; when the label changes the finished run segment is added to its
 // bin (the run of a label ends in exactly one lane, so these read-modify-writes never collide); the open
 // segments of the 32 lanes are combined by one segmented scan at the end of the tile.
@@ -338,8 +340,8 @@ __device__ __forceinline__ void reduce_tile(const Ctx& c, const longlong2* src_,
   const unsigned tile_addr = STAGED ? smem_u32(src_) : 0u;
   const unsigned part_addr = smem_u32(part), perm_addr = smem_u32(c.perm);
   const int g0 = c.tileStart[tile], g1 = c.tileStart[tile + 1];
-  const int cc = (g1 - g0 + 31) >> 5;
-  int g = g0 + lane * cc;
+  const int cc = (g1 - g0 + 32 * RC_PAIR - 1) / (32 * RC_PAIR);
+  int g = g0 + ((c.cwarp % RC_PAIR) * 32 + lane) * cc;        // the RC_PAIR warps of a tile form 32 * RC_PAIR virtual lanes
   const int ge = min(g1, g + cc);
   int cur = 0x100;
   long long d = 0, l = 0;
@@ -382,7 +384,7 @@ __device__ void reduce_row_global(const Ctx& c, int x) {
   zero_partial(c, 0);
   const longlong2* row = c.DL + (size_t)x * c.n;
   longlong2* part = c.partial + c.cwarp * c.cap;
-  for (int tile = c.cwarp; tile < c.tiles; tile += RC_BW) reduce_tile<false>(c, row + (size_t)tile * RC_W, tile, part);
+  for (int tile = c.cwarp / RC_PAIR; tile < c.tiles; tile += RC_NPAIR) reduce_tile<false>(c, row + (size_t)tile * RC_W, tile, part);
 }
 
 __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0) {
@@ -710,7 +712,7 @@ __device__ void decide_loop(const Ctx& c, unsigned it) {
 }
 
 // The row tiles are staged by the CTA's producer warp (produce_rows).  Tile T = row * tiles + tile of the stream is
-// reduced by bulk warp T % RC_BW of every chain, so up to RC_NSTAGE tiles are in flight on different warps.
+// reduced by bulk warp pair T % RC_NPAIR of every chain, so up to RC_NSTAGE tiles are in flight on different warps.
 __device__ void bulk_loop(const Ctx& c, unsigned it) {
   const int n = c.n, tiles = c.tiles, w = c.cwarp;
   CtaShared* cs = c.cta;
@@ -743,15 +745,15 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
     }
     zero_partial(c, buf);
     longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
-    // tiles of this row owned by this warp: T = i * tiles + tile with T % RC_BW == w; stage = w
-    const int first = (w - (int)(((long long)i * tiles) & (RC_BW - 1))) & (RC_BW - 1);
-    if (first == 0) {                           // this warp opens row i: noise of its candidates, patch level
+    // tiles of this row owned by this warp's pair: T = i * tiles + tile with T % RC_NPAIR == w / RC_PAIR
+    const int first = ((w / RC_PAIR) - (int)(((long long)i * tiles) % RC_NPAIR) + RC_NPAIR) % RC_NPAIR;
+    if (first == 0 && (w % RC_PAIR) == 0) {     // this warp opens row i: noise of its candidates, patch level
       const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);   // utils.jl:4-5
       ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
       ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
       if (c.lane == 0) ss->rowP[buf] = Papplied;
     }
-    for (int tile = first; tile < tiles; tile += RC_BW) {
+    for (int tile = first; tile < tiles; tile += RC_NPAIR) {
       const long long T = (long long)i * tiles + tile;
       const int st = (int)(T % RC_NSTAGE);
       const unsigned k = (unsigned)(T / RC_NSTAGE);
@@ -1584,6 +1586,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
       __syncthreads();
       __syncthreads();
+      if (kp.gridbar) __syncthreads();
       if (c.cta->nact > 0) produce_rows(kp, c.stages, c.stage_bytes, c.cta);
       __syncthreads();
     }
@@ -1672,11 +1675,22 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
       c.cta->nact = nact; c.cta->issuer = issuer;
       if (iter != kp.it0 + 1)
         for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
-      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1)); c.cta->issued[s] = -1; }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_PAIR); c.cta->issued[s] = -1; }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // All CTAs start the scan together (they are co-resident): the chains then walk the rows of DL within a window
+    // that fits L2, so a row is fetched from HBM about once per sweep instead of once per CTA.
+    if (kp.gridbar) {
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(kp.gridbar, 1u);
+        const unsigned target = gridDim.x * (unsigned)(iter - kp.it0);
+        while (*(volatile unsigned*)kp.gridbar < target) __nanosleep(200);
+      }
+      __syncthreads();
+    }
     const long long ts0 = clock64();
     if (do_scan) full_scan(c, it);
     __syncthreads();
@@ -1722,6 +1736,19 @@ __global__ void k_tables(rc_params P, int n, double* LGA, double* LGZ, double* L
 
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G) {
   return cta_header_bytes() + (size_t)RC_NSTAGE * stage_bytes_for(n) + (size_t)G * chain_layout(n, cap, tiles, npad_max).total;
+}
+
+bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device) {
+  int nsm = 0, per = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  if (G == 2) {
+    cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<2>, RC_NTHR * 2 + 32, smem);
+  } else {
+    cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<1>, RC_NTHR + 32, smem);
+  }
+  return (nchains + G - 1) / G <= nsm * per;
 }
 
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st) {

@@ -47,10 +47,12 @@ struct rc_kparams {
   double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   long long* stats;     // [nchains][16] cycle counters (debug / profiling aid)
+  unsigned* gridbar;    // grid-wide arrival counter (zeroed before every launch) or null when the CTAs are not co-resident
   // standalone log-likelihood mode (rc_loglik): skip iterations, write loglik to out_ll[chain]
   int loglik_only;
 };
 
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st);
+bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);
