@@ -23,6 +23,8 @@ struct rc_sampler {
   int64_t nchains, chain_offset, numsamples;
   uint64_t seed;
   int cap, tiles, npad_max, G;
+  int device;                  // copied from the data handle: the sampler may be destroyed after it
+  int64_t n;
   size_t smem;
   // device
   double *LGA, *LGZ, *LOGN;
@@ -94,7 +96,7 @@ int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, dou
 
 void rc_sampler_destroy(rc_sampler* s) {
   if (!s) return;
-  cudaSetDevice(s->d->device);
+  cudaSetDevice(s->device);
   cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
   cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
   cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->WDbak); cudaFree(s->WLbak); cudaFree(s->labbak); cudaFree(s->szbak); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats); cudaFree(s->gridbar);
@@ -120,8 +122,12 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   if (cap < 2 || cap > RC_MAXCAP) { rc_set_error("slot_cap must be in 2..%d", RC_MAXCAP); return RC_ERR_ARG; }
   if (par->maxK < 0 || !(par->proposalsd_r > 0)) { rc_set_error("invalid hyperparameters (maxK < 0 or proposalsd_r <= 0)"); return RC_ERR_ARG; }
   const int tiles = (int)((n + RC_W - 1) / RC_W);
-  const int64_t npad = (((n + 7) & ~7LL) + 7LL * tiles * cap + 7) & ~7LL;   // every (tile, slot) run is padded by at most 7
-  if (npad > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
+  // permutation length: every (tile, slot) run is padded by at most 7 entries.  The worst case (all slots live in
+  // every tile) is reserved when it fits; otherwise the reserve shrinks to what shared memory allows (never below
+  // 32 slots' worth per tile) and a chain whose runs need more stops with RC_ERR_SLOTS.
+  const int64_t npad_full = (((n + 7) & ~7LL) + 7LL * tiles * cap + 7) & ~7LL;
+  const int64_t npad_min = (((n + 7) & ~7LL) + 7LL * tiles * std::min(cap, 32) + 7) & ~7LL;
+  if (npad_min > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(d->device));
   int maxsmem = 0, nsm = 0;
   RC_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
@@ -129,23 +135,26 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   // chains per CTA: the chains of a CTA share every staged row tile.  Use the smallest G that lets all
   // chains be co-resident (so they stay in rough lock step and share rows through L2 as well).
   int G = 0, forceG = 0;
+  int64_t npad = 0;
   if (const char* e = getenv("RCB200_CHAINS_PER_CTA")) forceG = atoi(e);   // test hook
   for (int g : {1, 2}) {
     if (forceG && g != forceG) continue;
-    const size_t sm = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, g);
+    int64_t np = std::min<int64_t>(npad_full, 65528);
+    while (np > npad_min && rc_sampler_smem_bytes((int)n, cap, tiles, (int)np, g) > (size_t)maxsmem) np -= 64;
+    const size_t sm = rc_sampler_smem_bytes((int)n, cap, tiles, (int)np, g);
     if (sm > (size_t)maxsmem) break;
-    G = g;
+    G = g; npad = np;
     const int64_t ctas = (nchains + g - 1) / g;
-    const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g)));
+    const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g + 32)));
     if (ctas <= (int64_t)nsm * per_sm) break;
   }
   if (G == 0) {
     rc_set_error("chain state needs %zu bytes of shared memory (> %d available): reduce n or slot_cap",
-                 rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, 1), maxsmem);
+                 rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad_min, 1), maxsmem);
     return RC_ERR_ARG;
   }
   const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G);
-  if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles, (long long)npad, G, smem, maxsmem, (long long)nchains);
+  if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld (full %lld) G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles, (long long)npad, (long long)npad_full, G, smem, maxsmem, (long long)nchains);
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
   std::vector<uint8_t> lab((size_t)nchains * n);
   std::vector<int> sizes((size_t)nchains * cap, 0);
@@ -166,7 +175,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
     }
   rc_sampler* s = new rc_sampler();
   memset(s, 0, sizeof(*s));
-  s->d = d; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
+  s->d = d; s->device = d->device; s->n = d->n; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
   s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem; s->G = G;
   s->numsamples = (opt->numiters - opt->burnin) / opt->thin;   // floor((numiters - burnin) / thin), types.jl:55
   const size_t NS = (size_t)std::max<int64_t>(s->numsamples, 1);
@@ -211,7 +220,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
 
 int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   if (!s) { rc_set_error("rc_sampler_run: null handle"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(s->d->device));
+  RC_CUDA(cudaSetDevice(s->device));
   int64_t it1 = iters < 0 ? s->opt.numiters : std::min<int64_t>(s->opt.numiters, s->iters_done + iters);
   if (it1 <= s->iters_done && s->W_ready) return RC_OK;
   rc_kparams kp;
@@ -251,8 +260,8 @@ int64_t rc_sampler_numsamples(const rc_sampler* s) { return s ? s->numsamples : 
 int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* labels, int64_t* K, double* r, double* p,
                                 double* loglik, double* logposterior) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_samples: bad handle or chain"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(s->d->device));
-  const int64_t n = s->d->n, S = s->numsamples;
+  RC_CUDA(cudaSetDevice(s->device));
+  const int64_t n = s->n, S = s->numsamples;
   if (S == 0) return RC_OK;
   if (labels) {
     std::vector<uint8_t> tmp((size_t)S * n);
@@ -273,7 +282,7 @@ int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* lab
 
 int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t* r_acc, uint8_t* sm_acc, uint8_t* sm_split) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_acceptances: bad handle or chain"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(s->d->device));
+  RC_CUDA(cudaSetDevice(s->device));
   const size_t ni = (size_t)s->opt.numiters, nm = ni * (size_t)s->opt.numMH;
   if (r_acc) RC_CUDA(cudaMemcpy(r_acc, s->r_acc + chain * ni, ni, cudaMemcpyDeviceToHost));
   if (sm_acc && nm) RC_CUDA(cudaMemcpy(sm_acc, s->sm_acc + chain * nm, nm, cudaMemcpyDeviceToHost));
@@ -283,8 +292,8 @@ int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t*
 
 int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_state: bad handle or chain"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(s->d->device));
-  const int64_t n = s->d->n;
+  RC_CUDA(cudaSetDevice(s->device));
+  const int64_t n = s->n;
   if (labels) {
     std::vector<uint8_t> tmp((size_t)n);
     RC_CUDA(cudaMemcpy(tmp.data(), s->labels + (size_t)chain * n, n, cudaMemcpyDeviceToHost));
@@ -299,14 +308,14 @@ int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* label
 // bulk waits, split-merge phases, ...; slot names in rc_sampler.cu).  out: nchains x 16 int64.
 int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out) {
   if (!s || !out) { rc_set_error("rc_sampler_copy_stats: null pointer"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(s->d->device));
+  RC_CUDA(cudaSetDevice(s->device));
   RC_CUDA(cudaMemcpy(out, s->stats, sizeof(long long) * 16 * s->nchains, cudaMemcpyDeviceToHost));
   return RC_OK;
 }
 
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_chain_status: bad handle or chain"); return RC_ERR_ARG; }
-  cudaSetDevice(s->d->device);
+  cudaSetDevice(s->device);
   int st = 0;
   if (cudaMemcpy(&st, s->status + chain, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return RC_ERR_CUDA;
   return st;
@@ -343,9 +352,9 @@ int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels,
 // internal accessors used by rc_post.cu
 const uint8_t* rc_sampler_dev_labels(const rc_sampler* s, int64_t* S, int64_t* n, int64_t* nchains, int* device) {
   if (S) *S = s->numsamples;
-  if (n) *n = s->d->n;
+  if (n) *n = s->n;
   if (nchains) *nchains = s->nchains;
-  if (device) *device = s->d->device;
+  if (device) *device = s->device;
   return s->out_labels;
 }
 

@@ -117,6 +117,7 @@ int finish_data(rc_data* d) {
   RC_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
   RC_CUDA(cudaMemset(maxbits, 0, 2 * sizeof(unsigned long long)));
   const int grid = 148 * 8;
+  (void)cudaGetLastError();   // drop any stale error of an unrelated earlier call
   k_scan<<<grid, 256>>>(d->D, n, flags, maxbits);
   RC_CUDA(cudaGetLastError());
   int hflags[2]; unsigned long long hbits[2];

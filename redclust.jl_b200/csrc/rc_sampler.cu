@@ -33,7 +33,7 @@ namespace {
 // tiles are being reduced while one more is in flight.  A warp revisits a stage only every RC_NSTAGE * RC_BW tiles and
 // mbarrier parity waits are only unambiguous one phase ahead, so the producer publishes the tile it issues into a stage
 // (CtaShared::issued) and a consumer waits for that to reach its tile before it waits on the stage's `full` barrier.
-#define RC_NSTAGE (RC_BW + 1)
+#define RC_NSTAGE (RC_BW + 2)
 #define RC_PAIR 1                    // bulk warps that reduce one tile together (RC_BW / RC_PAIR tiles are reduced at a time)
 #define RC_NPAIR (RC_BW / RC_PAIR)
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
@@ -211,9 +211,13 @@ __device__ void build_perm(const Ctx& c, int buf = 0) {
     }
     unsigned run = incl - s;
     for (int t = b; t < e; ++t) { c.runStart[t] = (unsigned short)run; run += (cnt[t] + 7u) & ~7u; }
-    if (tid == 31) c.runStart[E] = (unsigned short)incl;
+    if (tid == 31) {
+      c.runStart[E] = (unsigned short)incl;
+      if (incl > (unsigned)c.kp->npad_max) c.sc->status = RC_ERR_SLOTS;   // padding of the (tile, label) runs exceeds the reserve
+    }
   }
   tsync<BULK>(c);
+  if (c.sc->status) return;
   const int total = c.runStart[E];
   for (int t = tid; t <= c.tiles; t += NT) c.tileStart[t] = c.runStart[t == c.tiles ? E : t * c.cap] >> 3;
   // Every entry is a byte offset (column * 16, low 4 bits free); the chunk's label rides in the low nibbles of its
@@ -486,6 +490,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
     const long long tw0 = clock64();
     const int buf = i & 1;
     mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
+    if (c.sc->status) dead = true;
     const long long tw1 = clock64();
     acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
@@ -718,6 +723,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
   CtaShared* cs = c.cta;
   ScanShared* ss = c.ss;
   int Papplied = 0;
+  bool bdead = false;
   long long a_cons = 0, a_full = 0, a_red = 0, a_rows = 0, a_patch = 0;
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
@@ -737,6 +743,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
         __threadfence_block();
         bsync(c);
         build_perm<true>(c, buf);
+        if (c.sc->status) bdead = true;         // the rebuilt permutation does not fit: the chain stops (tiles are still consumed)
         if (c.ctid == 0) { c.sc->rebuild = 0; ss->prebuilt = ss->M; st_add(c, ST_REBUILDS, 1); }
         bsync(c);
         Papplied = ss->prebuilt;
@@ -761,7 +768,8 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
       while (cs->issued[st] != T) __nanosleep(20);           // the stage has moved on to tile T (see RC_NSTAGE)
       mbar_wait(&cs->full[st], k & 1u);
       const long long tf1 = clock64();
-      reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)st * c.stage_bytes), tile, part);
+      if (!bdead) reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)st * c.stage_bytes), tile, part);
+      __syncwarp();
       if (c.lane == 0) mbar_arrive(&cs->empty[st]);
       a_full += tf1 - tf0; a_red += clock64() - tf1;
     }
@@ -1297,6 +1305,11 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     // row sums by slot of every member of S u {i, j} under the launch labels (all slots are needed for the
     // block sums of the proposed state)
     build_perm<false>(c);
+    if (c.sc->status) {                                      // does not fit: undo the in-place launch labels and stop the chain
+      for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+      csync(c);
+      return;
+    }
     for (int pos = 0; pos < nS + 2; ++pos) {
       reduce_row_global(c, c.Slist[pos]);
       csync(c);
@@ -1606,7 +1619,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     }
     csync(c);
     build_perm<false>(c);
-    if (kp.init_W) init_W(c);
+    if (kp.init_W && c.sc->status == 0) init_W(c);
     if (kp.loglik_only) {
       const double ll = loglik_eval(c, c.sizes);
       if (tid == 0) kp.out_ll[chain] = ll;
@@ -1663,7 +1676,10 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
         }
         csync(c);
       }
-      if (do_scan) build_perm<false>(c);   // the scan's last moves / the proposal's launch labels are not in it
+      if (do_scan) {
+        build_perm<false>(c);              // the scan's last moves / the proposal's launch labels are not in it
+        if (c.sc->status) do_scan = false;
+      }
     }
     // ---- CTA level: agree on the chains that scan, (re)arm the tile ring ----
     if (tid == 0) c.cta->active[cl] = do_scan ? 1 : 0;
