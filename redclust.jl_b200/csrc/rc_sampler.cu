@@ -806,7 +806,39 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
   }
 }
 
-__device__ void full_scan(const Ctx& c, unsigned it) {
+// Block sums from scratch as a scan without decisions: the decision warp's place is taken by this loop, which adds the
+// row sums of row x to W[k][t], k = label of x, for the slots t >= k (every unordered pair of slots is counted once).
+__device__ void initw_loop(const Ctx& c) {
+  ScanShared* ss = c.ss;
+  const int lane = c.lane, cap = c.cap;
+  for (int i = 0; i < c.n; ++i) {
+    const int buf = i & 1;
+    const int k = c.lab[i];
+    mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
+    longlong2 b[RC_NS];
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      const int t = w * 32 + lane;
+      b[w] = (t < cap && t >= k) ? bin_total(c, t, buf) : make_longlong2(0, 0);
+    }
+    if (lane == 0) ss->msnap[buf] = 0;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ss->consumed[buf]);
+#pragma unroll
+    for (int w = 0; w < RC_NS; ++w) {
+      const int t = w * 32 + lane;
+      if (b[w].x != 0 || b[w].y != 0) {
+        const int ix = k * cap + t;
+        rc_i128 a = c.WD[ix]; rc_add128(a, b[w].x); c.WD[ix] = a;
+        rc_i128 d = c.WL[ix]; rc_add128(d, b[w].y); c.WL[ix] = d;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// mode 0: the Gibbs scan; mode 1: block-sum initialisation (same row pipeline, no decisions)
+__device__ void full_scan(const Ctx& c, unsigned it, int mode = 0) {
   ScanShared* ss = c.ss;
   if (c.ctid == 0) {
     if (ss->inited)
@@ -818,7 +850,8 @@ __device__ void full_scan(const Ctx& c, unsigned it) {
   }
   csync(c);
   if (c.cwarp < RC_BW) bulk_loop(c, it);
-  else decide_loop(c, it);
+  else if (mode == 0) decide_loop(c, it);
+  else initw_loop(c);
   csync(c);
   // moves published after the last patch pass are not in the permutation: the next user rebuilds it
   if (c.cwarp == 0) {                                                       // :254
@@ -830,27 +863,13 @@ __device__ void full_scan(const Ctx& c, unsigned it) {
   csync(c);
 }
 
-// Block sums from scratch: W[k][t] = sum_{x in k, y in t} DL[x][y]  (n row reductions).
-__device__ void init_W(const Ctx& c) {
+// Block sums from scratch: W[k][t] = sum_{x in k, y in t} DL[x][y].  Zeroed here, accumulated by a scan pass in mode 1.
+__device__ void zero_W(const Ctx& c) {
   for (int t = c.ctid; t < c.cap * c.cap; t += RC_NTHR) {
     rc_i128 z; z.lo = 0; z.hi = 0;
     c.WD[t] = z; c.WL[t] = z;
   }
   csync(c);
-  for (int x = 0; x < c.n; ++x) {
-    reduce_row_global(c, x);
-    csync(c);
-    const int k = c.lab[x];
-    for (int t = k + c.ctid; t < c.cap; t += RC_NTHR) {
-      const longlong2 b = bin_total(c, t);
-      if (b.x != 0 || b.y != 0) {
-        const int ix = k * c.cap + t;
-        rc_i128 a = c.WD[ix]; rc_add128(a, b.x); c.WD[ix] = a;
-        rc_i128 d = c.WL[ix]; rc_add128(d, b.y); c.WL[ix] = d;
-      }
-    }
-    csync(c);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1592,17 +1611,19 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
 
   // zero slots behind every stage (padding entries of the permutation point there)
   if (is_producer) {   // mirrors the CTA-level barrier sequence of the chain warps below
-    if (kp.loglik_only) return;
     for (int t = threadIdx.x & 31; t < RC_NSTAGE * 8; t += 32)
       reinterpret_cast<longlong2*>(c.stages + (size_t)(t / 8) * c.stage_bytes + (size_t)c.dummy)[t % 8] = make_longlong2(0, 0);
     __syncthreads();
-    for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
+    auto mirror = [&](bool grid) {
       __syncthreads();
       __syncthreads();
-      if (kp.gridbar) __syncthreads();
+      if (grid) __syncthreads();
       if (c.cta->nact > 0) produce_rows(kp, c.stages, c.stage_bytes, c.cta);
       __syncthreads();
-    }
+    };
+    if (kp.init_W) mirror(false);
+    if (kp.loglik_only) return;
+    for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) mirror(kp.gridbar != nullptr);
     return;
   }
   if (valid) {   // load the chain's state
@@ -1619,14 +1640,47 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     }
     csync(c);
     build_perm<false>(c);
-    if (kp.init_W && c.sc->status == 0) init_W(c);
-    if (kp.loglik_only) {
+    if (kp.init_W && c.sc->status == 0) zero_W(c);
+  }
+  __syncthreads();
+  // ---- CTA level: agree on the chains that scan, (re)arm the tile ring, run the row pipeline ----
+  bool rings_used = false;
+  auto cta_scan = [&](bool do_scan, unsigned it, int mode, unsigned epoch) {
+    if (tid == 0) c.cta->active[cl] = do_scan ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int nact = 0;
+      for (int q = 0; q < G; ++q) nact += c.cta->active[q] ? 1 : 0;
+      c.cta->nact = nact;
+      if (rings_used)
+        for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
+      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_PAIR); c.cta->issued[s] = -1; }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    rings_used = true;
+    __syncthreads();
+    // experiment (RCB200_GRIDBAR): all CTAs start the scan together
+    if (kp.gridbar && mode == 0) {
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(kp.gridbar, 1u);
+        const unsigned target = gridDim.x * epoch;
+        while (*(volatile unsigned*)kp.gridbar < target) __nanosleep(200);
+      }
+      __syncthreads();
+    }
+    if (do_scan) full_scan(c, it, mode);
+    __syncthreads();
+  };
+  if (kp.init_W) cta_scan(valid && c.sc->status == 0, 0u, 1, 0u);
+  if (kp.loglik_only) {
+    if (valid) {
       const double ll = loglik_eval(c, c.sizes);
       if (tid == 0) kp.out_ll[chain] = ll;
     }
+    return;
   }
-  if (kp.loglik_only) return;
-  __syncthreads();
 
   for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
     const unsigned it = (unsigned)iter;
@@ -1681,35 +1735,8 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
         if (c.sc->status) do_scan = false;
       }
     }
-    // ---- CTA level: agree on the chains that scan, (re)arm the tile ring ----
-    if (tid == 0) c.cta->active[cl] = do_scan ? 1 : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int nact = 0, issuer = -1;
-      for (int q = 0; q < G; ++q)
-        if (c.cta->active[q]) { if (issuer < 0) issuer = q; ++nact; }
-      c.cta->nact = nact; c.cta->issuer = issuer;
-      if (iter != kp.it0 + 1)
-        for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
-      for (int s = 0; s < RC_NSTAGE; ++s) { mbar_init(&c.cta->full[s], 1); mbar_init(&c.cta->empty[s], (unsigned)max(nact, 1) * RC_PAIR); c.cta->issued[s] = -1; }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    // All CTAs start the scan together (they are co-resident): the chains then walk the rows of DL within a window
-    // that fits L2, so a row is fetched from HBM about once per sweep instead of once per CTA.
-    if (kp.gridbar) {
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(kp.gridbar, 1u);
-        const unsigned target = gridDim.x * (unsigned)(iter - kp.it0);
-        while (*(volatile unsigned*)kp.gridbar < target) __nanosleep(200);
-      }
-      __syncthreads();
-    }
     const long long ts0 = clock64();
-    if (do_scan) full_scan(c, it);
-    __syncthreads();
+    cta_scan(do_scan, it, 0, (unsigned)(iter - kp.it0));
     const long long ts1 = clock64();
     if (valid && tid == 0) st_add(c, ST_SCAN_TOTAL, ts1 - ts0);
     if (alive) alive = c.sc->status == 0;
