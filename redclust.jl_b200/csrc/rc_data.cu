@@ -1,6 +1,8 @@
 // rc_data.cu -- MCMCData on the device: validation, log D, fixed-point images, Euclidean distance
 // matrix.  Replaces /root/reference/src/types.jl:145-162 and the pairwise(Euclidean(), X, dims=2)
 // call sites (src/types.jl:160, src/utils.jl:144-145, src/prior.jl:51,180).
+#include <stdlib.h>
+#include <string.h>
 #include "rc_common.cuh"
 
 namespace {
@@ -109,6 +111,56 @@ __global__ void __launch_bounds__(256) k_distm(const double* __restrict__ X, con
   }
 }
 
+// FP64 tensor-core variant (RCB200_DISTM=dmma): the Gram block X_i X_j^T is accumulated with
+// mma.sync.aligned.m8n8k4.row.col.f64 (DMMA; tcgen05 has no f64 kind).  32x32 output tile per CTA of 4 warps, warp w
+// owns rows 8w..8w+7 and the four 8-column blocks; operands are staged through shared memory in chunks of 32
+// coordinates.  The summation order differs from the sequential kernel above (k-blocks of 4, fused multiply-add inside
+// the tensor core), so this path is checked to 1e-10 relative instead of bit-exactly; symmetry and the zero diagonal
+// stay exact (upper triangle mirrored).
+__global__ void __launch_bounds__(128) k_distm_dmma(const double* __restrict__ X, const double* __restrict__ sq, int64_t dim,
+                                                     int64_t n, double* __restrict__ D) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  __shared__ double Xi[DT][DT + 1], Xj[DT][DT + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;       // fragment row (A) / column (B), k index
+  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+  const int64_t i0 = (int64_t)bi * DT, j0 = (int64_t)bj * DT;
+  for (int64_t t0 = 0; t0 < dim; t0 += DT) {
+    for (int e = threadIdx.x; e < DT * DT; e += 128) {
+      const int r = e / DT, t = e % DT;
+      Xi[r][t] = (i0 + r < n && t0 + t < dim) ? X[(i0 + r) * dim + t0 + t] : 0.0;
+      Xj[r][t] = (j0 + r < n && t0 + t < dim) ? X[(j0 + r) * dim + t0 + t] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < DT; k += 4) {
+      const double a = Xi[8 * warp + fr][k + fk];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const double b = Xj[8 * nt + fr][k + fk];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(c0[nt]), "+d"(c1[nt]) : "d"(a), "d"(b));
+      }
+    }
+    __syncthreads();
+  }
+  // C fragment: lane holds C[row = lane / 4][col = 2 * (lane % 4) + {0, 1}]
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t i = i0 + 8 * warp + fr, j = j0 + 8 * nt + 2 * fk + h;
+      if (i >= n || j >= n) continue;
+      if (i == j) { D[i * n + i] = 0.0; continue; }
+      if (j < i) continue;
+      const double v = sq[i] + sq[j] - 2 * (h ? c1[nt] : c0[nt]);
+      const double r = sqrt(v > 0.0 ? v : 0.0);
+      D[i * n + j] = r;
+      D[j * n + i] = r;
+    }
+}
+
 int finish_data(rc_data* d) {
   const int64_t n = d->n;
   int* flags = nullptr; unsigned long long* maxbits = nullptr;
@@ -194,7 +246,9 @@ int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t dev
   cudaMemcpy(dX, X, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice);
   k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
   const unsigned nb = (unsigned)((n + DT - 1) / DT);
-  k_distm<<<dim3(nb, nb), 256>>>(dX, sq, dim, n, d->D);
+  const char* mode = getenv("RCB200_DISTM");
+  if (mode && !strcmp(mode, "dmma")) k_distm_dmma<<<dim3(nb, nb), 128>>>(dX, sq, dim, n, d->D);
+  else k_distm<<<dim3(nb, nb), 256>>>(dX, sq, dim, n, d->D);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(dX); cudaFree(sq);
   if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); rc_data_destroy(d); return RC_ERR_CUDA; }

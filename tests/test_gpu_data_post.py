@@ -115,3 +115,20 @@ def test_statistical_agreement_with_independent_streams(pkg, orc, golden):
     oK = np.concatenate(oK); opsm = ocnt / (nch * (iters - burn))
     assert abs(gK.mean() - oK.mean()) < 0.6
     assert np.abs(gpsm - opsm).mean() < 0.03
+
+
+def test_distance_matrix_fp64_tensor_core_path(pkg, orc, golden, monkeypatch):
+    """RCB200_DISTM=dmma: Gram block on the FP64 tensor cores (mma.sync m8n8k4 f64).  Different summation order than
+    the oracle, so 1e-10 relative (north-star tolerance); symmetry and zero diagonal stay exact."""
+    monkeypatch.setenv("RCB200_DISTM", "dmma")
+    for k in (1, 2, 3):
+        pts, ref = golden[k]["points"], golden[k]["distance_matrix"]
+        D = pkg.MCMCData.from_points(pts).D
+        assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+        off = ~np.eye(100, dtype=bool)
+        assert (np.abs(D[off] - ref[off]) / ref[off]).max() < 1e-10
+    X = np.random.default_rng(1).normal(size=(1000, 77))
+    D = pkg.MCMCData.from_points(X).D
+    ref = orc.distm(X)
+    off = ~np.eye(1000, dtype=bool)
+    assert np.array_equal(D, D.T) and (np.abs(D[off] - ref[off]) / ref[off]).max() < 1e-10
