@@ -6,8 +6,17 @@
 // The reference materialises S dense n x n Bool matrices; here the label matrix is transposed once
 // (point-major, samples contiguous) and co-clustering counts are byte-compare popcounts -- exact integers.
 #include <vector>
+#include <thread>
+#include <chrono>
+#include <atomic>
 #include <algorithm>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include "rc_common.cuh"
+
+int rc_psm_counts_tc(const uint8_t* Lt, int64_t n, int64_t Rpad, int64_t R, int kmax, int* counts, cudaStream_t st);
+double rc_psm_tc_macs(int64_t n, int64_t R, int kmax);
 
 extern "C" const uint8_t* rc_sampler_dev_labels(const rc_sampler* s, int64_t* S, int64_t* n, int64_t* nchains, int* device);
 
@@ -86,61 +95,122 @@ __global__ void __launch_bounds__(256) k_psm_counts(const uint8_t* __restrict__ 
     }
 }
 
-__global__ void k_counts_to_psm(const int* __restrict__ counts, int64_t total, double denom, double* __restrict__ out) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
-    out[t] = (double)counts[t] / denom;
+__global__ void k_maxlabel(const uint8_t* __restrict__ L, size_t total, int* __restrict__ out) {
+  unsigned m = 0;
+  const uint4* L4 = reinterpret_cast<const uint4*>(L);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total / 16; t += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = L4[t];
+    m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+  }
+  m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+  for (int off = 16; off; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (int)m);
 }
 
+// Co-clustering counts of R label vectors (device, sample-major).  Default: the tensor-core kernel of
+// rc_psm_tc.cu (labels up to 128); RCB200_PSM=compare or more labels: the byte-compare kernel.  Both are exact.
 int psm_counts_device(const uint8_t* L, int64_t R, int64_t n, int* counts) {
   const int64_t Rpad = (R + 63) & ~63LL;
-  uint8_t* Lt = nullptr;
+  uint8_t* Lt = nullptr; int* dmax = nullptr;
   RC_CUDA(cudaMalloc(&Lt, (size_t)n * Rpad));
+  if (cudaMalloc(&dmax, sizeof(int)) != cudaSuccess) { cudaFree(Lt); rc_set_error("out of device memory"); return RC_ERR_CUDA; }
+  cudaMemset(dmax, 0, sizeof(int));
   dim3 tb(32, 8), tg((unsigned)((n + 31) / 32), (unsigned)((Rpad + 31) / 32));
   k_transpose<<<tg, tb>>>(L, R, n, Rpad, Lt);
-  const unsigned nb = (unsigned)((n + PT - 1) / PT);
-  k_psm_counts<<<dim3(nb, nb), 256>>>(Lt, n, Rpad, R, counts);
-  cudaError_t e = cudaDeviceSynchronize();
+  k_maxlabel<<<148 * 4, 256>>>(Lt, (size_t)n * Rpad, dmax);     // n * Rpad is a multiple of 64
+  int kmax = 0;
+  cudaError_t e = cudaMemcpy(&kmax, dmax, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dmax);
+  if (e != cudaSuccess) { cudaFree(Lt); RC_CUDA(e); }
+  const char* mode = getenv("RCB200_PSM");
+  const bool tc = kmax <= 128 && !(mode && !strcmp(mode, "compare"));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool verbose = getenv("RCB200_VERBOSE") != nullptr;
+  if (verbose) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, 0); }
+  int st = RC_OK;
+  if (tc) st = rc_psm_counts_tc(Lt, n, Rpad, R, kmax, counts, 0);
+  else {
+    const unsigned nb = (unsigned)((n + PT - 1) / PT);
+    k_psm_counts<<<dim3(nb, nb), 256>>>(Lt, n, Rpad, R, counts);
+  }
+  if (verbose) cudaEventRecord(e1, 0);
+  e = cudaDeviceSynchronize();
+  if (verbose) {
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double macs = tc ? rc_psm_tc_macs(n, R, kmax) : 0.0;
+    fprintf(stderr, "[rcb200] psm counts: n=%lld samples=%lld kmax=%d kernel=%s %.3f ms  %.3e label compares/s  tensor %.1f TOP/s\n",
+            (long long)n, (long long)R, kmax, tc ? "tcgen05-i8" : "byte-compare", ms, (double)n * n * R / (ms * 1e-3), 2 * macs / (ms * 1e-3) * 1e-12);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   cudaFree(Lt);
+  if (st) return st;
   RC_CUDA(e);
   return RC_OK;
 }
 
 // ---- MPEL ----------------------------------------------------------------------------------------
-// One CTA per pair (i < j): contingency table in shared memory (packed 16-bit counters), then the loss.
+// One CTA per (i, block of PJ columns j > i): sample i's labels are staged once, then for every j the
+// contingency table is built in shared memory (packed 16-bit counters, shared-memory atomics) and reduced to the
+// loss.  Points are visited lane-spread (lane l walks segment l of the label vector), so the 32 lanes of an
+// atomic hit different table cells even when cluster members are contiguous; N log N comes from a table.
+#define PJ 8
+__global__ void k_nlogn(int64_t n, double* __restrict__ out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t <= n) out[t] = t ? (double)t * log((double)t) : 0.0;
+}
+__device__ __forceinline__ unsigned tab_get(const unsigned* tab, int t, int wide) {
+  return wide ? tab[t] : ((tab[t >> 1] >> ((t & 1) * 16)) & 0xffffu);
+}
 __global__ void __launch_bounds__(256) k_pair_loss(const uint8_t* __restrict__ L, const int* __restrict__ Kc, int64_t S,
-                                                   int64_t n, int loss, int wide, double* __restrict__ M) {
-  const int64_t i = blockIdx.y, j = blockIdx.x;
-  if (j <= i) return;
-  extern __shared__ unsigned tab[];
-  const int Ki = Kc[i], Kj = Kc[j];
-  const int cells = Ki * Kj;
-  const int nwords = wide ? cells : (cells + 1) / 2;
-  for (int t = threadIdx.x; t < nwords; t += blockDim.x) tab[t] = 0;
-  __syncthreads();
-  const uint8_t* a = L + i * n; const uint8_t* b = L + j * n;
-  for (int64_t x = threadIdx.x; x < n; x += blockDim.x) {
-    const int cell = (int)(a[x] - 1) * Kj + (int)(b[x] - 1);
-    if (wide) atomicAdd(&tab[cell], 1u);
-    else atomicAdd(&tab[cell >> 1], (cell & 1) ? 0x10000u : 1u);
-  }
-  __syncthreads();
-  // sums over the table: t2 = sum N^2, snl = sum N log N; margins via row / column passes
-  double t2 = 0, snl = 0, nis = 0, njs = 0, hA = 0, hB = 0;
-  const double dn = (double)n;
-  for (int t = threadIdx.x; t < cells; t += blockDim.x) {
-    const unsigned c = wide ? tab[t] : ((tab[t >> 1] >> ((t & 1) * 16)) & 0xffffu);
-    if (c) { const double d = (double)c; t2 += d * d; snl += d * log(d); }
-  }
-  for (int r = threadIdx.x; r < Ki + Kj; r += blockDim.x) {
-    unsigned s = 0;
-    if (r < Ki) { for (int q = 0; q < Kj; ++q) { const int t = r * Kj + q; s += wide ? tab[t] : ((tab[t >> 1] >> ((t & 1) * 16)) & 0xffffu); } }
-    else { const int q = r - Ki; for (int p = 0; p < Ki; ++p) { const int t = p * Kj + q; s += wide ? tab[t] : ((tab[t >> 1] >> ((t & 1) * 16)) & 0xffffu); } }
-    if (s) {
-      const double d = (double)s;
-      if (r < Ki) { nis += d * d; hA += d * log(d); } else { njs += d * d; hB += d * log(d); }
-    }
-  }
+                                                   int64_t n, int loss, int wide, int tabwords, int stride,
+                                                   const double* __restrict__ nlogn, double* __restrict__ M) {
+  const int64_t i = blockIdx.y;
+  const int64_t jlo = max((long long)(i + 1), (long long)blockIdx.x * PJ), jhi = min((long long)S, (long long)(blockIdx.x + 1) * PJ);
+  if (jlo >= jhi) return;
+  extern __shared__ __align__(16) unsigned tab[];
+  const int64_t nv = (n + 15) / 16;                       // 16-byte vectors per label vector
+  uint8_t* la = reinterpret_cast<uint8_t*>(tab + tabwords);
+  uint8_t* lb = la + nv * 16;
   __shared__ double red[6][8];
+  const bool vec = (n % 16) == 0;                          // rows of L are 16-byte aligned only then
+  auto stage = [&](uint8_t* dst, const uint8_t* src) {
+    if (vec) for (int64_t t = threadIdx.x; t < nv; t += blockDim.x) reinterpret_cast<uint4*>(dst)[t] = reinterpret_cast<const uint4*>(src)[t];
+    else for (int64_t t = threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
+  };
+  stage(la, L + i * n);
+  const int Ki = Kc[i];
+  const double dn = (double)n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t j = jlo; j < jhi; ++j) {
+    const int Kj = Kc[j];
+    const int cells = Ki * Kj;
+    const int nwords = wide ? cells : (cells + 1) / 2;
+    __syncthreads();                                       // previous j has finished with tab / lb / red
+    for (int t = threadIdx.x; t < nwords; t += blockDim.x) tab[t] = 0;
+    stage(lb, L + j * n);
+    __syncthreads();
+    for (int w = wid; w < stride; w += 8) {
+      const int64_t x = (int64_t)lane * stride + w;
+      if (x < n) {
+        const int cell = (int)(la[x] - 1) * Kj + (int)(lb[x] - 1);
+        if (wide) atomicAdd(&tab[cell], 1u);
+        else atomicAdd(&tab[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+      }
+    }
+    __syncthreads();
+    // sums over the table: t2 = sum N^2, snl = sum N log N; margins via row / column passes
+    double t2 = 0, snl = 0, nis = 0, njs = 0, hA = 0, hB = 0;
+    for (int t = threadIdx.x; t < cells; t += blockDim.x) {
+      const unsigned c = tab_get(tab, t, wide);
+      const double d = (double)c; t2 += d * d; snl += nlogn[c];
+    }
+    for (int r = threadIdx.x; r < Ki + Kj; r += blockDim.x) {
+      unsigned sm = 0;
+      if (r < Ki) { for (int q = 0; q < Kj; ++q) sm += tab_get(tab, r * Kj + q, wide); }
+      else { const int q = r - Ki; for (int pp = 0; pp < Ki; ++pp) sm += tab_get(tab, pp * Kj + q, wide); }
+      const double d = (double)sm;
+      if (r < Ki) { nis += d * d; hA += nlogn[sm]; } else { njs += d * d; hB += nlogn[sm]; }
+    }
   double v[6] = {t2, snl, nis, njs, hA, hB};
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -167,6 +237,7 @@ __global__ void __launch_bounds__(256) k_pair_loss(const uint8_t* __restrict__ L
     M[i * S + j] = out;
     M[j * S + i] = out;
   }
+  }
 }
 
 __global__ void k_colsum(const double* __restrict__ M, int64_t S, double* __restrict__ sums) {
@@ -178,6 +249,44 @@ __global__ void k_colsum(const double* __restrict__ M, int64_t S, double* __rest
 }
 
 }  // namespace
+
+// D2H of the counts as int32 through two pinned staging buffers; host threads turn each chunk into counts / denom
+// (fp64) while the next chunk is in flight -- half the PCIe bytes of an fp64 copy and no pageable-memory bounce.
+static int counts_to_host_psm(const int* counts, size_t total, double denom, double* out) {
+  const size_t CH = (size_t)8 << 20;                       // entries per chunk (32 MB)
+  int* stage[2] = {nullptr, nullptr};
+  cudaStream_t st; cudaEvent_t ev[2];
+  RC_CUDA(cudaStreamCreate(&st));
+  for (int b = 0; b < 2; ++b) { RC_CUDA(cudaMallocHost(&stage[b], sizeof(int) * std::min(CH, total))); RC_CUDA(cudaEventCreate(&ev[b])); }
+  const size_t nch = (total + CH - 1) / CH;
+  const int nthr = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  cudaError_t e = cudaSuccess;
+  for (size_t c = 0; c <= nch && e == cudaSuccess; ++c) {
+    if (c < nch) {
+      const size_t off = c * CH, len = std::min(CH, total - off);
+      e = cudaMemcpyAsync(stage[c & 1], counts + off, sizeof(int) * len, cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ev[c & 1], st);
+    }
+    if (c > 0) {
+      const size_t off = (c - 1) * CH, len = std::min(CH, total - off);
+      cudaError_t e2 = cudaEventSynchronize(ev[(c - 1) & 1]);
+      if (e2 != cudaSuccess) { e = e2; break; }
+      const int* src = stage[(c - 1) & 1];
+      auto body = [&](int w) {
+        const size_t lo = len * w / nthr, hi = len * (w + 1) / nthr;
+        for (size_t t = lo; t < hi; ++t) out[off + t] = (double)src[t] / denom;
+      };
+      std::vector<std::thread> pool;
+      for (int w = 1; w < nthr; ++w) pool.emplace_back(body, w);
+      body(0);
+      for (auto& t : pool) t.join();
+    }
+  }
+  for (int b = 0; b < 2; ++b) { cudaFreeHost(stage[b]); cudaEventDestroy(ev[b]); }
+  cudaStreamDestroy(st);
+  RC_CUDA(e);
+  return RC_OK;
+}
 
 extern "C" {
 
@@ -196,41 +305,62 @@ int32_t rc_sampler_psm(const rc_sampler* s, int64_t chain0, int64_t nch, double*
   int64_t S, n, nchains; int device;
   rc_sampler_dev_labels(s, &S, &n, &nchains, &device);
   RC_CUDA(cudaSetDevice(device));
-  int* counts = nullptr; double* out = nullptr;
+  int* counts = nullptr;
   RC_CUDA(cudaMalloc(&counts, sizeof(int) * (size_t)n * n));
   int st = rc_sampler_psm_counts_dev(s, chain0, nch, counts);
-  if (st) { cudaFree(counts); return st; }
-  if (cudaMalloc(&out, sizeof(double) * (size_t)n * n) != cudaSuccess) { cudaFree(counts); rc_set_error("out of device memory"); return RC_ERR_CUDA; }
-  k_counts_to_psm<<<148 * 8, 256>>>(counts, n * n, (double)(nch * S), out);   // ./ numsamples (0/0 = NaN if no samples)
-  cudaError_t e = cudaMemcpy(psm_out, out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
-  cudaFree(counts); cudaFree(out);
-  RC_CUDA(e);
-  return RC_OK;
+  if (!st) st = counts_to_host_psm(counts, (size_t)n * n, (double)(nch * S), psm_out);   // ./ numsamples (0/0 = NaN if no samples)
+  cudaFree(counts);
+  return st;
 }
 
-// first-appearance relabelling of host label vectors to 1..K (sortlabels, utils.jl:69-74) as bytes
+// first-appearance relabelling of host label vectors to 1..K (sortlabels, utils.jl:69-74) as bytes.  Samples are
+// independent: they are split over host threads.  Labels in a narrow range (the usual 1..K) go through a direct
+// table, anything else through a sort.
+static int compact_one(const int64_t* l, int64_t n, uint8_t* out, int* Kout, std::vector<int>& table,
+                       std::vector<std::pair<int64_t, int64_t>>& tmp) {
+  int64_t lo = l[0], hi = l[0];
+  for (int64_t x = 1; x < n; ++x) { lo = std::min(lo, l[x]); hi = std::max(hi, l[x]); }
+  if (hi - lo < (int64_t)1 << 20) {
+    table.assign((size_t)(hi - lo + 1), 0);
+    int K = 0;
+    for (int64_t x = 0; x < n; ++x) {
+      int& id = table[(size_t)(l[x] - lo)];
+      if (!id) { if (K == 255) return -1; id = ++K; }
+      out[x] = (uint8_t)id;
+    }
+    *Kout = K;
+    return 0;
+  }
+  tmp.resize((size_t)n);
+  for (int64_t x = 0; x < n; ++x) tmp[x] = {l[x], x};
+  std::sort(tmp.begin(), tmp.end());
+  std::vector<std::pair<int64_t, int64_t>> firsts;     // (first position, label)
+  for (int64_t x = 0; x < n; ++x) if (x == 0 || tmp[x].first != tmp[x - 1].first) firsts.push_back({tmp[x].second, tmp[x].first});
+  std::sort(firsts.begin(), firsts.end());
+  if (firsts.size() > 255) return -1;
+  *Kout = (int)firsts.size();
+  std::vector<std::pair<int64_t, int>> map;             // label -> id
+  for (size_t q = 0; q < firsts.size(); ++q) map.push_back({firsts[q].second, (int)q + 1});
+  std::sort(map.begin(), map.end());
+  for (int64_t x = 0; x < n; ++x) out[x] = (uint8_t)std::lower_bound(map.begin(), map.end(), std::make_pair(l[x], 0))->second;
+  return 0;
+}
+
 static int compact_labels(const int64_t* labels, int64_t S, int64_t n, std::vector<uint8_t>& out, std::vector<int>& K) {
   out.resize((size_t)S * n); K.resize((size_t)S);
-  std::vector<std::pair<int64_t, int64_t>> tmp((size_t)n);
-  std::vector<int64_t> ids((size_t)n);
-  for (int64_t s = 0; s < S; ++s) {
-    const int64_t* l = labels + s * n;
-    for (int64_t x = 0; x < n; ++x) tmp[x] = {l[x], x};
-    std::sort(tmp.begin(), tmp.end());
-    // first appearance position of every distinct label
-    std::vector<std::pair<int64_t, int64_t>> firsts;   // (first position, label)
-    for (int64_t x = 0; x < n; ++x) if (x == 0 || tmp[x].first != tmp[x - 1].first) firsts.push_back({tmp[x].second, tmp[x].first});
-    std::sort(firsts.begin(), firsts.end());
-    if (firsts.size() > 255) { rc_set_error("more than 255 clusters in sample %lld", (long long)s); return RC_ERR_SLOTS; }
-    K[s] = (int)firsts.size();
-    std::vector<std::pair<int64_t, int>> map;           // label -> id
-    for (size_t q = 0; q < firsts.size(); ++q) map.push_back({firsts[q].second, (int)q + 1});
-    std::sort(map.begin(), map.end());
-    for (int64_t x = 0; x < n; ++x) {
-      auto it = std::lower_bound(map.begin(), map.end(), std::make_pair(l[x], 0));
-      out[s * n + x] = (uint8_t)it->second;
-    }
-  }
+  const int64_t work = S * n;
+  const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, work / (1 << 20), S}));
+  std::atomic<int64_t> bad(-1);
+  auto body = [&](int w) {
+    std::vector<int> table; std::vector<std::pair<int64_t, int64_t>> tmp;
+    for (int64_t s = w; s < S; s += nthr)
+      if (compact_one(labels + s * n, n, out.data() + s * n, &K[s], table, tmp)) { int64_t e = -1; bad.compare_exchange_strong(e, s); }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nthr; ++w) pool.emplace_back(body, w);
+  body(0);
+  for (auto& t : pool) t.join();
+  if (bad.load() >= 0) { rc_set_error("more than 255 clusters in sample %lld", (long long)bad.load()); return RC_ERR_SLOTS; }
   return RC_OK;
 }
 
@@ -239,21 +369,22 @@ int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, doub
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
   RC_CUDA(cudaSetDevice(device));
+  const bool verbose = getenv("RCB200_VERBOSE") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   std::vector<uint8_t> L; std::vector<int> K;
   int st = compact_labels(labels, S, n, L, K);
   if (st) return st;
-  uint8_t* dL = nullptr; int* counts = nullptr; double* out = nullptr;
+  const double t1 = now();
+  uint8_t* dL = nullptr; int* counts = nullptr;
   RC_CUDA(cudaMalloc(&dL, L.size()));
   RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
-  RC_CUDA(cudaMalloc(&counts, sizeof(int) * (size_t)n * n));
+  if (cudaMalloc(&counts, sizeof(int) * (size_t)n * n) != cudaSuccess) { cudaFree(dL); rc_set_error("out of device memory"); return RC_ERR_CUDA; }
   st = psm_counts_device(dL, S, n, counts);
-  if (!st) {
-    RC_CUDA(cudaMalloc(&out, sizeof(double) * (size_t)n * n));
-    k_counts_to_psm<<<148 * 8, 256>>>(counts, n * n, (double)S, out);
-    cudaError_t e = cudaMemcpy(psm_out, out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { rc_set_error("rc_psm: %s", cudaGetErrorString(e)); st = RC_ERR_CUDA; }
-  }
-  cudaFree(dL); cudaFree(counts); cudaFree(out);
+  const double t2 = now();
+  if (!st) st = counts_to_host_psm(counts, (size_t)n * n, (double)S, psm_out);
+  cudaFree(dL); cudaFree(counts);
+  if (verbose) fprintf(stderr, "[rcb200] rc_psm: relabel %.3f s, upload + counts %.3f s, download + divide %.3f s\n", t1 - t0, t2 - t1, now() - t2);
   return st;
 }
 
@@ -268,22 +399,32 @@ int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32
   int kmax = 0;
   for (int k : K) kmax = std::max(kmax, k);
   const int wide = n > 65535;
-  const size_t smem = (size_t)kmax * kmax * (wide ? 4 : 2) + 8;
-  if (smem > 200 * 1024) { rc_set_error("rc_mpel: contingency table of %d x %d clusters does not fit shared memory", kmax, kmax); return RC_ERR_SLOTS; }
-  uint8_t* dL = nullptr; int* dK = nullptr; double *M = nullptr, *sums = nullptr;
+  const int tabwords = ((wide ? kmax * kmax : (kmax * kmax + 1) / 2) + 3) & ~3;
+  const size_t smem = (size_t)tabwords * 4 + 2 * (size_t)((n + 15) / 16) * 16;
+  if (smem > 220 * 1024) { rc_set_error("rc_mpel: n = %lld with %d x %d clusters does not fit shared memory", (long long)n, kmax, kmax); return RC_ERR_SLOTS; }
+  int stride = (int)((n + 31) / 32);
+  while ((stride & 3) || !((stride >> 2) & 1)) ++stride;      // multiple of 4 with an odd quotient: lane segments start in different banks
+  uint8_t* dL = nullptr; int* dK = nullptr; double *M = nullptr, *sums = nullptr, *nlogn = nullptr;
   RC_CUDA(cudaMalloc(&dL, L.size()));
   RC_CUDA(cudaMalloc(&dK, sizeof(int) * S));
   RC_CUDA(cudaMalloc(&M, sizeof(double) * (size_t)S * S));
   RC_CUDA(cudaMalloc(&sums, sizeof(double) * S));
+  RC_CUDA(cudaMalloc(&nlogn, sizeof(double) * (size_t)(n + 1)));
   RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
   RC_CUDA(cudaMemcpy(dK, K.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
   RC_CUDA(cudaMemset(M, 0, sizeof(double) * (size_t)S * S));
+  k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
   cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_pair_loss<<<dim3((unsigned)S, (unsigned)S), 256, smem>>>(dL, dK, S, n, loss, wide, M);
+  k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)S), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn, M);
   k_colsum<<<(unsigned)((S + 127) / 128), 128>>>(M, S, sums);
   std::vector<double> hs((size_t)S);
+  const double tk = getenv("RCB200_VERBOSE") ? std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
   cudaError_t e = cudaMemcpy(hs.data(), sums, sizeof(double) * S, cudaMemcpyDeviceToHost);
-  cudaFree(dL); cudaFree(dK); cudaFree(M); cudaFree(sums);
+  if (getenv("RCB200_VERBOSE"))
+    fprintf(stderr, "[rcb200] rc_mpel: S=%lld n=%lld kmax=%d loss=%d pair kernel + column sums %.3f s (%.3e pairs/s)\n", (long long)S, (long long)n, kmax, loss,
+            std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tk,
+            0.5 * S * (S - 1) / (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tk));
+  cudaFree(dL); cudaFree(dK); cudaFree(M); cudaFree(sums); cudaFree(nlogn);
   RC_CUDA(e);
   int64_t b = 0;
   for (int64_t i = 1; i < S; ++i) if (hs[i] < hs[b]) b = i;     // argmin: first minimum

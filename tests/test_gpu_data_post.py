@@ -132,3 +132,29 @@ def test_distance_matrix_fp64_tensor_core_path(pkg, orc, golden, monkeypatch):
     ref = orc.distm(X)
     off = ~np.eye(1000, dtype=bool)
     assert np.array_equal(D, D.T) and (np.abs(D[off] - ref[off]) / ref[off]).max() < 1e-10
+
+
+def test_psm_tensor_core_and_compare_kernels_agree(pkg, orc, monkeypatch):
+    """The tcgen05 int8 one-hot kernel (slot widths 32 / 64 / 128, ragged tiles, sample counts that are not a
+    multiple of a stage) and the byte-compare kernel both give the exact co-clustering counts (src/mcmc.jl:560)."""
+    rng = np.random.default_rng(5)
+    for n, S, K in ((300, 37, 20), (129, 5, 3), (1000, 130, 64), (777, 64, 128), (513, 257, 33), (2000, 300, 50), (260, 3, 200)):
+        L = rng.integers(1, K + 1, size=(S, n)).astype(np.int64)
+        L[0, :K] = np.arange(1, K + 1)
+        want = orc.psm_counts(L) / S
+        for mode in ("tc", "compare"):
+            monkeypatch.setenv("RCB200_PSM", mode)
+            assert np.array_equal(pkg.psm(L), want), (n, S, K, mode)
+
+
+def test_mpel_larger_sample_sets(pkg, orc):
+    """Column blocks (more samples than one CTA's block), ragged n (unaligned label rows) and sorted labels."""
+    rng = np.random.default_rng(11)
+    for n, S, K in ((203, 21, 5), (640, 19, 30)):
+        base = np.sort(rng.integers(1, K + 1, size=n))
+        L = np.tile(base, (S, 1)); flip = rng.random(L.shape) < 0.1; L[flip] = rng.integers(1, K + 1, size=int(flip.sum()))
+        for loss in ("binder", "omARI", "VI", "ID"):
+            sums, best = pkg.mpel_loss_sums(L, loss)
+            ref = orc.mpel_loss_sums(np.stack([orc.sortlabels(l) for l in L]), loss)
+            assert np.allclose(sums, ref, rtol=1e-10, atol=1e-12), (n, S, loss)
+            assert abs(ref[best] - ref.min()) <= 1e-10 * max(1.0, abs(ref.min()))
