@@ -133,8 +133,9 @@ class MCMCData:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h and _lib._lib is not None:
-            _lib._lib.rc_data_destroy(h)
+        L = getattr(_lib, "_lib", None)               # the module is already torn down at interpreter exit
+        if h and L is not None:
+            L.rc_data_destroy(h)
             self._h = None
 
     def __repr__(self):
@@ -236,9 +237,26 @@ class Sampler:
         nch = self.nchains - chain0 if nch is None else nch
         check(lib().rc_sampler_psm_counts_dev(self._h, chain0, nch, C.c_void_p(counts_ptr)))
 
+    def psm_allreduce(self, group=None, device=None):
+        """PSM over the samples of every rank (mcmc.jl:560 across chain shards): per-rank exact int32 co-clustering
+        counts stay on the device, ONE all_reduce(SUM) of the n x n matrix (NCCL over NVLink) combines them, then a
+        single divide by the global number of samples.  Without an initialised process group it is this rank's PSM."""
+        import torch
+        import torch.distributed as dist
+        n = self.data.n
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        counts = torch.empty((n, n), dtype=torch.int32, device=dev)
+        self.psm_counts_dev(counts.data_ptr())
+        total = torch.tensor([self.nchains * int(lib().rc_sampler_numsamples(self._h))], dtype=torch.int64, device=dev)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return (counts.to(torch.float64) / total.to(torch.float64)).cpu().numpy()
+
     def close(self):
-        if self._h and _lib._lib is not None:
-            _lib._lib.rc_sampler_destroy(self._h)
+        L = getattr(_lib, "_lib", None)
+        if getattr(self, "_h", None) and L is not None:
+            L.rc_sampler_destroy(self._h)
             self._h = None
 
     def __del__(self):
