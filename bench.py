@@ -160,6 +160,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout: stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = graft.load_package()
 
