@@ -72,6 +72,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   kp.lgd1 = rc_lgamma(s->par.delta1);
   kp.lgd2 = rc_lgamma(s->par.delta2);
   kp.LGA = s->LGA; kp.LGZ = s->LGZ; kp.LOGN = s->LOGN;
+  { const char* e = getenv("RCB200_L2PF"); kp.l2pf = e ? atoi(e) : 2; }   // rows of L2 lookahead (measured: 0 -> 2 rows = +2 %)
   kp.burnin = s->opt.burnin; kp.thin = s->opt.thin; kp.numGibbs = s->opt.numGibbs; kp.numMH = s->opt.numMH;
   kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
   kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;

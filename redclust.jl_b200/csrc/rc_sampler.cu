@@ -802,6 +802,12 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
     __threadfence_block();
     mbar_expect_tx(&cs->full[s], bytes);
     bulk_g2s(stages + (size_t)s * stage_bytes, kp.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
+    if (kp.l2pf > 0 && tile == 0 && row + kp.l2pf < n) {
+      // pull a later row towards L2 while this one is consumed: the ring only keeps two tiles in flight, too little to
+      // cover a DRAM miss; whichever CTA is ahead pays the miss early, the others hit
+      const longlong2* src = kp.DL + (size_t)(row + kp.l2pf) * n;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)n * 16u) : "memory");
+    }
     if (++tile == tiles) { tile = 0; ++row; }
   }
 }

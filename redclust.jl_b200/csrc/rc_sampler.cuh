@@ -50,6 +50,7 @@ struct rc_kparams {
   unsigned* gridbar;    // grid-wide arrival counter (zeroed before every launch) or null when the CTAs are not co-resident
   // standalone log-likelihood mode (rc_loglik): skip iterations, write loglik to out_ll[chain]
   int loglik_only;
+  int l2pf;             // rows of lookahead of the producer's L2 prefetch (0: off)
 };
 
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
