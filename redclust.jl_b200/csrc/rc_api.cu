@@ -16,6 +16,15 @@ void rc_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Host copy of every chain's recorded outputs, filled by ONE set of device-to-host copies on the first read after a
+// run (reading C chains one by one would otherwise cost 9 C small synchronous copies).
+struct rc_host_mirror {
+  bool valid = false;
+  std::vector<uint8_t> labels, r_acc, sm_acc, sm_split;
+  std::vector<int> K;
+  std::vector<double> r, p, ll, lp;
+};
+
 struct rc_sampler {
   const rc_data* d;
   rc_options opt;
@@ -36,9 +45,34 @@ struct rc_sampler {
   int64_t iters_done;
   double dev_seconds;
   bool W_ready;
+  bool shared_init;            // every chain starts from the same labels: the block sums are built once and copied
   cudaStream_t stream;
   cudaEvent_t e0, e1;
+  mutable rc_host_mirror mirror;
 };
+
+static bool pool_enabled() { static const bool on = getenv("RCB200_NO_POOL") == nullptr; return on; }
+cudaError_t rc_dev_malloc(void** p, size_t bytes) {
+  if (!pool_enabled()) return cudaMalloc(p, bytes);
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured[dev] = true;
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, 0);      // legacy default stream: ordered against every blocking stream
+  if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(p, bytes); }
+  return e;
+}
+void rc_dev_free(void* p) {
+  if (!p) return;
+  if (!pool_enabled() || cudaFreeAsync(p, 0) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); }
+}
 
 namespace {
 
@@ -57,9 +91,57 @@ template <class T>
 int dalloc(T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * count);
+  cudaError_t e = rc_dev_malloc((void**)p, sizeof(T) * count);
   if (e != cudaSuccess) { rc_set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e)); return RC_ERR_CUDA; }
   return RC_OK;
+}
+
+// ---- block sums of ONE label vector with the whole GPU (all chains start from the same labels) -------------------
+// W[k][t] (k <= t) = sum over rows x of cluster k of the row's sums over cluster t (src/mcmc.jl:1-56 needs exactly
+// these totals).  One CTA per row: every thread walks a contiguous strip of the row keeping a running sum while the
+// label stays the same (one shared-memory atomic per label run), then the row's bins are added to the 128-bit totals
+// with a carry-propagating pair of 64-bit atomics.  Integer sums: the result does not depend on any ordering and is
+// bit-identical to what the chain kernel's own initialisation pass produces.
+__device__ __forceinline__ void atomic_add128(rc_i128* a, long long v) {
+  const unsigned long long u = (unsigned long long)v;
+  const unsigned long long old = atomicAdd(&a->lo, u);
+  const long long hi = (v < 0 ? -1LL : 0LL) + ((old + u) < old ? 1LL : 0LL);
+  if (hi) atomicAdd(reinterpret_cast<unsigned long long*>(&a->hi), (unsigned long long)hi);
+}
+__global__ void __launch_bounds__(256) k_initw_shared(const longlong2* __restrict__ DL, int n, const uint8_t* __restrict__ lab, int cap,
+                                                      rc_i128* __restrict__ WD, rc_i128* __restrict__ WL) {
+  extern __shared__ unsigned long long bins[];          // [cap] D sums, [cap] L sums
+  for (int t = threadIdx.x; t < 2 * cap; t += blockDim.x) bins[t] = 0ull;
+  __syncthreads();
+  for (int x = blockIdx.x; x < n; x += gridDim.x) {
+    const longlong2* row = DL + (size_t)x * n;
+    const int w = (n + blockDim.x - 1) / blockDim.x;
+    const int j0 = threadIdx.x * w, j1 = min(n, j0 + w);
+    int cur = -1; long long d = 0, l = 0;
+    for (int j = j0; j < j1; ++j) {
+      const int lb = lab[j];
+      if (lb != cur) {
+        if (cur >= 0) { atomicAdd(&bins[cur], (unsigned long long)d); atomicAdd(&bins[cap + cur], (unsigned long long)l); }
+        cur = lb; d = 0; l = 0;
+      }
+      const longlong2 v = row[j];
+      d += v.x; l += v.y;
+    }
+    if (cur >= 0) { atomicAdd(&bins[cur], (unsigned long long)d); atomicAdd(&bins[cap + cur], (unsigned long long)l); }
+    __syncthreads();
+    const int k = lab[x];
+    for (int t = threadIdx.x; t < cap; t += blockDim.x) {
+      const long long bd = (long long)bins[t], bl = (long long)bins[cap + t];
+      bins[t] = 0ull; bins[cap + t] = 0ull;
+      if (t >= k && (bd != 0 || bl != 0)) { atomic_add128(&WD[k * cap + t], bd); atomic_add128(&WL[k * cap + t], bl); }
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_replicate_w(rc_i128* __restrict__ W, size_t per_chain, int64_t nchains) {
+  const size_t total = per_chain * (size_t)(nchains - 1);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    W[per_chain + t] = W[t % per_chain];
 }
 
 void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
@@ -98,11 +180,11 @@ int32_t rc_init_rp(const rc_params* params, uint64_t seed, int64_t chain_id, dou
 void rc_sampler_destroy(rc_sampler* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->LGA); cudaFree(s->LGZ); cudaFree(s->LOGN);
-  cudaFree(s->labels); cudaFree(s->sizes); cudaFree(s->r); cudaFree(s->p); cudaFree(s->status);
-  cudaFree(s->WD); cudaFree(s->WL); cudaFree(s->WDbak); cudaFree(s->WLbak); cudaFree(s->labbak); cudaFree(s->szbak); cudaFree(s->T); cudaFree(s->Slist); cudaFree(s->origM); cudaFree(s->AB); cudaFree(s->L2s); cudaFree(s->NZ); cudaFree(s->LPR); cudaFree(s->DG); cudaFree(s->terms); cudaFree(s->stats); cudaFree(s->gridbar);
-  cudaFree(s->out_labels); cudaFree(s->out_K); cudaFree(s->out_r); cudaFree(s->out_p); cudaFree(s->out_ll); cudaFree(s->out_lp);
-  cudaFree(s->r_acc); cudaFree(s->sm_acc); cudaFree(s->sm_split);
+  rc_dev_free(s->LGA); rc_dev_free(s->LGZ); rc_dev_free(s->LOGN);
+  rc_dev_free(s->labels); rc_dev_free(s->sizes); rc_dev_free(s->r); rc_dev_free(s->p); rc_dev_free(s->status);
+  rc_dev_free(s->WD); rc_dev_free(s->WL); rc_dev_free(s->WDbak); rc_dev_free(s->WLbak); rc_dev_free(s->labbak); rc_dev_free(s->szbak); rc_dev_free(s->T); rc_dev_free(s->Slist); rc_dev_free(s->origM); rc_dev_free(s->AB); rc_dev_free(s->L2s); rc_dev_free(s->NZ); rc_dev_free(s->LPR); rc_dev_free(s->DG); rc_dev_free(s->terms); rc_dev_free(s->stats); rc_dev_free(s->gridbar);
+  rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
+  rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -174,8 +256,9 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
     if (!(init_r[c] > 0) || !(init_p[c] > 0 && init_p[c] < 1)) {
       rc_set_error("initial r must be > 0 and p in (0, 1) (chain %lld)", (long long)c); return RC_ERR_ARG;
     }
-  rc_sampler* s = new rc_sampler();
-  memset(s, 0, sizeof(*s));
+  rc_sampler* s = new rc_sampler();     // value-initialised: every scalar member starts at zero
+  s->shared_init = nchains > 1;
+  for (int64_t c = 1; c < nchains && s->shared_init; ++c) s->shared_init = memcmp(lab.data(), lab.data() + c * n, (size_t)n) == 0;
   s->d = d; s->device = d->device; s->n = d->n; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
   s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem; s->G = G;
   s->numsamples = (opt->numiters - opt->burnin) / opt->thin;   // floor((numiters - burnin) / thin), types.jl:55
@@ -230,7 +313,17 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   kp.init_W = s->W_ready ? 0 : 1;
   RC_CUDA(cudaMemsetAsync(s->gridbar, 0, sizeof(unsigned), s->stream));
   RC_CUDA(cudaEventRecord(s->e0, s->stream));
-  rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
+  if (kp.init_W && s->shared_init && !getenv("RCB200_NO_SHARED_INIT")) {
+    const size_t per = (size_t)s->cap * s->cap;
+    RC_CUDA(cudaMemsetAsync(s->WD, 0, sizeof(rc_i128) * per, s->stream));
+    RC_CUDA(cudaMemsetAsync(s->WL, 0, sizeof(rc_i128) * per, s->stream));
+    k_initw_shared<<<148 * 8, 256, sizeof(unsigned long long) * 2 * s->cap, s->stream>>>(s->d->DL, (int)s->n, s->labels, s->cap, s->WD, s->WL);
+    k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WD, per, s->nchains);
+    k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WL, per, s->nchains);
+    RC_CUDA(cudaGetLastError());
+    kp.init_W = 0;
+  }
+  if (kp.init_W || kp.it1 > kp.it0) rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
   RC_CUDA(cudaGetLastError());
   RC_CUDA(cudaEventRecord(s->e1, s->stream));
   RC_CUDA(cudaStreamSynchronize(s->stream));
@@ -239,6 +332,7 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   s->dev_seconds += ms * 1e-3;
   s->iters_done = it1;
   s->W_ready = true;
+  s->mirror.valid = false;
   std::vector<int> status((size_t)s->nchains);
   RC_CUDA(cudaMemcpy(status.data(), s->status, sizeof(int) * s->nchains, cudaMemcpyDeviceToHost));
   for (int64_t c = 0; c < s->nchains; ++c)
@@ -258,12 +352,53 @@ int32_t rc_sampler_progress(const rc_sampler* s, int64_t* iters_done, double* de
 
 int64_t rc_sampler_numsamples(const rc_sampler* s) { return s ? s->numsamples : 0; }
 
+// Fills the host mirror when the whole set of recorded outputs is small enough to be worth one bulk download.
+static int mirror_fill(const rc_sampler* s) {
+  rc_host_mirror& m = s->mirror;
+  if (m.valid) return RC_OK;
+  const size_t C = (size_t)s->nchains, S = (size_t)s->numsamples, n = (size_t)s->n;
+  const size_t ni = (size_t)s->opt.numiters, nm = ni * (size_t)s->opt.numMH;
+  m.labels.resize(C * S * n); m.K.resize(C * S); m.r.resize(C * S); m.p.resize(C * S); m.ll.resize(C * S); m.lp.resize(C * S);
+  m.r_acc.resize(C * ni); m.sm_acc.resize(C * nm); m.sm_split.resize(C * nm);
+  if (S) {
+    RC_CUDA(cudaMemcpy(m.labels.data(), s->out_labels, m.labels.size(), cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.K.data(), s->out_K, sizeof(int) * C * S, cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.r.data(), s->out_r, sizeof(double) * C * S, cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.p.data(), s->out_p, sizeof(double) * C * S, cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.ll.data(), s->out_ll, sizeof(double) * C * S, cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.lp.data(), s->out_lp, sizeof(double) * C * S, cudaMemcpyDeviceToHost));
+  }
+  if (ni) RC_CUDA(cudaMemcpy(m.r_acc.data(), s->r_acc, C * ni, cudaMemcpyDeviceToHost));
+  if (nm) {
+    RC_CUDA(cudaMemcpy(m.sm_acc.data(), s->sm_acc, C * nm, cudaMemcpyDeviceToHost));
+    RC_CUDA(cudaMemcpy(m.sm_split.data(), s->sm_split, C * nm, cudaMemcpyDeviceToHost));
+  }
+  m.valid = true;
+  return RC_OK;
+}
+static bool mirror_wanted(const rc_sampler* s) {
+  return s->nchains > 1 && (size_t)s->nchains * (size_t)s->numsamples * (size_t)s->n <= ((size_t)256 << 20);
+}
+
 int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* labels, int64_t* K, double* r, double* p,
                                 double* loglik, double* logposterior) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_samples: bad handle or chain"); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(s->device));
   const int64_t n = s->n, S = s->numsamples;
   if (S == 0) return RC_OK;
+  if (mirror_wanted(s)) {
+    int st = mirror_fill(s);
+    if (st) return st;
+    const rc_host_mirror& m = s->mirror;
+    const size_t o = (size_t)chain * S;
+    if (labels) { const uint8_t* src = m.labels.data() + o * n; for (size_t t = 0; t < (size_t)S * n; ++t) labels[t] = src[t]; }
+    if (K) for (int64_t t = 0; t < S; ++t) K[t] = m.K[o + t];
+    if (r) memcpy(r, m.r.data() + o, sizeof(double) * S);
+    if (p) memcpy(p, m.p.data() + o, sizeof(double) * S);
+    if (loglik) memcpy(loglik, m.ll.data() + o, sizeof(double) * S);
+    if (logposterior) memcpy(logposterior, m.lp.data() + o, sizeof(double) * S);
+    return RC_OK;
+  }
   if (labels) {
     std::vector<uint8_t> tmp((size_t)S * n);
     RC_CUDA(cudaMemcpy(tmp.data(), s->out_labels + (size_t)chain * S * n, tmp.size(), cudaMemcpyDeviceToHost));
@@ -285,6 +420,14 @@ int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t*
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_acceptances: bad handle or chain"); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(s->device));
   const size_t ni = (size_t)s->opt.numiters, nm = ni * (size_t)s->opt.numMH;
+  if (mirror_wanted(s)) {
+    int st = mirror_fill(s);
+    if (st) return st;
+    if (r_acc && ni) memcpy(r_acc, s->mirror.r_acc.data() + chain * ni, ni);
+    if (sm_acc && nm) memcpy(sm_acc, s->mirror.sm_acc.data() + chain * nm, nm);
+    if (sm_split && nm) memcpy(sm_split, s->mirror.sm_split.data() + chain * nm, nm);
+    return RC_OK;
+  }
   if (r_acc) RC_CUDA(cudaMemcpy(r_acc, s->r_acc + chain * ni, ni, cudaMemcpyDeviceToHost));
   if (sm_acc && nm) RC_CUDA(cudaMemcpy(sm_acc, s->sm_acc + chain * nm, nm, cudaMemcpyDeviceToHost));
   if (sm_split && nm) RC_CUDA(cudaMemcpy(sm_split, s->sm_split + chain * nm, nm, cudaMemcpyDeviceToHost));

@@ -10,6 +10,11 @@
 
 // ---- error plumbing ----------------------------------------------------------------------------
 void rc_set_error(const char* fmt, ...);
+// Device memory of the long-lived handles comes from the device's stream-ordered pool with an unlimited release
+// threshold: a destroyed handle's gigabytes are reused by the next one instead of going back to the driver
+// (RCB200_NO_POOL=1: plain cudaMalloc / cudaFree).
+cudaError_t rc_dev_malloc(void** p, size_t bytes);
+void rc_dev_free(void* p);
 #define RC_CUDA(call)                                                                          \
   do {                                                                                         \
     cudaError_t e_ = (call);                                                                   \

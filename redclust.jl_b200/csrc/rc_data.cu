@@ -186,7 +186,7 @@ int finish_data(rc_data* d) {
   d->qD = rc_choose_q(mD, n);
   d->qL = rc_choose_q(mL, n);
   if (d->qD < 0 || d->qL < 0) { rc_set_error("dissimilarities too large for the fixed-point image."); return RC_ERR_DOMAIN; }
-  RC_CUDA(cudaMalloc(&d->DL, sizeof(longlong2) * (size_t)n * n));
+  RC_CUDA(rc_dev_malloc((void**)&d->DL, sizeof(longlong2) * (size_t)n * n));
   k_build_dl<<<grid, 256>>>(d->D, n, d->qD, d->qL, d->DL);
   RC_CUDA(cudaGetLastError());
   RC_CUDA(cudaDeviceSynchronize());
@@ -220,7 +220,7 @@ int32_t rc_data_from_dist(const double* D, int64_t n, int32_t device, rc_data** 
   if (st) return st;
   rc_data* d = new rc_data();
   d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
-  if (cudaMalloc(&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess) {
+  if (rc_dev_malloc((void**)&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess) {
     rc_set_error("out of device memory for D (%lld x %lld)", (long long)n, (long long)n); delete d; return RC_ERR_CUDA;
   }
   if (cudaMemcpy(d->D, D, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -239,7 +239,7 @@ int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t dev
   rc_data* d = new rc_data();
   d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
   double *dX = nullptr, *sq = nullptr;
-  if (cudaMalloc(&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess || cudaMalloc(&dX, sizeof(double) * (size_t)n * dim) != cudaSuccess ||
+  if (rc_dev_malloc((void**)&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess || cudaMalloc(&dX, sizeof(double) * (size_t)n * dim) != cudaSuccess ||
       cudaMalloc(&sq, sizeof(double) * (size_t)n) != cudaSuccess) {
     rc_set_error("out of device memory for the distance matrix"); cudaFree(dX); cudaFree(sq); rc_data_destroy(d); return RC_ERR_CUDA;
   }
@@ -289,8 +289,8 @@ int32_t rc_data_scales(const rc_data* d, int32_t* qD, int32_t* qL) {
 void rc_data_destroy(rc_data* d) {
   if (!d) return;
   cudaSetDevice(d->device);
-  cudaFree(d->D);
-  cudaFree(d->DL);
+  rc_dev_free(d->D);
+  rc_dev_free(d->DL);
   delete d;
 }
 
