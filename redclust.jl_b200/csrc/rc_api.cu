@@ -228,7 +228,7 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
     if (sm > (size_t)maxsmem) break;
     G = g; npad = np;
     const int64_t ctas = (nchains + g - 1) / g;
-    const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g + 32)));
+    const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g + 64)));
     if (ctas <= (int64_t)nsm * per_sm) break;
   }
   if (G == 0) {

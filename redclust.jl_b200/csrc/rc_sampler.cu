@@ -54,6 +54,8 @@ struct Scal {
 
 #define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
 #define RC_NOISE 64                  // precomputed Gumbel noise entries per row
+#define RC_NR 4                      // rows of noise the helper warp may run ahead of the decisions
+#define RC_XTHR 64                   // CTA-level helper threads: the tile producer warp and the noise warp
 struct ScanShared {                  // per chain: hand-off between the bulk warps and the decision warp
   unsigned long long ready[2];       // the row sums of parity b are complete             (count RC_BW)
   unsigned long long consumed[2];    // the decision warp has copied them to registers   (count 1)
@@ -65,7 +67,8 @@ struct ScanShared {                  // per chain: hand-off between the bulk war
   int inited;
   unsigned short mq_j[RC_MQ];
   unsigned char mq_a[RC_MQ], mq_b[RC_MQ];
-  double noise[2][RC_NOISE];
+  double noise[RC_NR][RC_NOISE];     // Gumbel noise of row i in noise[i % RC_NR] (written by the CTA's noise warp)
+  volatile int noise_ready;          // rows whose noise is complete
 };
 
 struct CtaShared {
@@ -103,6 +106,8 @@ struct Ctx {
   // shared memory (per CTA)
   unsigned char* stages;
   CtaShared* cta;
+  unsigned char* chain0;     // shared memory of chain slot 0; slot q starts chain_stride bytes further
+  size_t chain_stride, ss_off;
   // per-chain global memory
   rc_i128* WD;
   rc_i128* WL;
@@ -495,6 +500,10 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
     acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
     const int Prow = ss->rowP[buf];
+    if (!dead) {                                 // the noise warp runs rows ahead: this wait is normally already satisfied
+      while (ss->noise_ready <= i) __nanosleep(20);
+      __threadfence_block();
+    }
     long long bd[NSR], bl[NSR];
     double nzv[NSR];
 #pragma unroll
@@ -506,7 +515,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
           const longlong2 t = bin_total(c, s, buf);
           bd[w] = t.x; bl[w] = t.y;
         }
-        if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[buf][kk[w]];
+        if (have[w] && kk[w] < RC_NOISE) nzv[w] = ss->noise[i & (RC_NR - 1)][kk[w]];
       }
     }
     if (lane == 0) ss->msnap[buf] = M;
@@ -754,12 +763,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
     longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
     // tiles of this row owned by this warp's pair: T = i * tiles + tile with T % RC_NPAIR == w / RC_PAIR
     const int first = ((w / RC_PAIR) - (int)(((long long)i * tiles) % RC_NPAIR) + RC_NPAIR) % RC_NPAIR;
-    if (first == 0 && (w % RC_PAIR) == 0) {     // this warp opens row i: noise of its candidates, patch level
-      const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)c.lane);   // utils.jl:4-5
-      ss->noise[buf][2 * c.lane] = -rc_log(-rc_log(dr.u0));
-      ss->noise[buf][2 * c.lane + 1] = -rc_log(-rc_log(dr.u1));
-      if (c.lane == 0) ss->rowP[buf] = Papplied;
-    }
+    if (first == 0 && (w % RC_PAIR) == 0 && c.lane == 0) ss->rowP[buf] = Papplied;   // this warp opens row i: patch level
     for (int tile = first; tile < tiles; tile += RC_NPAIR) {
       const long long T = (long long)i * tiles + tile;
       const int st = (int)(T % RC_NSTAGE);
@@ -809,6 +813,44 @@ __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)n * 16u) : "memory");
     }
     if (++tile == tiles) { tile = 0; ++row; }
+  }
+}
+
+__device__ __forceinline__ ScanShared* scan_shared_of(const Ctx& c, int q) {
+  return reinterpret_cast<ScanShared*>(c.chain0 + (size_t)q * c.chain_stride + c.ss_off);
+}
+// Noise warp of the CTA: the Gumbel noise -log(-log(u)) of the first RC_NOISE candidates of every row (utils.jl:2-6) for each
+// scanning chain of the CTA, up to RC_NR rows ahead of that chain's decisions.  Four dependent-chain logarithms per
+// row and chain that used to sit on the bulk warps' critical path.
+template <int G>
+__device__ void noise_rows(const rc_kparams& kp, const Ctx& c, unsigned it) {
+  const int lane = threadIdx.x & 31, n = kp.n;
+  ScanShared* ssq[G]; unsigned long long key[G]; bool act[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    act[q] = c.cta->active[q] != 0;
+    ssq[q] = scan_shared_of(c, q);
+    key[q] = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + (long long)blockIdx.x * G + q));
+  }
+  for (int r = 0; r < n; ++r) {
+    double a[G], b[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      if (!act[q]) continue;
+      const rc_draw dr = rc_draw2(key[q], it, RC_SITE_SCAN, 0, (uint32_t)r, (uint32_t)lane);   // utils.jl:4-5
+      a[q] = -rc_log(-rc_log(dr.u0));
+      b[q] = -rc_log(-rc_log(dr.u1));
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      if (!act[q]) continue;
+      while (r >= ssq[q]->decided + RC_NR) __nanosleep(40);     // the slot's previous row has been decided
+      ssq[q]->noise[r & (RC_NR - 1)][2 * lane] = a[q];
+      ssq[q]->noise[r & (RC_NR - 1)][2 * lane + 1] = b[q];
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ssq[q]->noise_ready = r + 1;
+    }
   }
 }
 
@@ -1563,12 +1605,14 @@ __host__ __device__ inline ChainLayout chain_layout(int n, int cap, int tiles, i
 __host__ __device__ inline size_t cta_header_bytes() { return (sizeof(CtaShared) + 127) & ~(size_t)127; }
 
 template <int G>
-__global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_constant__ rc_kparams kp) {
+__global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid_constant__ rc_kparams kp) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const bool is_producer = threadIdx.x >= RC_NTHR * G;   // last warp: stages the row tiles during the scans
-  const int cl = is_producer ? 0 : threadIdx.x / RC_NTHR;   // chain slot within the CTA
+  const bool is_helper = threadIdx.x >= RC_NTHR * G;       // the two last warps serve the whole CTA:
+  const bool is_producer = is_helper && threadIdx.x < RC_NTHR * G + 32;   // stages the row tiles during the scans
+  const bool is_noise = is_helper && !is_producer;         // precomputes the Gumbel noise of the scans
+  const int cl = is_helper ? 0 : threadIdx.x / RC_NTHR;    // chain slot within the CTA
   const int chain = blockIdx.x * G + cl;
-  const bool valid = !is_producer && chain < kp.nchains;
+  const bool valid = !is_helper && chain < kp.nchains;
   const int n = kp.n, cap = kp.cap, tiles = kp.tiles;
   Ctx c;
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
@@ -1579,7 +1623,8 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     c.dummy = (unsigned)(c.stage_bytes - 128);   // byte offset of the zero slots
     c.cta = reinterpret_cast<CtaShared*>(smem);
     c.stages = smem + cta_header_bytes();
-    unsigned char* base = c.stages + (size_t)RC_NSTAGE * c.stage_bytes + (size_t)cl * L.total;
+    c.chain0 = c.stages + (size_t)RC_NSTAGE * c.stage_bytes; c.chain_stride = L.total; c.ss_off = L.ss;
+    unsigned char* base = c.chain0 + (size_t)cl * L.total;
     c.partial = reinterpret_cast<longlong2*>(base + L.partial);
     c.sc = reinterpret_cast<Scal*>(base + L.sc);
     c.ss = reinterpret_cast<ScanShared*>(base + L.ss);
@@ -1632,6 +1677,20 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) mirror(kp.gridbar != nullptr);
     return;
   }
+  if (is_noise) {      // same barrier sequence as the producer warp
+    __syncthreads();
+    auto mirror = [&](bool grid, bool scan, unsigned it) {
+      __syncthreads();
+      __syncthreads();
+      if (grid) __syncthreads();
+      if (scan && c.cta->nact > 0) noise_rows<G>(kp, c, it);
+      __syncthreads();
+    };
+    if (kp.init_W) mirror(false, false, 0u);
+    if (kp.loglik_only) return;
+    for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) mirror(kp.gridbar != nullptr, true, (unsigned)iter);
+    return;
+  }
   if (valid) {   // load the chain's state
     for (int j = tid; j < n; j += RC_NTHR) c.lab[j] = kp.labels[(size_t)chain * n + j];
     for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
@@ -1656,7 +1715,11 @@ __global__ void __launch_bounds__(RC_NTHR * G + 32, 1) k_chain(const __grid_cons
     __syncthreads();
     if (threadIdx.x == 0) {
       int nact = 0;
-      for (int q = 0; q < G; ++q) nact += c.cta->active[q] ? 1 : 0;
+      for (int q = 0; q < G; ++q) {
+        nact += c.cta->active[q] ? 1 : 0;
+        ScanShared* sq = scan_shared_of(c, q);               // the noise warp starts as soon as the next barrier opens
+        sq->noise_ready = 0; sq->decided = 0;
+      }
       c.cta->nact = nact;
       if (rings_used)
         for (int s = 0; s < RC_NSTAGE; ++s) { mbar_inval(&c.cta->full[s]); mbar_inval(&c.cta->empty[s]); }
@@ -1792,10 +1855,10 @@ bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device) {
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
   if (G == 2) {
     cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<2>, RC_NTHR * 2 + 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<2>, RC_NTHR * 2 + RC_XTHR, smem);
   } else {
     cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<1>, RC_NTHR + 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_chain<1>, RC_NTHR + RC_XTHR, smem);
   }
   return (nchains + G - 1) / G <= nsm * per;
 }
@@ -1804,10 +1867,10 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
   const int grid = (kp.nchains + G - 1) / G;
   if (G == 2) {
     cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chain<2><<<grid, RC_NTHR * 2 + 32, smem, st>>>(kp);
+    k_chain<2><<<grid, RC_NTHR * 2 + RC_XTHR, smem, st>>>(kp);
   } else {
     cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chain<1><<<grid, RC_NTHR + 32, smem, st>>>(kp);
+    k_chain<1><<<grid, RC_NTHR + RC_XTHR, smem, st>>>(kp);
   }
 }
 
