@@ -1108,21 +1108,11 @@ __device__ void build_lpr(const Ctx& c) {
 // Returns the log transition probability of the last scan in c.sc->ltp.
 // ------------------------------------------------------------------------------------------------
 #define RC_RS_NU 16
-struct RsItem {          // everything a restricted step needs that does not depend on the evolving state
-  int y;
-  longlong2 self;
-  longlong4 ab;
-  double2 l2s, nz;
-};
-__device__ __forceinline__ RsItem rs_load(const Ctx& c, int g, int pos, int nS, bool forced) {
-  RsItem t;
-  t.y = c.Slist[pos];
-  t.self = c.DG[pos];
-  t.ab = c.AB[pos];
-  t.l2s = c.L2s[pos];
-  t.nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
-  return t;
-}
+// Eight consecutive steps are evaluated at once (lane = 4 * step + role, one logarithm per lane) on the assumption that
+// none of the earlier ones moves its item; the steps up to and including the first move are exact and are committed,
+// the rest is evaluated again after the move has been applied.  Every committed step sees exactly the inputs of the
+// sequential scan, so the results are the same bits.
+#define RC_RS_B 8
 __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
@@ -1134,73 +1124,89 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
 #pragma unroll
   for (int u = 0; u < RC_RS_NU; ++u) { const int q = u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
   const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
+  const int st = lane >> 2, role = lane & 3, quad = lane & ~3;
+  const bool isA = (role & 1) == 0;
   double ltp = 0.0;
-  RsItem nx = rs_load(c, 0, 0, nS, numGibbs == 0 && !split);
   for (int g = 0; g <= numGibbs; ++g) {
     const bool last = g == numGibbs;
     const bool forced = last && !split;
-    for (int pos = 0; pos < nS; ++pos) {
-      const RsItem cu = nx;
-      const int y = cu.y;
-      const longlong2* row = c.DL + (size_t)y * c.n;
-      // inputs of the next step (its AB entry is re-read below if this step moves)
-      const int npos = pos + 1 < nS ? pos + 1 : 0, ng = pos + 1 < nS ? g : g + 1;
-      const bool more = ng <= numGibbs;
-      if (more) nx = rs_load(c, ng, npos, nS, ng == numGibbs && !split);
-      const int cur = c.lab[y];
-      // sums over the candidates with y detached (:303-304)
-      const long long sAd = cu.ab.x - (cur == ca ? cu.self.x : 0), sAl = cu.ab.y - (cur == ca ? cu.self.y : 0);
-      const long long sBd = cu.ab.z - (cur == cb ? cu.self.x : 0), sBl = cu.ab.w - (cur == cb ? cu.self.y : 0);
-      const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
-      // lanes 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
-      double X = 0.0;
-      {
-        const bool isA = (lane & 1) == 0;
-        const int szs = isA ? szA : szB;
-        const double szd = (double)szs;
-        const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
-        if ((lane & 2) == 0) {                                                                      // :313-319, 327-330
-          const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-          X = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-        } else {                                                                                    // :307-312, 321-326
-          const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-          X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+    int pos0 = 0;
+    while (pos0 < nS) {
+      const int nb = min(RC_RS_B, nS - pos0);
+      const int pos = pos0 + st;
+      const bool on = st < nb;
+      int y = 0, cur = 0, cnew = 0, k = 0;
+      double lt = 0.0;
+      if (on) {
+        y = c.Slist[pos];
+        const longlong2 self = c.DG[pos];
+        const longlong4 ab = c.AB[pos];
+        const double2 l2s = c.L2s[pos];
+        const double2 nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
+        cur = c.lab[y];
+        // sums over the candidates with y detached (:303-304)
+        const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
+        const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
+        const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
+        // roles 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
+        double X;
+        {
+          const int szs = isA ? szA : szB;
+          const double szd = (double)szs;
+          const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
+          if ((role & 2) == 0) {                                                                    // :313-319, 327-330
+            const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+            X = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+          } else {                                                                                  // :307-312, 321-326
+            const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+            X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+          }
+        }
+        const unsigned qm = 0xfu << quad;
+        const double L2pA = __shfl_sync(qm, X, quad), L2pB = __shfl_sync(qm, X, quad + 1);
+        const double L1A = __shfl_sync(qm, X, quad + 2), L1B = __shfl_sync(qm, X, quad + 3);
+        const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
+        const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
+        const double L2i = L2p1 + L2p2;                                                             // :331 (quirk Q2)
+        const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                            // :332-334
+        double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                 // :335
+        double lp1 = c.LPR[szB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
+        if (!forced) {                                                                              // :336-338
+          double mn = lp0;
+          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+          lp0 -= mn; lp1 -= mn;
+          const double g0 = nz.x + lp0, g1 = nz.y + lp1;
+          k = 0;
+          if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
+          cnew = k == 0 ? ca : cb;
+        } else {                                                                                    // :339-342
+          cnew = c.origM[pos];
+          k = (ca == cnew) ? 0 : 1;
+        }
+        if (last) {                                                                                 // :347-351
+          double mn = lp0;                                                                          // quirk Q3
+          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+          lp0 += mn; lp1 += mn;
+          double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
+          const double den = p0 + p1;
+          p0 /= den; p1 /= den;
+          lt = rc_log(k == 0 ? p0 : p1);
         }
       }
-      const double L2pA = __shfl_sync(0xffffffffu, X, 0), L2pB = __shfl_sync(0xffffffffu, X, 1);
-      const double L1A = __shfl_sync(0xffffffffu, X, 2), L1B = __shfl_sync(0xffffffffu, X, 3);
-      const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : cu.l2s.x;
-      const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : cu.l2s.y;
-      const double L2i = L2p1 + L2p2;                                                               // :331 (quirk Q2)
-      const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                              // :332-334
-      double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                   // :335
-      double lp1 = c.LPR[szB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
-      int k, cnew;
-      if (!forced) {                                                                                // :336-338
-        double mn = lp0;
-        if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-        lp0 -= mn; lp1 -= mn;
-        const double g0 = cu.nz.x + lp0, g1 = cu.nz.y + lp1;
-        k = 0;
-        if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
-        cnew = k == 0 ? ca : cb;
-      } else {                                                                                      // :339-342
-        cnew = c.origM[pos];
-        k = (ca == cnew) ? 0 : 1;
-      }
-      if (last) {                                                                                   // :347-351
-        double mn = lp0;                                                                            // quirk Q3
-        if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-        lp0 += mn; lp1 += mn;
-        double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
-        const double den = p0 + p1;
-        p0 /= den; p1 /= den;
-        ltp += rc_log(k == 0 ? p0 : p1);
-      }
-      if (cnew != cur) {                                                                            // :344-345
-        if (lane == 0) { c.lab[y] = (uint8_t)cnew; c.szL[cur] -= 1; c.szL[cnew] += 1; }
+      __syncwarp();
+      // the first step of the batch that moves its item: it and everything before it stand
+      const unsigned mv = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur);
+      const int sfirst = mv ? (__ffs(mv) - 1) >> 2 : -1;
+      const int nvalid = sfirst >= 0 ? sfirst + 1 : nb;
+      if (last)
+        for (int q = 0; q < nvalid; ++q) ltp += __shfl_sync(0xffffffffu, lt, 4 * q);               // in step order, as the scan adds them
+      if (sfirst >= 0) {                                                                            // :344-345
+        const int ym = __shfl_sync(0xffffffffu, y, 4 * sfirst);
+        const int curm = __shfl_sync(0xffffffffu, cur, 4 * sfirst), newm = __shfl_sync(0xffffffffu, cnew, 4 * sfirst);
+        if (lane == 0) { c.lab[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
         // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
-        const bool a2b = cur == ca;
+        const longlong2* row = c.DL + (size_t)ym * c.n;
+        const bool a2b = curm == ca;
         longlong2 ev[RC_RS_NU];                                 // row y at the member columns (only read when y moves)
 #pragma unroll
         for (int u = 0; u < RC_RS_NU; ++u) ev[u] = xs[u] >= 0 ? __ldg(row + xs[u]) : make_longlong2(0, 0);
@@ -1214,17 +1220,16 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
             c.AB[q] = t;
           }
         }
-        for (int q = RC_RS_NU * 32 + lane; q < mt; q += 32) {   // members beyond the speculative window
+        for (int q = RC_RS_NU * 32 + lane; q < mt; q += 32) {   // members beyond the register window
           const longlong2 e = __ldg(row + c.Slist[q]);
           longlong4 t = c.AB[q];
           if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
           else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
           c.AB[q] = t;
         }
-        __syncwarp();
-        if (more) nx.ab = c.AB[npos];
       }
       __syncwarp();
+      pos0 += nvalid;
     }
   }
   if (lane == 0) c.sc->ltp = ltp;
