@@ -762,14 +762,14 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
     zero_partial(c, buf);
     longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
     // tiles of this row owned by this warp's pair: T = i * tiles + tile with T % RC_NPAIR == w / RC_PAIR
-    const int first = ((w / RC_PAIR) - (int)(((long long)i * tiles) % RC_NPAIR) + RC_NPAIR) % RC_NPAIR;
+    const int first = ((w / RC_PAIR) - (int)(((unsigned)i * (unsigned)tiles) % RC_NPAIR) + RC_NPAIR) % RC_NPAIR;
     if (first == 0 && (w % RC_PAIR) == 0 && c.lane == 0) ss->rowP[buf] = Papplied;   // this warp opens row i: patch level
     for (int tile = first; tile < tiles; tile += RC_NPAIR) {
-      const long long T = (long long)i * tiles + tile;
+      const unsigned T = (unsigned)i * (unsigned)tiles + (unsigned)tile;      // n * tiles < 2^32: 32-bit constant division
       const int st = (int)(T % RC_NSTAGE);
-      const unsigned k = (unsigned)(T / RC_NSTAGE);
+      const unsigned k = T / RC_NSTAGE;
       const long long tf0 = clock64();
-      while (cs->issued[st] != T) __nanosleep(20);           // the stage has moved on to tile T (see RC_NSTAGE)
+      while (cs->issued[st] != (long long)T) __nanosleep(20);           // the stage has moved on to tile T (see RC_NSTAGE)
       mbar_wait(&cs->full[st], k & 1u);
       const long long tf1 = clock64();
       if (!bdead) reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)st * c.stage_bytes), tile, part);
@@ -795,14 +795,14 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
 __device__ void produce_rows(const rc_kparams& kp, unsigned char* stages, size_t stage_bytes, CtaShared* cs) {
   if ((threadIdx.x & 31) != 0) return;
   const int n = kp.n, tiles = kp.tiles;
-  const long long ntile = (long long)n * tiles;
+  const unsigned ntile = (unsigned)n * (unsigned)tiles;
   int row = 0, tile = 0;
-  for (long long t = 0; t < ntile; ++t) {
+  for (unsigned t = 0; t < ntile; ++t) {
     const int s = (int)(t % RC_NSTAGE);
-    if (t >= RC_NSTAGE) mbar_wait(&cs->empty[s], (unsigned)(((t / RC_NSTAGE) - 1) & 1));
+    if (t >= RC_NSTAGE) mbar_wait(&cs->empty[s], ((t / RC_NSTAGE) - 1) & 1u);
     const int cols = min(RC_W, n - tile * RC_W);
     const unsigned bytes = (unsigned)cols * 16u;
-    cs->issued[s] = t;
+    cs->issued[s] = (long long)t;
     __threadfence_block();
     mbar_expect_tx(&cs->full[s], bytes);
     bulk_g2s(stages + (size_t)s * stage_bytes, kp.DL + (size_t)row * n + (size_t)tile * RC_W, bytes, &cs->full[s]);
