@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--numGibbs", type=int, default=5)
     ap.add_argument("--numMH", type=int, default=1)
     ap.add_argument("--seed", type=int, default=44)
+    ap.add_argument("--slot-cap", type=int, default=0, help="cluster slots per chain (0: library default, 128)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -173,7 +174,7 @@ def main():
     rp = [pkg.init_rp(params, args.seed, chain0 + c) for c in range(args.chains)]
     r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
     labs = np.tile(lab, (args.chains, 1))
-    smp = pkg.Sampler(data, opts, params, labs, r0, p0, seed=args.seed, chain_offset=chain0)
+    smp = pkg.Sampler(data, opts, params, labs, r0, p0, seed=args.seed, chain_offset=chain0, slot_cap=args.slot_cap)
     smp.run(0)                       # builds the block-sum matrices (setup, like MCMCData construction)
     for _ in range(W):
         smp.run(1)
@@ -215,7 +216,7 @@ def main():
             """host D -> MCMCData -> Sampler -> run -> every chain's samples back on the host"""
             t = [time.perf_counter()]
             d2 = pkg.MCMCData(Dp.numpy(), device=local_rank); t.append(time.perf_counter())
-            s2 = pkg.Sampler(d2, o2, params, labs, r0, p0, seed=args.seed, chain_offset=chain0); t.append(time.perf_counter())
+            s2 = pkg.Sampler(d2, o2, params, labs, r0, p0, seed=args.seed, chain_offset=chain0, slot_cap=args.slot_cap); t.append(time.perf_counter())
             s2.run(-1); t.append(time.perf_counter())
             outs = [s2.samples(c) for c in range(args.chains)]
             barrier(); t.append(time.perf_counter())

@@ -33,7 +33,9 @@ namespace {
 // tiles are being reduced while one more is in flight.  A warp revisits a stage only every RC_NSTAGE * RC_BW tiles and
 // mbarrier parity waits are only unambiguous one phase ahead, so the producer publishes the tile it issues into a stage
 // (CtaShared::issued) and a consumer waits for that to reach its tile before it waits on the stage's `full` barrier.
+#ifndef RC_NSTAGE
 #define RC_NSTAGE (RC_BW + 2)
+#endif
 #define RC_PAIR 1                    // bulk warps that reduce one tile together (RC_BW / RC_PAIR tiles are reduced at a time)
 #define RC_NPAIR (RC_BW / RC_PAIR)
 // a stage holds one tile (min(n, RC_W) columns) + 8 zero slots that padding entries of the permutation read
@@ -53,6 +55,12 @@ struct Scal {
 };
 
 #define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
+// cycle counters of rc_sampler_copy_stats: compile with -DRC_NO_STATS to drop the clock reads from the hot loops
+#ifdef RC_NO_STATS
+#define RC_CLOCK() 0LL
+#else
+#define RC_CLOCK() clock64()
+#endif
 #define RC_NOISE 64                  // precomputed Gumbel noise entries per row
 #define RC_NR 4                      // rows of noise the helper warp may run ahead of the decisions
 #define RC_XTHR 64                   // CTA-level helper threads: the tile producer warp and the noise warp
@@ -492,11 +500,11 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
       }
     }
     // ---- row sums of row i ----
-    const long long tw0 = clock64();
+    const long long tw0 = RC_CLOCK();
     const int buf = i & 1;
     mbar_wait(&ss->ready[buf], (unsigned)((i >> 1) & 1));
     if (c.sc->status) dead = true;
-    const long long tw1 = clock64();
+    const long long tw1 = RC_CLOCK();
     acc_wait += tw1 - tw0; acc_work += tw0 - tlast;
     tlast = tw1;
     const int Prow = ss->rowP[buf];
@@ -715,7 +723,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
 
 __device__ void decide_loop(const Ctx& c, unsigned it) {
   DecCarry cy;
-  cy.M = 0; cy.nmoves = 0; cy.dead = false; cy.acc_wait = 0; cy.acc_work = 0; cy.tlast = clock64();
+  cy.M = 0; cy.nmoves = 0; cy.dead = false; cy.acc_wait = 0; cy.acc_work = 0; cy.tlast = RC_CLOCK();
   bool low = true;                                                          // every live slot below 64?
   for (int s = 64 + c.lane; s < c.cap; s += 32) low = low && c.sizes[s] == 0;
   low = __all_sync(0xffffffffu, low);
@@ -737,9 +745,9 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
   for (int i = 0; i < n; ++i) {
     const int buf = i & 1;
     int Msnap = 0;
-    const long long tb0 = clock64();
+    const long long tb0 = RC_CLOCK();
     if (i >= 2) { mbar_wait(&ss->consumed[buf], (unsigned)(((i - 2) >> 1) & 1)); Msnap = ss->msnap[buf]; }
-    const long long tb1 = clock64();
+    const long long tb1 = RC_CLOCK();
     a_cons += tb1 - tb0;
     if (Msnap > Papplied) {                     // uniform over the chain's bulk warps: patch the permutation
       bsync(c);                                 // every bulk warp is between two rows
@@ -757,7 +765,7 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
         bsync(c);
         Papplied = ss->prebuilt;
       }
-      a_patch += clock64() - tb1;
+      a_patch += RC_CLOCK() - tb1;
     }
     zero_partial(c, buf);
     longlong2* part = c.partial + (buf * RC_BW + w) * c.cap;
@@ -768,18 +776,18 @@ __device__ void bulk_loop(const Ctx& c, unsigned it) {
       const unsigned T = (unsigned)i * (unsigned)tiles + (unsigned)tile;      // n * tiles < 2^32: 32-bit constant division
       const int st = (int)(T % RC_NSTAGE);
       const unsigned k = T / RC_NSTAGE;
-      const long long tf0 = clock64();
+      const long long tf0 = RC_CLOCK();
       while (cs->issued[st] != (long long)T) __nanosleep(20);           // the stage has moved on to tile T (see RC_NSTAGE)
       mbar_wait(&cs->full[st], k & 1u);
-      const long long tf1 = clock64();
+      const long long tf1 = RC_CLOCK();
       if (!bdead) reduce_tile<true>(c, reinterpret_cast<const longlong2*>(c.stages + (size_t)st * c.stage_bytes), tile, part);
       __syncwarp();
       if (c.lane == 0) mbar_arrive(&cs->empty[st]);
-      a_full += tf1 - tf0; a_red += clock64() - tf1;
+      a_full += tf1 - tf0; a_red += RC_CLOCK() - tf1;
     }
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&ss->ready[buf]);
-    a_rows += clock64() - tb0;
+    a_rows += RC_CLOCK() - tb0;
   }
   if (c.lane == 0) {   // per-warp counters are summed over the chain's bulk warps
     atomicAdd((unsigned long long*)&c.stats[ST_BULK_WAIT_CONSUMED], (unsigned long long)a_cons);
@@ -1296,7 +1304,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   const int n = c.n, cap = c.cap;
   const double r = c.sc->r, p = c.sc->p;
   const int K = c.sc->K;
-  const long long tm0 = clock64();
+  const long long tm0 = RC_CLOCK();
   // (i, j) = sample(1:n, 2, replace = false)  (:379)
   const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_PAIR, mh, 0, 0);
   long long i1 = rc_randint(dr.u0, n), i2 = rc_randint(dr.u1, n - 1);
@@ -1436,10 +1444,10 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     }
   }
   csync(c);
-  const long long tm1 = clock64();
+  const long long tm1 = RC_CLOCK();
   if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
   csync(c);
-  const long long tm2 = clock64();
+  const long long tm2 = RC_CLOCK();
   if (tid == 0) { st_add(c, ST_MH_SETUP, tm1 - tm0); st_add(c, ST_MH_RSCAN, tm2 - tm1); }
   double log_prior_ratio = 0.0, log_proposal_ratio = 0.0;
   if (split) {                                                              // :416-434
@@ -1558,7 +1566,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
   }
   csync(c);
-  if (tid == 0) st_add(c, ST_MH_LOGLIK, clock64() - tm2);
+  if (tid == 0) st_add(c, ST_MH_LOGLIK, RC_CLOCK() - tm2);
 }
 
 // sortlabels (utils.jl:69-74): first-appearance relabelling to 1..K.
@@ -1758,7 +1766,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
 
   for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
     const unsigned it = (unsigned)iter;
-    const long long ti0 = clock64();
+    const long long ti0 = RC_CLOCK();
     bool alive = valid;
     if (alive) { csync(c); alive = c.sc->status == 0; }
     bool do_scan = alive;
@@ -1772,7 +1780,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
       }
       csync(c);
       build_lpr(c);
-      if (tid == 0) st_add(c, ST_RP, clock64() - ti0);
+      if (tid == 0) st_add(c, ST_RP, RC_CLOCK() - ti0);
       // sample_labels! (:540)
       const bool multi = kp.numMH > 1;
       if (multi) {                                           // the chain's own state, in case a proposal is accepted and committed
@@ -1809,9 +1817,9 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
         if (c.sc->status) do_scan = false;
       }
     }
-    const long long ts0 = clock64();
+    const long long ts0 = RC_CLOCK();
     cta_scan(do_scan, it, 0, (unsigned)(iter - kp.it0));
-    const long long ts1 = clock64();
+    const long long ts1 = RC_CLOCK();
     if (valid && tid == 0) st_add(c, ST_SCAN_TOTAL, ts1 - ts0);
     if (alive) alive = c.sc->status == 0;
     if (alive && iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0) {    // :546-554
@@ -1830,7 +1838,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
         csync(c);
       }
     }
-    if (valid && tid == 0) { st_add(c, ST_RECORD, clock64() - ts1); st_add(c, ST_ITER_TOTAL, clock64() - ti0); }
+    if (valid && tid == 0) { st_add(c, ST_RECORD, RC_CLOCK() - ts1); st_add(c, ST_ITER_TOTAL, RC_CLOCK() - ti0); }
   }
   if (valid) {   // store the chain's state
     csync(c);
