@@ -225,7 +225,10 @@ def main():
             del d2
             return t, dev, outs
 
-        one_pass()                   # untimed warm-up of the whole path (first-use kernel loading, pinned staging buffers)
+        tw, devw, _ = one_pass()     # untimed warm-up of the whole path (first-use kernel loading, pinned staging buffers)
+        if rank == 0:
+            print("[bench] e2e warm-up pass (s): data %.3f, sampler %.3f, run %.3f (device %.3f), readback %.3f" %
+                  (tw[1] - tw[0], tw[2] - tw[1], tw[3] - tw[2], devw, tw[4] - tw[3]), file=sys.stderr)
         barrier()
         t, dev, outs = one_pass()
         if rank == 0:
