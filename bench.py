@@ -107,7 +107,29 @@ def cpu_reference(args, X, lab, params_fields, steps, warmup, cores, D=None):
     return cores * steps / secs, secs / steps * 1e3, f"{cores} independent chains x {steps} sweeps of the n={args.n} workload, one chain per host thread"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that libraries print to fd 1 (NCCL's version banner,
+    for one) is sent to stderr from here on; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -154,14 +176,13 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "CPU restatement of RedClust.jl v1.2.2 (Julia is not installed; the reference itself is single-threaded)"}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout: stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = graft.load_package()
 
@@ -266,7 +287,7 @@ def main():
             "dtype": "f64 (exact i64 fixed-point cluster sums)", "data": "synthetic", "config": config,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": steps, "roofline": roofline, "cpu_baseline": cpu,
             "wall_ms_per_step": wall_s / steps * 1e3, "K_final_chain0": Kfinal}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
