@@ -72,6 +72,22 @@ int32_t rc_data_copy_logdist(const rc_data* d, double* logD_out);
 /* Fixed-point scales of the images the sampler streams: Dq = round(D * 2^qD), Lq = round(logD * 2^qL)
  * (largest q <= 50 with n * max|.| * 2^q < 2^61, so that every cluster sum is an exact 64-bit integer). */
 int32_t rc_data_scales(const rc_data* d, int32_t* qD, int32_t* qL);
+/* One row of data.D (the k-medoids++ seeding of the host draws its weights from medoid rows). */
+int32_t rc_data_copy_row(const rc_data* d, int64_t i, double* row_out);
+
+/* ---- the O(n^2) parts of fitprior (src/prior.jl:22-128) on the device-resident matrix ---------------
+ * rc_kmedoids: Clustering.kmedoids(dissM, k; maxiter) as called at src/prior.jl:55-71 (elbow scan and notional
+ * clustering) and src/mcmc.jl:519-527 (default init of runsampler): alternate nearest-medoid assignment (first
+ * minimum) and medoid update (member with the smallest sum of dissimilarities to its cluster, lowest index on
+ * ties) from the given initial medoids (0-based) until nothing changes or maxiter updates were made.  The sums
+ * run over the fixed-point image Dq, so ties and near-ties resolve identically on every machine.
+ * assignments: n, 1-based cluster ids; medoids: k, 0-based; totalcost = sum_i D[medoid(i)][i].
+ * rc_pair_stats: per row i the exact sums over j > i of (Dq, Lq) within i's cluster and over all j > i, and the
+ * number of within pairs -- rows_out is n x 5 int64 {within Dq, within Lq, all Dq, all Lq, within count}.  Their
+ * totals are the sufficient statistics of the Gamma fits to A and B (src/prior.jl:73-110). */
+int32_t rc_kmedoids(const rc_data* d, int64_t k, const int64_t* init_medoids, int64_t maxiter, int64_t* assignments,
+                    int64_t* medoids, double* totalcost, int32_t* converged, int64_t* iterations);
+int32_t rc_pair_stats(const rc_data* d, const int64_t* labels, int64_t* rows_out);
 void rc_data_destroy(rc_data* d);
 
 /* ---- runsampler ------------------------------------------------------------------------ */

@@ -300,12 +300,12 @@ def runsampler(data, options=None, params=None, init=None, verbose=True, nchains
         options = MCMCOptionsList()
     if params is None:
         from .prior import fitprior
-        params = fitprior(data.D, "k-medoids", True, verbose=verbose)
+        params = fitprior(data, "k-medoids", True, verbose=verbose)          # runs on the device-resident matrix
     n = data.n
     if init is None:                                                           # mcmc.jl:519-527
         from .prior import kmedoids
         k0 = min(params.maxK, params.K_initial) if params.maxK > 0 else params.K_initial
-        lab0 = kmedoids(data.D, int(k0), maxiter=1000)["assignments"]
+        lab0 = kmedoids(data, int(k0), maxiter=1000)["assignments"]         # rc_kmedoids on the resident matrix
         labs = np.tile(lab0, (nchains, 1))
         rp = [init_rp(params, seed, c) for c in range(nchains)]
         r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
@@ -451,14 +451,33 @@ def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None,
                 oracle_coclustering=None, data=data)
 
 
+def pair_stats(data, labels):
+    """Sufficient statistics of the within-cluster (A) and between-cluster (B) upper-triangle dissimilarities of a
+    device-resident MCMCData for the Gamma fits of fitprior (prior.jl:73-110): counts, sums and sums of logs.
+    The device returns exact integer row sums of the fixed-point images; they are added here as Python integers."""
+    lab = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    rows = np.zeros((data.n, 5), np.int64)
+    check(lib().rc_pair_stats(data._h, ptr(lab), ptr(rows)))
+    qD, qL = data.scales()
+    wd, wl, ad, al, nw = (sum(map(int, rows[:, c])) for c in range(5))
+    n = data.n
+    nA, nB = nw, n * (n - 1) // 2 - nw
+    return dict(nA=nA, sA=wd / 2.0 ** qD, lA=wl / 2.0 ** qL, nB=nB, sB=(ad - wd) / 2.0 ** qD, lB=(al - wl) / 2.0 ** qL)
+
+
 def params_from_labels(D, labels, eta=None, sigma=None, u=None, v=None, **kw):
     """Hyperparameters from a notional clustering, exactly as fitprior does after its clustering step
     (prior.jl:73-110): Gamma MLE shapes of within / between distances, alpha = |A| delta1, beta = sum(A),
     zeta = |B| delta2, gamma = sum(B).  eta, sigma, u, v default to moment matches of (r, p) ~ NegBin fit."""
     from .prior import gamma_shape_from_stats
-    D = np.asarray(D); labels = np.asarray(labels)
-    n = D.shape[0]
+    labels = np.asarray(labels)
     K = len(np.unique(labels))
+    if isinstance(D, MCMCData):                      # device path: one pass over the resident matrix
+        st = pair_stats(D, labels)
+        nA, sA, lA, nB, sB, lB = st["nA"], st["sA"], st["lA"], st["nB"], st["sB"], st["lB"]
+        return _params_from_stats(nA, sA, lA, nB, sB, lB, K, eta, sigma, u, v, kw)
+    D = np.asarray(D)
+    n = D.shape[0]
     # sufficient statistics of the within-cluster (A) and between-cluster (B) upper-triangle distances
     tot_s, tot_l = 0.0, 0.0
     for i0 in range(0, n, 1024):
@@ -479,6 +498,11 @@ def params_from_labels(D, labels, eta=None, sigma=None, u=None, v=None, **kw):
         vals = sub[iu]
         nA += vals.size; sA += float(vals.sum()); lA += float(np.log(vals).sum())
     nB, sB, lB = n * (n - 1) // 2 - nA, tot_s - sA, tot_l - lA
+    return _params_from_stats(nA, sA, lA, nB, sB, lB, K, eta, sigma, u, v, kw)
+
+
+def _params_from_stats(nA, sA, lA, nB, sB, lB, K, eta, sigma, u, v, kw):
+    from .prior import gamma_shape_from_stats
     if nA:
         d1 = gamma_shape_from_stats(sA / nA, lA / nA); al, be = nA * d1, sA
     else:

@@ -149,6 +149,31 @@ function mpel(clusts::Vector{ClustLabelVector}, loss::String; device::Integer = 
     return sums, best[] + 1
 end
 
+"Clustering.kmedoids(dissM, k) on the resident matrix (src/prior.jl:55-71, src/mcmc.jl:519-527); init: 1-based medoids."
+function kmedoids(data::MCMCData, k::Integer, init::Vector{Int}; maxiter::Integer = 1000)
+    n = getfield(data, :n)
+    assign = Vector{Int64}(undef, n); med = Vector{Int64}(undef, k)
+    cost = Ref{Float64}(0); conv = Ref{Int32}(0); its = Ref{Int64}(0)
+    init0 = Int64.(init .- 1)
+    GC.@preserve init0 check(ccall((:rc_kmedoids, LIB[]), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ref{Float64}, Ref{Int32}, Ref{Int64}),
+        getfield(data, :handle), k, init0, maxiter, assign, med, cost, conv, its))
+    return (assignments = assign, medoids = med .+ 1, totalcost = cost[], converged = conv[] != 0, iterations = its[])
+end
+
+"Counts, sums and log-sums of the within / between cluster dissimilarities (A and B of src/prior.jl:73-75)."
+function pairstats(data::MCMCData, labels::Vector{Int})
+    n = getfield(data, :n)
+    rows = Matrix{Int64}(undef, 5, n)                       # column i = row i of the C layout (n x 5 row-major)
+    qD = Ref{Int32}(0); qL = Ref{Int32}(0)
+    GC.@preserve labels check(ccall((:rc_pair_stats, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), getfield(data, :handle), Int64.(labels), rows))
+    check(ccall((:rc_data_scales, LIB[]), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}), getfield(data, :handle), qD, qL))
+    t = [sum(big.(rows[c, :])) for c in 1:5]
+    nA = Int(t[5]); nB = n * (n - 1) ÷ 2 - nA
+    return (nA = nA, sA = Float64(t[1] / big(2)^qD[]), lA = Float64(t[2] / big(2)^qL[]),
+            nB = nB, sB = Float64((t[3] - t[1]) / big(2)^qD[]), lB = Float64((t[4] - t[2]) / big(2)^qL[]))
+end
+
 function getpointestimate(samples::MCMCResult; method::String = "MAP", loss::Union{String,Function} = "VI")
     if method == "MPEL" && loss isa String && loss ∉ ["binder", "omARI", "VI", "ID"]
         throw(ArgumentError("Invalid loss function specifier."))

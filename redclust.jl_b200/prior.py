@@ -1,8 +1,9 @@
-"""Host-side prior fitting: fitprior / sampledist / sampleK and the notional clustering helpers
-(/root/reference/src/prior.jl:22-367, src/mcmc.jl:592-636 sample_rp).  SURVEY.md section 8(f) rank 1: caller
-of the hot path, kept on the host (one-off O(K) / O(n^2) work dominated by k-means / k-medoids, which
-are third-party Clustering.jl code in the reference).  The distance matrix it needs is built by the GPU
-kernel behind MCMCData (prior.jl:51,180)."""
+"""Prior fitting: fitprior / sampledist / sampleK and the notional clustering helpers
+(/root/reference/src/prior.jl:22-367, src/mcmc.jl:592-636 sample_rp).  SURVEY.md section 8(f) rank 1, the caller
+of the hot path.  The O(n^2) parts run on the device-resident matrix behind MCMCData (prior.jl:51,180): the
+distance build, k-medoids (rc_kmedoids) and the within / between sufficient statistics of the Gamma fits
+(rc_pair_stats).  k-means (points, O(n K dim)) and the O(K) fits stay on the host; k-means / k-medoids are
+third-party Clustering.jl code in the reference and are restated here."""
 import math
 import warnings
 import numpy as np
@@ -14,21 +15,49 @@ class ArgumentError(ValueError):
 
 
 # ---- third-party pieces restated (Clustering.jl kmeans / kmedoids, Distributions.fit_mle) -----------
-def kmedoids(D, k, maxiter=1000, rng=None):
-    """Clustering.kmedoids(D, k; maxiter): alternate assignment / medoid update from a random seeding."""
-    D = np.asarray(D)
-    n = D.shape[0]
-    g = np.random.default_rng(0 if rng is None else rng)
-    # k-medoids++ style seeding (Clustering.jl's default :kmpp)
+def _kmpp_seed(row, n, k, g):
+    """k-medoids++ style seeding (Clustering.jl's default :kmpp); row(i) returns row i of the dissimilarity matrix."""
     med = [int(g.integers(n))]
-    mind = D[med[0]].copy()
+    mind = np.array(row(med[0]), dtype=np.float64)
     for _ in range(1, k):
         w = mind ** 2
         tot = w.sum()
         nxt = int(g.choice(n, p=w / tot)) if tot > 0 else int(g.integers(n))
         med.append(nxt)
-        mind = np.minimum(mind, D[nxt])
-    med = np.array(med)
+        mind = np.minimum(mind, row(nxt))
+    return np.array(med, dtype=np.int64)
+
+
+def kmedoids_device(data, k, maxiter=1000, rng=None, init_medoids=None):
+    """Clustering.kmedoids on a device-resident MCMCData (librcb200 rc_kmedoids): same seeding and iteration as
+    kmedoids(), the O(n^2) medoid updates run on the GPU over the exact fixed-point image of D."""
+    import ctypes as C
+    from ._lib import lib, check, ptr
+    n = data.n
+    g = np.random.default_rng(0 if rng is None else rng)
+    if init_medoids is None:
+        def row(i):
+            out = np.empty(n)
+            check(lib().rc_data_copy_row(data._h, int(i), ptr(out)))
+            return out
+        init_medoids = _kmpp_seed(row, n, k, g)
+    init = np.ascontiguousarray(np.asarray(init_medoids, dtype=np.int64))
+    assign = np.zeros(n, np.int64); med = np.zeros(k, np.int64)
+    cost, conv, its = C.c_double(), C.c_int32(), C.c_int64()
+    check(lib().rc_kmedoids(data._h, k, ptr(init), maxiter, ptr(assign), ptr(med), C.byref(cost), C.byref(conv), C.byref(its)))
+    return dict(assignments=assign, medoids=med, totalcost=cost.value, converged=bool(conv.value), iterations=its.value)
+
+
+def kmedoids(D, k, maxiter=1000, rng=None):
+    """Clustering.kmedoids(D, k; maxiter): alternate assignment / medoid update from a random seeding.
+    D: host matrix (numpy path below) or a device-resident MCMCData (GPU path)."""
+    from .host import MCMCData
+    if isinstance(D, MCMCData):
+        return kmedoids_device(D, k, maxiter=maxiter, rng=rng)
+    D = np.asarray(D)
+    n = D.shape[0]
+    g = np.random.default_rng(0 if rng is None else rng)
+    med = _kmpp_seed(lambda i: D[i], n, k, g)
     converged = False
     assign = np.argmin(D[med], axis=0)
     for _ in range(maxiter):
@@ -187,6 +216,16 @@ def sample_rp(clustsizes, numiters=5000, burnin=None, thin=1, params=None, rng=N
 
 def _prepare(data, algo, diss, Kmin, Kmax, device):
     from .host import MCMCData, makematrix
+    if isinstance(data, MCMCData):                   # an already resident dissimilarity matrix
+        if algo == "k-means":
+            raise ArgumentError("Cannot use algorithm `k-means` with a dissimilarity matrix.")
+        if algo != "k-medoids":
+            raise ArgumentError("Algo must be 'k-means' or 'k-medoids'.")
+        N = data.n
+        Kmax = N // 2 if Kmax is None else Kmax
+        if not (1 <= Kmin <= Kmax <= N):
+            raise ArgumentError("Kmin and Kmax must satisfy 1 ≤ Kmin ≤ Kmax ≤ N")
+        return None, N, data, Kmax
     if isinstance(data, (list, tuple)):
         if diss:
             raise ArgumentError("diss = true but data is not a dissimilarity matrix. Assuming that the data is a vector of observations.")
@@ -204,17 +243,17 @@ def _prepare(data, algo, diss, Kmin, Kmax, device):
     Kmax = N // 2 if Kmax is None else Kmax
     if not (1 <= Kmin <= Kmax <= N):
         raise ArgumentError("Kmin and Kmax must satisfy 1 ≤ Kmin ≤ Kmax ≤ N")
-    dissM = x if diss else MCMCData.from_points(x.T, device=device).D      # pairwise(Euclidean(), x, dims=2)
-    return x, N, dissM, Kmax
+    dev = MCMCData(np.ascontiguousarray(x), device=device) if diss else MCMCData.from_points(x.T, device=device)   # pairwise(Euclidean(), x, dims=2)
+    return x, N, dev, Kmax
 
 
 def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, rng=None):
     """fitprior(data, algo, diss = false; Kmin, Kmax, verbose) -> PriorHyperparamsList   (prior.jl:22-128)."""
-    from .host import PriorHyperparamsList, uppertriangle
-    x, N, dissM, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
+    from .host import PriorHyperparamsList, pair_stats
+    x, N, dev, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
     if verbose:
         print("Fitting prior hyperparameters")
-    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dissM)
+    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)      # k-medoids runs on the device-resident matrix
     objective = np.zeros(Kmax - Kmin + 1)
     for k in range(1, Kmax - Kmin + 2):            # quirk Q11: clusters with k = loop index (prior.jl:63-64)
         t = clustfn(inp, k, maxiter=1000, rng=rng)
@@ -223,9 +262,7 @@ def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, 
             warnings.warn(f"Clustering did not converge at K = {k}")
     K = int(detectknee(np.arange(Kmin, Kmax + 1), objective)[0])
     notional = clustfn(inp, K, maxiter=1000, rng=rng)["assignments"]
-    adj = uppertriangle(notional[:, None] == notional[None, :])
-    ut = uppertriangle(dissM)
-    A, B = ut[adj], ut[~adj]
+    st = pair_stats(dev, notional)          # A = within-cluster, B = between-cluster upper-triangle dissimilarities (:73-75)
     sizes = np.bincount(notional)[1:]
     t = sample_rp(sizes, rng=rng)
     proposalsd_r = float(np.std(t["r"], ddof=1))
@@ -235,12 +272,12 @@ def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, 
         warnings.warn("Got a notional clustering of entirely singletons. Falling back to defaults for cohesion parameters.")
         d1, al, be = 1.0, 1.0, 1.0
     else:
-        d1 = gamma_mle_shape(A); al = A.size * d1; be = float(A.sum())
+        d1 = gamma_shape_from_stats(st["sA"] / st["nA"], st["lA"] / st["nA"]); al = st["nA"] * d1; be = float(st["sA"])
     if K == 1:
         warnings.warn("Got a notional clustering with a single cluster. Falling back to defaults for repulsion parameters.")
         d2, ze, ga = 1.0, 1.0, 1.0
     else:
-        d2 = gamma_mle_shape(B); ze = B.size * d2; ga = float(B.sum())
+        d2 = gamma_shape_from_stats(st["sB"] / st["nB"], st["lB"] / st["nB"]); ze = st["nB"] * d2; ga = float(st["sB"])
     return PriorHyperparamsList(delta1=d1, delta2=d2, alpha=al, beta=be, zeta=ze, gamma=ga, eta=eta, sigma=sigma,
                                 proposalsd_r=proposalsd_r, u=u, v=v, K_initial=K)
 
