@@ -280,3 +280,41 @@ def getpointestimate(result, method="MAP", loss="VI"):
     else:
         i = int(np.argmin(mpel_loss_sums(result["labels"], loss)))
     return result["labels"][i], i
+
+
+# ---- fitprior pieces ------------------------------------------------------------------
+def kmedoids_fixed_point(D, q, init, maxiter=1000):
+    """Clustering.kmedoids(dissM, k; maxiter) as used at /root/reference/src/prior.jl:55-71 and src/mcmc.jl:519-527
+    (third-party code, restated: alternate nearest-medoid assignment -- first minimum -- and medoid update -- member
+    with the smallest sum of dissimilarities to its cluster, lowest index on ties -- until nothing changes), with the
+    medoid sums over the fixed-point image Dq = round(D 2^q) so that they are exact integers.
+    Returns (assignments 1-based, medoids 0-based, converged, total cost as an integer in units of 2^-q)."""
+    D = np.asarray(D, dtype=np.float64)
+    Dq = np.rint(D * 2.0 ** q).astype(np.int64)
+    med = np.array(init, dtype=np.int64)
+    k = med.size
+    assign = np.argmin(D[med], axis=0)
+    conv = False
+    for _ in range(maxiter):
+        newmed = med.copy()
+        for c in range(k):
+            mem = np.where(assign == c)[0]
+            if mem.size:
+                newmed[c] = mem[np.argmin(Dq[np.ix_(mem, mem)].sum(0))]
+        newassign = np.argmin(D[newmed], axis=0)
+        same = np.array_equal(newmed, med) and np.array_equal(newassign, assign)
+        med, assign = newmed, newassign
+        if same:
+            conv = True
+            break
+    return assign + 1, med, conv, int(Dq[med[assign], np.arange(D.shape[0])].sum())
+
+
+def pair_stats(D, labels):
+    """A = uppertriangle(dissM)[adjacency], B = the rest (/root/reference/src/prior.jl:73-75): counts, sums, log-sums."""
+    D = np.asarray(D, dtype=np.float64); labels = np.asarray(labels)
+    iu = np.triu_indices(D.shape[0], 1)
+    adj = (labels[:, None] == labels[None, :])[iu]
+    ut = D[iu]
+    A, B = ut[adj], ut[~adj]
+    return dict(nA=int(A.size), sA=float(A.sum()), lA=float(np.log(A).sum()), nB=int(B.size), sB=float(B.sum()), lB=float(np.log(B).sum()))

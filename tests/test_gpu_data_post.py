@@ -160,29 +160,7 @@ def test_mpel_larger_sample_sets(pkg, orc):
             assert abs(ref[best] - ref.min()) <= 1e-10 * max(1.0, abs(ref.min()))
 
 
-def _kmedoids_fixed_point(D, q, init, maxiter=1000):
-    """numpy restatement of rc_kmedoids over the same fixed-point image Dq = round(D 2^q) (exact integers)."""
-    Dq = np.rint(D * 2.0 ** q).astype(np.int64)
-    med = np.array(init, dtype=np.int64)
-    k = med.size
-    assign = np.argmin(D[med], axis=0)
-    conv = False
-    for _ in range(maxiter):
-        newmed = med.copy()
-        for c in range(k):
-            mem = np.where(assign == c)[0]
-            if mem.size:
-                newmed[c] = mem[np.argmin(Dq[np.ix_(mem, mem)].sum(0))]
-        newassign = np.argmin(D[newmed], axis=0)
-        same = np.array_equal(newmed, med) and np.array_equal(newassign, assign)
-        med, assign = newmed, newassign
-        if same:
-            conv = True
-            break
-    return assign + 1, med, conv, int(Dq[med[assign], np.arange(D.shape[0])].sum())
-
-
-def test_kmedoids_device_matches_fixed_point_restatement(pkg, golden):
+def test_kmedoids_device_matches_fixed_point_restatement(pkg, orc, golden):
     """rc_kmedoids (fitprior's elbow scan and runsampler's default init, prior.jl:55-71, mcmc.jl:519-527)."""
     from redclust_jl_b200.prior import kmedoids_device
     rng = np.random.default_rng(4)
@@ -195,7 +173,7 @@ def test_kmedoids_device_matches_fixed_point_restatement(pkg, golden):
         qD, _ = data.scales()
         init = rng.choice(data.n, size=k, replace=False)
         got = kmedoids_device(data, k, init_medoids=init)
-        a, med, conv, cost_q = _kmedoids_fixed_point(Dh, qD, init)
+        a, med, conv, cost_q = orc.kmedoids_fixed_point(Dh, qD, init)
         assert np.array_equal(got["assignments"], a) and np.array_equal(got["medoids"], med) and got["converged"] == conv
         assert got["totalcost"] == cost_q / 2.0 ** qD
         assert abs(got["totalcost"] - Dh[med[a - 1], np.arange(data.n)].sum()) <= 1e-10 * got["totalcost"]
@@ -207,18 +185,15 @@ def test_kmedoids_device_matches_fixed_point_restatement(pkg, golden):
     assert sorted(pkg.kmedoids(data, data.n)["assignments"]) == list(range(1, data.n + 1))
 
 
-def test_pair_stats_and_fitprior_on_device(pkg, golden):
+def test_pair_stats_and_fitprior_on_device(pkg, orc, golden):
     """Within / between sufficient statistics (prior.jl:73-110) against numpy; fitprior end to end on the device."""
     D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
     data = pkg.MCMCData(D)
     st = pkg.pair_stats(data, lab)
-    iu = np.triu_indices(D.shape[0], 1)
-    adj = (lab[:, None] == lab[None, :])[iu]
-    ut = D[iu]
-    A, B = ut[adj], ut[~adj]
-    assert st["nA"] == A.size and st["nB"] == B.size
-    for got, want in ((st["sA"], A.sum()), (st["lA"], np.log(A).sum()), (st["sB"], B.sum()), (st["lB"], np.log(B).sum())):
-        assert abs(got - want) <= 1e-10 * abs(want)
+    ref = orc.pair_stats(D, lab)
+    assert st["nA"] == ref["nA"] and st["nB"] == ref["nB"]
+    for f in ("sA", "lA", "sB", "lB"):
+        assert abs(st[f] - ref[f]) <= 1e-10 * abs(ref[f]), f
     p_dev = pkg.params_from_labels(data, lab)
     p_host = pkg.params_from_labels(D, lab)
     for f in ("delta1", "alpha", "beta", "delta2", "zeta", "gamma"):

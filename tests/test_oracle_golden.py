@@ -117,3 +117,21 @@ def test_numMH0_is_pure_gibbs_and_deterministic(orc, pkg, golden):
         assert first == sorted(first) and a["labels"][s].max() == a["K"][s]
     c = orc.run_chain(D, orc.Options(30, 5, 2, 5, 0), P, lab, 1.2, 0.4, seed=10)
     assert not np.array_equal(a["labels"], c["labels"])
+
+
+def test_prior_restatements(orc, golden):
+    """k-medoids and the within / between split of fitprior (prior.jl:55-75) on the reference's fixture."""
+    import numpy as np
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    n = D.shape[0]
+    a, med, conv, cost = orc.kmedoids_fixed_point(D, 40, [3, 50, 77, 90])
+    assert conv and set(np.unique(a)) == {1, 2, 3, 4}
+    assert np.array_equal(a[med], np.arange(1, 5))                       # every medoid sits in its own cluster
+    for c in range(4):                                                   # no member beats the medoid (fixed point)
+        mem = np.where(a == c + 1)[0]
+        assert D[np.ix_(mem, mem)].sum(0).min() >= D[np.ix_(mem, [med[c]])].sum() - 1e-9
+    assert np.array_equal(a - 1, np.argmin(D[med], axis=0))
+    st = orc.pair_stats(D, lab)
+    assert st["nA"] + st["nB"] == n * (n - 1) // 2
+    assert st["nA"] == sum(int(s) * (int(s) - 1) // 2 for s in np.bincount(lab))
+    assert abs(st["sA"] + st["sB"] - np.triu(D, 1).sum()) < 1e-8
