@@ -65,6 +65,11 @@ int32_t rc_data_from_dist(const double* D, int64_t n, int32_t device, rc_data** 
 /* MCMCData(points): src/types.jl:159-162 = pairwise(Euclidean(), X, dims=2) with X dim x n
  * column-major (point i = X[i*dim .. i*dim+dim-1]); also src/utils.jl:144-145, src/prior.jl:51,180. */
 int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t device, rc_data** out);
+/* Multi-GPU distance build (row blocks + all-gather): rows [row0, row0 + nrows) of pairwise(Euclidean(), X) into a
+ * caller DEVICE buffer of nrows x n fp64, bit-equal to the same rows of rc_data_from_points' matrix; and MCMCData(D)
+ * from a complete matrix that already lives on the device (src/types.jl:148-162 across GPUs). */
+int32_t rc_distm_rows_dev(const double* X, int64_t dim, int64_t n, int64_t row0, int64_t nrows, int32_t device, void* D_rows_dev);
+int32_t rc_data_from_dist_dev(const void* D_dev, int64_t n, int32_t device, rc_data** out);
 int64_t rc_data_n(const rc_data* d);
 /* data.D and data.logD back to the host as n x n fp64. */
 int32_t rc_data_copy_dist(const rc_data* d, double* D_out);
@@ -145,6 +150,13 @@ int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, doub
  * *best = first argmin (0-based).  loss: 0 binder (Mirkin), 1 omARI, 2 VI, 3 ID (un-normalised). */
 int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device,
                 double* loss_sums, int64_t* best);
+/* Multi-GPU MPEL (candidates sharded over GPUs): rows row_first, row_first + row_stride, ... (nrows of them) of the
+ * strict upper triangle of the pairwise loss matrix into a caller DEVICE buffer (nrows x S fp64); after an
+ * all-gather of the blocks into the S x S upper triangle, rc_mpel_finish_dev sums the columns in ascending row
+ * order and returns the first argmin -- bit-equal to rc_mpel on one GPU (src/pointestimate.jl:34-59). */
+int32_t rc_mpel_rows_dev(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device, int64_t row_first,
+                         int64_t row_stride, int64_t nrows, void* M_rows_dev);
+int32_t rc_mpel_finish_dev(const void* M_upper_dev, int64_t S, int32_t device, double* loss_sums, int64_t* best);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rc_device_count": (C.c_int32, []),
     "rc_data_from_dist": (C.c_int32, [_vp, C.c_int64, C.c_int32, _P(_vp)]),
     "rc_data_from_points": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, _P(_vp)]),
+    "rc_distm_rows_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _vp]),
+    "rc_data_from_dist_dev": (C.c_int32, [_vp, C.c_int64, C.c_int32, _P(_vp)]),
     "rc_data_n": (C.c_int64, [_vp]),
     "rc_data_copy_dist": (C.c_int32, [_vp, _vp]),
     "rc_data_copy_logdist": (C.c_int32, [_vp, _vp]),
@@ -64,6 +66,8 @@ SIGNATURES = {
     "rc_loglik": (C.c_int32, [_vp, _P(rc_params), _vp, _P(C.c_double)]),
     "rc_psm": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, _vp]),
     "rc_mpel": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _P(C.c_int64)]),
+    "rc_mpel_rows_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _vp]),
+    "rc_mpel_finish_dev": (C.c_int32, [_vp, C.c_int64, C.c_int32, _vp, _P(C.c_int64)]),
 }
 
 

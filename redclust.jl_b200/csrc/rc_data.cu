@@ -193,6 +193,42 @@ int finish_data(rc_data* d) {
   return RC_OK;
 }
 
+// Rows [row0, row0 + nrows) of the distance matrix, every entry computed (no mirroring) with the operation order of
+// k_distm: products and sums commute pairwise, so the block equals the same rows of the single-GPU matrix bit for bit.
+__global__ void __launch_bounds__(256) k_distm_rows(const double* __restrict__ X, const double* __restrict__ sq, int64_t dim, int64_t n,
+                                                    int64_t row0, int64_t nrows, double* __restrict__ Drows) {
+  __shared__ double Xi[DT][DT + 1], Xj[DT][DT + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t i0 = row0 + (int64_t)blockIdx.y * DT, j0 = (int64_t)blockIdx.x * DT, iend = row0 + nrows;
+  for (int64_t t0 = 0; t0 < dim; t0 += DT) {
+    for (int r = ty; r < DT; r += 8) {
+      const int64_t t = t0 + tx;
+      Xi[r][tx] = (i0 + r < iend && t < dim) ? X[(i0 + r) * dim + t] : 0.0;
+      Xj[r][tx] = (j0 + r < n && t < dim) ? X[(j0 + r) * dim + t] : 0.0;
+    }
+    __syncthreads();
+    const int tmax = (int)((dim - t0) < DT ? (dim - t0) : DT);
+    for (int t = 0; t < tmax; ++t) {
+      const double xj = Xj[tx][t];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += Xi[ty + 8 * q][t] * xj;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t i = i0 + ty + 8 * q, j = j0 + tx;
+    if (i >= iend || j >= n) continue;
+    double r = 0.0;
+    if (i != j) {
+      const double v = (i < j ? sq[i] + sq[j] : sq[j] + sq[i]) - 2 * acc[q];
+      r = sqrt(v > 0.0 ? v : 0.0);
+    }
+    Drows[(i - row0) * n + j] = r;
+  }
+}
+
 int select_device(int32_t device) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
@@ -252,6 +288,45 @@ int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t dev
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(dX); cudaFree(sq);
   if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); rc_data_destroy(d); return RC_ERR_CUDA; }
+  st = finish_data(d);
+  if (st) { rc_data_destroy(d); return st; }
+  *out = d;
+  return RC_OK;
+}
+
+// Multi-GPU distance build: this rank's block of rows into a caller device buffer (nrows x n fp64); the
+// caller all-gathers the blocks and hands the complete matrix to rc_data_from_dist_dev.
+int32_t rc_distm_rows_dev(const double* X, int64_t dim, int64_t n, int64_t row0, int64_t nrows, int32_t device, void* D_rows_dev) {
+  if (!X || !D_rows_dev || n < 1 || dim < 1 || row0 < 0 || nrows < 0 || row0 + nrows > n) { rc_set_error("rc_distm_rows_dev: bad arguments"); return RC_ERR_ARG; }
+  int st = select_device(device);
+  if (st) return st;
+  if (nrows == 0) return RC_OK;
+  double *dX = nullptr, *sq = nullptr;
+  if (cudaMalloc(&dX, sizeof(double) * (size_t)n * dim) != cudaSuccess || cudaMalloc(&sq, sizeof(double) * (size_t)n) != cudaSuccess) {
+    rc_set_error("out of device memory for the points"); cudaFree(dX); cudaFree(sq); return RC_ERR_CUDA;
+  }
+  cudaMemcpy(dX, X, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice);
+  k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
+  k_distm_rows<<<dim3((unsigned)((n + DT - 1) / DT), (unsigned)((nrows + DT - 1) / DT)), 256>>>(dX, sq, dim, n, row0, nrows, (double*)D_rows_dev);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(dX); cudaFree(sq);
+  if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
+  return RC_OK;
+}
+
+// MCMCData(D) from a matrix that already lives on the device (same checks and images as rc_data_from_dist).
+int32_t rc_data_from_dist_dev(const void* D_dev, int64_t n, int32_t device, rc_data** out) {
+  if (!D_dev || !out || n < 1) { rc_set_error("rc_data_from_dist_dev: null pointer or n < 1"); return RC_ERR_ARG; }
+  int st = select_device(device);
+  if (st) return st;
+  rc_data* d = new rc_data();
+  d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
+  if (rc_dev_malloc((void**)&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess) {
+    rc_set_error("out of device memory for D (%lld x %lld)", (long long)n, (long long)n); delete d; return RC_ERR_CUDA;
+  }
+  if (cudaMemcpy(d->D, D_dev, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+    rc_set_error("copy of D failed"); rc_data_destroy(d); return RC_ERR_CUDA;
+  }
   st = finish_data(d);
   if (st) { rc_data_destroy(d); return st; }
   *out = d;

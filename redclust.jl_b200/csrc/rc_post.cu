@@ -163,8 +163,10 @@ __device__ __forceinline__ unsigned tab_get(const unsigned* tab, int t, int wide
 }
 __global__ void __launch_bounds__(256) k_pair_loss(const uint8_t* __restrict__ L, const int* __restrict__ Kc, int64_t S,
                                                    int64_t n, int loss, int wide, int tabwords, int stride,
-                                                   const double* __restrict__ nlogn, double* __restrict__ M) {
-  const int64_t i = blockIdx.y;
+                                                   const double* __restrict__ nlogn, double* __restrict__ M, int64_t row_first,
+                                                   int64_t row_stride, int mirror) {
+  const int64_t i = row_first + (int64_t)blockIdx.y * row_stride;       // sharded: this rank's rows are row_first, + stride, ...
+  if (i >= S) return;
   const int64_t jlo = max((long long)(i + 1), (long long)blockIdx.x * PJ), jhi = min((long long)S, (long long)(blockIdx.x + 1) * PJ);
   if (jlo >= jhi) return;
   extern __shared__ __align__(16) unsigned tab[];
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(256) k_pair_loss(const uint8_t* __restrict__ L
       const double I = snl / dn - hA / dn - hB / dn + log(dn);
       out = loss == 2 ? (HA + HB - 2 * I) : ((HA > HB ? HA : HB) - I);
     }
-    M[i * S + j] = out;
-    M[j * S + i] = out;
+    if (mirror) { M[i * S + j] = out; M[j * S + i] = out; }
+    else M[(int64_t)blockIdx.y * S + j] = out;                         // row block of the upper triangle
   }
   }
 }
@@ -245,6 +247,16 @@ __global__ void k_colsum(const double* __restrict__ M, int64_t S, double* __rest
   if (j >= S) return;
   double s = 0;
   for (int64_t i = 0; i < S; ++i) s += M[i * S + j];   // ascending-row order, as sum(lossmatrix, dims = 1)
+  sums[j] = s;
+}
+
+// column sums of the symmetric loss matrix given its strict upper triangle U, rows in ascending order (= k_colsum on
+// the mirrored matrix: the diagonal contributes +0.0)
+__global__ void k_colsum_upper(const double* __restrict__ U, int64_t S, double* __restrict__ sums) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= S) return;
+  double s = 0;
+  for (int64_t i = 0; i < S; ++i) s += i < j ? U[i * S + j] : (i > j ? U[j * S + i] : 0.0);
   sums[j] = s;
 }
 
@@ -388,6 +400,64 @@ int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, doub
   return st;
 }
 
+// Multi-GPU MPEL: the candidate rows row_first, row_first + row_stride, ... (nrows of them) of the strict
+// upper triangle of the pairwise loss matrix into a caller DEVICE buffer (nrows x S fp64, zero where j <= i); the
+// caller all-gathers the row blocks into the S x S upper triangle and calls rc_mpel_finish_dev, which sums the columns
+// in ascending row order -- the result is bit-equal to rc_mpel on one GPU.
+int32_t rc_mpel_rows_dev(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device, int64_t row_first,
+                         int64_t row_stride, int64_t nrows, void* M_rows_dev) {
+  if (!labels || !M_rows_dev || S < 1 || n < 1 || loss < 0 || loss > 3 || row_first < 0 || row_stride < 1 || nrows < 0) {
+    rc_set_error("rc_mpel_rows_dev: bad arguments"); return RC_ERR_ARG;
+  }
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
+  RC_CUDA(cudaSetDevice(device));
+  std::vector<uint8_t> L; std::vector<int> K;
+  int st = compact_labels(labels, S, n, L, K);
+  if (st) return st;
+  int kmax = 0;
+  for (int k : K) kmax = std::max(kmax, k);
+  const int wide = n > 65535;
+  const int tabwords = ((wide ? kmax * kmax : (kmax * kmax + 1) / 2) + 3) & ~3;
+  const size_t smem = (size_t)tabwords * 4 + 2 * (size_t)((n + 15) / 16) * 16;
+  if (smem > 220 * 1024) { rc_set_error("rc_mpel: n = %lld with %d x %d clusters does not fit shared memory", (long long)n, kmax, kmax); return RC_ERR_SLOTS; }
+  int stride = (int)((n + 31) / 32);
+  while ((stride & 3) || !((stride >> 2) & 1)) ++stride;
+  uint8_t* dL = nullptr; int* dK = nullptr; double* nlogn = nullptr;
+  RC_CUDA(cudaMalloc(&dL, L.size()));
+  RC_CUDA(cudaMalloc(&dK, sizeof(int) * S));
+  RC_CUDA(cudaMalloc(&nlogn, sizeof(double) * (size_t)(n + 1)));
+  RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
+  RC_CUDA(cudaMemcpy(dK, K.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  RC_CUDA(cudaMemset(M_rows_dev, 0, sizeof(double) * (size_t)nrows * S));
+  k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
+  cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (nrows > 0)
+    k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)nrows), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn,
+                                                                                  (double*)M_rows_dev, row_first, row_stride, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(dL); cudaFree(dK); cudaFree(nlogn);
+  RC_CUDA(e);
+  return RC_OK;
+}
+
+int32_t rc_mpel_finish_dev(const void* M_upper_dev, int64_t S, int32_t device, double* loss_sums, int64_t* best) {
+  if (!M_upper_dev || S < 1) { rc_set_error("rc_mpel_finish_dev: bad arguments"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(device));
+  double* sums = nullptr;
+  RC_CUDA(cudaMalloc(&sums, sizeof(double) * S));
+  k_colsum_upper<<<(unsigned)((S + 127) / 128), 128>>>((const double*)M_upper_dev, S, sums);
+  std::vector<double> hs((size_t)S);
+  cudaError_t e = cudaMemcpy(hs.data(), sums, sizeof(double) * S, cudaMemcpyDeviceToHost);
+  cudaFree(sums);
+  RC_CUDA(e);
+  int64_t b = 0;
+  for (int64_t i = 1; i < S; ++i) if (hs[i] < hs[b]) b = i;     // argmin: first minimum
+  if (loss_sums) memcpy(loss_sums, hs.data(), sizeof(double) * S);
+  if (best) *best = b;
+  return RC_OK;
+}
+
 int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device, double* loss_sums, int64_t* best) {
   if (!labels || S < 1 || n < 1 || loss < 0 || loss > 3) { rc_set_error("rc_mpel: bad arguments"); return RC_ERR_ARG; }
   int cnt = 0;
@@ -415,7 +485,7 @@ int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32
   RC_CUDA(cudaMemset(M, 0, sizeof(double) * (size_t)S * S));
   k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
   cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)S), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn, M);
+  k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)S), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn, M, 0, 1, 1);
   k_colsum<<<(unsigned)((S + 127) / 128), 128>>>(M, S, sums);
   std::vector<double> hs((size_t)S);
   const double tk = getenv("RCB200_VERBOSE") ? std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;

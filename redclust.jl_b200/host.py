@@ -114,6 +114,32 @@ class MCMCData:
         obj.n = int(lib().rc_data_n(obj._h))
         return obj
 
+    @classmethod
+    def from_points_sharded(cls, points, group=None, device=None):
+        """MCMCData(points) with the distance build split over the ranks of a torch.distributed process group
+        (SURVEY 8e): rank r computes a block of rows, one all_gather (NCCL) gives every GPU the whole matrix, which
+        stays on the device.  Bit-equal to from_points on one GPU.  Without a process group: this rank builds all rows."""
+        import torch
+        import torch.distributed as dist
+        P = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+        n, dim = P.shape
+        dev = torch.cuda.current_device() if device is None else device
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        per = (n + world - 1) // world                                 # equal blocks (the last one is padded)
+        full = torch.zeros((world * per, n), dtype=torch.float64, device=torch.device("cuda", dev))
+        row0 = min(rank * per, n); nrows = min(per, n - row0)
+        mine = full[rank * per:(rank + 1) * per]
+        check(lib().rc_distm_rows_dev(ptr(P), dim, n, row0, nrows, dev, C.c_void_p(mine.data_ptr())))
+        if world > 1:
+            dist.all_gather_into_tensor(full, mine.clone(), group=group)
+        obj = cls.__new__(cls)
+        obj._h = C.c_void_p()
+        obj.device = dev
+        check(lib().rc_data_from_dist_dev(C.c_void_p(full.data_ptr()), n, dev, C.byref(obj._h)))
+        obj.n = int(lib().rc_data_n(obj._h))
+        return obj
+
     @property
     def D(self):
         out = np.empty((self.n, self.n))
@@ -371,6 +397,33 @@ def mpel_loss_sums(labels, loss, device=0):
     best = C.c_int64()
     check(lib().rc_mpel(ptr(L), L.shape[0], L.shape[1], _LOSS[loss], device, ptr(sums), C.byref(best)))
     return sums, best.value
+
+
+def mpel_loss_sums_sharded(labels, loss, group=None, device=None):
+    """mpel_loss_sums with the candidate samples split over the ranks of a torch.distributed process group:
+    rank r evaluates rows r, r + world, ... of the upper triangle of the pairwise loss matrix (cyclic, so the ranks
+    do equal work), one all_gather (NCCL) assembles it on every GPU, the column sums run in ascending row order --
+    bit-equal to the single-GPU result."""
+    import torch
+    import torch.distributed as dist
+    L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    S, n = L.shape
+    dev = torch.cuda.current_device() if device is None else device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    per = (S + world - 1) // world
+    tdev = torch.device("cuda", dev)
+    mine = torch.zeros((per, S), dtype=torch.float64, device=tdev)
+    check(lib().rc_mpel_rows_dev(ptr(L), S, n, _LOSS[loss], dev, rank, world, per, C.c_void_p(mine.data_ptr())))
+    if world > 1:
+        allrows = torch.empty((world, per, S), dtype=torch.float64, device=tdev)
+        dist.all_gather_into_tensor(allrows, mine, group=group)
+        upper = allrows.permute(1, 0, 2).reshape(per * world, S)[:S].contiguous()    # row i came from rank i % world
+    else:
+        upper = mine[:S].contiguous()
+    sums = np.zeros(S); best = C.c_int64()
+    check(lib().rc_mpel_finish_dev(C.c_void_p(upper.data_ptr()), S, dev, ptr(sums), C.byref(best)))
+    return sums, int(best.value)
 
 
 def getpointestimate(samples, method="MAP", loss="VI", device=0):

@@ -204,3 +204,17 @@ def test_pair_stats_and_fitprior_on_device(pkg, orc, golden):
     if pts is not None:
         p2 = pkg.fitprior(list(np.asarray(pts)), "k-means", False, Kmin=1, Kmax=15, verbose=False, rng=1)   # vector of observations
         assert p2.K_initial >= 2 and p2.alpha > 0
+
+
+def test_sharded_entry_points_single_rank(pkg, golden):
+    """Row-block distance build and row-block MPEL (the multi-GPU paths of SURVEY 8e) with one rank: bit-equal to the
+    plain calls.  tools/multigpu_check.py runs the same comparison across ranks over NCCL."""
+    rng = np.random.default_rng(12)
+    X = rng.normal(size=(333, 17))
+    a, b = pkg.MCMCData.from_points(X), pkg.MCMCData.from_points_sharded(X)
+    assert np.array_equal(a.D, b.D) and np.array_equal(a.logD, b.logD) and a.scales() == b.scales()
+    L = np.stack([rng.integers(1, 7, size=90) for _ in range(37)])
+    for loss in ("binder", "omARI", "VI", "ID"):
+        s1, b1 = pkg.mpel_loss_sums(L, loss)
+        s2, b2 = pkg.mpel_loss_sums_sharded(L, loss)
+        assert np.array_equal(s1, s2) and b1 == b2, loss
