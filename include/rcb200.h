@@ -127,7 +127,8 @@ int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t*
  * a resumed run (src/mcmc.jl:504,519-529).                                                     */
 int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p);
 /* Profiling aid (no reference equivalent): 16 SM-cycle counters per chain accumulated by the chain kernel.
- * out: nchains x 16 int64. */
+ * out: nchains x 16 int64.  Only librcb200_stats.so carries the clock reads; the default library returns the
+ * move / rebuild counts and zeros for the cycle slots. */
 int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out);
 /* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the slot capacity overflowed.           */
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain);

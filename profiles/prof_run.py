@@ -4,6 +4,9 @@ import argparse, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+_stats_lib = os.path.join(ROOT, "redclust.jl_b200", "librcb200_stats.so")
+if os.path.exists(_stats_lib):
+    os.environ.setdefault("RCB200_LIB", _stats_lib)      # the build with the in-kernel cycle counters
 import __graft_entry__ as graft
 import bench
 
