@@ -41,16 +41,20 @@ RC_HD double rc_scalbn(double x, int k) {
   return x * rc_from_bits((uint64_t)(0x3ff + k) << 52);
 }
 
-// Natural logarithm, fdlibm-style argument reduction + degree-14 odd polynomial in s=f/(2+f).
+// Natural logarithm.  x = 2^k m with m in [sqrt(1/2), sqrt(2)) (fdlibm's normalisation, so k = 0 around 1);
+// F = round(128 m) / 128, f = m - F (exact), u = f * (1/F) from a table, log x = k ln2 + log F + log1p(u) with
+// log1p(u) - u as a degree-7 polynomial (|u| < 0.0056) in Estrin form.  k ln2_hi + head(log F) is exact (both carry
+// 21 trailing zero bits), so the result is within ~1 ulp.  No division and a dependent chain of ~14 operations
+// (the fdlibm form it replaces had ~45 with a division): this function sits on the sampler's sequential paths.
 // Straight-line: the main path is always evaluated (subnormals are pre-scaled by a select) and the special
-// cases (NaN, negative, zero, +Inf) override the result at the end, so two independent calls can be
-// interleaved by the compiler.  For every input the value is the one the branching formulation returns.
+// cases (NaN, negative, zero, +Inf) override the result at the end, so independent calls interleave.
+#include "rc_logtab.h"
+static const double rc_logtab_h[][3] = {RC_LOGTAB_ROWS};
+#if defined(__CUDACC__)
+static __device__ const double rc_logtab_d[][3] = {RC_LOGTAB_ROWS};
+#endif
 RC_HD double rc_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-               Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-               Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-               Lg7 = 1.479819860511658591e-01;
   const uint64_t ix0 = rc_to_bits(x);
   const bool sub = ix0 < 0x0010000000000000ULL;          // subnormal (or +0): pre-scale
   const double xs = sub ? x * 0x1p54 : x;
@@ -62,17 +66,24 @@ RC_HD double rc_log(double x) {
   k += (int)(hx >> 20) - 0x3ff;
   hx = (hx & 0x000fffff) + 0x3fe6a09e;
   ix = ((uint64_t)hx << 32) | (ix & 0xffffffffULL);
-  double m = rc_from_bits(ix);
-  double f = m - 1.0;
-  double hfsq = 0.5 * f * f;
-  double s = f / (2.0 + f);
-  double z = s * s;
-  double w = z * z;
-  double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
-  double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
-  double R = t2 + t1;
-  double dk = (double)k;
-  double res = s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  const double m = rc_from_bits(ix);
+  int j = (int)(m * 128.0 + 0.5);
+  j = j < RC_LOGTAB_J0 ? RC_LOGTAB_J0 : (j > RC_LOGTAB_J0 + 92 ? RC_LOGTAB_J0 + 92 : j);   // only NaN / Inf patterns leave the range
+#if defined(__CUDA_ARCH__)
+  const double* T = rc_logtab_d[j - RC_LOGTAB_J0];
+#else
+  const double* T = rc_logtab_h[j - RC_LOGTAB_J0];
+#endif
+  const double f = m - (double)j * 0.0078125;            // exact
+  const double u = f * T[0];
+  const double u2 = u * u;
+  const double u4 = u2 * u2;
+  const double p01 = -0.5 + u * 3.33333333333333314830e-01;
+  const double p23 = -0.25 + u * 2.00000000000000011102e-01;
+  const double p45 = -1.66666666666666657415e-01 + u * 1.42857142857142849213e-01;
+  const double q = u2 * ((p01 + u2 * p23) + u4 * p45);   // log1p(u) - u
+  const double dk = (double)k;
+  double res = (dk * ln2_hi + T[1]) + (u + ((dk * ln2_lo + T[2]) + q));
   if (ix0 >= 0x7ff0000000000000ULL) res = x;              // +Inf, and every negative / NaN pattern lands here too
   if ((int64_t)ix0 < 0) res = ((ix0 << 1) == 0) ? -RC_INF : RC_NAN;   // -0 -> -Inf, negative -> NaN
   if (ix0 == 0) res = -RC_INF;
