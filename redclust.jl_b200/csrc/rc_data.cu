@@ -3,6 +3,8 @@
 // call sites (src/types.jl:160, src/utils.jl:144-145, src/prior.jl:51,180).
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
+#include <cstdio>
 #include "rc_common.cuh"
 
 namespace {
@@ -164,8 +166,8 @@ __global__ void __launch_bounds__(128) k_distm_dmma(const double* __restrict__ X
 int finish_data(rc_data* d) {
   const int64_t n = d->n;
   int* flags = nullptr; unsigned long long* maxbits = nullptr;
-  RC_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
-  RC_CUDA(cudaMalloc(&maxbits, 2 * sizeof(unsigned long long)));
+  RC_CUDA(rc_dev_malloc((void**)&flags, 2 * sizeof(int)));
+  RC_CUDA(rc_dev_malloc((void**)&maxbits, 2 * sizeof(unsigned long long)));
   RC_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
   RC_CUDA(cudaMemset(maxbits, 0, 2 * sizeof(unsigned long long)));
   const int grid = 148 * 8;
@@ -175,7 +177,7 @@ int finish_data(rc_data* d) {
   int hflags[2]; unsigned long long hbits[2];
   RC_CUDA(cudaMemcpy(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost));
   RC_CUDA(cudaMemcpy(hbits, maxbits, sizeof(hbits), cudaMemcpyDeviceToHost));
-  cudaFree(flags); cudaFree(maxbits);
+  rc_dev_free(flags); rc_dev_free(maxbits);
   if (hflags[0]) { rc_set_error("D must be symmetric."); return RC_ERR_NOTSYM; }
   if (hflags[1]) {
     rc_set_error("D must have finite entries and strictly positive off-diagonal dissimilarities (log D must be finite).");
@@ -256,13 +258,19 @@ int32_t rc_data_from_dist(const double* D, int64_t n, int32_t device, rc_data** 
   if (st) return st;
   rc_data* d = new rc_data();
   d->n = n; d->device = device; d->D = nullptr; d->DL = nullptr;
+  const bool verbose = getenv("RCB200_VERBOSE") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (rc_dev_malloc((void**)&d->D, sizeof(double) * (size_t)n * n) != cudaSuccess) {
     rc_set_error("out of device memory for D (%lld x %lld)", (long long)n, (long long)n); delete d; return RC_ERR_CUDA;
   }
+  const double t1 = now();
   if (cudaMemcpy(d->D, D, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice) != cudaSuccess) {
     rc_set_error("upload of D failed"); rc_data_destroy(d); return RC_ERR_CUDA;
   }
+  const double t2 = now();
   st = finish_data(d);
+  if (verbose) fprintf(stderr, "[rcb200] rc_data_from_dist n=%lld: alloc %.4f s, upload %.4f s, checks + images %.4f s\n", (long long)n, t1 - t0, t2 - t1, now() - t2);
   if (st) { rc_data_destroy(d); return st; }
   *out = d;
   return RC_OK;
