@@ -428,6 +428,31 @@ __device__ __forceinline__ longlong2 bin_total(const Ctx& c, int s, int buf = 0)
 // NSR = rounds of 32 slots held in registers.  decide_rows<2> serves chains whose live slots (and next free slot)
 // are all below 64 -- half the register state, no spills -- and returns the row at which a slot >= 64 is needed;
 // decide_rows<NSR> continues from there.  `M` (moves published) and the counters carry over.
+// Warp-wide minimum / maximum of doubles that are not NaN (infinities allowed) with two 32-bit REDUX operations on an
+// order-preserving integer key instead of a five-round shuffle butterfly of fp64 compares (the decision warp's
+// latency chain).  -0.0 is folded onto +0.0 first; minimum and maximum are exact, so nothing else changes.
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unkey(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ double warp_min_f64(double v) {
+  const unsigned long long k = f64_key(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned hm = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned lm = __reduce_min_sync(0xffffffffu, hi == hm ? lo : 0xffffffffu);
+  return f64_unkey(((unsigned long long)hm << 32) | lm);
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+  const unsigned long long k = f64_key(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned hm = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned lm = __reduce_max_sync(0xffffffffu, hi == hm ? lo : 0u);
+  return f64_unkey(((unsigned long long)hm << 32) | lm);
+}
+
 struct DecCarry { int M, nmoves; bool dead; long long acc_wait, acc_work, tlast; };
 template <int NSR>
 __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) {
@@ -588,11 +613,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
         }
       }
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const double o = __shfl_xor_sync(0xffffffffu, mn, off);
-      if (o < mn) mn = o;
-    }
+    mn = warp_min_f64(mn);
     anynan = __any_sync(0xffffffffu, anynan);
     if (anynan) mn = RC_NAN;                                                // Julia minimum propagates NaN
     // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
@@ -616,11 +637,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
     int cnew;
     if (!__any_sync(0xffffffffu, gnan)) {
       // fast path: maximum value, then the smallest candidate index that attains it
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, gbest, off);
-        if (o > gbest) gbest = o;
-      }
+      gbest = warp_max_f64(gbest);
       int kbest = 0x7fffffff, sbest = -1;
 #pragma unroll
       for (int w = 0; w < NSR; ++w)
