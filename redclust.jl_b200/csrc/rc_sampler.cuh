@@ -2,7 +2,9 @@
 #pragma once
 #include "rc_common.cuh"
 
+#ifndef RC_BW
 #define RC_BW 4                      // bulk (row-reduction) warps per chain
+#endif
 #define RC_NWARP (RC_BW + 1)         // + one decision warp
 #define RC_NTHR (RC_NWARP * 32)      // threads per chain
 
