@@ -147,6 +147,9 @@ void rc_sampler_destroy(rc_sampler* s);
 int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels, double* out);
 /* PSM of host label vectors (S x n, any positive labels): src/mcmc.jl:560.                    */
 int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, double* psm_out);
+/* The same counts (not divided) for S host label vectors into a caller DEVICE buffer of n x n int32: one rank's share
+ * of a PSM whose samples are sharded over GPUs; all-reduce(SUM) the buffers, divide by the global sample count. */
+int32_t rc_psm_counts_dev(const int64_t* labels, int64_t S, int64_t n, int32_t device, void* counts_dev);
 /* MPEL search of getpointestimate (src/pointestimate.jl:34-59): loss_sums[i] = sum_j loss(c_i,c_j),
  * *best = first argmin (0-based).  loss: 0 binder (Mirkin), 1 omARI, 2 VI, 3 ID (un-normalised). */
 int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device,

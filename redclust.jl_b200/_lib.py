@@ -65,6 +65,7 @@ SIGNATURES = {
     "rc_sampler_destroy": (None, [_vp]),
     "rc_loglik": (C.c_int32, [_vp, _P(rc_params), _vp, _P(C.c_double)]),
     "rc_psm": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, _vp]),
+    "rc_psm_counts_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, _vp]),
     "rc_mpel": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _P(C.c_int64)]),
     "rc_mpel_rows_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "rc_mpel_finish_dev": (C.c_int32, [_vp, C.c_int64, C.c_int32, _vp, _P(C.c_int64)]),

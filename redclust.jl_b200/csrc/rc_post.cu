@@ -376,6 +376,26 @@ static int compact_labels(const int64_t* labels, int64_t S, int64_t n, std::vect
   return RC_OK;
 }
 
+// Exact co-clustering counts of S host label vectors into a caller DEVICE buffer (n x n int32): the per-rank half of
+// a PSM whose samples are sharded over GPUs (the caller all-reduces the counts and divides by the global S).
+int32_t rc_psm_counts_dev(const int64_t* labels, int64_t S, int64_t n, int32_t device, void* counts_dev) {
+  if (!labels || !counts_dev || S < 0 || n < 1) { rc_set_error("rc_psm_counts_dev: bad arguments"); return RC_ERR_ARG; }
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
+  RC_CUDA(cudaSetDevice(device));
+  if (S == 0) { RC_CUDA(cudaMemset(counts_dev, 0, sizeof(int) * (size_t)n * n)); return RC_OK; }
+  std::vector<uint8_t> L; std::vector<int> K;
+  int st = compact_labels(labels, S, n, L, K);
+  if (st) return st;
+  uint8_t* dL = nullptr;
+  RC_CUDA(cudaMalloc(&dL, L.size()));
+  cudaError_t e = cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) st = psm_counts_device(dL, S, n, (int*)counts_dev);
+  cudaFree(dL);
+  RC_CUDA(e);
+  return st;
+}
+
 int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, double* psm_out) {
   if (!labels || !psm_out || S < 1 || n < 1) { rc_set_error("rc_psm: null pointer or empty input"); return RC_ERR_ARG; }
   int cnt = 0;

@@ -399,6 +399,25 @@ def mpel_loss_sums(labels, loss, device=0):
     return sums, best.value
 
 
+def psm_sharded(labels, group=None, device=None, total=None):
+    """PSM of label vectors that are sharded over the ranks of a torch.distributed process group (BASELINE
+    configs[4]): `labels` is THIS rank's S_r x n share; exact int32 counts per rank on the device, one all_reduce(SUM)
+    of the n x n matrix (NCCL), one divide by the global number of samples.  Every rank returns the full PSM."""
+    import torch
+    import torch.distributed as dist
+    L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    S, n = L.shape
+    dev = torch.cuda.current_device() if device is None else device
+    tdev = torch.device("cuda", dev)
+    counts = torch.empty((n, n), dtype=torch.int32, device=tdev)
+    check(lib().rc_psm_counts_dev(ptr(L), S, n, dev, C.c_void_p(counts.data_ptr())))
+    tot = torch.tensor([S], dtype=torch.int64, device=tdev)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return (counts.to(torch.float64) / tot.to(torch.float64)).cpu().numpy()
+
+
 def mpel_loss_sums_sharded(labels, loss, group=None, device=None):
     """mpel_loss_sums with the candidate samples split over the ranks of a torch.distributed process group:
     rank r evaluates rows r, r + world, ... of the upper triangle of the pairwise loss matrix (cyclic, so the ranks

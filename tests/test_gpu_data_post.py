@@ -214,6 +214,7 @@ def test_sharded_entry_points_single_rank(pkg, golden):
     a, b = pkg.MCMCData.from_points(X), pkg.MCMCData.from_points_sharded(X)
     assert np.array_equal(a.D, b.D) and np.array_equal(a.logD, b.logD) and a.scales() == b.scales()
     L = np.stack([rng.integers(1, 7, size=90) for _ in range(37)])
+    assert np.array_equal(pkg.psm_sharded(L), pkg.psm(L))
     for loss in ("binder", "omARI", "VI", "ID"):
         s1, b1 = pkg.mpel_loss_sums(L, loss)
         s2, b2 = pkg.mpel_loss_sums_sharded(L, loss)

@@ -49,9 +49,21 @@ if rank == 0:
     print(f"world={world} n={n} chains={cpr * world} samples/chain={iters}: psm_allreduce {dt * 1e3:.1f} ms; "
           f"equal to the single-process PSM of the same chains: {np.array_equal(psm, ref)}", flush=True)
     assert np.array_equal(psm, ref)
+# one common set of label vectors on every rank: rank 0's samples, broadcast, then 5 % of the labels reshuffled with a
+# fixed seed so that the samples differ from each other
+S = np.ascontiguousarray(smp.samples(0)["labels"])
+tS = torch.from_numpy(S).cuda(); dist.broadcast(tS, 0); S = tS.cpu().numpy()
+g5 = np.random.default_rng(5)
+flip = g5.random(S.shape) < 0.05
+S[flip] = g5.integers(1, 21, size=int(flip.sum()))
+S = np.concatenate([S, S[::-1][:23] % 3 + 1])          # and a few coarse clusterings
+# PSM of host label vectors sharded by sample: per-rank counts + all_reduce
+P = pkg.psm_sharded(S[rank::world])
+if rank == 0:
+    okp = np.array_equal(P, pkg.psm(S, device=local))
+    print(f"world={world} PSM of {S.shape[0]} host label vectors sharded by sample: equal to one GPU: {okp}", flush=True)
+    assert okp
 # MPEL: candidates sharded (cyclic rows of the pairwise loss matrix) + all_gather
-S = smp.samples(0)["labels"]
-S = np.concatenate([S, S[::-1][:23] % 3 + 1])          # a few coarse clusterings so the losses are not all tiny
 for loss in ("binder", "VI"):
     torch.cuda.synchronize(); dist.barrier()
     t = time.perf_counter()
