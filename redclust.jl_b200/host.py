@@ -494,6 +494,42 @@ def infodist(a, b, normalised=True):
     return 1 - (m - d) / m if m > 0 else float("nan")
 
 
+def evaluateclustering(clusts, truth, device=0):
+    """evaluateclustering(clusts, truth) (summaries.jl:13-24): nbloss, ari, vi, nvi, id, nid, nmi -- the four pair losses
+    come from the contingency-table kernel (rc_mpel on the two label vectors), the entropies for the normalised
+    mutual information (Clustering.mutualinfo: I / sqrt(H(a) H(b))) from the label counts."""
+    a = np.asarray(clusts, dtype=np.int64); b = np.asarray(truth, dtype=np.int64)
+    if a.size != b.size:
+        raise ArgumentError("Length of inputs must be equal.")
+    n = a.size
+    two = np.stack([a, b])
+    val = {loss: float(mpel_loss_sums(two, loss, device)[0][0]) for loss in ("binder", "omARI", "VI", "ID")}
+
+    def entropy(x):
+        c = np.bincount(np.unique(x, return_inverse=True)[1]).astype(np.float64)
+        return float(math.log(n) - (c * np.log(c)).sum() / n)
+
+    Ha, Hb = entropy(a), entropy(b)
+    I = (Ha + Hb - val["VI"]) / 2
+    nmi = I / math.sqrt(Ha * Hb) if Ha > 0 and Hb > 0 else (1.0 if Ha == Hb else 0.0)
+    logn = math.log(n)
+    return dict(nbloss=val["binder"], ari=1 - val["omARI"], vi=val["VI"], nvi=val["VI"] / logn, id=val["ID"], nid=val["ID"] / logn, nmi=nmi)
+
+
+def summarise(clusts, truth, io=None, device=0):
+    """summarise([io], clusts, truth) (summaries.jl:31-44)."""
+    import sys as _sys
+    out = _sys.stdout if io is None else io
+    t = evaluateclustering(clusts, truth, device)
+    print("Clustering summary", file=out)
+    print(f"Number of clusters : {len(np.unique(np.asarray(clusts)))}", file=out)
+    print(f"Normalised Binder loss : {t['nbloss']}", file=out)
+    print(f"Adjusted Rand Index : {t['ari']}", file=out)
+    print(f"Normalised Variation of Information (NVI) distance : {t['nvi']}", file=out)
+    print(f"Normalised Information Distance (NID) : {t['nid']}", file=out)
+    print(f"Normalised Mutual Information : {t['nmi']}", file=out)
+
+
 def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None, device=0, oracle=False):
     """generatemixture(N, K; α, dim, radius, σ, rng) (utils.jl:101-147): Dirichlet weights, sorted labels,
     simplex-vertex centres, isotropic normal points, Euclidean distance matrix (built on the GPU).

@@ -282,6 +282,57 @@ def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, 
                                 proposalsd_r=proposalsd_r, u=u, v=v, K_initial=K)
 
 
+def fitprior2(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, rng=None):
+    """fitprior2(data, algo, diss = false; Kmin, Kmax, verbose) -> PriorHyperparamsList   (prior.jl:152-277): partition
+    prior as in fitprior; cohesion / repulsion parameters from the within / between dissimilarities of the clusterings
+    with K = Kmin..Kmax clusters, weighted by the prior predictive distribution of K.  The weighted Gamma fits only
+    need the weighted counts, sums and log-sums, which come from rc_pair_stats per clustering; k-medoids runs on
+    the device.  (The reference clusters for every k in 1:N and then uses Kmin:Kmax; only that range is computed.)"""
+    from .host import PriorHyperparamsList, pair_stats
+    x, N, dev, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
+    if verbose:
+        print("Fitting prior hyperparameters")
+    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)
+    ks = list(range(Kmin, Kmax + 1))
+    objective = np.zeros(len(ks))
+    stats = []
+    for q, k in enumerate(ks):
+        t = clustfn(inp, k, maxiter=1000, rng=rng)
+        objective[q] = t["totalcost"]
+        if not t["converged"]:
+            warnings.warn(f"Clustering did not converge at K = {k}")
+        stats.append(pair_stats(dev, t["assignments"]))
+    K = int(detectknee(np.arange(Kmin, Kmax + 1), objective)[0])
+    notional = clustfn(inp, K, maxiter=1000, rng=rng)["assignments"]
+    sizes = np.bincount(notional)[1:]
+    t = sample_rp(sizes, rng=rng)
+    proposalsd_r = float(np.std(t["r"], ddof=1))
+    eta, sigma = gamma_mle(t["r"])
+    u, v = beta_mle(t["p"])
+    Ks = sampleK(eta, sigma, u, v, max(10000, 100 * N), N, rng=rng)           # prior on K (:232-233)
+    Kprior = np.bincount(Ks, minlength=N + 1)[1:N + 1] / Ks.size
+    w = np.array([Kprior[k - 1] for k in ks])
+    nA = np.array([s["nA"] for s in stats], dtype=np.float64); nB = np.array([s["nB"] for s in stats], dtype=np.float64)
+    sA = np.array([s["sA"] for s in stats]); lA = np.array([s["lA"] for s in stats])
+    sB = np.array([s["sB"] for s in stats]); lB = np.array([s["lB"] for s in stats])
+    if nA.sum() == 0:
+        warnings.warn("The ensemble of clusterings has only one clustering, consisting of all singletons. Falling back to defaults for cohesion parameters.")
+        d1, al, be = 1.0, 1.0, 1.0
+    else:
+        W = float((w * nA).sum())                                            # fit_mle(Gamma, A, wtsA) from weighted statistics
+        d1 = gamma_shape_from_stats(float((w * sA).sum()) / W, float((w * lA).sum()) / W) if W > 0 else 1e8
+        al = W * d1; be = float((w * sA).sum())
+    if nB.sum() == 0:
+        warnings.warn("The ensemble of clusterings has only one clustering, consisting of a single cluster. Falling back to defaults for repulsion parameters.")
+        d2, ze, ga = 1.0, 1.0, 1.0
+    else:
+        W = float((w * nB).sum())
+        d2 = gamma_shape_from_stats(float((w * sB).sum()) / W, float((w * lB).sum()) / W) if W > 0 else 1e8
+        ze = W * d2; ga = float((w * sB).sum())
+    return PriorHyperparamsList(delta1=d1, delta2=d2, alpha=al, beta=be, zeta=ze, gamma=ga, eta=eta, sigma=sigma,
+                                proposalsd_r=proposalsd_r, u=u, v=v, K_initial=K)
+
+
 def sampledist(params, type, numsamples=1, rng=None):
     """prior.jl:284-308."""
     if type not in ("intercluster", "intracluster"):

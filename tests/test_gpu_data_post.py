@@ -219,3 +219,32 @@ def test_sharded_entry_points_single_rank(pkg, golden):
         s1, b1 = pkg.mpel_loss_sums(L, loss)
         s2, b2 = pkg.mpel_loss_sums_sharded(L, loss)
         assert np.array_equal(s1, s2) and b1 == b2, loss
+
+
+def test_fitprior2_and_summaries(pkg, orc, golden):
+    """fitprior2 (prior.jl:152-277) on the device pieces; evaluateclustering / summarise (summaries.jl:13-44)."""
+    import io
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    data = pkg.MCMCData(D)
+    p = pkg.fitprior2(data, "k-medoids", True, Kmin=2, Kmax=12, verbose=False, rng=2)
+    assert 2 <= p.K_initial <= 12
+    for f in ("delta1", "delta2", "alpha", "beta", "zeta", "gamma", "eta", "sigma", "u", "v", "proposalsd_r"):
+        assert getattr(p, f) > 0 and np.isfinite(getattr(p, f)), f
+    # a single K: the shapes are those of that clustering's within / between fits
+    p1 = pkg.fitprior2(data, "k-medoids", True, Kmin=6, Kmax=6, verbose=False, rng=2)
+    notional = pkg.kmedoids(data, 6, rng=2)["assignments"]
+    st = pkg.pair_stats(data, notional)
+    from redclust_jl_b200.prior import gamma_shape_from_stats
+    assert abs(p1.delta1 - gamma_shape_from_stats(st["sA"] / st["nA"], st["lA"] / st["nA"])) < 1e-9 * p1.delta1
+    assert abs(p1.delta2 - gamma_shape_from_stats(st["sB"] / st["nB"], st["lB"] / st["nB"])) < 1e-9 * p1.delta2
+    rng = np.random.default_rng(0)
+    other = lab.copy(); idx = rng.choice(lab.size, 15, replace=False); other[idx] = rng.integers(1, lab.max() + 1, size=15)
+    ev = pkg.evaluateclustering(other, lab)
+    assert abs(ev["nbloss"] - orc.binderloss(other, lab)) < 1e-12 and abs(ev["id"] - orc.infodist(other, lab, normalised=False)) < 1e-12
+    assert 0 < ev["ari"] < 1 and 0 < ev["nmi"] < 1 and abs(ev["nvi"] - ev["vi"] / np.log(lab.size)) < 1e-15
+    same = pkg.evaluateclustering(lab, lab)
+    assert abs(same["nbloss"]) < 1e-12 and abs(same["ari"] - 1) < 1e-12 and abs(same["nmi"] - 1) < 1e-12 and abs(same["vi"]) < 1e-9
+    buf = io.StringIO(); pkg.summarise(other, lab, io=buf)
+    assert "Adjusted Rand Index" in buf.getvalue() and "Number of clusters" in buf.getvalue()
+    with pytest.raises(ValueError):
+        pkg.evaluateclustering(lab[:-1], lab)
