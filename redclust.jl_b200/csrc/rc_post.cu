@@ -420,6 +420,68 @@ int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, doub
   return st;
 }
 
+}  // extern "C"
+
+// Device buffers that are released when the call returns, whatever the path.
+struct DevScratch {
+  std::vector<void*> p;
+  ~DevScratch() { for (void* q : p) cudaFree(q); }
+  template <class T> cudaError_t get(T** out, size_t count) {
+    cudaError_t e = cudaMalloc((void**)out, sizeof(T) * (count ? count : 1));
+    if (e == cudaSuccess) p.push_back(*out);
+    return e;
+  }
+};
+
+// Shared front end of the MPEL entry points: relabel, upload, size the contingency table, and launch the pair-loss
+// kernel for the rows row_first, row_first + row_stride, ... (nrows of them).  mirror = 1 writes the full symmetric
+// S x S matrix M; mirror = 0 writes the rows' strict upper triangle into an nrows x S block.
+static int mpel_pairs(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int64_t row_first, int64_t row_stride,
+                      int64_t nrows, int mirror, double* M, DevScratch& scr, int* kmax_out) {
+  std::vector<uint8_t> L; std::vector<int> K;
+  int st = compact_labels(labels, S, n, L, K);
+  if (st) return st;
+  int kmax = 0;
+  for (int k : K) kmax = std::max(kmax, k);
+  if (kmax_out) *kmax_out = kmax;
+  const int wide = n > 65535;
+  const int tabwords = ((wide ? kmax * kmax : (kmax * kmax + 1) / 2) + 3) & ~3;
+  const size_t smem = (size_t)tabwords * 4 + 2 * (size_t)((n + 15) / 16) * 16;
+  if (smem > 220 * 1024) { rc_set_error("rc_mpel: n = %lld with %d x %d clusters does not fit shared memory", (long long)n, kmax, kmax); return RC_ERR_SLOTS; }
+  int stride = (int)((n + 31) / 32);
+  while ((stride & 3) || !((stride >> 2) & 1)) ++stride;      // multiple of 4 with an odd quotient: lane segments start in different banks
+  uint8_t* dL = nullptr; int* dK = nullptr; double* nlogn = nullptr;
+  if (scr.get(&dL, L.size()) || scr.get(&dK, (size_t)S) || scr.get(&nlogn, (size_t)(n + 1))) { rc_set_error("rc_mpel: out of device memory"); return RC_ERR_CUDA; }
+  RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
+  RC_CUDA(cudaMemcpy(dK, K.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
+  RC_CUDA(cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (nrows > 0)
+    k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)nrows), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn, M,
+                                                                                  row_first, row_stride, mirror);
+  RC_CUDA(cudaGetLastError());
+  return RC_OK;
+}
+
+static int mpel_argmin(const double* sums_dev, int64_t S, double* loss_sums, int64_t* best) {
+  std::vector<double> hs((size_t)S);
+  RC_CUDA(cudaMemcpy(hs.data(), sums_dev, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  int64_t b = 0;
+  for (int64_t i = 1; i < S; ++i) if (hs[i] < hs[b]) b = i;     // argmin: first minimum
+  if (loss_sums) memcpy(loss_sums, hs.data(), sizeof(double) * S);
+  if (best) *best = b;
+  return RC_OK;
+}
+
+static int mpel_device_ready(int32_t device) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
+  RC_CUDA(cudaSetDevice(device));
+  return RC_OK;
+}
+
+extern "C" {
+
 // Multi-GPU MPEL: the candidate rows row_first, row_first + row_stride, ... (nrows of them) of the strict
 // upper triangle of the pairwise loss matrix into a caller DEVICE buffer (nrows x S fp64, zero where j <= i); the
 // caller all-gathers the row blocks into the S x S upper triangle and calls rc_mpel_finish_dev, which sums the columns
@@ -429,98 +491,49 @@ int32_t rc_mpel_rows_dev(const int64_t* labels, int64_t S, int64_t n, int32_t lo
   if (!labels || !M_rows_dev || S < 1 || n < 1 || loss < 0 || loss > 3 || row_first < 0 || row_stride < 1 || nrows < 0) {
     rc_set_error("rc_mpel_rows_dev: bad arguments"); return RC_ERR_ARG;
   }
-  int cnt = 0;
-  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
-  RC_CUDA(cudaSetDevice(device));
-  std::vector<uint8_t> L; std::vector<int> K;
-  int st = compact_labels(labels, S, n, L, K);
+  int st = mpel_device_ready(device);
   if (st) return st;
-  int kmax = 0;
-  for (int k : K) kmax = std::max(kmax, k);
-  const int wide = n > 65535;
-  const int tabwords = ((wide ? kmax * kmax : (kmax * kmax + 1) / 2) + 3) & ~3;
-  const size_t smem = (size_t)tabwords * 4 + 2 * (size_t)((n + 15) / 16) * 16;
-  if (smem > 220 * 1024) { rc_set_error("rc_mpel: n = %lld with %d x %d clusters does not fit shared memory", (long long)n, kmax, kmax); return RC_ERR_SLOTS; }
-  int stride = (int)((n + 31) / 32);
-  while ((stride & 3) || !((stride >> 2) & 1)) ++stride;
-  uint8_t* dL = nullptr; int* dK = nullptr; double* nlogn = nullptr;
-  RC_CUDA(cudaMalloc(&dL, L.size()));
-  RC_CUDA(cudaMalloc(&dK, sizeof(int) * S));
-  RC_CUDA(cudaMalloc(&nlogn, sizeof(double) * (size_t)(n + 1)));
-  RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
-  RC_CUDA(cudaMemcpy(dK, K.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  DevScratch scr;
   RC_CUDA(cudaMemset(M_rows_dev, 0, sizeof(double) * (size_t)nrows * S));
-  k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
-  cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (nrows > 0)
-    k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)nrows), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn,
-                                                                                  (double*)M_rows_dev, row_first, row_stride, 0);
-  cudaError_t e = cudaDeviceSynchronize();
-  cudaFree(dL); cudaFree(dK); cudaFree(nlogn);
-  RC_CUDA(e);
+  st = mpel_pairs(labels, S, n, loss, row_first, row_stride, nrows, 0, (double*)M_rows_dev, scr, nullptr);
+  if (st) return st;
+  RC_CUDA(cudaDeviceSynchronize());
   return RC_OK;
 }
 
 int32_t rc_mpel_finish_dev(const void* M_upper_dev, int64_t S, int32_t device, double* loss_sums, int64_t* best) {
   if (!M_upper_dev || S < 1) { rc_set_error("rc_mpel_finish_dev: bad arguments"); return RC_ERR_ARG; }
-  RC_CUDA(cudaSetDevice(device));
+  int st = mpel_device_ready(device);
+  if (st) return st;
+  DevScratch scr;
   double* sums = nullptr;
-  RC_CUDA(cudaMalloc(&sums, sizeof(double) * S));
+  if (scr.get(&sums, (size_t)S)) { rc_set_error("rc_mpel: out of device memory"); return RC_ERR_CUDA; }
   k_colsum_upper<<<(unsigned)((S + 127) / 128), 128>>>((const double*)M_upper_dev, S, sums);
-  std::vector<double> hs((size_t)S);
-  cudaError_t e = cudaMemcpy(hs.data(), sums, sizeof(double) * S, cudaMemcpyDeviceToHost);
-  cudaFree(sums);
-  RC_CUDA(e);
-  int64_t b = 0;
-  for (int64_t i = 1; i < S; ++i) if (hs[i] < hs[b]) b = i;     // argmin: first minimum
-  if (loss_sums) memcpy(loss_sums, hs.data(), sizeof(double) * S);
-  if (best) *best = b;
-  return RC_OK;
+  return mpel_argmin(sums, S, loss_sums, best);
 }
 
 int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device, double* loss_sums, int64_t* best) {
   if (!labels || S < 1 || n < 1 || loss < 0 || loss > 3) { rc_set_error("rc_mpel: bad arguments"); return RC_ERR_ARG; }
-  int cnt = 0;
-  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
-  RC_CUDA(cudaSetDevice(device));
-  std::vector<uint8_t> L; std::vector<int> K;
-  int st = compact_labels(labels, S, n, L, K);
+  int st = mpel_device_ready(device);
   if (st) return st;
-  int kmax = 0;
-  for (int k : K) kmax = std::max(kmax, k);
-  const int wide = n > 65535;
-  const int tabwords = ((wide ? kmax * kmax : (kmax * kmax + 1) / 2) + 3) & ~3;
-  const size_t smem = (size_t)tabwords * 4 + 2 * (size_t)((n + 15) / 16) * 16;
-  if (smem > 220 * 1024) { rc_set_error("rc_mpel: n = %lld with %d x %d clusters does not fit shared memory", (long long)n, kmax, kmax); return RC_ERR_SLOTS; }
-  int stride = (int)((n + 31) / 32);
-  while ((stride & 3) || !((stride >> 2) & 1)) ++stride;      // multiple of 4 with an odd quotient: lane segments start in different banks
-  uint8_t* dL = nullptr; int* dK = nullptr; double *M = nullptr, *sums = nullptr, *nlogn = nullptr;
-  RC_CUDA(cudaMalloc(&dL, L.size()));
-  RC_CUDA(cudaMalloc(&dK, sizeof(int) * S));
-  RC_CUDA(cudaMalloc(&M, sizeof(double) * (size_t)S * S));
-  RC_CUDA(cudaMalloc(&sums, sizeof(double) * S));
-  RC_CUDA(cudaMalloc(&nlogn, sizeof(double) * (size_t)(n + 1)));
-  RC_CUDA(cudaMemcpy(dL, L.data(), L.size(), cudaMemcpyHostToDevice));
-  RC_CUDA(cudaMemcpy(dK, K.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  DevScratch scr;
+  double *M = nullptr, *sums = nullptr;
+  if (scr.get(&M, (size_t)S * S) || scr.get(&sums, (size_t)S)) { rc_set_error("rc_mpel: out of device memory"); return RC_ERR_CUDA; }
   RC_CUDA(cudaMemset(M, 0, sizeof(double) * (size_t)S * S));
-  k_nlogn<<<(unsigned)((n + 256) / 256), 256>>>(n, nlogn);
-  cudaFuncSetAttribute(k_pair_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_pair_loss<<<dim3((unsigned)((S + PJ - 1) / PJ), (unsigned)S), 256, smem>>>(dL, dK, S, n, loss, wide, tabwords, stride, nlogn, M, 0, 1, 1);
+  const bool verbose = getenv("RCB200_VERBOSE") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  int kmax = 0;
+  st = mpel_pairs(labels, S, n, loss, 0, 1, S, 1, M, scr, &kmax);
+  if (st) return st;
+  const double tk = now();
   k_colsum<<<(unsigned)((S + 127) / 128), 128>>>(M, S, sums);
-  std::vector<double> hs((size_t)S);
-  const double tk = getenv("RCB200_VERBOSE") ? std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
-  cudaError_t e = cudaMemcpy(hs.data(), sums, sizeof(double) * S, cudaMemcpyDeviceToHost);
-  if (getenv("RCB200_VERBOSE"))
-    fprintf(stderr, "[rcb200] rc_mpel: S=%lld n=%lld kmax=%d loss=%d pair kernel + column sums %.3f s (%.3e pairs/s)\n", (long long)S, (long long)n, kmax, loss,
-            std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tk,
-            0.5 * S * (S - 1) / (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tk));
-  cudaFree(dL); cudaFree(dK); cudaFree(M); cudaFree(sums); cudaFree(nlogn);
-  RC_CUDA(e);
-  int64_t b = 0;
-  for (int64_t i = 1; i < S; ++i) if (hs[i] < hs[b]) b = i;     // argmin: first minimum
-  if (loss_sums) memcpy(loss_sums, hs.data(), sizeof(double) * S);
-  if (best) *best = b;
-  return RC_OK;
+  st = mpel_argmin(sums, S, loss_sums, best);
+  if (verbose) {
+    const double dt = now() - tk;
+    fprintf(stderr, "[rcb200] rc_mpel: S=%lld n=%lld kmax=%d loss=%d pair kernel + column sums %.3f s (%.3e pairs/s)\n", (long long)S, (long long)n, kmax,
+            loss, dt, 0.5 * S * (S - 1) / dt);
+  }
+  return st;
 }
 
 }  // extern "C"
