@@ -172,3 +172,28 @@ def test_several_proposals_per_iteration(pkg, orc, golden):
         params = pkg.params_from_labels(D, lab)
         (res,), _ = run_both(pkg, orc, D, lab, params, 80, 10, 2, 5, 3, seed=60 + k)
         assert_same(*res)
+
+
+def test_tiny_problems_and_many_slots(pkg, orc):
+    """n = 2 ... 65 with weak priors: chains wander between 1 and n clusters, i.e. through the empty-slot allocation, the
+    64-slot -> 128-slot switch of the decision warp, singleton split / merge proposals and numMH in {0, 1, 3}."""
+    rng = np.random.default_rng(0)
+    params = pkg.PriorHyperparamsList(delta1=2.0, alpha=5.0, beta=3.0, delta2=2.5, zeta=6.0, gamma=4.0, eta=4.0, sigma=2.0,
+                                      u=2.0, v=10.0, K_initial=2)
+    P = oparams(orc, params)
+    seen = set()
+    for n in (2, 3, 5, 33, 65):
+        X = rng.normal(size=(n, 3)); X[: n // 2] += 3
+        data = pkg.MCMCData.from_points(X)
+        D = data.D
+        lab = np.array([1] * (n // 2) + [2] * (n - n // 2), dtype=np.int64)
+        for numMH in (0, 1, 3):
+            opts = pkg.MCMCOptionsList(numiters=30, burnin=3, thin=2, numGibbs=2, numMH=numMH)
+            r0, p0 = pkg.init_rp(params, 9, 0)
+            smp = pkg.Sampler(data, opts, params, lab, r0, p0, seed=9)
+            smp.run(-1)
+            got = smp.samples(0)
+            ref = orc.run_chain(D, orc.Options(30, 3, 2, 2, numMH), P, lab, r0, p0, seed=9, chain=0)
+            assert_same(got, ref, smp.state(0))
+            seen.update(int(k) for k in got["K"])
+    assert 1 in seen and max(seen) >= 60            # from a single cluster to (nearly) one cluster per point
