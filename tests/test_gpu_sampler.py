@@ -197,3 +197,19 @@ def test_tiny_problems_and_many_slots(pkg, orc):
             assert_same(got, ref, smp.state(0))
             seen.update(int(k) for k in got["K"])
     assert 1 in seen and max(seen) >= 60            # from a single cluster to (nearly) one cluster per point
+
+
+def test_points_in_random_order(pkg, orc):
+    """Cluster members scattered over the columns (every row tile holds every label: many short (tile, label) runs,
+    frequent bin flushes, random shared-memory banks) and a start that is 4 % off: three tiles, two chains per CTA."""
+    X, lab = mixture(3000, 25, 30, 0.15, 21)
+    perm = np.random.default_rng(4).permutation(lab.size)
+    X, lab = X[perm], orc.sortlabels(lab[perm])
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(data, lab)
+    g = np.random.default_rng(6)
+    init = lab.copy(); idx = g.choice(lab.size, 120, replace=False); init[idx] = g.integers(1, lab.max() + 1, size=idx.size)
+    res, smp = run_both(pkg, orc, D, init, params, 5, 0, 1, 5, 1, seed=13, nchains=3)
+    for got, ref, st in res:
+        assert_same(got, ref, st)
