@@ -38,7 +38,9 @@ struct rc_sampler {
   // device
   double *LGA, *LGZ, *LOGN;
   uint8_t* labels; int* sizes; double *r, *p; int* status;
-  rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist; uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms; long long* stats; unsigned* gridbar; bool coresident;
+  rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
+  uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
+  long long* stats; unsigned* gridbar; bool coresident;
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
@@ -159,7 +161,11 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   kp.numiters = s->opt.numiters; kp.numsamples = s->numsamples;
   kp.seed = s->seed; kp.chain_offset = s->chain_offset; kp.nchains = (int)s->nchains;
   kp.labels = s->labels; kp.sizes = s->sizes; kp.r = s->r; kp.p = s->p; kp.status = s->status;
-  kp.WD = s->WD; kp.WL = s->WL; kp.WDbak = s->WDbak; kp.WLbak = s->WLbak; kp.labbak = s->labbak; kp.szbak = s->szbak; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s; kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats; kp.gridbar = (s->coresident && getenv("RCB200_GRIDBAR")) ? s->gridbar : nullptr;   // experiment: align the scans of all CTAs (no gain measured)
+  // experiment: align the scans of all CTAs (no gain measured)
+  kp.WD = s->WD; kp.WL = s->WL; kp.WDbak = s->WDbak; kp.WLbak = s->WLbak; kp.labbak = s->labbak;
+  kp.szbak = s->szbak; kp.T = s->T; kp.Slist = s->Slist; kp.origM = s->origM; kp.AB = s->AB; kp.L2s = s->L2s;
+  kp.NZ = s->NZ; kp.LPR = s->LPR; kp.DG = s->DG; kp.terms = s->terms; kp.stats = s->stats;
+  kp.gridbar = (s->coresident && getenv("RCB200_GRIDBAR")) ? s->gridbar : nullptr;
   kp.out_labels = s->out_labels; kp.out_K = s->out_K; kp.out_r = s->out_r; kp.out_p = s->out_p;
   kp.out_ll = s->out_ll; kp.out_lp = s->out_lp; kp.r_acc = s->r_acc; kp.sm_acc = s->sm_acc; kp.sm_split = s->sm_split;
 }
@@ -182,7 +188,10 @@ void rc_sampler_destroy(rc_sampler* s) {
   cudaSetDevice(s->device);
   rc_dev_free(s->LGA); rc_dev_free(s->LGZ); rc_dev_free(s->LOGN);
   rc_dev_free(s->labels); rc_dev_free(s->sizes); rc_dev_free(s->r); rc_dev_free(s->p); rc_dev_free(s->status);
-  rc_dev_free(s->WD); rc_dev_free(s->WL); rc_dev_free(s->WDbak); rc_dev_free(s->WLbak); rc_dev_free(s->labbak); rc_dev_free(s->szbak); rc_dev_free(s->T); rc_dev_free(s->Slist); rc_dev_free(s->origM); rc_dev_free(s->AB); rc_dev_free(s->L2s); rc_dev_free(s->NZ); rc_dev_free(s->LPR); rc_dev_free(s->DG); rc_dev_free(s->terms); rc_dev_free(s->stats); rc_dev_free(s->gridbar);
+  rc_dev_free(s->WD); rc_dev_free(s->WL); rc_dev_free(s->WDbak); rc_dev_free(s->WLbak); rc_dev_free(s->labbak);
+  rc_dev_free(s->szbak); rc_dev_free(s->T); rc_dev_free(s->Slist); rc_dev_free(s->origM); rc_dev_free(s->AB);
+  rc_dev_free(s->L2s); rc_dev_free(s->NZ); rc_dev_free(s->LPR); rc_dev_free(s->DG); rc_dev_free(s->terms);
+  rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
   if (s->e0) cudaEventDestroy(s->e0);
@@ -237,7 +246,9 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
     return RC_ERR_ARG;
   }
   const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G);
-  if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld (full %lld) G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles, (long long)npad, (long long)npad_full, G, smem, maxsmem, (long long)nchains);
+  if (getenv("RCB200_VERBOSE"))
+    fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld (full %lld) G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles,
+            (long long)npad, (long long)npad_full, G, smem, maxsmem, (long long)nchains);
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
   std::vector<uint8_t> lab((size_t)nchains * n);
   std::vector<int> sizes((size_t)nchains * cap, 0);
@@ -275,7 +286,9 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   }
   TRY(dalloc(&s->Slist, (size_t)nchains * (n + 2))); TRY(dalloc(&s->origM, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->AB, (size_t)nchains * (n + 2))); TRY(dalloc(&s->L2s, (size_t)nchains * n));
-  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1)); TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2))); TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->gridbar, 1));
+  TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1));
+  TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2)));
+  TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->gridbar, 1));
   s->coresident = rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
