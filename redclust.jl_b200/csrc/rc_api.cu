@@ -41,6 +41,8 @@ struct rc_sampler {
   rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
+  longlong2* DLp;              // copy of the data's DL with label-sorted columns (null: the data's own matrix is streamed)
+  unsigned short *colpos, *colpt;   // [n] point -> column and column -> point of DLp
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
@@ -98,6 +100,15 @@ int dalloc(T** p, size_t count) {
   return RC_OK;
 }
 
+// DLp[i][c] = DL[i][pt[c]]: the streamed matrix with its columns in label-sorted order (see rc_sampler_create)
+__global__ void k_permute_cols(const longlong2* __restrict__ DL, int64_t n, const unsigned short* __restrict__ pt, longlong2* __restrict__ out) {
+  const int64_t total = n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n, c = t - i * n;
+    out[t] = DL[i * n + pt[c]];
+  }
+}
+
 // ---- block sums of ONE label vector with the whole GPU (all chains start from the same labels) -------------------
 // W[k][t] (k <= t) = sum over rows x of cluster k of the row's sums over cluster t (src/mcmc.jl:1-56 needs exactly
 // these totals).  One CTA per row: every thread walks a contiguous strip of the row keeping a running sum while the
@@ -111,7 +122,8 @@ __device__ __forceinline__ void atomic_add128(rc_i128* a, long long v) {
   if (hi) atomicAdd(reinterpret_cast<unsigned long long*>(&a->hi), (unsigned long long)hi);
 }
 __global__ void __launch_bounds__(256) k_initw_shared(const longlong2* __restrict__ DL, int n, const uint8_t* __restrict__ lab, int cap,
-                                                      rc_i128* __restrict__ WD, rc_i128* __restrict__ WL) {
+                                                      rc_i128* __restrict__ WD, rc_i128* __restrict__ WL,
+                                                      const unsigned short* __restrict__ colpt) {
   extern __shared__ unsigned long long bins[];          // [cap] D sums, [cap] L sums
   for (int t = threadIdx.x; t < 2 * cap; t += blockDim.x) bins[t] = 0ull;
   __syncthreads();
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(256) k_initw_shared(const longlong2* __restric
     const int j0 = threadIdx.x * w, j1 = min(n, j0 + w);
     int cur = -1; long long d = 0, l = 0;
     for (int j = j0; j < j1; ++j) {
-      const int lb = lab[j];
+      const int lb = lab[colpt ? (int)colpt[j] : j];       // j is a column of the streamed matrix
       if (lb != cur) {
         if (cur >= 0) { atomicAdd(&bins[cur], (unsigned long long)d); atomicAdd(&bins[cap + cur], (unsigned long long)l); }
         cur = lb; d = 0; l = 0;
@@ -149,7 +161,8 @@ __global__ void k_replicate_w(rc_i128* __restrict__ W, size_t per_chain, int64_t
 void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
-  kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->d->DL;
+  kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
+  kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
   kp.zgratio = s->par.zeta * rc_log(s->par.gamma) - rc_lgamma(s->par.zeta);     // mcmc.jl:18,187,294
@@ -194,13 +207,14 @@ void rc_sampler_destroy(rc_sampler* s) {
   rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
+  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
 
-int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par, int64_t nchains,
+static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const rc_options* opt, const rc_params* par, int64_t nchains,
                           int64_t chain_offset, const int64_t* init_labels, const double* init_r,
                           const double* init_p, uint64_t seed, int32_t slot_cap, rc_sampler** out) {
   if (!d || !opt || !par || !init_labels || !init_r || !init_p || !out || nchains < 1) {
@@ -298,6 +312,37 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   TRY(dalloc(&s->sm_split, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
 #undef TRY
   cudaMemcpy(s->labels, lab.data(), lab.size(), cudaMemcpyHostToDevice);
+  // Column order of the streamed matrix.  The row reduction is fastest when the members of a cluster are contiguous
+  // columns (few (tile, label) runs, little padding, conflict-free shared-memory gathers).  When the initial labels
+  // of chain 0 are scattered over the points, the sampler streams its own copy of DL whose columns are sorted by those
+  // labels (stable).  Every sum is an exact integer, so no result changes; only direct element reads need the map.
+  {
+    int64_t changes = 0, distinct = 0;
+    std::vector<char> seen((size_t)cap, 0);
+    for (int64_t j = 0; j < n; ++j) {
+      if (j && lab[j] != lab[j - 1]) ++changes;
+      if (!seen[lab[j]]) { seen[lab[j]] = 1; ++distinct; }
+    }
+    const char* env = getenv("RCB200_COLPERM");
+    const bool want = env ? atoi(env) != 0 : changes > 4 * distinct + 8;
+    if (want && !opt_loglik_only) {
+      std::vector<unsigned short> pt((size_t)n), pos((size_t)n);
+      std::vector<int64_t> idx((size_t)n);
+      for (int64_t j = 0; j < n; ++j) idx[j] = j;
+      std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return lab[a] < lab[b]; });
+      for (int64_t c = 0; c < n; ++c) { pt[c] = (unsigned short)idx[c]; pos[idx[c]] = (unsigned short)c; }
+      if (dalloc(&s->DLp, (size_t)n * n) == RC_OK && dalloc(&s->colpos, (size_t)n) == RC_OK && dalloc(&s->colpt, (size_t)n) == RC_OK) {
+        cudaMemcpy(s->colpos, pos.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(s->colpt, pt.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice);
+        k_permute_cols<<<148 * 16, 256>>>(d->DL, n, s->colpt, s->DLp);
+        if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] columns of the streamed matrix sorted by the initial labels (%lld label changes along the points, %lld clusters)\n", (long long)changes, (long long)distinct);
+      } else {                                   // not enough memory for the copy: stream the data's own matrix
+        rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt);
+        s->DLp = nullptr; s->colpos = nullptr; s->colpt = nullptr;
+        (void)cudaGetLastError();
+      }
+    }
+  }
   cudaMemcpy(s->sizes, sizes.data(), sizes.size() * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(s->r, init_r, sizeof(double) * nchains, cudaMemcpyHostToDevice);
   cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice);
@@ -315,6 +360,12 @@ int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_para
   return RC_OK;
 }
 
+int32_t rc_sampler_create(const rc_data* d, const rc_options* opt, const rc_params* par, int64_t nchains,
+                          int64_t chain_offset, const int64_t* init_labels, const double* init_r,
+                          const double* init_p, uint64_t seed, int32_t slot_cap, rc_sampler** out) {
+  return sampler_create_impl(false, d, opt, par, nchains, chain_offset, init_labels, init_r, init_p, seed, slot_cap, out);
+}
+
 int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   if (!s) { rc_set_error("rc_sampler_run: null handle"); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(s->device));
@@ -330,7 +381,7 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
     const size_t per = (size_t)s->cap * s->cap;
     RC_CUDA(cudaMemsetAsync(s->WD, 0, sizeof(rc_i128) * per, s->stream));
     RC_CUDA(cudaMemsetAsync(s->WL, 0, sizeof(rc_i128) * per, s->stream));
-    k_initw_shared<<<148 * 8, 256, sizeof(unsigned long long) * 2 * s->cap, s->stream>>>(s->d->DL, (int)s->n, s->labels, s->cap, s->WD, s->WL);
+    k_initw_shared<<<148 * 8, 256, sizeof(unsigned long long) * 2 * s->cap, s->stream>>>(s->DLp ? s->DLp : s->d->DL, (int)s->n, s->labels, s->cap, s->WD, s->WL, s->colpt);
     k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WD, per, s->nchains);
     k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WL, per, s->nchains);
     RC_CUDA(cudaGetLastError());
@@ -493,7 +544,7 @@ int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels,
   for (int64_t j = 0; j < n; ++j) lab[j] = (std::lower_bound(uniq.begin(), uniq.end(), labels[j]) - uniq.begin()) + 1;
   double r0 = 1.0, p0 = 0.5;
   rc_sampler* s = nullptr;
-  int st = rc_sampler_create(d, &opt, par, 1, 0, lab.data(), &r0, &p0, 0, 0, &s);
+  int st = sampler_create_impl(true, d, &opt, par, 1, 0, lab.data(), &r0, &p0, 0, 0, &s);
   if (st) return st;
   rc_kparams kp;
   fill_kparams(s, kp);

@@ -114,6 +114,8 @@ struct Ctx {
   // shared memory (per CTA)
   unsigned char* stages;
   CtaShared* cta;
+  const unsigned short* colpos;  // column of point j in the streamed matrix (null: column j), see rc_kparams::colpos
+  const unsigned short* colpt;   // point of column c (null: point c)
   unsigned char* chain0;     // shared memory of chain slot 0; slot q starts chain_stride bytes further
   size_t chain_stride, ss_off;
   // per-chain global memory
@@ -135,6 +137,10 @@ struct Ctx {
   long long* stats;       // [16] cycle counters of this chain (see rc_sampler_copy_stats)
   unsigned long long key;
 };
+// The streamed matrix may have its COLUMNS permuted (label-sorted by the initial clustering, rc_api.cu): element (i, j)
+// of D then sits in column cpos(j) of row i.  Sums over columns do not care; direct element reads go through cpos.
+__device__ __forceinline__ int cpos(const Ctx& c, int j) { return c.colpos ? (int)__ldg(c.colpos + j) : j; }
+__device__ __forceinline__ int cpt(const Ctx& c, int col) { return c.colpt ? (int)__ldg(c.colpt + col) : col; }
 // stats slots
 enum { ST_DEC_WAIT = 0, ST_DEC_WORK, ST_BULK_WAIT_CONSUMED, ST_BULK_WAIT_FULL, ST_BULK_ROWS, ST_BULK_PATCH, ST_MOVES, ST_REBUILDS,
        ST_MH_SETUP, ST_MH_RSCAN, ST_MH_LOGLIK, ST_SCAN_TOTAL, ST_RECORD, ST_ITER_TOTAL, ST_RP, ST_BULK_REDUCE };
@@ -210,7 +216,7 @@ __device__ void build_perm(const Ctx& c, int buf = 0) {
   unsigned char* const cmask = c.bscratch[buf] + sizeof(unsigned int) * E;          // [chunks] occupied slots
   for (int t = tid; t < E; t += NT) cnt[t] = 0;
   tsync<BULK>(c);
-  for (int j = tid; j < c.n; j += NT) atomicAdd(&cnt[(j >> RC_LOGW) * c.cap + lab[j]], 1u);
+  for (int j = tid; j < c.n; j += NT) atomicAdd(&cnt[(j >> RC_LOGW) * c.cap + lab[cpt(c, j)]], 1u);      // j: column
   tsync<BULK>(c);
   if (tid < 32) {
     const int chunk = (E + 31) / 32;
@@ -251,7 +257,7 @@ __device__ void build_perm(const Ctx& c, int buf = 0) {
   tsync<BULK>(c);
   for (int j = tid; j < c.n; j += NT) {
     const int tile = j >> RC_LOGW;
-    const int e = tile * c.cap + lab[j];
+    const int e = tile * c.cap + lab[cpt(c, j)];
     const unsigned rk = atomicAdd(&cnt[e], 1u);
     const int g = (c.runStart[e] >> 3) + (int)(rk >> 3);                 // chunk of the run that takes the element
     const int g0 = c.tileStart[tile], cc = (c.tileStart[tile + 1] - g0 + 32 * RC_PAIR - 1) / (32 * RC_PAIR);
@@ -276,8 +282,9 @@ __device__ void build_perm(const Ctx& c, int buf = 0) {
 
 // Point j (column) moved from slot a to slot b: patch the permutation in place (warp 0 of the chain).  If the
 // run of (tile, b) has no free padding entry the caller rebuilds.
-__device__ void patch_perm(const Ctx& c, int j, int a, int b) {
+__device__ void patch_perm(const Ctx& c, int jpoint, int a, int b) {
   const int lane = c.lane;
+  const int j = cpos(c, jpoint);                 // the point's column
   const int tile = j >> RC_LOGW;
   const unsigned idx = ((unsigned)j & (RC_W - 1)) << 4;
   {
@@ -480,13 +487,13 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
   long long tlast = cy.tlast, acc_wait = cy.acc_wait, acc_work = cy.acc_work;
   int nmoves = cy.nmoves;
   int istop = n;
-  longlong2 self1 = __ldg(c.DL + (size_t)istart * n + istart);              // diagonal entry of row i (prefetched two rows ahead)
-  longlong2 self2 = istart + 1 < n ? __ldg(c.DL + (size_t)(istart + 1) * n + (istart + 1)) : make_longlong2(0, 0);
+  longlong2 self1 = __ldg(c.DL + (size_t)istart * n + cpos(c, istart));              // diagonal entry of row i (prefetched two rows ahead)
+  longlong2 self2 = istart + 1 < n ? __ldg(c.DL + (size_t)(istart + 1) * n + cpos(c, istart + 1)) : make_longlong2(0, 0);
   for (int i = istart; i < n; ++i) {
     const int li = c.lab[i];
     const longlong2 self = self1;
     self1 = self2;
-    if (i + 2 < n) self2 = __ldg(c.DL + (size_t)(i + 2) * n + (i + 2));
+    if (i + 2 < n) self2 = __ldg(c.DL + (size_t)(i + 2) * n + cpos(c, i + 2));
     // occupancy with i detached (:193-202) -- independent of the row sums
     unsigned occ[NSR];
 #pragma unroll
@@ -558,7 +565,7 @@ __device__ int decide_rows(const Ctx& c, unsigned it, int istart, DecCarry& cy) 
     // moves of earlier steps that the permutation did not contain when row i was reduced
     for (int m = Prow; m < M; ++m) {
       const int j = ss->mq_j[m % RC_MQ], a = ss->mq_a[m % RC_MQ], b = ss->mq_b[m % RC_MQ];
-      const longlong2 ev = __ldg(c.DL + (size_t)i * n + j);
+      const longlong2 ev = __ldg(c.DL + (size_t)i * n + cpos(c, j));
 #pragma unroll
       for (int w = 0; w < NSR; ++w) {
         const int s = w * 32 + lane;
@@ -1147,7 +1154,7 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
   if (nS == 0) { if (lane == 0) c.sc->ltp = 0.0; __syncwarp(); return; }
   int xs[RC_RS_NU];
 #pragma unroll
-  for (int u = 0; u < RC_RS_NU; ++u) { const int q = u * 32 + lane; xs[u] = q < mt ? (int)c.Slist[q] : -1; }
+  for (int u = 0; u < RC_RS_NU; ++u) { const int q = u * 32 + lane; xs[u] = q < mt ? cpos(c, (int)c.Slist[q]) : -1; }   // member columns
   const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
   const int st = lane >> 2, role = lane & 3, quad = lane & ~3;
   const bool isA = (role & 1) == 0;
@@ -1246,7 +1253,7 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
           }
         }
         for (int q = RC_RS_NU * 32 + lane; q < mt; q += 32) {   // members beyond the register window
-          const longlong2 e = __ldg(row + c.Slist[q]);
+          const longlong2 e = __ldg(row + cpos(c, c.Slist[q]));
           longlong4 t = c.AB[q];
           if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
           else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
@@ -1276,19 +1283,19 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
     long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // aD aL bD bL c1D c1L c2D c2L
     for (int q2 = lane; q2 < mt; q2 += 32) {
       const int y = c.Slist[q2];
-      const longlong2 e = __ldg(row + y);
+      const longlong2 e = __ldg(row + cpos(c, y));
       const int l = c.lab[y];
       if (l == ca) { v[0] += e.x; v[1] += e.y; } else if (l == cb) { v[2] += e.x; v[3] += e.y; }
     }
-    for (int t = lane; t < n1; t += 32) { const longlong2 e = __ldg(row + CL1[t]); v[4] += e.x; v[5] += e.y; }
-    for (int t = lane; t < n2; t += 32) { const longlong2 e = __ldg(row + CL2[t]); v[6] += e.x; v[7] += e.y; }
+    for (int t = lane; t < n1; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL1[t])); v[4] += e.x; v[5] += e.y; }
+    for (int t = lane; t < n2; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL2[t])); v[6] += e.x; v[7] += e.y; }
 #pragma unroll
     for (int h = 0; h < 8; ++h)
       for (int off = 16; off; off >>= 1) v[h] += shfl_xor_ll(v[h], off);
     if (lane == 0) {
       longlong4 ab; ab.x = v[0]; ab.y = v[1]; ab.z = v[2]; ab.w = v[3];
       c.AB[q] = ab;
-      c.DG[q] = __ldg(row + x);
+      c.DG[q] = __ldg(row + cpos(c, x));
     }
     if (q < nS) {
       double val = 0.0;
@@ -1420,7 +1427,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       longlong4 ab; ab.x = ta.x; ab.y = ta.y; ab.z = tb.x; ab.w = tb.y;
       c.AB[q] = ab;
       const int x = c.Slist[q];
-      c.DG[q] = __ldg(c.DL + (size_t)x * n + x);
+      c.DG[q] = __ldg(c.DL + (size_t)x * n + cpos(c, x));
     }
     for (int pos = tid; pos < nS; pos += RC_NTHR) {
       double v[2] = {0.0, 0.0};
@@ -1646,6 +1653,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   const int n = kp.n, cap = kp.cap, tiles = kp.tiles;
   Ctx c;
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
+  c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);

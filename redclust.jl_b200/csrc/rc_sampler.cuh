@@ -11,7 +11,9 @@
 struct rc_kparams {
   int n, cap, tiles, npad_max;
   int qD, qL;
-  const longlong2* DL;
+  const longlong2* DL;  // the streamed matrix: rc_data::DL, or the sampler's copy with label-sorted columns
+  const unsigned short* colpos;   // [n] column of point j in DL (null: identity)
+  const unsigned short* colpt;    // [n] point of column c in DL (null: identity)
   rc_params P;
   double abratio, zgratio, lgd1, lgd2;
   const double* LGA;    // lgamma(alpha + delta1 * s), s = 0..n+1
