@@ -418,6 +418,19 @@ def psm_sharded(labels, group=None, device=None, total=None):
     return (counts.to(torch.float64) / tot.to(torch.float64)).cpu().numpy()
 
 
+def cyclic_rows(rank, world, S):
+    """Rows of an S-row matrix owned by `rank` when they are dealt out cyclically (row i -> rank i % world), and the
+    padded per-rank row count every rank allocates for the all_gather."""
+    per = (S + world - 1) // world
+    return list(range(rank, S, world)), per
+
+
+def assemble_cyclic_rows(allrows, S):
+    """Inverse of the cyclic deal: allrows[r, k] is row r + k * world (all_gather output, world x per x S) -> S x S."""
+    world, per, cols = allrows.shape
+    return allrows.permute(1, 0, 2).reshape(per * world, cols)[:S].contiguous()
+
+
 def mpel_loss_sums_sharded(labels, loss, group=None, device=None):
     """mpel_loss_sums with the candidate samples split over the ranks of a torch.distributed process group:
     rank r evaluates rows r, r + world, ... of the upper triangle of the pairwise loss matrix (cyclic, so the ranks
@@ -435,9 +448,9 @@ def mpel_loss_sums_sharded(labels, loss, group=None, device=None):
     mine = torch.zeros((per, S), dtype=torch.float64, device=tdev)
     check(lib().rc_mpel_rows_dev(ptr(L), S, n, _LOSS[loss], dev, rank, world, per, C.c_void_p(mine.data_ptr())))
     if world > 1:
-        allrows = torch.empty((world, per, S), dtype=torch.float64, device=tdev)
-        dist.all_gather_into_tensor(allrows, mine, group=group)
-        upper = allrows.permute(1, 0, 2).reshape(per * world, S)[:S].contiguous()    # row i came from rank i % world
+        flat = torch.empty((world * per, S), dtype=torch.float64, device=tdev)       # rank-major blocks
+        dist.all_gather_into_tensor(flat, mine, group=group)
+        upper = assemble_cyclic_rows(flat.view(world, per, S), S)
     else:
         upper = mine[:S].contiguous()
     sums = np.zeros(S); best = C.c_int64()
