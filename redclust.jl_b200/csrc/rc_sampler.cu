@@ -4,27 +4,32 @@
 //   sample_r!  (mcmc.jl:80-136)      -> update_r()
 //   sample_p!  (mcmc.jl:138-155)     -> update_p()
 //   sample_labels! (mcmc.jl:356-479) -> splitmerge_step() x numMH, then full_scan()
-//   sample_labels_Gibbs! (:158-256)  -> full_scan(): reduce_row_staged() + scan_decide()
-//   sample_labels_Gibbs_restricted! (:259-354) -> restricted_scan()
+//   sample_labels_Gibbs! (:158-256)  -> full_scan(): bulk_loop() / reduce_tile() + decide_rows()
+//   sample_labels_Gibbs_restricted! (:259-354) -> restricted_scans()
 //   loglik (:1-56), logprior (:58-78), record step (:546-554), sortlabels (utils.jl:69-74)
 //
-// Organisation (DESIGN.md sections 2-4):
-//   * One CTA runs G chains (G x 128 threads).  During the full Gibbs scan all chains of a CTA visit
-//     rows 0..n-1 in lock step, so every 2048-column tile of row i of DL is staged ONCE into shared
-//     memory by a bulk async copy (cp.async.bulk -> UBLKCP, mbarrier full/empty ring) and reduced by all
-//     G chains against their own label vectors.  CTAs on other SMs walk the same rows at about the same
-//     time and hit L2, so HBM traffic per sweep is ~ n^2 x 16 B / (chains sharing a row load).
+// Organisation (DESIGN.md sections 2-3):
+//   * One CTA runs G chains (G x 160 threads: 4 bulk warps + 1 decision warp per chain) plus two CTA-level helper
+//     warps.  During the full Gibbs scan all chains of a CTA visit rows 0..n-1 together, so every 1024-column tile
+//     of row i of DL is staged ONCE into a 6-stage shared-memory ring by the producer warp (cp.async.bulk -> UBLKCP,
+//     mbarrier full/empty) and reduced by all G chains against their own label vectors.  CTAs on other SMs walk the
+//     same rows at about the same time and hit L2, so HBM traffic per sweep is ~ n^2 x 16 B / (chains sharing a
+//     row load).  The noise warp precomputes the Gumbel noise of the rows ahead of the decisions.
 //   * DL[i][j] = {Dq, Lq}: 64-bit fixed-point images of D and log D.  Every cluster sum is an exact
 //     integer, so results do not depend on tiling, lane count or reduction order: the kernel is
-//     bit-identical to the CPU oracle by construction.
+//     bit-identical to the CPU oracle by construction.  (The COLUMNS of the streamed matrix may be label-sorted,
+//     see cpos().)
 //   * Row reduction: columns are kept in a (tile, label)-sorted permutation whose label runs are padded to
-//     groups of 8; a lane sums one group (8 gathers from the staged tile), a warp-shuffle segmented scan
-//     combines the groups of a run, run tails accumulate into per-warp bins.  No atomics, no label
-//     compares in the inner loop.  A move patches the permutation in place (rebuild when a run is full).
+//     chunks of 8; one warp reduces a tile, a lane walks its contiguous chunks (8 gathers from the staged tile per
+//     chunk) keeping a running sum, a warp-shuffle segmented scan merges runs that span lanes, totals go to per-warp
+//     bins.  No atomics, no label compares in the inner loop.  A move patches the permutation in place (rebuild
+//     when a run is full).
+//   * The decision warp does the sequential part: bins of row i -> log-weights (lane = slot) -> Gumbel arg-max ->
+//     move; it runs one row behind the bulk warps.
 //   * The K x K block-sum matrices W (128-bit integers) are maintained incrementally from the row sums
 //     of every move, so loglik() never re-reads D: it is O(K^2) transcendentals.
 //   * Split-merge: row sums of the members of ci u cj are taken once (launch state); the restricted
-//     scans then only gather the |ci u cj| entries of one row per step, on a single warp.
+//     scans then run on a single warp from running candidate sums, eight steps at a time.
 #include "rc_sampler.cuh"
 
 namespace {
