@@ -248,3 +248,45 @@ def test_fitprior2_and_summaries(pkg, orc, golden):
     assert "Adjusted Rand Index" in buf.getvalue() and "Number of clusters" in buf.getvalue()
     with pytest.raises(ValueError):
         pkg.evaluateclustering(lab[:-1], lab)
+
+
+def test_reference_fitprior_and_sampler_cases(pkg, golden):
+    """The reference's own test/test_fitprior.jl:1-22 and test/test_sampler.jl:1-11, case by case."""
+    import warnings
+    pts = np.asarray(golden[1]["points"]); distM = golden[1]["distance_matrix"]
+    pnts = list(pts)                                                     # Vector{Vector{Float64}}
+    N = len(pnts)
+    for fit in (pkg.fitprior, pkg.fitprior2):
+        kw = dict(verbose=False, rng=3)
+        if fit is pkg.fitprior2:
+            kw.update(Kmin=1, Kmax=12)                                   # the reference scans 1:N/2; keep the test short
+        fit(pnts, "k-means", False, **kw)                                # kmeans with points
+        fit(pnts, "k-medoids", False, **kw)                              # kmedoids with points
+        fit(distM, "k-medoids", True, **kw)                              # kmedoids with distances
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            p = fit(pnts, "k-means", False, verbose=False, Kmin=1, Kmax=1, rng=3)
+            assert p.K_initial == 1 and len(w) >= 1                      # single cluster: repulsion defaults + warning
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            p = fit(pnts, "k-means", False, verbose=False, Kmin=N, Kmax=N, rng=3)
+            assert p.K_initial == N and len(w) >= 1                      # all singletons: cohesion defaults + warning
+        for bad in (lambda: fit(distM, "hierarchical", True, verbose=False),
+                    lambda: fit(pnts, "k-means", True, verbose=False),
+                    lambda: fit(distM, "k-means", True, verbose=False),
+                    lambda: fit(pnts, "k-means", False, Kmin=0, verbose=False),
+                    lambda: fit(pnts, "k-means", False, Kmin=N, Kmax=1, verbose=False),
+                    lambda: fit(pnts, "k-means", False, Kmax=N + 1, verbose=False)):
+            with pytest.raises(ValueError):                               # ArgumentError
+                bad()
+    repr(p)
+    # test_sampler.jl: defaults (fitprior inside, k-medoids init, 5000 iterations), then pure Gibbs
+    for data in (pkg.MCMCData.from_points(pts), pkg.MCMCData(distM)):
+        repr(data)
+        result = pkg.runsampler(data, verbose=False)
+        assert len(result.clusts) == 4000 and result.posterior_coclustering.shape == (N, N)
+    options = pkg.MCMCOptionsList(numMH=0)
+    repr(options)
+    result = pkg.runsampler(data, options, verbose=False)
+    repr(result)
+    assert np.all(np.diag(result.posterior_coclustering) == 1.0)
