@@ -290,3 +290,28 @@ def test_reference_fitprior_and_sampler_cases(pkg, golden):
     result = pkg.runsampler(data, options, verbose=False)
     repr(result)
     assert np.all(np.diag(result.posterior_coclustering) == 1.0)
+
+
+def test_reference_datagen_cases(pkg):
+    """test/test_datagen.jl:1-15, plus the oracle co-clustering against a direct numpy evaluation of utils.jl:130-143."""
+    K, N, dim, sig = 10, 100, 10, 0.25
+    data = pkg.generatemixture(N, K, alpha=10, sigma=sig, dim=dim, rng=5)
+    pnts, distM, clusts, probs, occ = (data[k] for k in ("points", "distancematrix", "clusts", "probs", "oracle_coclustering"))
+    assert len(pnts) == N and len(pnts[0]) == dim and len(np.unique(clusts)) == K
+    assert distM.shape == (N, N) and np.array_equal(distM, distM.T) and abs(probs.sum() - 1) < 1e-12
+    assert occ.shape == (N, N) and np.allclose(occ, occ.T) and np.all(occ >= 0) and np.all(occ <= 1 + 1e-12)
+    same = clusts[:, None] == clusts[None, :]
+    assert occ[same].mean() > 0.5 > occ[~same].mean()                     # co-clustered pairs look co-clustered
+    # one Dirichlet draw evaluated as the reference does: P[j, i] = w_j pdf_j(x_i) / sum_j, P' P
+    from redclust_jl_b200.host import _oracle_coclustering
+    X = np.asarray(pnts)
+    g = np.random.default_rng(9)
+    got = _oracle_coclustering(X, K, 10.0, 1.0, sig, np.random.default_rng(9), 0, numiters=3, batch=2)
+    W = g.dirichlet(np.full(K, 10.0), size=3)
+    C = np.eye(K, dim)
+    ref = np.zeros((N, N))
+    for w in W:
+        pdf = np.exp(-((X[None, :, :] - C[:, None, :]) ** 2).sum(2) / (2 * sig * sig)) * w[:, None]
+        P = pdf / pdf.sum(0, keepdims=True)
+        ref += P.T @ P
+    assert np.allclose(got, ref / 3, rtol=1e-10, atol=1e-14)
