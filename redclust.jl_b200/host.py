@@ -357,6 +357,33 @@ def runsampler(data, options=None, params=None, init=None, verbose=True, nchains
 
 
 # ------------------------------------------------------------------------------------------------
+def prettytime(t):
+    """utils.jl:158-187: human-readable duration (Dates.canonicalize splits whole seconds into weeks / days / hours /
+    minutes / seconds; only days and below are named by the reference)."""
+    if t < 1e-6:
+        return "%.2f ns" % (t * 1e9)
+    if t < 1e-3:
+        return "%.2f μs" % (t * 1e6)
+    if t < 1:
+        return "%.2f ms" % (t * 1e3)
+    if t < 60:
+        return "%.2f s" % t
+    sec = int(math.floor(t))
+    parts = []
+    for name, span in (("day", 86400), ("hr", 3600), ("min", 60)):
+        v, sec = divmod(sec, span)
+        if v:
+            parts.append(f"{v} {name}" + ("s" if v != 1 else ""))
+    if sec:
+        parts.append(f"{sec} s")
+    return " ".join(parts)
+
+
+def prettynumber(x):
+    """utils.jl:189."""
+    return "%.3e" % x if x < 1 else "%.3f" % x
+
+
 def makematrix(x):
     """utils.jl:154-156: vector of vectors -> matrix whose COLUMNS are the vectors."""
     return np.asarray([np.asarray(v, dtype=np.float64) for v in x], dtype=np.float64).T.copy()

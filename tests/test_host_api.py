@@ -125,3 +125,22 @@ def test_fitprior_and_kmedoids_host(pkg, golden):
     assert sampleK(p, 5, 30).shape == (5,) and sampledist(p, "intracluster", 4).shape == (4,)
     with pytest.raises(ValueError):
         sampledist(p, "foo")
+
+
+def test_reference_utils_cases(pkg):
+    """test/test_utils.jl:1-61 case by case (makematrix, adjacencymatrix, sortlabels, prettytime)."""
+    rng = np.random.default_rng(0)
+    m, n = 50, 100
+    temp = [rng.random(m) for _ in range(n)]
+    M = pkg.makematrix(temp)
+    assert M.shape == (m, n) and sum(int((M[:, i] == temp[i]).sum()) for i in range(n)) == m * n
+    K, n = 20, 500
+    lab = rng.integers(1, K + 1, size=n)
+    A = pkg.adjacencymatrix(lab)
+    assert int((A == (lab[:, None] == lab[None, :])).sum()) == n * n
+    assert int((pkg.adjacencymatrix(lab) == pkg.adjacencymatrix(pkg.sortlabels(lab))).sum()) == n * n
+    cases = {1e-9: "1.00 ns", 999e-9: "999.00 ns", 1e-6: "1.00 μs", 999e-6: "999.00 μs", 1e-3: "1.00 ms", 999e-3: "999.00 ms",
+             1: "1.00 s", 5: "5.00 s", 60: "1 min", 120: "2 mins", 65: "1 min 5 s", 125: "2 mins 5 s", 3600: "1 hr", 7200: "2 hrs",
+             7205: "2 hrs 5 s", 7265: "2 hrs 1 min 5 s", 7325: "2 hrs 2 mins 5 s", 24 * 3600: "1 day", 2 * 24 * 3600: "2 days"}
+    for t, want in cases.items():
+        assert pkg.prettytime(t) == want, (t, pkg.prettytime(t), want)
