@@ -41,6 +41,10 @@ struct rc_sampler {
   rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
+  longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
+  bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
+  int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
+  size_t inc_smem, terms_stride;
   longlong2* DLp;              // copy of the data's DL with label-sorted columns (null: the data's own matrix is streamed)
   unsigned short *colpos, *colpt;   // [n] point -> column and column -> point of DLp
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
@@ -162,6 +166,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
+  kp.S = s->S; kp.terms_stride = s->terms_stride;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -207,7 +212,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
-  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt);
+  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -293,7 +298,28 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRY(dalloc(&s->labels, (size_t)nchains * n)); TRY(dalloc(&s->sizes, (size_t)nchains * cap));
   TRY(dalloc(&s->r, nchains)); TRY(dalloc(&s->p, nchains)); TRY(dalloc(&s->status, nchains));
   TRY(dalloc(&s->WD, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WL, (size_t)nchains * cap * cap));
-  TRY(dalloc(&s->T, opt->numMH > 0 ? (size_t)nchains * n * cap : 1));
+  // Scan mode.  Incremental (default when it fits): every chain keeps S[slot][x], the sums of row x by cluster, and a
+  // Gibbs step reads cap entries instead of a row; a move streams one row.  Streaming: the round-1 kernel that
+  // re-reduces every row against the labels (no per-chain matrix; needed when nchains * cap * n * 16 B does not fit).
+  {
+    const char* env = getenv("RCB200_SCAN");
+    const size_t needS = sizeof(longlong2) * (size_t)nchains * cap * n;
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    bool want = !opt_loglik_only && needS <= freeb / 10 * 6;
+    if (env && !strcmp(env, "stream")) want = false;
+    if (env && !strcmp(env, "inc") && !opt_loglik_only) want = true;
+    s->inc = want;
+    int nthr = nchains <= nsm ? 512 : (nchains <= 2 * nsm ? 256 : 256);
+    if (const char* e = getenv("RCB200_INC_THREADS")) nthr = std::max(32, std::min(512, atoi(e) / 32 * 32));
+    s->inc_nthr = nthr;
+    s->inc_smem = rc_sampler_inc_smem_bytes((int)n, cap);
+    if (s->inc && s->inc_smem > (size_t)maxsmem) s->inc = false;
+    if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] scan mode: %s (S needs %.2f GB, %.2f GB free), %d threads per chain\n", s->inc ? "incremental" : "streaming", needS / 1e9, freeb / 1e9, nthr);
+  }
+  s->terms_stride = (size_t)std::max(cap * cap, 8192);
+  if (s->inc) TRY(dalloc(&s->S, (size_t)nchains * cap * n));
+  TRY(dalloc(&s->T, (opt->numMH > 0 && !s->inc) ? (size_t)nchains * n * cap : 1));
   if (opt->numMH > 1) {
     TRY(dalloc(&s->WDbak, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WLbak, (size_t)nchains * cap * cap));
     TRY(dalloc(&s->labbak, (size_t)nchains * n)); TRY(dalloc(&s->szbak, (size_t)nchains * (cap + 1)));
@@ -303,7 +329,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1));
   TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->gridbar, 1));
-  s->coresident = rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * std::max(cap * cap, 2048)));
+  s->coresident = rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * s->terms_stride));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
   TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));
@@ -325,7 +351,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     }
     const char* env = getenv("RCB200_COLPERM");
     const bool want = env ? atoi(env) != 0 : changes > 4 * distinct + 8;
-    if (want && !opt_loglik_only) {
+    if (want && !opt_loglik_only && !s->inc) {      // (the incremental mode never reduces rows by label: no copy needed)
       std::vector<unsigned short> pt((size_t)n), pos((size_t)n);
       std::vector<int64_t> idx((size_t)n);
       for (int64_t j = 0; j < n; ++j) idx[j] = j;
@@ -377,6 +403,13 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   kp.init_W = s->W_ready ? 0 : 1;
   RC_CUDA(cudaMemsetAsync(s->gridbar, 0, sizeof(unsigned), s->stream));
   RC_CUDA(cudaEventRecord(s->e0, s->stream));
+  if (s->inc) {
+    if (kp.init_W) {
+      if (rc_launch_inc_init(kp, s->shared_init, s->stream)) { rc_set_error("incremental-mode initialisation failed: %s", cudaGetErrorString(cudaGetLastError())); return RC_ERR_CUDA; }
+      kp.init_W = 0;
+    }
+    if (kp.it1 > kp.it0) rc_launch_chain_inc(kp, s->inc_smem, s->inc_nthr, s->stream);
+  } else {
   if (kp.init_W && s->shared_init && !getenv("RCB200_NO_SHARED_INIT")) {
     const size_t per = (size_t)s->cap * s->cap;
     RC_CUDA(cudaMemsetAsync(s->WD, 0, sizeof(rc_i128) * per, s->stream));
@@ -388,6 +421,7 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
     kp.init_W = 0;
   }
   if (kp.init_W || kp.it1 > kp.it0) rc_launch_chain_kernel(kp, s->smem, s->G, s->stream);
+  }
   RC_CUDA(cudaGetLastError());
   RC_CUDA(cudaEventRecord(s->e1, s->stream));
   RC_CUDA(cudaStreamSynchronize(s->stream));

@@ -30,6 +30,7 @@
 //     of every move, so loglik() never re-reads D: it is O(K^2) transcendentals.
 //   * Split-merge: row sums of the members of ci u cj are taken once (launch state); the restricted
 //     scans then run on a single warp from running candidate sums, eight steps at a time.
+#include <algorithm>
 #include "rc_sampler.cuh"
 
 namespace {
@@ -97,6 +98,7 @@ struct Ctx {
   int n, cap, tiles;
   int qD, qL;
   int ctid, cwarp, lane, barid;           // thread / warp index within the chain, named barrier of the chain
+  int nthr, nwarp;                        // threads / warps of the chain's team (RC_NTHR in k_chain, the whole CTA in k_chain_inc)
   int bbarid;                             // named barrier of the chain's bulk warps
   unsigned dummy;                         // permutation padding entry = byte offset of the zero slots behind a staged tile
   size_t stage_bytes;
@@ -131,6 +133,8 @@ struct Ctx {
   uint8_t* labbak;
   int* szbak;
   longlong2* T;
+  longlong2* S;           // incremental mode (k_chain_inc): [cap][n] row sums by slot, S[k][x] = sum_{j in k} DL[x][j]; null otherwise
+  struct IncShared* inc;  // incremental mode: hand-off block of the scan
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
   longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
@@ -146,12 +150,38 @@ struct Ctx {
 // of D then sits in column cpos(j) of row i.  Sums over columns do not care; direct element reads go through cpos.
 __device__ __forceinline__ int cpos(const Ctx& c, int j) { return c.colpos ? (int)__ldg(c.colpos + j) : j; }
 __device__ __forceinline__ int cpt(const Ctx& c, int col) { return c.colpt ? (int)__ldg(c.colpt + col) : col; }
+// Incremental mode: point y moved from slot a to slot b.  Every x's sums over a and b follow from row y (D is symmetric:
+// DL[x][y] == DL[y][x]); exact integers, so S stays what a from-scratch build would give.  Thread t always owns the same
+// x's, so successive moves need no barrier between them (one before the sums are read again).
+__device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b) {
+  const longlong2* __restrict__ row = c.DL + (size_t)y * c.n;
+  longlong2* Sa = c.S + (size_t)a * c.n;
+  longlong2* Sb = c.S + (size_t)b * c.n;
+  const int n = c.n, nt = c.nthr;
+  int x = c.ctid;
+  for (; x + 3 * nt < n; x += 4 * nt) {
+    longlong2 v[4], sa[4], sb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u] = __ldg(row + x + u * nt); sa[u] = Sa[x + u * nt]; sb[u] = Sb[x + u * nt]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sa[u].x -= v[u].x; sa[u].y -= v[u].y; sb[u].x += v[u].x; sb[u].y += v[u].y;
+      Sa[x + u * nt] = sa[u]; Sb[x + u * nt] = sb[u];
+    }
+  }
+  for (; x < n; x += nt) {
+    const longlong2 v = __ldg(row + x);
+    longlong2 sa = Sa[x], sb = Sb[x];
+    sa.x -= v.x; sa.y -= v.y; sb.x += v.x; sb.y += v.y;
+    Sa[x] = sa; Sb[x] = sb;
+  }
+}
 // stats slots
 enum { ST_DEC_WAIT = 0, ST_DEC_WORK, ST_BULK_WAIT_CONSUMED, ST_BULK_WAIT_FULL, ST_BULK_ROWS, ST_BULK_PATCH, ST_MOVES, ST_REBUILDS,
        ST_MH_SETUP, ST_MH_RSCAN, ST_MH_LOGLIK, ST_SCAN_TOTAL, ST_RECORD, ST_ITER_TOTAL, ST_RP, ST_BULK_REDUCE };
 __device__ __forceinline__ void st_add(const Ctx& c, int slot, long long v) { c.stats[slot] += v; }
 
-__device__ __forceinline__ void csync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.barid), "r"(RC_NTHR) : "memory"); }
+__device__ __forceinline__ void csync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.barid), "r"(c.nthr) : "memory"); }
 __device__ __forceinline__ void bsync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bbarid), "r"(RC_BW * 32) : "memory"); }
 // a team is either the whole chain (RC_NTHR threads, csync) or its bulk warps (RC_BW*32 threads, bsync)
 template <bool BULK> __device__ __forceinline__ void tsync(const Ctx& c) { if (BULK) bsync(c); else csync(c); }
@@ -950,7 +980,7 @@ __device__ void full_scan(const Ctx& c, unsigned it, int mode = 0) {
 
 // Block sums from scratch: W[k][t] = sum_{x in k, y in t} DL[x][y].  Zeroed here, accumulated by a scan pass in mode 1.
 __device__ void zero_W(const Ctx& c) {
-  for (int t = c.ctid; t < c.cap * c.cap; t += RC_NTHR) {
+  for (int t = c.ctid; t < c.cap * c.cap; t += c.nthr) {
     rc_i128 z; z.lo = 0; z.hi = 0;
     c.WD[t] = z; c.WL[t] = z;
   }
@@ -994,7 +1024,7 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
   }
   csync(c);
   const int K = c.sc->itmp[0];
-  for (int idx = c.ctid; idx < K * K; idx += RC_NTHR) {
+  for (int idx = c.ctid; idx < K * K; idx += c.nthr) {
     const int ki = idx / K, ti = idx - ki * K;
     if (ti < ki) continue;
     const int k = c.clist[ki], t = c.clist[ti];
@@ -1126,7 +1156,7 @@ __device__ void update_p(const Ctx& c, unsigned it) {
 __device__ void build_lpr(const Ctx& c) {
   const rc_kparams& kp = *c.kp;
   const double r = c.sc->r, logp = c.sc->logp;
-  for (int s = 1 + c.ctid; s <= c.n; s += RC_NTHR)
+  for (int s = 1 + c.ctid; s <= c.n; s += c.nthr)
     c.LPR[s] = kp.LOGN[s + 1] + logp + rc_log((double)(s - 1) + r) - kp.LOGN[s];
   csync(c);
 }
@@ -1282,7 +1312,7 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int lane = c.lane, mt = nS + 2;
-  for (int q = c.cwarp; q < mt; q += RC_NWARP) {
+  for (int q = c.cwarp; q < mt; q += c.nwarp) {
     const int x = c.Slist[q];
     const longlong2* row = c.DL + (size_t)x * c.n;
     long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // aD aL bD bL c1D c1L c2D c2L
@@ -1292,11 +1322,18 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
       const int l = c.lab[y];
       if (l == ca) { v[0] += e.x; v[1] += e.y; } else if (l == cb) { v[2] += e.x; v[3] += e.y; }
     }
-    for (int t = lane; t < n1; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL1[t])); v[4] += e.x; v[5] += e.y; }
-    for (int t = lane; t < n2; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL2[t])); v[6] += e.x; v[7] += e.y; }
+    if (c.S) {                                    // incremental mode: the sums over an untouched cluster are already in S
+      if (q < nS && lane < 2) {
+        const int t = lane == 0 ? c1 : c2;
+        if (t != ca && t != cb) { const longlong2 e = c.S[(size_t)t * c.n + x]; v[lane == 0 ? 4 : 6] = e.x; v[lane == 0 ? 5 : 7] = e.y; }
+      }
+    } else {
+      for (int t = lane; t < n1; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL1[t])); v[4] += e.x; v[5] += e.y; }
+      for (int t = lane; t < n2; t += 32) { const longlong2 e = __ldg(row + cpos(c, CL2[t])); v[6] += e.x; v[7] += e.y; }
+    }
 #pragma unroll
     for (int h = 0; h < 8; ++h)
-      for (int off = 16; off; off >>= 1) v[h] += shfl_xor_ll(v[h], off);
+      for (int off = 16; off; off >>= 1) v[h] += shfl_xor_ll(v[h], off);   // (incremental mode: lanes 0 / 1 hold the only non-zero v[4..7])
     if (lane == 0) {
       longlong4 ab; ab.x = v[0]; ab.y = v[1]; ab.z = v[2]; ab.w = v[3];
       c.AB[q] = ab;
@@ -1345,7 +1382,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   if (P.maxK > 0 && ci == cj && K >= P.maxK) { csync(c); return; }          // :384-386
   // S = members of ci or cj except i, j, ascending (:389-390): ordered compaction
   {
-    const int chunk = (n + RC_NTHR - 1) / RC_NTHR;
+    const int chunk = (n + c.nthr - 1) / c.nthr;
     const int b = tid * chunk, e = min(n, b + chunk);
     int cntm = 0;
     for (int k = b; k < e; ++k) cntm += ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj);
@@ -1358,13 +1395,13 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     int o = woff + incl - cntm;
     for (int k = b; k < e; ++k)
       if ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj) { c.Slist[o] = (unsigned short)k; c.origM[o] = c.lab[k]; ++o; }
-    if (tid == RC_NTHR - 1) c.sc->itmp[3] = woff + incl;
+    if (tid == c.nthr - 1) c.sc->itmp[3] = woff + incl;
     csync(c);
   }
   const int nS = c.sc->itmp[3];
   if (tid == 0) { c.Slist[nS] = (unsigned short)pi; c.origM[nS] = (uint8_t)ci; c.Slist[nS + 1] = (unsigned short)pj; c.origM[nS + 1] = (uint8_t)cj; }
   // launch state (:393-408), in place in c.lab / c.szL
-  for (int s = tid; s < cap; s += RC_NTHR) c.szL[s] = c.sizes[s];
+  for (int s = tid; s < cap; s += c.nthr) c.szL[s] = c.sizes[s];
   const bool split = ci == cj;
   int ca = ci;
   if (split) {
@@ -1386,7 +1423,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   csync(c);
   {
     int na = 0, nb = 0;   // launch allocation of S (:402-407)
-    for (int pos = tid; pos < nS; pos += RC_NTHR) {
+    for (int pos = tid; pos < nS; pos += c.nthr) {
       const int k = c.Slist[pos];
       const double u = rc_draw1(c.key, it, RC_SITE_SM_LAUNCH, mh, (uint32_t)pos, 0);
       const int cn = rc_randint(u, 2) == 1 ? ca : cb;
@@ -1398,7 +1435,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     csync(c);
     if (tid == 0) {
       int ta = 0, tb = 0;
-      for (int w = 0; w < RC_NWARP; ++w) { ta += c.itmp[w * 2]; tb += c.itmp[w * 2 + 1]; }
+      for (int w = 0; w < c.nwarp; ++w) { ta += c.itmp[w * 2]; tb += c.itmp[w * 2 + 1]; }
       if (split) c.szL[ci] = 0;
       c.szL[ca] = 1 + ta;
       c.szL[cb] = 1 + tb;
@@ -1410,31 +1447,31 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     csync(c);
   }
   const int c1 = c.sc->itmp[5], c2 = c.sc->itmp[6];
-  if (split) {
+  if (split && !c.S) {
     // row sums by slot of every member of S u {i, j} under the launch labels (all slots are needed for the
     // block sums of the proposed state)
     build_perm<false>(c);
     if (c.sc->status) {                                      // does not fit: undo the in-place launch labels and stop the chain
-      for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+      for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
       csync(c);
       return;
     }
     for (int pos = 0; pos < nS + 2; ++pos) {
       reduce_row_global(c, c.Slist[pos]);
       csync(c);
-      for (int s = tid; s < cap; s += RC_NTHR) c.T[(size_t)pos * cap + s] = bin_total(c, s);
+      for (int s = tid; s < cap; s += c.nthr) c.T[(size_t)pos * cap + s] = bin_total(c, s);
       csync(c);
     }
     // state-independent inputs of the restricted scans: candidate sums under the launch labels, diagonal
     // entries, repulsion terms of the first two live slots when they are not candidates
-    for (int q = tid; q < nS + 2; q += RC_NTHR) {
+    for (int q = tid; q < nS + 2; q += c.nthr) {
       const longlong2 ta = c.T[(size_t)q * cap + ca], tb = c.T[(size_t)q * cap + cb];
       longlong4 ab; ab.x = ta.x; ab.y = ta.y; ab.z = tb.x; ab.w = tb.y;
       c.AB[q] = ab;
       const int x = c.Slist[q];
       c.DG[q] = __ldg(c.DL + (size_t)x * n + cpos(c, x));
     }
-    for (int pos = tid; pos < nS; pos += RC_NTHR) {
+    for (int pos = tid; pos < nS; pos += c.nthr) {
       double v[2] = {0.0, 0.0};
       for (int h = 0; h < 2; ++h) {
         const int t = h == 0 ? c1 : c2;
@@ -1448,6 +1485,10 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       }
       c.L2s[pos] = make_double2(v[0], v[1]);
     }
+  } else if (c.S) {
+    // incremental mode (split or merge): member x member entries by launch label; the sums over the first two live
+    // slots, when they are not candidates, are clusters the launch did not touch and come straight from S
+    member_sums_gather(c, nS, ca, cb, c1, c2, nullptr, 0, nullptr, 0);
   } else {
     // merge: only member-restricted sums are needed; T's memory serves as scratch for the member lists of the
     // first two live slots (unordered: integer sums do not depend on the order)
@@ -1456,7 +1497,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     if (tid == 0) { c.itmp[8] = 0; c.itmp[9] = 0; }
     csync(c);
     const bool need1 = c1 != ca && c1 != cb, need2 = c2 != ca && c2 != cb;
-    for (int k = tid; k < n; k += RC_NTHR) {
+    for (int k = tid; k < n; k += c.nthr) {
       const int l = c.lab[k];
       if (need1 && l == c1) CL1[atomicAdd(&c.itmp[8], 1)] = (unsigned short)k;
       else if (need2 && l == c2) CL2[atomicAdd(&c.itmp[9], 1)] = (unsigned short)k;
@@ -1466,7 +1507,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   }
   {
     const int nfree = (int)kp.numGibbs + (split ? 1 : 0);
-    for (int e = tid; e < nfree * nS; e += RC_NTHR) {
+    for (int e = tid; e < nfree * nS; e += c.nthr) {
       const int g = e / nS, pos = e - g * nS;
       const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SM_RGIBBS, mh, (uint32_t)g, (uint32_t)pos);
       c.NZ[e] = make_double2(-rc_log(-rc_log(dr.u0)), -rc_log(-rc_log(dr.u1)));
@@ -1490,28 +1531,36 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     }
     // block sums of the proposed state: rows a (= new slot ca) and b (= cb)
     rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);   // [rowA_D | rowA_L | rowB_D | rowB_L] x cap
-    for (int t = tid; t < cap; t += RC_NTHR) {
+    for (int t = tid; t < cap; t += c.nthr) {
       rc_i128 sd, sl; sd.lo = 0; sd.hi = 0; sl.lo = 0; sl.hi = 0;
-      for (int q = 0; q < nS + 2; ++q)
-        if (c.lab[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+      if (c.S) {                               // the slots other than ca / cb are untouched clusters: their sums are in S
+        if (t != ca && t != cb && c.sizes[t] > 0)
+          for (int q = 0; q < nS + 2; ++q) {
+            const int x = c.Slist[q];
+            if (c.lab[x] == ca) { const longlong2 v = c.S[(size_t)t * n + x]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+          }
+      } else {
+        for (int q = 0; q < nS + 2; ++q)
+          if (c.lab[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+      }
       rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
     }
     // within / cross sums from the running candidate sums of the final state:
     //   aa = sum_{x in a_F} sum_{y in a_F} DL[x][y],  ab = sum_{x in a_F} sum_{y in b_F} DL[x][y]
     rc_i128 acc[4];
     for (int h = 0; h < 4; ++h) { acc[h].lo = 0; acc[h].hi = 0; }
-    for (int q = tid; q < nS + 2; q += RC_NTHR)
+    for (int q = tid; q < nS + 2; q += c.nthr)
       if (c.lab[c.Slist[q]] == ca) {
         const longlong4 ab = c.AB[q];
         rc_add128(acc[0], ab.x); rc_add128(acc[1], ab.y); rc_add128(acc[2], ab.z); rc_add128(acc[3], ab.w);
       }
-    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch [RC_NTHR][4]
+    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch [c.nthr][4]
     for (int h = 0; h < 4; ++h) red128[tid * 4 + h] = acc[h];
     csync(c);
     if (tid == 0) {
       rc_i128 tot[4];
       for (int h = 0; h < 4; ++h) { tot[h].lo = 0; tot[h].hi = 0; }
-      for (int w = 0; w < RC_NTHR; ++w)
+      for (int w = 0; w < c.nthr; ++w)
         for (int h = 0; h < 4; ++h) rc_add128(tot[h], red128[w * 4 + h]);
       const rc_i128 aaD = tot[0], aaL = tot[1], xD = tot[2], xL = tot[3];
       rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
@@ -1520,7 +1569,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       c.sc->aaD = aaD; c.sc->aaL = aaL; c.sc->abD = xD; c.sc->abL = xL; c.sc->bbD = bbD; c.sc->bbL = bbL;
     }
     csync(c);
-    for (int t = tid; t < cap; t += RC_NTHR) {                               // row b = row ci of the current state - row a
+    for (int t = tid; t < cap; t += c.nthr) {                               // row b = row ci of the current state - row a
       rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
       rc_sub128(bD, rows[0 * cap + t]); rc_sub128(bL, rows[1 * cap + t]);
       rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
@@ -1537,7 +1586,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       log_proposal_ratio = -c.sc->ltp;
     }
     rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);
-    for (int t = tid; t < cap; t += RC_NTHR) {                               // row cj of the merged state
+    for (int t = tid; t < cap; t += c.nthr) {                               // row cj of the merged state
       rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
       rc_add128(bD, c.WD[tri(cj, t, cap)]); rc_add128(bL, c.WL[tri(cj, t, cap)]);
       rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
@@ -1553,7 +1602,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       c.sc->aaD = z; c.sc->aaL = z; c.sc->abD = z; c.sc->abL = z; c.sc->bbD = bbD; c.sc->bbL = bbL;
       c.sc->fslotA = ci; c.sc->fslotB = cj;
     }
-    for (int s = tid; s < cap; s += RC_NTHR) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
+    for (int s = tid; s < cap; s += c.nthr) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
     csync(c);
   }
   const double ll_fin = loglik_eval(c, c.szL);                              // :462-464
@@ -1569,13 +1618,13 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   if (commit && c.sc->itmp[1]) {
     // the proposed state becomes the local state of the remaining proposals of this iteration
     if (!c.sc->forked) {                                   // first accepted proposal: keep the chain's own block sums
-      for (int t = tid; t < cap * cap; t += RC_NTHR) { c.WDbak[t] = c.WD[t]; c.WLbak[t] = c.WL[t]; }
+      for (int t = tid; t < cap * cap; t += c.nthr) { c.WDbak[t] = c.WD[t]; c.WLbak[t] = c.WL[t]; }
       csync(c);
       if (tid == 0) c.sc->forked = 1;
     }
     const rc_i128* rows = reinterpret_cast<const rc_i128*>(c.partial);   // [rowA_D | rowA_L | rowB_D | rowB_L] x cap
     const int A = split ? ca : ci, B = split ? cb : cj;
-    for (int t = tid; t < cap; t += RC_NTHR) {
+    for (int t = tid; t < cap; t += c.nthr) {
       if (t != A && t != B) {
         c.WD[tri(A, t, cap)] = rows[0 * cap + t]; c.WL[tri(A, t, cap)] = rows[1 * cap + t];
         c.WD[tri(B, t, cap)] = rows[2 * cap + t]; c.WL[tri(B, t, cap)] = rows[3 * cap + t];
@@ -1588,11 +1637,18 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
       c.sc->K = split ? K + 1 : K - 1;
     }
     if (!split)
-      for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = (uint8_t)cj;     // :436-445 (split: labels are final in place)
-    for (int s = tid; s < cap; s += RC_NTHR) c.sizes[s] = c.szL[s];
+      for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = (uint8_t)cj;     // :436-445 (split: labels are final in place)
+    for (int s = tid; s < cap; s += c.nthr) c.sizes[s] = c.szL[s];
+    if (c.S) {                                  // incremental mode: the row sums follow the members that changed slot
+      csync(c);
+      for (int q = 0; q < nS + 2; ++q) {
+        const int y = c.Slist[q], from = c.origM[q], to = c.lab[y];
+        if (from != to) inc_update_S(c, y, from, to);
+      }
+    }
   } else {
     // restore the labels of the members (the proposal lived in place)
-    for (int q = tid; q < nS + 2; q += RC_NTHR) c.lab[c.Slist[q]] = c.origM[q];
+    for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
   }
   csync(c);
   if (tid == 0) st_add(c, ST_MH_LOGLIK, RC_CLOCK() - tm2);
@@ -1601,19 +1657,534 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
 // sortlabels (utils.jl:69-74): first-appearance relabelling to 1..K.
 __device__ void record_labels(const Ctx& c, uint8_t* out) {
   const int tid = c.ctid;
-  for (int s = tid; s < c.cap; s += RC_NTHR) c.itmp[s] = 0x7fffffff;
+  for (int s = tid; s < c.cap; s += c.nthr) c.itmp[s] = 0x7fffffff;
   csync(c);
-  for (int j = tid; j < c.n; j += RC_NTHR) atomicMin(&c.itmp[c.lab[j]], j);
+  for (int j = tid; j < c.n; j += c.nthr) atomicMin(&c.itmp[c.lab[j]], j);
   csync(c);
-  for (int s = tid; s < c.cap; s += RC_NTHR) {
+  for (int s = tid; s < c.cap; s += c.nthr) {
     const int f = c.itmp[s];
     int id = 1;
     for (int t = 0; t < c.cap; ++t) id += c.itmp[t] < f;
     c.clist[s] = (uint8_t)id;
   }
   csync(c);
-  for (int j = tid; j < c.n; j += RC_NTHR) out[j] = c.clist[c.lab[j]];
+  for (int j = tid; j < c.n; j += c.nthr) out[j] = c.clist[c.lab[j]];
   csync(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Incremental mode (k_chain_inc): the full Gibbs scan (mcmc.jl:158-256) WITHOUT streaming the matrix.
+//   S[k][x] = sum_{j in k} DL[x][j] is kept per chain in global memory ([cap][n], exact integers).  Row x's candidate
+//   sums are then cap 16-byte loads instead of a 16 n-byte row; a move of point i from a to b streams row i once and
+//   updates S[a][.] and S[b][.] (inc_update_S).  The W warps of the chain evaluate W consecutive rows at once on the
+//   assumption that none of the earlier ones moves its point; the rows up to and including the first one that moves are
+//   exactly what the sequential scan computes and are committed, the rest is evaluated again after the move has been
+//   applied.  Every committed row sees the inputs of the sequential scan, so the results are the same bits as the
+//   streaming kernel's and the oracle's.
+// ------------------------------------------------------------------------------------------------
+struct IncShared {
+  int first[3];      // lowest warp of a batch whose row needs a commit (three rotating slots, see inc_scan_rows)
+  int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
+  int mv_i, mv_a, mv_b;
+  int nmoves;
+};
+#define RC_INC_NONE 0x7fffffff
+
+template <int NSR>
+__device__ int inc_scan_rows(const Ctx& c, unsigned it, int istart, int& batch) {
+  const int lane = c.lane, warp = c.cwarp, NW = c.nwarp;
+  const rc_kparams& kp = *c.kp;
+  const rc_params& P = kp.P;
+  const int cap = c.cap, n = c.n;
+  IncShared* sh = c.inc;
+  const double r = c.sc->r, log1mp = c.sc->log1mp;
+  const unsigned ltmask = (1u << lane) - 1u;
+  // register-resident per-slot state (every warp holds the same copy): size and the size-dependent table terms at
+  // the current size; the slot a visited point is detached from looks its terms up at size - 1.
+  int sz[NSR];
+  double tA[NSR], tZ[NSR], tP[NSR];
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    const int s = w * 32 + lane;
+    sz[w] = s < cap ? c.sizes[s] : 0;
+    tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1];
+  }
+  int i0 = istart, istop = n;
+  while (i0 < n) {
+    const int slot3 = batch % 3;
+    if (c.ctid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
+    ++batch;
+    const int i = i0 + warp;
+    int li = -1, cnew = -1, flag = 0;
+    long long bd[NSR], bl[NSR];
+    unsigned occ[NSR];
+    longlong2 self = make_longlong2(0, 0);
+#pragma unroll
+    for (int w = 0; w < NSR; ++w) { bd[w] = 0; bl[w] = 0; occ[w] = 0u; }
+    if (i < n) {
+      li = c.lab[i];
+      // occupancy with i detached (:193-202)
+#pragma unroll
+      for (int w = 0; w < NSR; ++w) {
+        const int s = w * 32 + lane;
+        occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);
+      }
+      // row sums of row i over the live slots: S[s][i]
+#pragma unroll
+      for (int w = 0; w < NSR; ++w) {
+        const int s = w * 32 + lane;
+        if ((occ[w] >> lane) & 1u) { const longlong2 t = c.S[(size_t)s * n + i]; bd[w] = t.x; bl[w] = t.y; }
+      }
+      self = __ldg(c.DL + (size_t)i * n + i);
+      int Ki = 0, e = -1, nw = 0;
+#pragma unroll
+      for (int w = 0; w < NSR; ++w) {
+        Ki += __popc(occ[w]);
+        if (occ[w]) nw = w + 1;
+        const int lim = cap - w * 32;
+        const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+        const unsigned emp = ~occ[w] & capmask;
+        if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                      // findfirst(clustsizes .== 0)
+      }
+      const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;           // :198
+      if (NSR * 32 < RC_MAXCAP && hasnew && e < 0 && cap > NSR * 32) flag = 2;   // needs a slot beyond this instantiation
+      else if (hasnew && e < 0) flag = 3;                                   // slot capacity exhausted
+      else {
+        if (hasnew && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;                 // rounds of 32 slots that hold a candidate
+        int kk[NSR];
+        bool have[NSR];
+        {
+          int base = 0;
+#pragma unroll
+          for (int w = 0; w < NSR; ++w) {
+            const int s = w * 32 + lane;
+            const bool live = (occ[w] >> lane) & 1u;
+            have[w] = live || (hasnew && s == e);
+            kk[w] = live ? base + __popc(occ[w] & ltmask) : Ki;
+            base += __popc(occ[w]);
+          }
+        }
+        // per-slot terms (:206-242)
+        double L1[NSR], L2p[NSR], pr[NSR];
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NSR; ++w) {
+          L1[w] = 0.0; L2p[w] = 0.0; pr[w] = 0.0;
+          if (w < nw) {
+            const int s = w * 32 + lane;
+            if ((occ[w] >> lane) & 1u) {
+              double lgA = tA[w], lgZ = tZ[w];
+              pr[w] = tP[w];
+              int szs = sz[w];
+              if (s == li) {                                                // :193-194 detach i
+                bd[w] -= self.x; bl[w] -= self.y;
+                szs -= 1;
+                lgA = kp.LGA[szs]; lgZ = kp.LGZ[szs]; pr[w] = c.LPR[szs];
+              }
+              const double szd = (double)szs;
+              const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
+              const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+              const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+              L1[w] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+              L2p[w] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+              acc += L2p[w];                                                // vecsum: lane-wise ascending slots
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
+        const double L2i = acc;
+        // log-probabilities (:244-247)
+        double lp[NSR];
+        bool anynan = false;
+        double mn = RC_INF;
+#pragma unroll
+        for (int w = 0; w < NSR; ++w) {
+          lp[w] = 0.0;
+          if (w < nw) {
+            if ((occ[w] >> lane) & 1u) {
+              const double L2 = L2i - L2p[w];
+              lp[w] = pr[w] + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
+            } else if (have[w]) {                                           // :228-230 new cluster
+              const double L2 = L2i - 0.0;
+              lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+            }
+            if (have[w]) {
+              if (rc_isnan(lp[w])) anynan = true;
+              else if (lp[w] < mn) mn = lp[w];
+            }
+          }
+        }
+        mn = warp_min_f64(mn);
+        anynan = __any_sync(0xffffffffu, anynan);
+        if (anynan) mn = RC_NAN;                                            // Julia minimum propagates NaN
+        // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
+        double g[NSR];
+        double gbest = -RC_INF;
+        bool gnan = false;
+#pragma unroll
+        for (int w = 0; w < NSR; ++w) {
+          g[w] = -RC_INF;
+          if (w < nw && have[w]) {
+            const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
+            const double nz = -rc_log(-rc_log((kk[w] & 1) ? dr.u1 : dr.u0));
+            g[w] = nz + (lp[w] - mn);
+            if (rc_isnan(g[w])) gnan = true;
+            else if (g[w] > gbest) gbest = g[w];
+          }
+        }
+        if (!__any_sync(0xffffffffu, gnan)) {
+          gbest = warp_max_f64(gbest);
+          int kbest = 0x7fffffff, sbest = -1;
+#pragma unroll
+          for (int w = 0; w < NSR; ++w)
+            if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
+          const int kmin = __reduce_min_sync(0xffffffffu, kbest);
+          const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
+          cnew = __shfl_sync(0xffffffffu, sbest, __ffs(who) - 1);
+        } else {
+          // NaN is maximal for argmax and the first NaN wins
+          double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+#pragma unroll
+          for (int w = 0; w < NSR; ++w) {
+            if (!(w < nw && have[w])) continue;
+            const bool gn = rc_isnan(g[w]);
+            bool better;
+            if (bs < 0) better = true;
+            else if (gn) better = !bnan || kk[w] < bk;
+            else if (bnan) better = false;
+            else better = g[w] > bg || (g[w] == bg && kk[w] < bk);
+            if (better) { bg = g[w]; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const double og = __shfl_xor_sync(0xffffffffu, bg, off);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+            const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
+            bool better;
+            if (os < 0) better = false;
+            else if (bs < 0) better = true;
+            else if (on) better = !bnan || ok < bk;
+            else if (bnan) better = false;
+            else better = og > bg || (og == bg && ok < bk);
+            if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
+          }
+          cnew = bs;
+        }
+        if (cnew != li) flag = 1;
+      }
+    }
+    if (flag && lane == 0) atomicMin(&sh->first[slot3], warp);
+    csync(c);
+    const int first = sh->first[slot3];
+    if (first == RC_INC_NONE) { i0 += NW; continue; }                       // nobody moved: the whole batch stands
+    if (warp == first) {
+      if (flag == 1) {
+        // ---- the point moved (:250-252): labels, sizes, block sums ----
+        const int a = li, b = cnew;
+        if (lane == 0) { c.lab[i] = (uint8_t)cnew; c.sizes[a] -= 1; c.sizes[b] += 1; sh->mv_a = a; sh->mv_b = b; sh->nmoves += 1; }
+#pragma unroll
+        for (int w = 0; w < NSR; ++w) {
+          const int s = w * 32 + lane;
+          if (s >= cap) continue;
+          if (s == a) {
+            const int ix = tri(a, a, cap);
+            rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
+            rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
+          } else if ((occ[w] >> lane) & 1u) {
+            const int ix = tri(a, s, cap);
+            rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(bd[w])); c.WD[ix] = x;
+            rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(bl[w])); c.WL[ix] = y;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < NSR; ++w) {
+          const int s = w * 32 + lane;
+          if (s >= cap) continue;
+          if (s == b) {
+            const int ix = tri(b, b, cap);
+            rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
+            rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
+          } else if ((occ[w] >> lane) & 1u) {
+            const int ix = tri(b, s, cap);
+            rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(bd[w])); c.WD[ix] = x;
+            rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(bl[w])); c.WL[ix] = y;
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        sh->ev = flag; sh->mv_i = i;
+        if (flag == 3) c.sc->status = RC_ERR_SLOTS;
+      }
+    }
+    csync(c);
+    const int ev = sh->ev, mi = sh->mv_i;
+    if (ev == 2) { istop = mi; break; }
+    if (ev == 3) { istop = -1; break; }
+    const int a = sh->mv_a, b = sh->mv_b;
+#pragma unroll
+    for (int w = 0; w < NSR; ++w) {
+      const int s = w * 32 + lane;
+      if (s == a) { sz[w] -= 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1]; }
+      if (s == b) { sz[w] += 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]]; }
+    }
+    inc_update_S(c, mi, a, b);
+    csync(c);
+    i0 = mi + 1;
+  }
+  return istop;
+}
+
+__device__ void inc_full_scan(const Ctx& c, unsigned it) {
+  IncShared* sh = c.inc;
+  if (c.ctid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; sh->ev = 0; sh->nmoves = 0; }
+  csync(c);
+  bool low = true;                                                          // every live slot below 64?
+  for (int s = 64 + c.lane; s < c.cap; s += 32) low = low && c.sizes[s] == 0;
+  low = __all_sync(0xffffffffu, low);
+  int batch = 0, i = 0;
+  if (low) i = inc_scan_rows<2>(c, it, 0, batch);
+  if (i >= 0 && i < c.n) inc_scan_rows<RC_NS>(c, it, i, batch);
+  csync(c);
+  if (c.cwarp == 0) {                                                       // :254
+    int K = 0;
+    for (int s = c.lane; s < c.cap; s += 32) K += c.sizes[s] > 0;
+    for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
+    if (c.lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); }
+  }
+  csync(c);
+}
+
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, total; };
+__host__ __device__ inline IncLayout inc_layout(int n, int cap) {
+  IncLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
+  L.partial = take(sizeof(rc_i128) * 4 * cap);      // rows of the proposed state during a split-merge step
+  L.sc = take(sizeof(Scal));
+  L.inc = take(sizeof(IncShared));
+  L.red = take(sizeof(long long) * 16 * 4);
+  L.sizes = take(sizeof(int) * cap);
+  L.szL = take(sizeof(int) * cap);
+  L.itmp = take(sizeof(int) * (cap > 64 ? cap : 64));
+  L.clist = take(cap);
+  L.lab = take(n);
+  L.total = (o + 127) & ~(size_t)127;
+  return L;
+}
+
+// One CTA = one chain = the team; blockDim.x = kp.inc_nthr (a multiple of 32, at most 512).  S and W are built by
+// k_init_S / k_initw_from_S before the first launch.
+__global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc_kparams kp) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int chain = blockIdx.x;
+  const int n = kp.n, cap = kp.cap;
+  Ctx c;
+  c.n = n; c.cap = cap; c.tiles = kp.tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
+  c.colpos = nullptr; c.colpt = nullptr;
+  c.ctid = threadIdx.x; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1; c.bbarid = 2;
+  c.nthr = blockDim.x; c.nwarp = blockDim.x >> 5;
+  c.dummy = 0; c.stage_bytes = 0; c.stages = nullptr; c.cta = nullptr; c.chain0 = nullptr; c.chain_stride = 0; c.ss_off = 0;
+  c.perm = nullptr; c.runStart = nullptr; c.bscratch[0] = nullptr; c.bscratch[1] = nullptr; c.tileStart = nullptr; c.ss = nullptr;
+  {
+    const IncLayout L = inc_layout(n, cap);
+    c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
+    c.sc = reinterpret_cast<Scal*>(smem + L.sc);
+    c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
+    c.red = reinterpret_cast<long long*>(smem + L.red);
+    c.sizes = reinterpret_cast<int*>(smem + L.sizes);
+    c.szL = reinterpret_cast<int*>(smem + L.szL);
+    c.itmp = reinterpret_cast<int*>(smem + L.itmp);
+    c.clist = smem + L.clist;
+    c.lab = smem + L.lab;
+  }
+  const int ch = chain;
+  c.WD = kp.WD + (size_t)ch * cap * cap;
+  c.WL = kp.WL + (size_t)ch * cap * cap;
+  c.T = nullptr;
+  c.S = kp.S + (size_t)ch * cap * n;
+  c.WDbak = kp.WDbak ? kp.WDbak + (size_t)ch * cap * cap : nullptr;
+  c.WLbak = kp.WLbak ? kp.WLbak + (size_t)ch * cap * cap : nullptr;
+  c.labbak = kp.labbak ? kp.labbak + (size_t)ch * n : nullptr;
+  c.szbak = kp.szbak ? kp.szbak + (size_t)ch * (cap + 1) : nullptr;
+  c.Slist = kp.Slist + (size_t)ch * (n + 2);
+  c.origM = kp.origM + (size_t)ch * (n + 2);
+  c.AB = kp.AB + (size_t)ch * (n + 2);
+  c.L2s = kp.L2s + (size_t)ch * n;
+  c.NZ = kp.NZ + (size_t)ch * (kp.numGibbs + 1) * n;
+  c.LPR = kp.LPR + (size_t)ch * (n + 2);
+  c.DG = kp.DG + (size_t)ch * (n + 2);
+  c.stats = kp.stats + (size_t)ch * 16;
+  c.terms = kp.terms + (size_t)ch * kp.terms_stride;
+  c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
+  const int tid = c.ctid, nt = c.nthr;
+
+  for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
+  for (int s = tid; s < cap; s += nt) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
+  if (tid == 0) {
+    Scal& s = *c.sc;
+    s.r = kp.r[chain]; s.p = kp.p[chain];
+    s.logp = rc_log(s.p); s.log1mp = rc_log(1 - s.p);
+    s.status = kp.status[chain]; s.rebuild = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0; s.forked = 0;
+    int K = 0;
+    for (int q = 0; q < cap; ++q) K += kp.sizes[(size_t)chain * cap + q] > 0;
+    s.K = K;
+  }
+  csync(c);
+
+  for (long long iter = kp.it0 + 1; iter <= kp.it1; ++iter) {
+    const unsigned it = (unsigned)iter;
+    const long long ti0 = RC_CLOCK();
+    csync(c);
+    if (c.sc->status != 0) break;                                            // the chain stopped (slot capacity)
+    bool do_scan = true;
+    if (c.cwarp == 0) {
+      const bool ra = update_r(c, it);                                       // mcmc.jl:538
+      if (tid == 0) {
+        kp.r_acc[(size_t)chain * kp.numiters + (iter - 1)] = ra ? 1 : 0;
+        update_p(c, it);                                                     // :539
+      }
+    }
+    csync(c);
+    build_lpr(c);
+    if (tid == 0) st_add(c, ST_RP, RC_CLOCK() - ti0);
+    // sample_labels! (:540)
+    const bool multi = kp.numMH > 1;
+    if (multi) {                                             // the chain's own state, in case a proposal is accepted and committed
+      for (int j = tid; j < n; j += nt) c.labbak[j] = c.lab[j];
+      for (int s = tid; s < cap; s += nt) c.szbak[s] = c.sizes[s];
+      if (tid == 0) { c.szbak[cap] = c.sc->K; c.sc->forked = 0; }
+      csync(c);
+    }
+    for (unsigned mh = 0; mh < (unsigned)kp.numMH; ++mh) {
+      splitmerge_step(c, it, mh, mh + 1 < (unsigned)kp.numMH);
+      if (c.sc->status) { do_scan = false; break; }
+      const int acc = c.sc->itmp[1], spl = c.sc->itmp[2];
+      if (tid == 0) {
+        kp.sm_acc[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)acc;
+        kp.sm_split[((size_t)chain * kp.numiters + (iter - 1)) * kp.numMH + mh] = (uint8_t)spl;
+      }
+      csync(c);
+      if (acc) do_scan = false;                              // quirk Q1, see k_chain
+    }
+    if (multi && c.sc->status == 0) {                        // back to the chain's own state
+      if (c.sc->forked) {
+        for (int t = tid; t < cap * cap; t += nt) { c.WD[t] = c.WDbak[t]; c.WL[t] = c.WLbak[t]; }
+        for (int j = 0; j < n; ++j) {                        // the row sums follow every point back to its own slot
+          const int from = c.lab[j], to = c.labbak[j];
+          if (from != to) inc_update_S(c, j, from, to);
+        }
+        csync(c);
+        for (int j = tid; j < n; j += nt) c.lab[j] = c.labbak[j];
+        for (int s = tid; s < cap; s += nt) c.sizes[s] = c.szbak[s];
+        if (tid == 0) c.sc->K = c.szbak[cap];
+      }
+      csync(c);
+    }
+    const long long ts0 = RC_CLOCK();
+    if (do_scan) inc_full_scan(c, it);
+    const long long ts1 = RC_CLOCK();
+    if (tid == 0) st_add(c, ST_SCAN_TOTAL, ts1 - ts0);
+    csync(c);
+    if (c.sc->status == 0 && iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0) {    // :546-554
+      const long long j = (iter - kp.burnin) / kp.thin - 1;
+      if (j < kp.numsamples) {
+        record_labels(c, kp.out_labels + ((size_t)chain * kp.numsamples + j) * n);
+        const double ll = loglik_eval(c, c.sizes);
+        if (c.cwarp == 0) {
+          const double lpv = logprior_eval(c);
+          if (tid == 0) {
+            const size_t o = (size_t)chain * kp.numsamples + j;
+            kp.out_K[o] = c.sc->K; kp.out_r[o] = c.sc->r; kp.out_p[o] = c.sc->p;
+            kp.out_ll[o] = ll; kp.out_lp[o] = ll + lpv;
+          }
+        }
+        csync(c);
+      }
+    }
+    if (tid == 0) { st_add(c, ST_RECORD, RC_CLOCK() - ts1); st_add(c, ST_ITER_TOTAL, RC_CLOCK() - ti0); }
+  }
+  csync(c);
+  for (int j = tid; j < n; j += nt) kp.labels[(size_t)chain * n + j] = c.lab[j];
+  for (int s = tid; s < cap; s += nt) kp.sizes[(size_t)chain * cap + s] = c.sizes[s];
+  if (tid == 0) { kp.r[chain] = c.sc->r; kp.p[chain] = c.sc->p; kp.status[chain] = c.sc->status; }
+}
+
+// ---- incremental mode: S and W from scratch (first launch) ----------------------------------------------
+// S[ch][t][x] = sum over columns j with label t of DL[x][j].  One CTA per row x at a time; every thread walks a
+// contiguous strip of the row keeping a running sum while the label stays the same (one pair of shared-memory atomics
+// per label run).  Zero entries are not written (S is zero-filled before).
+__global__ void __launch_bounds__(256) k_init_S(const longlong2* __restrict__ DL, int n, const uint8_t* __restrict__ labels, int cap,
+                                                longlong2* __restrict__ S, int nch) {
+  extern __shared__ unsigned long long sbins[];          // [cap] D sums, [cap] L sums
+  for (int t = threadIdx.x; t < 2 * cap; t += blockDim.x) sbins[t] = 0ull;
+  __syncthreads();
+  const int w = (n + blockDim.x - 1) / blockDim.x;
+  const int j0 = threadIdx.x * w, j1 = min(n, j0 + w);
+  for (int x = blockIdx.x; x < n; x += gridDim.x) {
+    const longlong2* row = DL + (size_t)x * n;
+    for (int ch = blockIdx.y; ch < nch; ch += gridDim.y) {
+      const uint8_t* lab = labels + (size_t)ch * n;
+      int cur = -1; long long d = 0, l = 0;
+      for (int j = j0; j < j1; ++j) {
+        const int lb = lab[j];
+        if (lb != cur) {
+          if (cur >= 0) { atomicAdd(&sbins[cur], (unsigned long long)d); atomicAdd(&sbins[cap + cur], (unsigned long long)l); }
+          cur = lb; d = 0; l = 0;
+        }
+        const longlong2 v = row[j];
+        d += v.x; l += v.y;
+      }
+      if (cur >= 0) { atomicAdd(&sbins[cur], (unsigned long long)d); atomicAdd(&sbins[cap + cur], (unsigned long long)l); }
+      __syncthreads();
+      longlong2* Sc = S + (size_t)ch * cap * n;
+      for (int t = threadIdx.x; t < cap; t += blockDim.x) {
+        const long long bd = (long long)sbins[t], bl = (long long)sbins[cap + t];
+        sbins[t] = 0ull; sbins[cap + t] = 0ull;
+        if (bd != 0 || bl != 0) Sc[(size_t)t * n + x] = make_longlong2(bd, bl);
+      }
+      __syncthreads();
+    }
+  }
+}
+__global__ void k_replicate_S(longlong2* __restrict__ S, size_t per_chain, int64_t nchains) {
+  const size_t total = per_chain * (size_t)(nchains - 1);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    S[per_chain + t] = S[t % per_chain];
+}
+// W[ch][k][t] (k <= t) = sum over x with label k of S[ch][t][x]: the block sums loglik needs (mcmc.jl:1-56).
+// One CTA per (slot t, chain); 128-bit totals by carry-propagating 64-bit atomics; W is zero-filled before.
+__device__ __forceinline__ void atomic_add128g(rc_i128* a, const rc_i128& v) {
+  const unsigned long long old = atomicAdd(&a->lo, v.lo);
+  const long long hi = v.hi + ((old + v.lo) < old ? 1LL : 0LL);
+  if (hi) atomicAdd(reinterpret_cast<unsigned long long*>(&a->hi), (unsigned long long)hi);
+}
+__global__ void __launch_bounds__(256) k_initw_from_S(const longlong2* __restrict__ S, int n, const uint8_t* __restrict__ labels,
+                                                      const int* __restrict__ sizes, int cap, rc_i128* __restrict__ WD,
+                                                      rc_i128* __restrict__ WL) {
+  const int t = blockIdx.x, ch = blockIdx.y;
+  if (sizes[(size_t)ch * cap + t] == 0) return;
+  const uint8_t* lab = labels + (size_t)ch * n;
+  const longlong2* St = S + ((size_t)ch * cap + t) * n;
+  rc_i128* wd = WD + (size_t)ch * cap * cap;
+  rc_i128* wl = WL + (size_t)ch * cap * cap;
+  const int w = (n + blockDim.x - 1) / blockDim.x;
+  const int x0 = threadIdx.x * w, x1 = min(n, x0 + w);
+  int cur = -1;
+  rc_i128 d, l; d.lo = 0; d.hi = 0; l.lo = 0; l.hi = 0;
+  for (int x = x0; x < x1; ++x) {
+    const int k = lab[x];
+    if (k != cur) {
+      if (cur >= 0 && cur <= t) { atomic_add128g(&wd[cur * cap + t], d); atomic_add128g(&wl[cur * cap + t], l); }
+      cur = k; d.lo = 0; d.hi = 0; l.lo = 0; l.hi = 0;
+    }
+    const longlong2 v = St[x];
+    rc_add128(d, v.x); rc_add128(l, v.y);
+  }
+  if (cur >= 0 && cur <= t) { atomic_add128g(&wd[cur * cap + t], d); atomic_add128g(&wl[cur * cap + t], l); }
 }
 
 struct ChainLayout {
@@ -1660,6 +2231,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
@@ -1699,7 +2271,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.LPR = kp.LPR + (size_t)ch * (n + 2);
   c.DG = kp.DG + (size_t)ch * (n + 2);
   c.stats = kp.stats + (size_t)ch * 16;
-  c.terms = kp.terms + (size_t)ch * (cap * cap > 2048 ? cap * cap : 2048);
+  c.terms = kp.terms + (size_t)ch * kp.terms_stride;
   c.key = rc_chain_key(kp.seed, (unsigned long long)(kp.chain_offset + ch));
   const int tid = c.ctid;
 
@@ -1915,6 +2487,27 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
     cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_chain<1><<<grid, RC_NTHR + RC_XTHR, smem, st>>>(kp);
   }
+}
+
+size_t rc_sampler_inc_smem_bytes(int n, int cap) { return inc_layout(n, cap).total; }
+
+// Incremental mode: (re)build S (and W) of every chain from the labels, then one launch of k_chain_inc.
+int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st) {
+  const size_t per = (size_t)kp.cap * kp.n;
+  const size_t nS = shared_labels ? 1 : (size_t)kp.nchains;
+  if (cudaMemsetAsync(kp.S, 0, sizeof(longlong2) * per * nS, st) != cudaSuccess) return 1;
+  if (cudaMemsetAsync(kp.WD, 0, sizeof(rc_i128) * (size_t)kp.cap * kp.cap * kp.nchains, st) != cudaSuccess) return 1;
+  if (cudaMemsetAsync(kp.WL, 0, sizeof(rc_i128) * (size_t)kp.cap * kp.cap * kp.nchains, st) != cudaSuccess) return 1;
+  const int gy = (int)std::min<size_t>(nS, 64);
+  const int gx = std::max(1, std::min(kp.n, (148 * 8 + gy - 1) / gy));
+  k_init_S<<<dim3(gx, gy), 256, sizeof(unsigned long long) * 2 * kp.cap, st>>>(kp.DL, kp.n, kp.labels, kp.cap, kp.S, (int)nS);
+  if (shared_labels && kp.nchains > 1) k_replicate_S<<<148 * 8, 256, 0, st>>>(kp.S, per, kp.nchains);
+  k_initw_from_S<<<dim3(kp.cap, kp.nchains), 256, 0, st>>>(kp.S, kp.n, kp.labels, kp.sizes, kp.cap, kp.WD, kp.WL);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st) {
+  cudaFuncSetAttribute(k_chain_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_chain_inc<<<kp.nchains, nthr, smem, st>>>(kp);
 }
 
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st) {

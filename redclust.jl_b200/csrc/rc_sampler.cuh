@@ -36,7 +36,8 @@ struct rc_kparams {
   rc_i128 *WDbak, *WLbak; // [nchains][cap*cap]  numMH > 1 only: the chain's own block sums while a proposal is committed
   uint8_t* labbak;      // [nchains][n]
   int* szbak;           // [nchains][cap+1]
-  longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj
+  longlong2* T;         // [nchains][n][cap]   split-merge scratch: row sums by slot of the members of ci u cj (streaming mode)
+  longlong2* S;         // [nchains][cap][n]   incremental mode: row sums by slot of EVERY point, S[k][x] = sum_{j in k} DL[x][j]
   unsigned short* Slist;// [nchains][n+2]  members of ci u cj of the current split-merge step
   uint8_t* origM;       // [nchains][n+2]  their labels in the chain's state
   longlong4* AB;        // [nchains][n+2]  running candidate sums of the members (restricted scans)
@@ -44,7 +45,8 @@ struct rc_kparams {
   double2* NZ;          // [nchains][(numGibbs+1)*n] Gumbel noise of the free restricted scans
   double* LPR;          // [nchains][n+2]  prior term by cluster size for the current (r, p)
   longlong2* DG;        // [nchains][n+2]  diagonal entries DL[x][x] of the split-merge members
-  double* terms;        // [nchains][max(cap*cap, 1024)]  log-likelihood terms / reduction scratch
+  double* terms;        // [nchains][terms_stride]  log-likelihood terms / reduction scratch
+  size_t terms_stride;  // max(cap*cap, 8192) doubles
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
   int* out_K;           // [nchains][numsamples]
@@ -60,4 +62,7 @@ struct rc_kparams {
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st);
 bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
+size_t rc_sampler_inc_smem_bytes(int n, int cap);
+int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st);
+void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);
