@@ -45,6 +45,7 @@ struct rc_sampler {
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
   size_t inc_smem, terms_stride;
+  int inc_mcap;                // split-merge members whose running sums fit the chain's shared memory
   longlong2* DLp;              // copy of the data's DL with label-sorted columns (null: the data's own matrix is streamed)
   unsigned short *colpos, *colpt;   // [n] point -> column and column -> point of DLp
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
@@ -166,7 +167,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -313,9 +314,19 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     int nthr = nchains <= nsm ? 512 : (nchains <= 2 * nsm ? 256 : 256);
     if (const char* e = getenv("RCB200_INC_THREADS")) nthr = std::max(32, std::min(512, atoi(e) / 32 * 32));
     s->inc_nthr = nthr;
-    s->inc_smem = rc_sampler_inc_smem_bytes((int)n, cap);
+    {
+      // shared memory per chain: the fixed part plus as many split-merge members (64 B each) as fit next to the other
+      // CTAs of the SM (two chains per SM when there are more chains than SMs)
+      const size_t base = rc_sampler_inc_smem_bytes((int)n, cap, 0);
+      const size_t budget = nchains <= nsm ? (size_t)maxsmem : ((size_t)maxsmem + 1024) / 2 - 1024;
+      int mcap = base < budget ? (int)((budget - base) / 64) : 0;
+      mcap = std::min<int>(mcap, (int)n + 2) / 8 * 8;
+      s->inc_mcap = std::max(mcap, 0);
+      s->inc_smem = rc_sampler_inc_smem_bytes((int)n, cap, s->inc_mcap);
+      if (s->inc_smem > (size_t)maxsmem) { s->inc_mcap = 0; s->inc_smem = base; }
+    }
     if (s->inc && s->inc_smem > (size_t)maxsmem) s->inc = false;
-    if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] scan mode: %s (S needs %.2f GB, %.2f GB free), %d threads per chain\n", s->inc ? "incremental" : "streaming", needS / 1e9, freeb / 1e9, nthr);
+    if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] scan mode: %s (S needs %.2f GB, %.2f GB free), %d threads per chain, %zu B shared memory (%d split-merge members)\n", s->inc ? "incremental" : "streaming", needS / 1e9, freeb / 1e9, nthr, s->inc_smem, s->inc_mcap);
   }
   s->terms_stride = (size_t)std::max(cap * cap, 8192);
   if (s->inc) TRY(dalloc(&s->S, (size_t)nchains * cap * n));

@@ -94,6 +94,18 @@ struct CtaShared {
   int issuer;
 };
 
+// Incremental mode (k_chain_inc): hand-off block of the chain's team.
+#define RC_INC_MAXW 16               // warps per chain, at most
+struct IncShared {
+  int first[3];      // lowest warp / step of a batch that needs a commit (three rotating slots, see inc_scan_rows)
+  int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
+  int mv_i, mv_a, mv_b;
+  int nmoves;
+  int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
+  double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
+};
+#define RC_INC_NONE 0x7fffffff
+
 struct Ctx {
   int n, cap, tiles;
   int qD, qL;
@@ -135,6 +147,8 @@ struct Ctx {
   longlong2* T;
   longlong2* S;           // incremental mode (k_chain_inc): [cap][n] row sums by slot, S[k][x] = sum_{j in k} DL[x][j]; null otherwise
   struct IncShared* inc;  // incremental mode: hand-off block of the scan
+  int mcap;               // incremental mode: members of a split-merge step whose AB / DG / L2s fit the shared-memory scratch
+  longlong4* mAB; longlong2* mDG; double2* mL2s;   // that scratch
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
   longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
@@ -1358,12 +1372,198 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Incremental mode versions of the two functions above, run by the whole team of the chain.
+// member_sums_inc: thread t owns the members q = t, t + nthr, ...; it walks ALL members y and adds DL[y][x_q]
+// (= DL[x_q][y], D is symmetric; reading row y makes the threads of a warp hit neighbouring columns) to the sum of
+// y's launch label.  No reductions; the sums over the first two live slots, clusters the launch did not touch, are
+// single entries of S.
+// ------------------------------------------------------------------------------------------------
+__device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, int c2) {
+  const rc_kparams& kp = *c.kp;
+  const rc_params& P = kp.P;
+  const int mt = nS + 2, n = c.n;
+  for (int q0 = 0; q0 < mt; q0 += 2 * c.nthr) {
+    const int qa = q0 + c.ctid, qb = q0 + c.nthr + c.ctid;
+    const bool oa = qa < mt, ob = qb < mt;
+    const int xa = oa ? (int)c.Slist[qa] : 0, xb = ob ? (int)c.Slist[qb] : 0;
+    long long va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+    for (int q2 = 0; q2 < mt; ++q2) {
+      const int y = c.Slist[q2];                               // uniform over the team
+      const bool isA = c.lab[y] == ca;
+      const longlong2* row = c.DL + (size_t)y * n;
+      const longlong2 ea = oa ? __ldg(row + xa) : make_longlong2(0, 0);
+      const longlong2 eb = ob ? __ldg(row + xb) : make_longlong2(0, 0);
+      if (isA) { va[0] += ea.x; va[1] += ea.y; vb[0] += eb.x; vb[1] += eb.y; }
+      else { va[2] += ea.x; va[3] += ea.y; vb[2] += eb.x; vb[3] += eb.y; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = h ? qb : qa;
+      if (!(h ? ob : oa)) continue;
+      const int x = h ? xb : xa;
+      const long long* v = h ? vb : va;
+      longlong4 ab; ab.x = v[0]; ab.y = v[1]; ab.z = v[2]; ab.w = v[3];
+      c.AB[q] = ab;
+      c.DG[q] = __ldg(c.DL + (size_t)x * n + x);
+      if (q < nS) {
+        double val[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int t = e == 0 ? c1 : c2;
+          if (t != ca && t != cb) {
+            const longlong2 sv = c.S[(size_t)t * n + x];
+            const int szs = c.szL[t];
+            const double szd = (double)szs;
+            const double sD = rc_dequant(sv.x, c.qD), sL = rc_dequant(sv.y, c.qL);
+            const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+            val[e] = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+          }
+        }
+        c.L2s[q] = make_double2(val[0], val[1]);
+      }
+    }
+  }
+}
+
+// restricted_scans for the whole team: every warp evaluates eight consecutive steps (as restricted_scans does), so a
+// batch covers 8 * nwarp steps; the steps up to and including the first one that moves its item are committed, the move
+// is applied to the running candidate sums of all members by all threads, and the scan continues behind it.
+__device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
+  const rc_kparams& kp = *c.kp;
+  const rc_params& P = kp.P;
+  const int lane = c.lane, warp = c.cwarp, NW = c.nwarp;
+  const int mt = nS + 2;
+  const int numGibbs = (int)kp.numGibbs;
+  IncShared* sh = c.inc;
+  if (nS == 0) { if (c.ctid == 0) c.sc->ltp = 0.0; csync(c); return; }
+  if (c.ctid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; }
+  csync(c);
+  const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
+  const int st = lane >> 2, role = lane & 3, quad = lane & ~3;
+  const bool isA = (role & 1) == 0;
+  double ltp = 0.0;                                   // accumulated by thread 0 in step order
+  int batch = 0;
+  int nwact = NW;                                     // warps that evaluate a batch: follows the observed run length between moves
+  for (int g = 0; g <= numGibbs; ++g) {
+    const bool last = g == numGibbs;
+    const bool forced = last && !split;
+    int pos0 = 0;
+    while (pos0 < nS) {
+      const int slot3 = batch % 3, par = batch & 1;
+      if (c.ctid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
+      ++batch;
+      const long long tr0 = RC_CLOCK();
+      const int nb = min(RC_RS_B * nwact, nS - pos0);
+      const int stepi = warp * RC_RS_B + st;           // step within the batch
+      const int pos = pos0 + stepi;
+      const bool on = stepi < nb;
+      int y = 0, cur = 0, cnew = 0, k = 0;
+      double lt = 0.0;
+      if (on) {
+        y = c.Slist[pos];
+        const longlong2 self = c.DG[pos];
+        const longlong4 ab = c.AB[pos];
+        const double2 l2s = c.L2s[pos];
+        const double2 nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
+        cur = c.lab[y];
+        // sums over the candidates with y detached (:303-304)
+        const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
+        const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
+        const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
+        // roles 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
+        double X;
+        {
+          const int szs = isA ? szA : szB;
+          const double szd = (double)szs;
+          const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
+          if ((role & 2) == 0) {                                                                    // :313-319, 327-330
+            const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+            X = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+          } else {                                                                                  // :307-312, 321-326
+            const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+            X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+          }
+        }
+        const unsigned qm = 0xfu << quad;
+        const double L2pA = __shfl_sync(qm, X, quad), L2pB = __shfl_sync(qm, X, quad + 1);
+        const double L1A = __shfl_sync(qm, X, quad + 2), L1B = __shfl_sync(qm, X, quad + 3);
+        const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
+        const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
+        const double L2i = L2p1 + L2p2;                                                             // :331 (quirk Q2)
+        const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                            // :332-334
+        double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                 // :335
+        double lp1 = c.LPR[szB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
+        if (!forced) {                                                                              // :336-338
+          double mn = lp0;
+          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+          lp0 -= mn; lp1 -= mn;
+          const double g0 = nz.x + lp0, g1 = nz.y + lp1;
+          k = 0;
+          if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
+          cnew = k == 0 ? ca : cb;
+        } else {                                                                                    // :339-342
+          cnew = c.origM[pos];
+          k = (ca == cnew) ? 0 : 1;
+        }
+        if (last) {                                                                                 // :347-351
+          double mn = lp0;                                                                          // quirk Q3
+          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+          lp0 += mn; lp1 += mn;
+          double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
+          const double den = p0 + p1;
+          p0 /= den; p1 /= den;
+          lt = rc_log(k == 0 ? p0 : p1);
+          if (role == 0) sh->ltbuf[par][stepi] = lt;
+        }
+      }
+      __syncwarp();
+      // the warp's first step that moves its item
+      const unsigned mv = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur);
+      if (mv) {
+        const int sf = (__ffs(mv) - 1) >> 2;
+        if (lane == 4 * sf) {
+          sh->rs_cand[warp][0] = y; sh->rs_cand[warp][1] = cur; sh->rs_cand[warp][2] = cnew;
+          atomicMin(&sh->first[slot3], warp * RC_RS_B + sf);
+        }
+      }
+      csync(c);
+      const long long tr1 = RC_CLOCK();
+      const int F = sh->first[slot3];
+      const int nvalid = F == RC_INC_NONE ? nb : F + 1;
+      nwact = F == RC_INC_NONE ? min(NW, nwact * 2) : max(1, min(NW, (2 * nvalid + RC_RS_B - 1) / RC_RS_B));
+      if (last && c.ctid == 0)
+        for (int q = 0; q < nvalid; ++q) ltp += sh->ltbuf[par][q];                                  // in step order, as the scan adds them
+      if (F != RC_INC_NONE) {                                                                       // :344-345
+        const int fw = F / RC_RS_B;
+        const int ym = sh->rs_cand[fw][0], curm = sh->rs_cand[fw][1], newm = sh->rs_cand[fw][2];
+        if (c.ctid == 0) { c.lab[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
+        // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
+        const longlong2* row = c.DL + (size_t)ym * c.n;
+        const bool a2b = curm == ca;
+        for (int q = c.ctid; q < mt; q += c.nthr) {
+          const longlong2 e = __ldg(row + c.Slist[q]);
+          longlong4 t = c.AB[q];
+          if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
+          else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
+          c.AB[q] = t;
+        }
+        csync(c);
+      }
+      if (c.ctid == 0) { st_add(c, ST_DEC_WAIT, tr1 - tr0); st_add(c, ST_DEC_WORK, RC_CLOCK() - tr1); st_add(c, ST_BULK_WAIT_CONSUMED, 1); st_add(c, ST_BULK_WAIT_FULL, F != RC_INC_NONE); }
+      pos0 += nvalid;
+    }
+  }
+  if (c.ctid == 0) c.sc->ltp = ltp;
+  csync(c);
+}
+
 // One split-merge proposal (mcmc.jl:372-474) on the current LOCAL state of sample_labels!.  Returns accept through
 // c.sc->itmp[1], split through itmp[2].  With commit == false the state is unchanged on return.  With commit == true
 // (more proposals follow in this iteration, numMH > 1) an accepted proposal becomes the local state (:470): labels,
 // sizes, K and the block sums W are replaced -- the caller backs the chain's own state up first and restores it
 // after the last proposal (quirk Q1: the accepted state never reaches runsampler's state).
-__device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool commit) {
+__device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int tid = c.ctid, lane = c.lane, warp = c.cwarp;
@@ -1399,6 +1599,11 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     csync(c);
   }
   const int nS = c.sc->itmp[3];
+  // incremental mode: the per-member running sums live in shared memory when the members fit (the restricted scans
+  // are a chain of dependent reads and writes of exactly these arrays)
+  longlong4* const gAB = c.AB; longlong2* const gDG = c.DG; double2* const gL2s = c.L2s;
+  if (c.S && nS + 2 <= c.mcap) { c.AB = c.mAB; c.DG = c.mDG; c.L2s = c.mL2s; }
+  auto unswap = [&]() { c.AB = gAB; c.DG = gDG; c.L2s = gL2s; };
   if (tid == 0) { c.Slist[nS] = (unsigned short)pi; c.origM[nS] = (uint8_t)ci; c.Slist[nS + 1] = (unsigned short)pj; c.origM[nS + 1] = (uint8_t)cj; }
   // launch state (:393-408), in place in c.lab / c.szL
   for (int s = tid; s < cap; s += c.nthr) c.szL[s] = c.sizes[s];
@@ -1416,7 +1621,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     }
     csync(c);
     ca = c.sc->itmp[4];
-    if (ca < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; csync(c); return; }
+    if (ca < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; csync(c); unswap(); return; }
     if (tid == 0) c.lab[pi] = (uint8_t)ca;
   }
   const int cb = cj;
@@ -1454,6 +1659,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     if (c.sc->status) {                                      // does not fit: undo the in-place launch labels and stop the chain
       for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
       csync(c);
+      unswap();
       return;
     }
     for (int pos = 0; pos < nS + 2; ++pos) {
@@ -1488,7 +1694,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   } else if (c.S) {
     // incremental mode (split or merge): member x member entries by launch label; the sums over the first two live
     // slots, when they are not candidates, are clusters the launch did not touch and come straight from S
-    member_sums_gather(c, nS, ca, cb, c1, c2, nullptr, 0, nullptr, 0);
+    member_sums_inc(c, nS, ca, cb, c1, c2);
   } else {
     // merge: only member-restricted sums are needed; T's memory serves as scratch for the member lists of the
     // first two live slots (unordered: integer sums do not depend on the order)
@@ -1515,7 +1721,8 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
   }
   csync(c);
   const long long tm1 = RC_CLOCK();
-  if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
+  if (c.S) restricted_scans_team(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
+  else if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);
   csync(c);
   const long long tm2 = RC_CLOCK();
   if (tid == 0) { st_add(c, ST_MH_SETUP, tm1 - tm0); st_add(c, ST_MH_RSCAN, tm2 - tm1); }
@@ -1651,6 +1858,7 @@ __device__ void splitmerge_step(const Ctx& c, unsigned it, unsigned mh, bool com
     for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
   }
   csync(c);
+  unswap();
   if (tid == 0) st_add(c, ST_MH_LOGLIK, RC_CLOCK() - tm2);
 }
 
@@ -1682,13 +1890,6 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 //   applied.  Every committed row sees the inputs of the sequential scan, so the results are the same bits as the
 //   streaming kernel's and the oracle's.
 // ------------------------------------------------------------------------------------------------
-struct IncShared {
-  int first[3];      // lowest warp of a batch whose row needs a commit (three rotating slots, see inc_scan_rows)
-  int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
-  int mv_i, mv_a, mv_b;
-  int nmoves;
-};
-#define RC_INC_NONE 0x7fffffff
 
 template <int NSR>
 __device__ int inc_scan_rows(const Ctx& c, unsigned it, int istart, int& batch) {
@@ -1931,8 +2132,10 @@ __device__ int inc_scan_rows(const Ctx& c, unsigned it, int istart, int& batch) 
       if (s == a) { sz[w] -= 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1]; }
       if (s == b) { sz[w] += 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]]; }
     }
+    const long long tu0 = RC_CLOCK();
     inc_update_S(c, mi, a, b);
     csync(c);
+    if (c.ctid == 0) st_add(c, ST_BULK_PATCH, RC_CLOCK() - tu0);             // (incremental mode: cycles in the move updates of S)
     i0 = mi + 1;
   }
   return istop;
@@ -1958,8 +2161,8 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, total; };
-__host__ __device__ inline IncLayout inc_layout(int n, int cap) {
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, mAB, mDG, mL2s, total; };
+__host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   IncLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
@@ -1972,6 +2175,9 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap) {
   L.itmp = take(sizeof(int) * (cap > 64 ? cap : 64));
   L.clist = take(cap);
   L.lab = take(n);
+  L.mAB = take(sizeof(longlong4) * mcap);
+  L.mDG = take(sizeof(longlong2) * mcap);
+  L.mL2s = take(sizeof(double2) * mcap);
   L.total = (o + 127) & ~(size_t)127;
   return L;
 }
@@ -1990,7 +2196,11 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   c.dummy = 0; c.stage_bytes = 0; c.stages = nullptr; c.cta = nullptr; c.chain0 = nullptr; c.chain_stride = 0; c.ss_off = 0;
   c.perm = nullptr; c.runStart = nullptr; c.bscratch[0] = nullptr; c.bscratch[1] = nullptr; c.tileStart = nullptr; c.ss = nullptr;
   {
-    const IncLayout L = inc_layout(n, cap);
+    const IncLayout L = inc_layout(n, cap, kp.inc_mcap);
+    c.mcap = kp.inc_mcap;
+    c.mAB = reinterpret_cast<longlong4*>(smem + L.mAB);
+    c.mDG = reinterpret_cast<longlong2*>(smem + L.mDG);
+    c.mL2s = reinterpret_cast<double2*>(smem + L.mL2s);
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2231,7 +2441,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
@@ -2489,7 +2699,7 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
   }
 }
 
-size_t rc_sampler_inc_smem_bytes(int n, int cap) { return inc_layout(n, cap).total; }
+size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap) { return inc_layout(n, cap, mcap).total; }
 
 // Incremental mode: (re)build S (and W) of every chain from the labels, then one launch of k_chain_inc.
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st) {

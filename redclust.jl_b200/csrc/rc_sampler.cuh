@@ -47,6 +47,7 @@ struct rc_kparams {
   longlong2* DG;        // [nchains][n+2]  diagonal entries DL[x][x] of the split-merge members
   double* terms;        // [nchains][terms_stride]  log-likelihood terms / reduction scratch
   size_t terms_stride;  // max(cap*cap, 8192) doubles
+  int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
   int* out_K;           // [nchains][numsamples]
@@ -62,7 +63,7 @@ struct rc_kparams {
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st);
 bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
-size_t rc_sampler_inc_smem_bytes(int n, int cap);
+size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap);
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st);
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);
