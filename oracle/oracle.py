@@ -318,3 +318,38 @@ def pair_stats(D, labels):
     ut = D[iu]
     A, B = ut[adj], ut[~adj]
     return dict(nA=int(A.size), sA=float(A.sum()), lA=float(np.log(A).sum()), nB=int(B.size), sB=float(B.sum()), lB=float(np.log(B).sum()))
+
+
+# ---- probes used by tests/test_oracle_pins.py ------------------------------------------------------------------
+def scan_only(D, params, labels, r, p, iters, seed=0, chain=0, sum_mode=0):
+    """`iters` full Gibbs scans (mcmc.jl:158-256) at fixed (r, p); returns the sortlabels'd state after each scan."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    lab = np.ascontiguousarray(labels, dtype=np.int64)
+    out = np.zeros((iters, n), np.int64)
+    lib().rco_scan_only(_p(D, C.c_double), C.c_int64(n), C.byref(params), _p(lab, C.c_int64), C.c_double(r), C.c_double(p),
+                        C.c_uint64(seed), C.c_uint64(chain), C.c_int64(iters), C.c_int(sum_mode), _p(out, C.c_int64))
+    return out
+
+
+def gibbs_logprobs(D, params, labels, r, p, i, sum_mode=1):
+    """Candidate slots (1-based, the reference's order) and the un-normalised log-probabilities of the scan step of
+    point i (0-based) in the given state (mcmc.jl:193-247)."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    lab = np.ascontiguousarray(labels, dtype=np.int64)
+    cand = np.zeros(n + 1, np.int64); lp = np.zeros(n + 1)
+    L = lib()
+    L.rco_gibbs_logprobs.restype = C.c_int64
+    m = L.rco_gibbs_logprobs(_p(D, C.c_double), C.c_int64(n), C.byref(params), _p(lab, C.c_int64), C.c_double(r), C.c_double(p),
+                             C.c_int64(i), C.c_int(sum_mode), _p(cand, C.c_int64), _p(lp, C.c_double))
+    return cand[:m].copy(), lp[:m].copy()
+
+
+def draws(kind, a, b, count, seed=0):
+    """Raw draws of the shared samplers: kind 'gamma' (shape a), 'beta' (a, b), 'truncnorm' (mean a, sd b, lower 0),
+    'randint' (1..a)."""
+    k = {"gamma": 0, "beta": 1, "truncnorm": 2, "randint": 3}[kind]
+    out = np.zeros(count)
+    lib().rco_draws(C.c_int(k), C.c_double(a), C.c_double(b), C.c_uint64(seed), C.c_int64(count), _p(out, C.c_double))
+    return out

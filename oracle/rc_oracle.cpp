@@ -201,19 +201,23 @@ double logprior(const State& s, const rc_params& P) {
   return L;
 }
 
+// rand(truncated(Normal(r, sd), lower = 0)): rejection of r + sd*z against the lower bound (mcmc.jl:104-109)
+double draw_truncnorm0(double r, double sd, uint64_t key, uint32_t it) {
+  double lb = (0.0 - r) / sd;
+  double z = 0;
+  for (uint32_t att = 0; att < 100000u; ++att) {
+    z = rc_norminv(rc_open01(rc_draw1(key, it, RC_SITE_R_NORMAL, 0, att, 0)));
+    if (z >= lb) break;
+  }
+  return r + sd * z;
+}
+
 // sample_r! / sample_r, mcmc.jl:80-136
 bool sample_r(State& s, const rc_params& P, uint64_t key, uint32_t it) {
   const int64_t n = (int64_t)s.clusts.size();
   const double r = s.r, p = s.p, sd = P.proposalsd_r;
   const double K = (double)s.K;
-  // truncated(Normal(r, sd), lower=0): rejection of r + sd*z against the lower bound (mcmc.jl:104-109)
-  double lb = (0.0 - r) / sd;
-  double z = 0, cand = r;
-  for (uint32_t att = 0; att < 100000u; ++att) {
-    z = rc_norminv(rc_open01(rc_draw1(key, it, RC_SITE_R_NORMAL, 0, att, 0)));
-    if (z >= lb) break;
-  }
-  cand = r + sd * z;
+  double cand = draw_truncnorm0(r, sd, key, it);
   double l1mp = rc_log(1 - p);
   double lpc = (P.eta - 1) * rc_log(cand) + K * (cand * l1mp - rc_lgamma(cand)) - cand * P.sigma;   // :117
   double lpr = (P.eta - 1) * rc_log(r) + K * (r * l1mp - rc_lgamma(r)) - r * P.sigma;               // :118
@@ -247,7 +251,8 @@ void sample_p(State& s, const rc_params& P, uint64_t key, uint32_t it) {
 }
 
 // sample_labels_Gibbs!, mcmc.jl:158-256
-void gibbs_full(const Data& d, State& s, const rc_params& P, uint64_t key, uint32_t it) {
+struct GibbsProbe { int64_t i; std::vector<int64_t> cand; std::vector<double> lp; };   // tests: candidates / log-probabilities of one step
+void gibbs_full(const Data& d, State& s, const rc_params& P, uint64_t key, uint32_t it, GibbsProbe* probe = nullptr) {
   const int64_t n = d.n;
   const double r = s.r, p = s.p;
   Consts c = make_consts(P);
@@ -297,6 +302,7 @@ void gibbs_full(const Data& d, State& s, const rc_params& P, uint64_t key, uint3
     }
     for (int64_t kk = 0; kk < m; ++kk)                                               // :247
       lp[kk] = lpr[kk] + (L1[kk] + (P.repulsion ? L2[kk] : copysign(0.0, L2[kk])));
+    if (probe && probe->i == i) { probe->cand = cand; probe->lp = lp; }
     std::vector<double> u(m);
     for (int64_t kk = 0; kk < m; ++kk) {   // candidates 2q and 2q+1 share one Philox block (u0, u1)
       rc_draw dr = rc_draw2(key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
@@ -582,6 +588,53 @@ double rco_time_chains(const double* D, int64_t n, const rc_options* O, const rc
     });
   for (auto& x : th) x.join();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- probes for tests/test_oracle_pins.py ----------------------------------------------------------------
+// `iters` full Gibbs scans (mcmc.jl:158-256) at FIXED (r, p): the Markov chain on partitions whose exact transition
+// matrix the test builds from an independent numpy statement of the conditionals.  states: iters x n, sortlabels'd.
+void rco_scan_only(const double* D, int64_t n, const rc_params* P, const int64_t* labels, double r, double p, uint64_t seed,
+                   uint64_t chain, int64_t iters, int sum_mode, int64_t* states) {
+  Data d; build_data(d, D, n, sum_mode);
+  State s = make_state(labels, n, r, p);
+  const uint64_t key = rc_chain_key(seed, chain);
+  for (int64_t it = 1; it <= iters; ++it) {
+    gibbs_full(d, s, *P, key, (uint32_t)it);
+    sortlabels(s.clusts, states + (it - 1) * n);
+  }
+}
+// Candidate slots and un-normalised log-probabilities (mcmc.jl:247) of the scan step of point i (0-based) when the
+// points before it keep their labels: returns the number of candidates m; cand / lp hold m entries.
+int64_t rco_gibbs_logprobs(const double* D, int64_t n, const rc_params* P, const int64_t* labels, double r, double p, int64_t i,
+                           int sum_mode, int64_t* cand, double* lp) {
+  // gibbs_full visits the points in index order, so point i is swapped with point 0 (rows / columns of D and the
+  // labels): it is then visited first, in exactly the given state; slot ids -- hence the candidate order -- are unchanged
+  std::vector<double> Dp((size_t)n * n);
+  std::vector<int64_t> perm(n), lab(n);
+  for (int64_t t = 0; t < n; ++t) perm[t] = t;
+  std::swap(perm[0], perm[i]);
+  for (int64_t a = 0; a < n; ++a)
+    for (int64_t b = 0; b < n; ++b) Dp[a * n + b] = D[perm[a] * n + perm[b]];
+  for (int64_t t = 0; t < n; ++t) lab[t] = labels[perm[t]];
+  Data dp; build_data(dp, Dp.data(), n, sum_mode);
+  State sp = make_state(lab.data(), n, r, p);
+  GibbsProbe q; q.i = 0;
+  gibbs_full(dp, sp, *P, 12345u, 1u, &q);
+  for (size_t t = 0; t < q.cand.size(); ++t) { cand[t] = q.cand[t]; lp[t] = q.lp[t]; }
+  return (int64_t)q.cand.size();
+}
+// Raw draws of the samplers shared by the oracle and the kernels (rc_rng.h), one per iteration index, for
+// goodness-of-fit tests against scipy: kind 0 Gamma(a, 1) (Marsaglia-Tsang, mcmc.jl:154 / :524), 1 Beta(a, b)
+// (mcmc.jl:154), 2 truncated(Normal(a, b), lower = 0) (mcmc.jl:104-109), 3 rand(1:a) (mcmc.jl:379, 404).
+void rco_draws(int kind, double a, double b, uint64_t seed, int64_t count, double* out) {
+  const uint64_t key = rc_chain_key(seed, 0);
+  for (int64_t t = 0; t < count; ++t) {
+    const uint32_t it = (uint32_t)(t + 1);
+    if (kind == 0) out[t] = rc_gamma_mt(a, key, it, RC_SITE_P_GAMMA_A, 0);
+    else if (kind == 1) out[t] = rc_beta(a, b, key, it);
+    else if (kind == 2) out[t] = draw_truncnorm0(a, b, key, it);
+    else out[t] = (double)rc_randint(rc_draw1(key, it, RC_SITE_SM_PAIR, 0, 0, 0), (int64_t)a);
+  }
 }
 
 // probes for tests/test_math.py

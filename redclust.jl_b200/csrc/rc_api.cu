@@ -41,6 +41,7 @@ struct rc_sampler {
   rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
+  double2* sc2;                // incremental mode: [nchains][cap][inc_nthr] scratch of the scan
   longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
@@ -167,7 +168,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.sc2 = s->sc2;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -213,7 +214,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
-  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S);
+  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S); rc_dev_free(s->sc2);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -329,7 +330,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] scan mode: %s (S needs %.2f GB, %.2f GB free), %d threads per chain, %zu B shared memory (%d split-merge members)\n", s->inc ? "incremental" : "streaming", needS / 1e9, freeb / 1e9, nthr, s->inc_smem, s->inc_mcap);
   }
   s->terms_stride = (size_t)std::max(cap * cap, 8192);
-  if (s->inc) TRY(dalloc(&s->S, (size_t)nchains * cap * n));
+  if (s->inc) { TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->sc2, (size_t)nchains * cap * s->inc_nthr)); }
   TRY(dalloc(&s->T, (opt->numMH > 0 && !s->inc) ? (size_t)nchains * n * cap : 1));
   if (opt->numMH > 1) {
     TRY(dalloc(&s->WDbak, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WLbak, (size_t)nchains * cap * cap));

@@ -101,6 +101,7 @@ struct IncShared {
   int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
   int mv_i, mv_a, mv_b;
   int nmoves;
+  int nlive, e0;     // live slots of the chain's state and its first empty slot (-1: none), see inc_build_tables
   int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
   double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
 };
@@ -149,6 +150,10 @@ struct Ctx {
   struct IncShared* inc;  // incremental mode: hand-off block of the scan
   int mcap;               // incremental mode: members of a split-merge step whose AB / DG / L2s fit the shared-memory scratch
   longlong4* mAB; longlong2* mDG; double2* mL2s;   // that scratch
+  uint8_t* live;          // incremental mode (shared memory): live slots, ascending
+  double* tabs;           // incremental mode (shared memory): [6][cap] lgamma(alpha + delta1 s), lgamma(zeta + delta2 s), prior term at the slot's size / at size - 1
+  int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
+  double2* sc2;           // incremental mode (global): [cap][nthr] per-slot terms of the rows of a batch
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
   longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
@@ -167,7 +172,7 @@ __device__ __forceinline__ int cpt(const Ctx& c, int col) { return c.colpt ? (in
 // Incremental mode: point y moved from slot a to slot b.  Every x's sums over a and b follow from row y (D is symmetric:
 // DL[x][y] == DL[y][x]); exact integers, so S stays what a from-scratch build would give.  Thread t always owns the same
 // x's, so successive moves need no barrier between them (one before the sums are read again).
-__device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b) {
+__device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b, int skip = -1) {
   const longlong2* __restrict__ row = c.DL + (size_t)y * c.n;
   longlong2* Sa = c.S + (size_t)a * c.n;
   longlong2* Sb = c.S + (size_t)b * c.n;
@@ -179,11 +184,13 @@ __device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b) 
     for (int u = 0; u < 4; ++u) { v[u] = __ldg(row + x + u * nt); sa[u] = Sa[x + u * nt]; sb[u] = Sb[x + u * nt]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      if (x + u * nt == skip) continue;                  // (the caller updates this entry itself)
       sa[u].x -= v[u].x; sa[u].y -= v[u].y; sb[u].x += v[u].x; sb[u].y += v[u].y;
       Sa[x + u * nt] = sa[u]; Sb[x + u * nt] = sb[u];
     }
   }
   for (; x < n; x += nt) {
+    if (x == skip) continue;
     const longlong2 v = __ldg(row + x);
     longlong2 sa = Sa[x], sb = Sb[x];
     sa.x -= v.x; sa.y -= v.y; sb.x += v.x; sb.y += v.y;
@@ -1884,284 +1891,335 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 // Incremental mode (k_chain_inc): the full Gibbs scan (mcmc.jl:158-256) WITHOUT streaming the matrix.
 //   S[k][x] = sum_{j in k} DL[x][j] is kept per chain in global memory ([cap][n], exact integers).  Row x's candidate
 //   sums are then cap 16-byte loads instead of a 16 n-byte row; a move of point i from a to b streams row i once and
-//   updates S[a][.] and S[b][.] (inc_update_S).  The W warps of the chain evaluate W consecutive rows at once on the
-//   assumption that none of the earlier ones moves its point; the rows up to and including the first one that moves are
-//   exactly what the sequential scan computes and are committed, the rest is evaluated again after the move has been
-//   applied.  Every committed row sees the inputs of the sequential scan, so the results are the same bits as the
+//   updates S[a][.] and S[b][.] (inc_update_S).  The threads of the chain evaluate consecutive rows at once (one row per
+//   thread) on the assumption that none of the earlier ones moves its point; the rows up to and including the first one
+//   that moves are exactly what the sequential scan computes and are committed, the rest is evaluated again after the
+//   move has been applied.  Every committed row sees the inputs of the sequential scan, so the results are the same bits as the
 //   streaming kernel's and the oracle's.
 // ------------------------------------------------------------------------------------------------
 
-template <int NSR>
-__device__ int inc_scan_rows(const Ctx& c, unsigned it, int istart, int& batch) {
-  const int lane = c.lane, warp = c.cwarp, NW = c.nwarp;
+// One row of the scan, evaluated by ONE thread (lane = row: the 32 lanes of a warp hold 32 consecutive rows, so the loads
+// of S[k][i .. i+31] are one 512-byte segment and no lane idles on an absent candidate).  Per-slot terms go through a
+// per-chain scratch column (sc[k * RB], L1 / L2' then the log-probability) because they are needed again once the
+// canonical sum L2_i is known.  Returns the chosen slot, or -2 when a new cluster is a candidate and no slot is free.
+#define RC_NZMAX 37.0   // Gumbel noise -log(-log u) <= 36.74 for every 53-bit u < 1: candidates further than this below the leader cannot win
+// What a row evaluation reads, passed BY VALUE: inc_eval_row is deliberately not inlined (its register allocation stays
+// its own) and a reference to the kernel's Ctx would force that whole structure into local memory.
+struct RowCtx {
+  int n, cap, qD, qL;
+  const longlong2* DL;
+  const longlong2* S;
+  const uint8_t* lab;
+  const int* sizes;
+  const uint8_t* live;
+  const double* tabs;
+  const IncShared* inc;
+  const Scal* sc;
+  const rc_kparams* kp;
+  unsigned long long key;
+};
+__device__ __forceinline__ double inc_noise(const RowCtx& c, unsigned it, int i, int kk) {          // utils.jl:4-5
+  const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
+  return -rc_log(-rc_log((kk & 1) ? dr.u1 : dr.u0));
+}
+__device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, double2* __restrict__ sc, int RB) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
-  const int cap = c.cap, n = c.n;
-  IncShared* sh = c.inc;
-  const double r = c.sc->r, log1mp = c.sc->log1mp;
-  const unsigned ltmask = (1u << lane) - 1u;
-  // register-resident per-slot state (every warp holds the same copy): size and the size-dependent table terms at
-  // the current size; the slot a visited point is detached from looks its terms up at size - 1.
-  int sz[NSR];
-  double tA[NSR], tZ[NSR], tP[NSR];
+  const int n = c.n, cap = c.cap;
+  const IncShared* sh = c.inc;
+  const int nlive = sh->nlive;
+  const int li = c.lab[i];
+  const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
+  const bool single = c.sizes[li] == 1;
+  const int Ki = nlive - (single ? 1 : 0);                                  // :195-196, i detached
+  int e = sh->e0;
+  if (single && (e < 0 || li < e)) e = li;                                  // findfirst(clustsizes .== 0), :199
+  const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
+  if (hasnew && e < 0) return -2;
+  const longlong2* __restrict__ Si = c.S + i;
+  const double* __restrict__ tabs = c.tabs;
+  // ---- pass 1: per-slot terms (:206-242), four slots at a time: the four loads of S are in flight together and the
+  //      eight logarithms interleave ----
+  for (int idx0 = 0; idx0 < nlive; idx0 += 4) {
+    int k[4];
+    longlong2 sv[4];
 #pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    const int s = w * 32 + lane;
-    sz[w] = s < cap ? c.sizes[s] : 0;
-    tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1];
+    for (int u = 0; u < 4; ++u) {
+      k[u] = idx0 + u < nlive ? (int)c.live[idx0 + u] : -1;
+      if (k[u] == li && single) k[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sv[u] = k[u] >= 0 ? Si[(size_t)k[u] * n] : make_longlong2(0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k[u] < 0) continue;
+      const bool own = k[u] == li;
+      if (own) { sv[u].x -= self.x; sv[u].y -= self.y; }                    // :193-194 detach i
+      const int szs = c.sizes[k[u]] - (own ? 1 : 0);
+      const double szd = (double)szs;
+      const double lgA = own ? tabs[3 * cap + k[u]] : tabs[k[u]];
+      const double lgZ = own ? tabs[4 * cap + k[u]] : tabs[cap + k[u]];
+      const double sD = rc_dequant(sv[u].x, c.qD), sL = rc_dequant(sv[u].y, c.qL);
+      const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+      const double L1 = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+      const double L2p = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+      sc[(size_t)k[u] * RB] = make_double2(L1, L2p);
+    }
   }
-  int i0 = istart, istop = n;
-  while (i0 < n) {
-    const int slot3 = batch % 3;
-    if (c.ctid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
-    ++batch;
-    const int i = i0 + warp;
-    int li = -1, cnew = -1, flag = 0;
-    long long bd[NSR], bl[NSR];
-    unsigned occ[NSR];
-    longlong2 self = make_longlong2(0, 0);
+  // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
+  //      xor-butterfly tree over the 32 classes (16, 8, 4, 2, 1) as lane 0 of a warp would evaluate it ----
+  double L2i = 0.0;
+  {
+    double t5 = 0.0;
 #pragma unroll
-    for (int w = 0; w < NSR; ++w) { bd[w] = 0; bl[w] = 0; occ[w] = 0u; }
-    if (i < n) {
-      li = c.lab[i];
-      // occupancy with i detached (:193-202)
+    for (int b1 = 0; b1 < 2; ++b1) {
+      double t4 = 0.0;
 #pragma unroll
-      for (int w = 0; w < NSR; ++w) {
-        const int s = w * 32 + lane;
-        occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);
-      }
-      // row sums of row i over the live slots: S[s][i]
+      for (int b2 = 0; b2 < 2; ++b2) {
+        double t3 = 0.0;
 #pragma unroll
-      for (int w = 0; w < NSR; ++w) {
-        const int s = w * 32 + lane;
-        if ((occ[w] >> lane) & 1u) { const longlong2 t = c.S[(size_t)s * n + i]; bd[w] = t.x; bl[w] = t.y; }
-      }
-      self = __ldg(c.DL + (size_t)i * n + i);
-      int Ki = 0, e = -1, nw = 0;
+        for (int b4 = 0; b4 < 2; ++b4) {
+          double t2 = 0.0;
 #pragma unroll
-      for (int w = 0; w < NSR; ++w) {
-        Ki += __popc(occ[w]);
-        if (occ[w]) nw = w + 1;
-        const int lim = cap - w * 32;
-        const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
-        const unsigned emp = ~occ[w] & capmask;
-        if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                      // findfirst(clustsizes .== 0)
-      }
-      const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;           // :198
-      if (NSR * 32 < RC_MAXCAP && hasnew && e < 0 && cap > NSR * 32) flag = 2;   // needs a slot beyond this instantiation
-      else if (hasnew && e < 0) flag = 3;                                   // slot capacity exhausted
-      else {
-        if (hasnew && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;                 // rounds of 32 slots that hold a candidate
-        int kk[NSR];
-        bool have[NSR];
-        {
-          int base = 0;
+          for (int b8 = 0; b8 < 2; ++b8) {
+            double t1 = 0.0;
 #pragma unroll
-          for (int w = 0; w < NSR; ++w) {
-            const int s = w * 32 + lane;
-            const bool live = (occ[w] >> lane) & 1u;
-            have[w] = live || (hasnew && s == e);
-            kk[w] = live ? base + __popc(occ[w] & ltmask) : Ki;
-            base += __popc(occ[w]);
-          }
-        }
-        // per-slot terms (:206-242)
-        double L1[NSR], L2p[NSR], pr[NSR];
-        double acc = 0.0;
+            for (int b16 = 0; b16 < 2; ++b16) {
+              const int r = b1 + 2 * b2 + 4 * b4 + 8 * b8 + 16 * b16;
+              double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < NSR; ++w) {
-          L1[w] = 0.0; L2p[w] = 0.0; pr[w] = 0.0;
-          if (w < nw) {
-            const int s = w * 32 + lane;
-            if ((occ[w] >> lane) & 1u) {
-              double lgA = tA[w], lgZ = tZ[w];
-              pr[w] = tP[w];
-              int szs = sz[w];
-              if (s == li) {                                                // :193-194 detach i
-                bd[w] -= self.x; bl[w] -= self.y;
-                szs -= 1;
-                lgA = kp.LGA[szs]; lgZ = kp.LGZ[szs]; pr[w] = c.LPR[szs];
+              for (int w = 0; w < RC_NS; ++w) {
+                const int k = r + 32 * w;
+                if (k < cap && c.sizes[k] > 0 && !(single && k == li)) a += sc[(size_t)k * RB].y;
               }
-              const double szd = (double)szs;
-              const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
-              const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-              const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-              L1[w] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-              L2p[w] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-              acc += L2p[w];                                                // vecsum: lane-wise ascending slots
+              t1 = b16 == 0 ? a : t1 + a;
             }
+            t2 = b8 == 0 ? t1 : t2 + t1;
           }
+          t3 = b4 == 0 ? t2 : t3 + t2;
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
-        const double L2i = acc;
-        // log-probabilities (:244-247)
-        double lp[NSR];
-        bool anynan = false;
-        double mn = RC_INF;
-#pragma unroll
-        for (int w = 0; w < NSR; ++w) {
-          lp[w] = 0.0;
-          if (w < nw) {
-            if ((occ[w] >> lane) & 1u) {
-              const double L2 = L2i - L2p[w];
-              lp[w] = pr[w] + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
-            } else if (have[w]) {                                           // :228-230 new cluster
-              const double L2 = L2i - 0.0;
-              lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
-            }
-            if (have[w]) {
-              if (rc_isnan(lp[w])) anynan = true;
-              else if (lp[w] < mn) mn = lp[w];
-            }
-          }
-        }
-        mn = warp_min_f64(mn);
-        anynan = __any_sync(0xffffffffu, anynan);
-        if (anynan) mn = RC_NAN;                                            // Julia minimum propagates NaN
-        // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
-        double g[NSR];
-        double gbest = -RC_INF;
-        bool gnan = false;
-#pragma unroll
-        for (int w = 0; w < NSR; ++w) {
-          g[w] = -RC_INF;
-          if (w < nw && have[w]) {
-            const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk[w] >> 1));
-            const double nz = -rc_log(-rc_log((kk[w] & 1) ? dr.u1 : dr.u0));
-            g[w] = nz + (lp[w] - mn);
-            if (rc_isnan(g[w])) gnan = true;
-            else if (g[w] > gbest) gbest = g[w];
-          }
-        }
-        if (!__any_sync(0xffffffffu, gnan)) {
-          gbest = warp_max_f64(gbest);
-          int kbest = 0x7fffffff, sbest = -1;
-#pragma unroll
-          for (int w = 0; w < NSR; ++w)
-            if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
-          const int kmin = __reduce_min_sync(0xffffffffu, kbest);
-          const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
-          cnew = __shfl_sync(0xffffffffu, sbest, __ffs(who) - 1);
-        } else {
-          // NaN is maximal for argmax and the first NaN wins
-          double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
-#pragma unroll
-          for (int w = 0; w < NSR; ++w) {
-            if (!(w < nw && have[w])) continue;
-            const bool gn = rc_isnan(g[w]);
-            bool better;
-            if (bs < 0) better = true;
-            else if (gn) better = !bnan || kk[w] < bk;
-            else if (bnan) better = false;
-            else better = g[w] > bg || (g[w] == bg && kk[w] < bk);
-            if (better) { bg = g[w]; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const double og = __shfl_xor_sync(0xffffffffu, bg, off);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
-            const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-            const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
-            bool better;
-            if (os < 0) better = false;
-            else if (bs < 0) better = true;
-            else if (on) better = !bnan || ok < bk;
-            else if (bnan) better = false;
-            else better = og > bg || (og == bg && ok < bk);
-            if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
-          }
-          cnew = bs;
-        }
-        if (cnew != li) flag = 1;
+        t4 = b2 == 0 ? t3 : t4 + t3;
       }
+      t5 = b1 == 0 ? t4 : t5 + t4;
     }
-    if (flag && lane == 0) atomicMin(&sh->first[slot3], warp);
-    csync(c);
-    const int first = sh->first[slot3];
-    if (first == RC_INC_NONE) { i0 += NW; continue; }                       // nobody moved: the whole batch stands
-    if (warp == first) {
-      if (flag == 1) {
-        // ---- the point moved (:250-252): labels, sizes, block sums ----
-        const int a = li, b = cnew;
-        if (lane == 0) { c.lab[i] = (uint8_t)cnew; c.sizes[a] -= 1; c.sizes[b] += 1; sh->mv_a = a; sh->mv_b = b; sh->nmoves += 1; }
-#pragma unroll
-        for (int w = 0; w < NSR; ++w) {
-          const int s = w * 32 + lane;
-          if (s >= cap) continue;
-          if (s == a) {
-            const int ix = tri(a, a, cap);
-            rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
-            rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
-          } else if ((occ[w] >> lane) & 1u) {
-            const int ix = tri(a, s, cap);
-            rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(bd[w])); c.WD[ix] = x;
-            rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(bl[w])); c.WL[ix] = y;
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int w = 0; w < NSR; ++w) {
-          const int s = w * 32 + lane;
-          if (s >= cap) continue;
-          if (s == b) {
-            const int ix = tri(b, b, cap);
-            rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
-            rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
-          } else if ((occ[w] >> lane) & 1u) {
-            const int ix = tri(b, s, cap);
-            rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(bd[w])); c.WD[ix] = x;
-            rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(bl[w])); c.WL[ix] = y;
-          }
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        sh->ev = flag; sh->mv_i = i;
-        if (flag == 3) c.sc->status = RC_ERR_SLOTS;
-      }
-    }
-    csync(c);
-    const int ev = sh->ev, mi = sh->mv_i;
-    if (ev == 2) { istop = mi; break; }
-    if (ev == 3) { istop = -1; break; }
-    const int a = sh->mv_a, b = sh->mv_b;
-#pragma unroll
-    for (int w = 0; w < NSR; ++w) {
-      const int s = w * 32 + lane;
-      if (s == a) { sz[w] -= 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w] > 0 ? sz[w] : 1]; }
-      if (s == b) { sz[w] += 1; tA[w] = kp.LGA[sz[w]]; tZ[w] = kp.LGZ[sz[w]]; tP[w] = c.LPR[sz[w]]; }
-    }
-    const long long tu0 = RC_CLOCK();
-    inc_update_S(c, mi, a, b);
-    csync(c);
-    if (c.ctid == 0) st_add(c, ST_BULK_PATCH, RC_CLOCK() - tu0);             // (incremental mode: cycles in the move updates of S)
-    i0 = mi + 1;
+    L2i = t5;
   }
-  return istop;
+  // log-probability of live slot k (:244-247) from the stored terms -- evaluated identically wherever it is needed
+  auto logprob = [&](int k) -> double {
+    const double2 v = sc[(size_t)k * RB];
+    const double L2 = L2i - v.y;
+    return (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + (v.x + (P.repulsion ? L2 : copysign(0.0, L2)));
+  };
+  // ---- pass 2: minimum of the log-probabilities and the leader ----
+  const double r = c.sc->r, log1mp = c.sc->log1mp;
+  bool anynan = false;
+  double mn = RC_INF, toplp = -RC_INF;
+  int topkk = -1, topk = -1;
+#pragma unroll 4
+  for (int idx = 0; idx < nlive; ++idx) {
+    const int k = c.live[idx];
+    if (k == li && single) continue;
+    const double lp = logprob(k);
+    if (rc_isnan(lp)) anynan = true;
+    else {
+      if (lp < mn) mn = lp;
+      if (lp > toplp) { toplp = lp; topkk = idx - ((single && k > li) ? 1 : 0); topk = k; }
+    }
+  }
+  double lpnew = 0.0;
+  if (hasnew) {                                                             // :228-230 new cluster
+    const double L2 = L2i - 0.0;
+    lpnew = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+    if (rc_isnan(lpnew)) anynan = true;
+    else {
+      if (lpnew < mn) mn = lpnew;
+      if (lpnew > toplp) { toplp = lpnew; topkk = Ki; topk = e; }
+    }
+  }
+  if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
+  // ---- Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties ----
+  if (!anynan && mn > -RC_INF && mn < RC_INF && toplp < RC_INF && topkk >= 0) {
+    // every shifted log-probability is finite: a candidate whose value plus the largest possible noise stays below the
+    // leader's exact value cannot be the arg-max, so its noise is never drawn (same result, far fewer logarithms)
+    double best = inc_noise(c, it, i, topkk) + (toplp - mn);
+    int bestkk = topkk, bestk = topk;
+    int ck0 = -1, ck1 = -1, ck2 = -1, ckk0 = 0, ckk1 = 0, ckk2 = 0;
+    double clp0 = 0.0, clp1 = 0.0, clp2 = 0.0;
+    int nc = 0;
+    auto contender = [&](int k, int kk, double lpm) {
+      if (nc == 0) { ck0 = k; ckk0 = kk; clp0 = lpm; }
+      else if (nc == 1) { ck1 = k; ckk1 = kk; clp1 = lpm; }
+      else if (nc == 2) { ck2 = k; ckk2 = kk; clp2 = lpm; }
+      ++nc;
+    };
+#pragma unroll 4
+    for (int idx = 0; idx < nlive; ++idx) {
+      const int k = c.live[idx];
+      if ((k == li && single) || k == topk) continue;
+      const double lpm = logprob(k) - mn;
+      if (lpm + RC_NZMAX >= best) contender(k, idx - ((single && k > li) ? 1 : 0), lpm);
+    }
+    if (hasnew && topk != e) {
+      const double lpm = lpnew - mn;
+      if (lpm + RC_NZMAX >= best) contender(e, Ki, lpm);
+    }
+    if (nc <= 3) {
+      if (nc > 0) { const double g = inc_noise(c, it, i, ckk0) + clp0; if (g > best || (g == best && ckk0 < bestkk)) { best = g; bestkk = ckk0; bestk = ck0; } }
+      if (nc > 1) { const double g = inc_noise(c, it, i, ckk1) + clp1; if (g > best || (g == best && ckk1 < bestkk)) { best = g; bestkk = ckk1; bestk = ck1; } }
+      if (nc > 2) { const double g = inc_noise(c, it, i, ckk2) + clp2; if (g > best || (g == best && ckk2 < bestkk)) { best = g; bestkk = ckk2; bestk = ck2; } }
+      return bestk;
+    }
+  }
+  // general path (NaN / infinities among the log-probabilities, or more than three contenders): every candidate in
+  // index order, NaN is maximal for argmax and the first NaN wins
+  {
+    int bestk = -1; double bv = 0.0;
+    bool first = true;
+    for (int idx = 0; idx <= nlive; ++idx) {
+      int k, kk; double lp;
+      if (idx < nlive) {
+        k = c.live[idx];
+        if (k == li && single) continue;
+        kk = idx - ((single && k > li) ? 1 : 0);
+        lp = logprob(k);
+      } else {
+        if (!hasnew) break;
+        k = e; kk = Ki; lp = lpnew;
+      }
+      const double g = inc_noise(c, it, i, kk) + (lp - mn);
+      if (first) { bestk = k; bv = g; first = false; if (rc_isnan(g)) break; continue; }
+      if (rc_isnan(g)) { bestk = k; break; }
+      if (g > bv) { bestk = k; bv = g; }
+    }
+    return bestk;
+  }
 }
 
+// (Re)build the chain's slot tables in shared memory from the sizes: the live list, the first empty slot and the
+// size-dependent terms at the current size / at size - 1.  Warp 0.
+__device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1) {
+  const rc_kparams& kp = *c.kp;
+  IncShared* sh = c.inc;
+  const int cap = c.cap, lane = c.lane;
+  int base = 0, e0 = -1;
+  for (int w = 0; w * 32 < cap; ++w) {
+    const int s = w * 32 + lane;
+    const int sz = s < cap ? c.sizes[s] : 0;
+    const bool live = s < cap && sz > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const unsigned em = __ballot_sync(0xffffffffu, s < cap && sz == 0);
+    if (live) c.live[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)s;
+    base += __popc(m);
+    if (e0 < 0 && em) e0 = w * 32 + __ffs(em) - 1;
+    if (s < cap && (only_a < 0 || s == only_a || s == only_b)) {
+      c.tabs[s] = kp.LGA[sz]; c.tabs[cap + s] = kp.LGZ[sz]; c.tabs[2 * cap + s] = c.LPR[sz > 0 ? sz : 1];
+      c.tabs[3 * cap + s] = kp.LGA[sz > 0 ? sz - 1 : 0]; c.tabs[4 * cap + s] = kp.LGZ[sz > 0 ? sz - 1 : 0];
+      c.tabs[5 * cap + s] = c.LPR[sz > 1 ? sz - 1 : 1];
+    }
+  }
+  if (lane == 0) { sh->nlive = base; sh->e0 = e0; }
+  __syncwarp();
+}
+
+// The full scan (mcmc.jl:192-253) in batches of up to nthr consecutive rows.
 __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   IncShared* sh = c.inc;
-  if (c.ctid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; sh->ev = 0; sh->nmoves = 0; }
+  const int n = c.n, cap = c.cap, NT = c.nthr, tid = c.ctid, lane = c.lane;
+  if (tid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; sh->nmoves = 0; }
+  if (c.cwarp == 0) inc_build_tables(c);
   csync(c);
-  bool low = true;                                                          // every live slot below 64?
-  for (int s = 64 + c.lane; s < c.cap; s += 32) low = low && c.sizes[s] == 0;
-  low = __all_sync(0xffffffffu, low);
-  int batch = 0, i = 0;
-  if (low) i = inc_scan_rows<2>(c, it, 0, batch);
-  if (i >= 0 && i < c.n) inc_scan_rows<RC_NS>(c, it, i, batch);
+  double2* const sc = c.sc2 + tid;
+  RowCtx rc;
+  rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.live = c.live;
+  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key;
+  int batch = 0, i0 = 0;
+  int nrows = NT;                                                           // rows per batch: follows the observed run length between moves
+  while (i0 < n) {
+    const int slot3 = batch % 3;
+    if (tid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
+    ++batch;
+    const int i = i0 + tid;
+    if (tid < nrows && i < n) {
+      const int cnew = inc_eval_row(rc, it, i, sc, NT);
+      c.res[tid] = cnew;
+      if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], tid);
+    }
+    csync(c);
+    const int F = sh->first[slot3];
+    if (F == RC_INC_NONE) { i0 += nrows; nrows = min(NT, nrows * 2); continue; }   // nobody moved: the whole batch stands
+    const int mi = i0 + F, b = c.res[F];
+    if (b < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; break; }        // slot capacity exhausted at row mi
+    const int a = c.lab[mi];
+    const long long tu0 = RC_CLOCK();
+    if (c.cwarp == 0) {
+      // ---- the point moved (:250-252): block sums from row mi's sums over the live slots, then labels, sizes, tables ----
+      const longlong2 self = __ldg(c.DL + (size_t)mi * n + mi);
+      long long bd[RC_NS], bl[RC_NS];
+      bool live[RC_NS];
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w) {
+        const int s = w * 32 + lane;
+        bd[w] = 0; bl[w] = 0;
+        live[w] = s < cap && c.sizes[s] - (s == a ? 1 : 0) > 0;
+        if (live[w]) { const longlong2 t = c.S[(size_t)s * n + mi]; bd[w] = t.x; bl[w] = t.y; if (s == a) { bd[w] -= self.x; bl[w] -= self.y; } }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w) {
+        const int s = w * 32 + lane;
+        if (s >= cap) continue;
+        if (s == a) {
+          const int ix = tri(a, a, cap);
+          rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
+          rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
+          const size_t o = (size_t)a * n + mi;                              // S[a][mi] loses the point's own entry (inc_update_S skips x = mi)
+          longlong2 t = c.S[o]; t.x -= self.x; t.y -= self.y; c.S[o] = t;
+        } else if (live[w]) {
+          const int ix = tri(a, s, cap);
+          rc_i128 x = c.WD[ix]; rc_sub128(x, rc_make128(bd[w])); c.WD[ix] = x;
+          rc_i128 y = c.WL[ix]; rc_sub128(y, rc_make128(bl[w])); c.WL[ix] = y;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < RC_NS; ++w) {
+        const int s = w * 32 + lane;
+        if (s >= cap) continue;
+        if (s == b) {
+          const int ix = tri(b, b, cap);
+          rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(2 * bd[w] + self.x)); c.WD[ix] = x;
+          rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(2 * bl[w] + self.y)); c.WL[ix] = y;
+          const size_t o = (size_t)b * n + mi;
+          longlong2 t = c.S[o]; t.x += self.x; t.y += self.y; c.S[o] = t;
+        } else if (live[w]) {
+          const int ix = tri(b, s, cap);
+          rc_i128 x = c.WD[ix]; rc_add128(x, rc_make128(bd[w])); c.WD[ix] = x;
+          rc_i128 y = c.WL[ix]; rc_add128(y, rc_make128(bl[w])); c.WL[ix] = y;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { c.lab[mi] = (uint8_t)b; c.sizes[a] -= 1; c.sizes[b] += 1; sh->nmoves += 1; }
+      __syncwarp();
+      inc_build_tables(c, a, b);
+    }
+    inc_update_S(c, mi, a, b, mi);
+    csync(c);
+    if (tid == 0) st_add(c, ST_BULK_PATCH, RC_CLOCK() - tu0);               // (incremental mode: cycles in the move updates)
+    i0 = mi + 1;
+    nrows = min(NT, max(32, (2 * (F + 1) + 31) & ~31));
+  }
   csync(c);
   if (c.cwarp == 0) {                                                       // :254
     int K = 0;
-    for (int s = c.lane; s < c.cap; s += 32) K += c.sizes[s] > 0;
+    for (int s = lane; s < cap; s += 32) K += c.sizes[s] > 0;
     for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
-    if (c.lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); }
+    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); }
   }
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, mAB, mDG, mL2s, total; };
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, tabs, res, mAB, mDG, mL2s, total; };
 __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   IncLayout L;
   size_t o = 0;
@@ -2175,6 +2233,9 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   L.itmp = take(sizeof(int) * (cap > 64 ? cap : 64));
   L.clist = take(cap);
   L.lab = take(n);
+  L.live = take(cap);
+  L.tabs = take(sizeof(double) * 6 * cap);
+  L.res = take(sizeof(int) * 512);
   L.mAB = take(sizeof(longlong4) * mcap);
   L.mDG = take(sizeof(longlong2) * mcap);
   L.mL2s = take(sizeof(double2) * mcap);
@@ -2201,6 +2262,9 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.mAB = reinterpret_cast<longlong4*>(smem + L.mAB);
     c.mDG = reinterpret_cast<longlong2*>(smem + L.mDG);
     c.mL2s = reinterpret_cast<double2*>(smem + L.mL2s);
+    c.live = smem + L.live;
+    c.tabs = reinterpret_cast<double*>(smem + L.tabs);
+    c.res = reinterpret_cast<int*>(smem + L.res);
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2216,6 +2280,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   c.WL = kp.WL + (size_t)ch * cap * cap;
   c.T = nullptr;
   c.S = kp.S + (size_t)ch * cap * n;
+  c.sc2 = kp.sc2 + (size_t)ch * cap * blockDim.x;
   c.WDbak = kp.WDbak ? kp.WDbak + (size_t)ch * cap * cap : nullptr;
   c.WLbak = kp.WLbak ? kp.WLbak + (size_t)ch * cap * cap : nullptr;
   c.labbak = kp.labbak ? kp.labbak + (size_t)ch * n : nullptr;
@@ -2441,7 +2506,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.tabs = nullptr; c.res = nullptr; c.sc2 = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);

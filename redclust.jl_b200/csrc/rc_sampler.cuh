@@ -47,6 +47,7 @@ struct rc_kparams {
   longlong2* DG;        // [nchains][n+2]  diagonal entries DL[x][x] of the split-merge members
   double* terms;        // [nchains][terms_stride]  log-likelihood terms / reduction scratch
   size_t terms_stride;  // max(cap*cap, 8192) doubles
+  double2* sc2;         // [nchains][cap][threads per chain]  incremental mode: per-slot terms of the rows of a batch
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
