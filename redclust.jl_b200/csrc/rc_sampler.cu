@@ -102,6 +102,8 @@ struct IncShared {
   int mv_i, mv_a, mv_b;
   int nmoves;
   int nlive, e0;     // live slots of the chain's state and its first empty slot (-1: none), see inc_build_tables
+  int hint;          // rows per batch the previous scan ended with (0: none yet)
+  int narrow;        // every live slot and the first empty slot lie below 64: the warp evaluator runs two rounds instead of four
   int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
   double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
 };
@@ -171,13 +173,15 @@ __device__ __forceinline__ int cpos(const Ctx& c, int j) { return c.colpos ? (in
 __device__ __forceinline__ int cpt(const Ctx& c, int col) { return c.colpt ? (int)__ldg(c.colpt + col) : col; }
 // Incremental mode: point y moved from slot a to slot b.  Every x's sums over a and b follow from row y (D is symmetric:
 // DL[x][y] == DL[y][x]); exact integers, so S stays what a from-scratch build would give.  Thread t always owns the same
-// x's, so successive moves need no barrier between them (one before the sums are read again).
-__device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b, int skip = -1) {
+// x's for a given t0, so successive moves with the same t0 need no barrier between them (one before the sums are read again).
+__device__ __forceinline__ void inc_update_S(const Ctx& c, int y, int a, int b, int skip = -1, int t0 = 0) {
   const longlong2* __restrict__ row = c.DL + (size_t)y * c.n;
   longlong2* Sa = c.S + (size_t)a * c.n;
   longlong2* Sb = c.S + (size_t)b * c.n;
-  const int n = c.n, nt = c.nthr;
-  int x = c.ctid;
+  // threads t0 .. nthr-1 share the work (the scan keeps warp 0 busy with the block sums meanwhile)
+  const int n = c.n, nt = c.nthr - t0;
+  int x = c.ctid - t0;
+  if (x < 0) return;
   for (; x + 3 * nt < n; x += 4 * nt) {
     longlong2 v[4], sa[4], sb[4];
 #pragma unroll
@@ -1395,6 +1399,7 @@ __device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, in
     const bool oa = qa < mt, ob = qb < mt;
     const int xa = oa ? (int)c.Slist[qa] : 0, xb = ob ? (int)c.Slist[qb] : 0;
     long long va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+#pragma unroll 4
     for (int q2 = 0; q2 < mt; ++q2) {
       const int y = c.Slist[q2];                               // uniform over the team
       const bool isA = c.lab[y] == ca;
@@ -1548,12 +1553,29 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
         // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
         const longlong2* row = c.DL + (size_t)ym * c.n;
         const bool a2b = curm == ca;
-        for (int q = c.ctid; q < mt; q += c.nthr) {
-          const longlong2 e = __ldg(row + c.Slist[q]);
-          longlong4 t = c.AB[q];
-          if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
-          else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
-          c.AB[q] = t;
+        {
+          const int nt = c.nthr;
+          int q = c.ctid;
+          for (; q + 3 * nt < mt; q += 4 * nt) {                 // four members per thread in flight: the gathers are DRAM latency
+            int xq[4]; longlong2 e[4]; longlong4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xq[u] = c.Slist[q + u * nt];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { e[u] = __ldg(row + xq[u]); t[u] = c.AB[q + u * nt]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (a2b) { t[u].x -= e[u].x; t[u].y -= e[u].y; t[u].z += e[u].x; t[u].w += e[u].y; }
+              else { t[u].x += e[u].x; t[u].y += e[u].y; t[u].z -= e[u].x; t[u].w -= e[u].y; }
+              c.AB[q + u * nt] = t[u];
+            }
+          }
+          for (; q < mt; q += nt) {
+            const longlong2 e = __ldg(row + c.Slist[q]);
+            longlong4 t = c.AB[q];
+            if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
+            else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
+            c.AB[q] = t;
+          }
         }
         csync(c);
       }
@@ -1902,6 +1924,7 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 // of S[k][i .. i+31] are one 512-byte segment and no lane idles on an absent candidate).  Per-slot terms go through a
 // per-chain scratch column (sc[k * RB], L1 / L2' then the log-probability) because they are needed again once the
 // canonical sum L2_i is known.  Returns the chosen slot, or -2 when a new cluster is a candidate and no slot is free.
+#define RC_INC_WARPROWS 128   // batches of at most this many expected rows are evaluated one row per warp
 #define RC_NZMAX 37.0   // Gumbel noise -log(-log u) <= 36.74 for every 53-bit u < 1: candidates further than this below the leader cannot win
 // What a row evaluation reads, passed BY VALUE: inc_eval_row is deliberately not inlined (its register allocation stays
 // its own) and a reference to the kernel's Ctx would force that whole structure into local memory.
@@ -2096,6 +2119,160 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, dou
   }
 }
 
+// The same row evaluated by a WARP (lane = slot, rounds of 32 slots): used while the chain moves often and the batches
+// are short -- the per-slot work of a row is spread over the lanes, so a batch of nwarp rows costs the latency of ~NSR
+// slots instead of all of them.  Same arithmetic as inc_eval_row; the canonical vecsum is the warp butterfly itself.
+template <int NSR>
+__device__ __noinline__ int inc_eval_row_warp(const RowCtx c, unsigned it, int i) {
+  const rc_kparams& kp = *c.kp;
+  const rc_params& P = kp.P;
+  const int n = c.n, cap = c.cap, lane = threadIdx.x & 31;
+  const unsigned ltmask = (1u << lane) - 1u;
+  const int li = c.lab[i];
+  const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
+  int sz[NSR];
+  unsigned occ[NSR];
+  long long bd[NSR], bl[NSR];
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    const int s = w * 32 + lane;
+    sz[w] = s < cap ? c.sizes[s] : 0;
+    occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);      // occupancy with i detached (:193-202)
+    bd[w] = 0; bl[w] = 0;
+    if ((occ[w] >> lane) & 1u) { const longlong2 t = c.S[(size_t)s * n + i]; bd[w] = t.x; bl[w] = t.y; }
+  }
+  int Ki = 0, e = -1, nw = 0;
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    Ki += __popc(occ[w]);
+    if (occ[w]) nw = w + 1;
+    const int lim = cap - w * 32;
+    const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+    const unsigned emp = ~occ[w] & capmask;
+    if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                          // findfirst(clustsizes .== 0)
+  }
+  const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
+  if (hasnew && e < 0) return -2;                                           // (the caller picks NSR so that every slot is covered)
+  if (hasnew && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;
+  int kk[NSR];
+  bool have[NSR];
+  {
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < NSR; ++w) {
+      const int s = w * 32 + lane;
+      const bool live = (occ[w] >> lane) & 1u;
+      have[w] = live || (hasnew && s == e);
+      kk[w] = live ? base + __popc(occ[w] & ltmask) : Ki;
+      base += __popc(occ[w]);
+    }
+  }
+  double L1[NSR], L2p[NSR], pr[NSR];
+  double acc = 0.0;
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    L1[w] = 0.0; L2p[w] = 0.0; pr[w] = 0.0;
+    if (w < nw) {
+      const int s = w * 32 + lane;
+      if ((occ[w] >> lane) & 1u) {
+        const bool own = s == li;
+        if (own) { bd[w] -= self.x; bl[w] -= self.y; }                      // :193-194 detach i
+        const double lgA = own ? c.tabs[3 * cap + s] : c.tabs[s];
+        const double lgZ = own ? c.tabs[4 * cap + s] : c.tabs[cap + s];
+        pr[w] = own ? c.tabs[5 * cap + s] : c.tabs[2 * cap + s];
+        const double szd = (double)(sz[w] - (own ? 1 : 0));
+        const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
+        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+        L1[w] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+        L2p[w] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+        acc += L2p[w];                                                      // vecsum: lane-wise ascending slots
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
+  const double L2i = acc;
+  const double r = c.sc->r, log1mp = c.sc->log1mp;
+  double lp[NSR];
+  bool anynan = false;
+  double mn = RC_INF;
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    lp[w] = 0.0;
+    if (w < nw) {
+      if ((occ[w] >> lane) & 1u) {
+        const double L2 = L2i - L2p[w];
+        lp[w] = pr[w] + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
+      } else if (have[w]) {                                                 // :228-230 new cluster
+        const double L2 = L2i - 0.0;
+        lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+      }
+      if (have[w]) {
+        if (rc_isnan(lp[w])) anynan = true;
+        else if (lp[w] < mn) mn = lp[w];
+      }
+    }
+  }
+  mn = warp_min_f64(mn);
+  anynan = __any_sync(0xffffffffu, anynan);
+  if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
+  // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
+  double g[NSR];
+  double gbest = -RC_INF;
+  bool gnan = false;
+#pragma unroll
+  for (int w = 0; w < NSR; ++w) {
+    g[w] = -RC_INF;
+    if (w < nw && have[w]) {
+      g[w] = inc_noise(c, it, i, kk[w]) + (lp[w] - mn);
+      if (rc_isnan(g[w])) gnan = true;
+      else if (g[w] > gbest) gbest = g[w];
+    }
+  }
+  int cnew;
+  if (!__any_sync(0xffffffffu, gnan)) {
+    gbest = warp_max_f64(gbest);
+    int kbest = 0x7fffffff, sbest = -1;
+#pragma unroll
+    for (int w = 0; w < NSR; ++w)
+      if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
+    const int kmin = __reduce_min_sync(0xffffffffu, kbest);
+    const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
+    cnew = __shfl_sync(0xffffffffu, sbest, __ffs(who) - 1);
+  } else {
+    // NaN is maximal for argmax and the first NaN wins
+    double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+#pragma unroll
+    for (int w = 0; w < NSR; ++w) {
+      if (!(w < nw && have[w])) continue;
+      const bool gn = rc_isnan(g[w]);
+      bool better;
+      if (bs < 0) better = true;
+      else if (gn) better = !bnan || kk[w] < bk;
+      else if (bnan) better = false;
+      else better = g[w] > bg || (g[w] == bg && kk[w] < bk);
+      if (better) { bg = g[w]; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, bg, off);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
+      bool better;
+      if (os < 0) better = false;
+      else if (bs < 0) better = true;
+      else if (on) better = !bnan || ok < bk;
+      else if (bnan) better = false;
+      else better = og > bg || (og == bg && ok < bk);
+      if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
+    }
+    cnew = bs;
+  }
+  return cnew;
+}
+
 // (Re)build the chain's slot tables in shared memory from the sizes: the live list, the first empty slot and the
 // size-dependent terms at the current size / at size - 1.  Warp 0.
 __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1) {
@@ -2118,7 +2295,7 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
       c.tabs[5 * cap + s] = c.LPR[sz > 1 ? sz - 1 : 1];
     }
   }
-  if (lane == 0) { sh->nlive = base; sh->e0 = e0; }
+  if (lane == 0) { sh->nlive = base; sh->e0 = e0; sh->narrow = (base == 0 || c.live[base - 1] < 64) && (e0 >= 0 && e0 < 64); }
   __syncwarp();
 }
 
@@ -2134,20 +2311,42 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.live = c.live;
   rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key;
   int batch = 0, i0 = 0;
-  int nrows = NT;                                                           // rows per batch: follows the observed run length between moves
+  // Rows per batch follow the observed run length between moves.  Long runs: one row per THREAD (throughput: no lane
+  // idles, coalesced loads).  Short runs (nrows <= RC_INC_WARPROWS): one row per WARP (latency: a row's slots are spread
+  // over the lanes), `streak` counting the rows that stood since the last move.
+  int nrows = sh->hint > 0 ? min(NT, sh->hint) : NT, streak = 0;
+  const int NW = c.nwarp;
   while (i0 < n) {
     const int slot3 = batch % 3;
     if (tid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
     ++batch;
-    const int i = i0 + tid;
-    if (tid < nrows && i < n) {
-      const int cnew = inc_eval_row(rc, it, i, sc, NT);
-      c.res[tid] = cnew;
-      if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], tid);
+    const bool warpmode = nrows <= RC_INC_WARPROWS;
+    const int nb = warpmode ? NW : nrows;                                  // rows of this batch
+    if (warpmode) {
+      const int i = i0 + c.cwarp;
+      if (i < n) {
+        const int cnew = sh->narrow ? inc_eval_row_warp<2>(rc, it, i) : inc_eval_row_warp<RC_NS>(rc, it, i);
+        if (lane == 0) {
+          c.res[c.cwarp] = cnew;
+          if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], c.cwarp);
+        }
+      }
+    } else {
+      const int i = i0 + tid;
+      if (tid < nrows && i < n) {
+        const int cnew = inc_eval_row(rc, it, i, sc, NT);
+        c.res[tid] = cnew;
+        if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], tid);
+      }
     }
     csync(c);
     const int F = sh->first[slot3];
-    if (F == RC_INC_NONE) { i0 += nrows; nrows = min(NT, nrows * 2); continue; }   // nobody moved: the whole batch stands
+    if (F == RC_INC_NONE) {                                                 // nobody moved: the whole batch stands
+      i0 += nb;
+      if (warpmode) { streak += nb; if (streak >= nrows) { nrows = min(NT, nrows * 2); streak = 0; } }
+      else nrows = min(NT, nrows * 2);
+      continue;
+    }
     const int mi = i0 + F, b = c.res[F];
     if (b < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; break; }        // slot capacity exhausted at row mi
     const int a = c.lab[mi];
@@ -2203,18 +2402,19 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
       __syncwarp();
       inc_build_tables(c, a, b);
     }
-    inc_update_S(c, mi, a, b, mi);
+    inc_update_S(c, mi, a, b, mi, NT > 32 ? 32 : 0);
     csync(c);
     if (tid == 0) st_add(c, ST_BULK_PATCH, RC_CLOCK() - tu0);               // (incremental mode: cycles in the move updates)
     i0 = mi + 1;
-    nrows = min(NT, max(32, (2 * (F + 1) + 31) & ~31));
+    nrows = min(NT, max(32, (2 * (streak + F + 1) + 31) & ~31));
+    streak = 0;
   }
   csync(c);
   if (c.cwarp == 0) {                                                       // :254
     int K = 0;
     for (int s = lane; s < cap; s += 32) K += c.sizes[s] > 0;
     for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
-    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); }
+    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); sh->hint = nrows; }
   }
   csync(c);
 }
@@ -2304,6 +2504,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     s.r = kp.r[chain]; s.p = kp.p[chain];
     s.logp = rc_log(s.p); s.log1mp = rc_log(1 - s.p);
     s.status = kp.status[chain]; s.rebuild = 0; s.fslotA = -1; s.fslotB = -1; s.ltp = 0.0; s.forked = 0;
+    c.inc->hint = 0;
     int K = 0;
     for (int q = 0; q < cap; ++q) K += kp.sizes[(size_t)chain * cap + q] > 0;
     s.K = K;
