@@ -4,8 +4,13 @@
 One *step* = one iteration of runsampler's loop (sample_r, sample_p, one split-merge proposal with 5 restricted
 Gibbs scans, one full Gibbs scan, record) for EVERY chain on the GPU = one launch of the persistent chain
 kernel.  Workload at N=1: BASELINE configs[2] "generatemixture n=10,000 K~50 dim=100, fp64 distM (800 MB),
-256 chains"; with N GPUs every rank runs its own 256 chains (independent chains shard with no data-path
-collective -> weak scaling).  Prints ONE JSON line (see the task contract).
+256 chains".  The headline `value` keeps round 1's definition (sigma = 0.1, 256 chains PER GPU: independent chains
+shard with no data-path collective -> weak scaling) so the rounds compare; the same JSON line also carries
+  "strong"  configs[2] taken literally: 256 chains in TOTAL, sharded over the N GPUs (strong scaling),
+  "moving"  the same sizes at sigma = 0.25 with the reference's own cluster cap maxK = 100: a chain that keeps
+            moving points (moves_per_sweep is reported for every workload; the sigma = 0.1 chain is stationary),
+  "post"    the other half of BASELINE's metric: distance build, PSM and point-estimate seconds (rank 0, N = 1).
+Prints ONE JSON line (see the task contract).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   torchrun ... bench.py --gpus N ...        (N > 1)
@@ -82,14 +87,14 @@ def measured_peaks():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def profile_traffic(n):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this n."""
+def profile_numbers():
+    """Per-launch numbers of the dominant kernel from the committed ncu capture of this workload (profiles/traffic.json:
+    dram bytes, fp64-pipe activity, the launch duration under ncu), or {}."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)
-        return t.get(str(n))
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
 def cpu_reference(args, X, lab, params_fields, steps, warmup, cores, D=None):
@@ -128,6 +133,92 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def timed_sampler(pkg, torch, dist, world, data, params, lab, chains, chain0, args, warm, steps, local_rank):
+    """`warm` untimed sweeps then `steps` timed ones (one kernel launch each) of `chains` chains on this rank.
+    Returns (device seconds max over ranks, wall seconds max over ranks, moves per chain-sweep, K of chain 0, clock summary)."""
+    opts = pkg.MCMCOptionsList(numiters=warm + steps, burnin=0, thin=1, numGibbs=args.numGibbs, numMH=args.numMH)
+    rp = [pkg.init_rp(params, args.seed, chain0 + c) for c in range(chains)]
+    r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
+    labs = np.tile(lab, (chains, 1))
+    smp = pkg.Sampler(data, opts, params, labs, r0, p0, seed=args.seed, chain_offset=chain0, slot_cap=args.slot_cap)
+    smp.run(0)                       # builds the per-chain sums (setup, like MCMCData construction)
+    for _ in range(warm):
+        smp.run(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clk = ClockSampler(local_rank)
+    barrier()
+    clk.start()
+    m0 = smp.stats()["moves"].sum()
+    _, t0 = smp.progress()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        smp.run(1)                   # ONE launch of the persistent chain kernel per step
+    barrier()
+    w1 = time.perf_counter()
+    _, t1 = smp.progress()
+    clk.stop_flag = True
+    moves = float(smp.stats()["moves"].sum() - m0) / (chains * steps)
+    tt = torch.tensor([t1 - t0, w1 - w0, moves], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tt = torch.stack([mx[0], mx[1], sm[2] / world])
+    Kfinal = int(smp.samples(0)["K"][-1])
+    smp.close()
+    return float(tt[0]), float(tt[1]), float(tt[2]), Kfinal, clk.summary(), (labs, r0, p0)
+
+
+def post_block(pkg, args, data, lab):
+    """PSM + point-estimate seconds (the second half of BASELINE's metric) through the host API, rank 0 at N = 1:
+    synthetic label samples around the truth (15 % of the entries re-drawn), sizes named in the output."""
+    import torch
+    out = {}
+    g = np.random.default_rng(args.seed)
+
+    def samples(S, n, K):
+        base = np.sort(g.integers(1, K + 1, size=n))
+        L = np.tile(base, (S, 1))
+        flip = g.random((S, n)) < 0.15
+        L[flip] = g.integers(1, K + 11, size=int(flip.sum()))
+        return np.ascontiguousarray(L, dtype=np.int64)
+
+    # distance build (MCMCData(points), types.jl:159-162) at the bench size
+    X, _ = synth(args.n, args.K, args.dim, args.sigma, args.K, args.seed)
+    pkg.MCMCData.from_points(X)
+    t = time.perf_counter(); pkg.MCMCData.from_points(X); out["distm_s"] = time.perf_counter() - t
+    out["distm"] = f"MCMCData(points) n={args.n} dim={args.dim}: upload, Euclidean distances, checks, logD and fixed-point images"
+    # PSM of host label vectors into a host fp64 matrix (mcmc.jl:560)
+    n1, S1 = 10000, 2000
+    L = samples(S1, n1, 50)
+    pkg.psm(L[:50])
+    t = time.perf_counter(); pkg.psm(L); out["psm_s"] = time.perf_counter() - t
+    out["psm"] = f"psm(labels) n={n1} S={S1}: host int64 labels -> host fp64 n x n"
+    # configs[4]-shaped PSM: exact int32 counts left on the device (the all-reduce input of the multi-GPU path)
+    n2, S2 = 50000, 10000
+    try:
+        L2 = samples(S2, n2, 90)
+        cnt = torch.empty((n2, n2), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        t = time.perf_counter(); pkg.psm_counts_dev(L2, cnt.data_ptr()); torch.cuda.synchronize()
+        out["psm_c4_s"] = time.perf_counter() - t
+        out["psm_c4"] = f"psm_counts_dev n={n2} S={S2} (BASELINE configs[4]): host labels -> device int32 counts (relabel, upload, transpose, tcgen05 one-hot counts)"
+        del cnt
+        # MPEL search over candidate samples (pointestimate.jl:34-59)
+        S3 = 2000
+        for loss in ("binder", "VI"):
+            t = time.perf_counter(); pkg.mpel_loss_sums(L2[:S3], loss); out[f"mpel_{loss}_s"] = time.perf_counter() - t
+        out["mpel"] = f"getpointestimate(method=MPEL) search, n={n2}, {S3} candidate samples ({S3 * (S3 - 1) // 2} pairs)"
+    except Exception as e:  # noqa: BLE001
+        out["psm_c4_error"] = str(e)[:200]
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -139,13 +230,21 @@ def main():
     ap.add_argument("--K", type=int, default=50)
     ap.add_argument("--dim", type=int, default=100)
     ap.add_argument("--sigma", type=float, default=0.1)
-    ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--maxK", type=int, default=0)
+    ap.add_argument("--chains", type=int, default=256, help="chains per GPU (headline, weak scaling) / in total (the strong block)")
     ap.add_argument("--numGibbs", type=int, default=5)
     ap.add_argument("--numMH", type=int, default=1)
     ap.add_argument("--seed", type=int, default=44)
     ap.add_argument("--slot-cap", type=int, default=0, help="cluster slots per chain (0: library default, 128)")
+    ap.add_argument("--moving-sigma", type=float, default=0.25)
+    ap.add_argument("--moving-maxK", type=int, default=100)
+    ap.add_argument("--moving-warmup", type=int, default=5)
+    ap.add_argument("--moving-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-moving", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-post", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -156,17 +255,17 @@ def main():
     workload = (f"generatemixture(N={args.n}, K={args.K}; alpha={args.K}, sigma={args.sigma}, dim={args.dim}) seed {args.seed}, "
                 f"{args.chains} chains per GPU, numGibbs={args.numGibbs}, numMH={args.numMH}, every sweep recorded")
     config = {"workload": workload, "n": args.n, "chains_per_gpu": args.chains, "hyperparameters": "from true labels as prior.jl:73-110",
-              "init": "true labels, r/p from their priors", "l2": f"inputs larger than L2 (DL = {16 * args.n * args.n / 1e9:.2f} GB streamed per chain-sweep)"}
+              "init": "true labels, r/p from their priors",
+              "l2": f"inputs larger than L2 (DL = {16 * args.n * args.n / 1e9:.2f} GB, per-chain row sums {16 * 128 * args.n * args.chains / 1e9:.2f} GB)"}
     X, lab = synth(args.n, args.K, args.dim, args.sigma, args.K, args.seed)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        pkg_fields = None
         orc = graft.load_oracle()
         D = orc.distm(X)
         pkg = graft.load_package()
-        params = pkg.params_from_labels(D, lab)
+        params = pkg.params_from_labels(D, lab, maxK=args.maxK)
         fields = {k: getattr(params, k) for k in params._fields}
         cores = os.cpu_count() or 1
         val, ms, sample = cpu_reference(args, X, lab, fields, steps, W, cores, D=D)
@@ -186,46 +285,53 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = graft.load_package()
 
-    # ---- setup (untimed): distance matrix on the GPU, hyperparameters, chains ----
-    data = pkg.MCMCData.from_points(X, device=local_rank)
-    Dh = data.D
-    params = pkg.params_from_labels(Dh, lab)
-    opts = pkg.MCMCOptionsList(numiters=W + steps, burnin=0, thin=1, numGibbs=args.numGibbs, numMH=args.numMH)
-    chain0 = rank * args.chains
-    rp = [pkg.init_rp(params, args.seed, chain0 + c) for c in range(args.chains)]
-    r0 = np.array([x[0] for x in rp]); p0 = np.array([x[1] for x in rp])
-    labs = np.tile(lab, (args.chains, 1))
-    smp = pkg.Sampler(data, opts, params, labs, r0, p0, seed=args.seed, chain_offset=chain0, slot_cap=args.slot_cap)
-    smp.run(0)                       # builds the block-sum matrices (setup, like MCMCData construction)
-    for _ in range(W):
-        smp.run(1)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    clk = ClockSampler(local_rank)
-    barrier()
-    clk.start()
-    _, t0 = smp.progress()
-    w0 = time.perf_counter()
-    for _ in range(steps):
-        smp.run(1)                   # ONE launch of the persistent chain kernel per step
-    barrier()
-    w1 = time.perf_counter()
-    _, t1 = smp.progress()
-    clk.stop_flag = True
-    dev_s = t1 - t0                  # CUDA events on the launching stream, summed over the K launches
-    tt = torch.tensor([dev_s, w1 - w0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_s, wall_s = float(tt[0]), float(tt[1])
+    # ---- setup (untimed): distance matrix on the GPU, hyperparameters ----
+    data = pkg.MCMCData.from_points(X, device=local_rank)
+    Dh = data.D
+    params = pkg.params_from_labels(Dh, lab, maxK=args.maxK)
+    chain0 = rank * args.chains
+
+    # ---- headline: `chains` chains per GPU (weak scaling, round 1's definition) ----
+    dev_s, wall_s, moves, Kfinal, clocks, (labs, r0, p0) = timed_sampler(pkg, torch, dist, world, data, params, lab, args.chains, chain0,
+                                                                        args, W, steps, local_rank)
     value = world * args.chains * steps / dev_s
-    st = smp.samples(0)
-    Kfinal = int(st["K"][-1])
-    smp.close()
+
+    # ---- configs[2] literally: `chains` chains in total over the N GPUs (strong scaling) ----
+    strong = None
+    if not args.no_strong:
+        per = max(args.chains // world, 1)
+        if world == 1:
+            strong = {"value": value, "unit": "chain-sweeps/s", "ms_per_step": dev_s / steps * 1e3, "chains_total": args.chains, "chains_per_gpu": per,
+                      "note": "N = 1: the headline run"}
+        else:
+            d2, w2, mv2, _, _, _ = timed_sampler(pkg, torch, dist, world, data, params, lab, per, rank * per, args, W, steps, local_rank)
+            strong = {"value": world * per * steps / d2, "unit": "chain-sweeps/s", "ms_per_step": d2 / steps * 1e3, "chains_total": world * per,
+                      "chains_per_gpu": per, "moves_per_sweep": mv2,
+                      "note": "256 chains sharded over the GPUs: a sweep of one chain is sequential in the points, so fewer chains per GPU leave SMs idle"}
+
+    # ---- a chain that moves: sigma = 0.25, the reference's own cap maxK (PriorHyperparamsList.maxK, src/types.jl:107) ----
+    moving = None
+    if not args.no_moving:
+        X2, lab2 = synth(args.n, args.K, args.dim, args.moving_sigma, args.K, args.seed)
+        data2 = pkg.MCMCData.from_points(X2, device=local_rank)
+        params2 = pkg.params_from_labels(data2.D, lab2, maxK=args.moving_maxK)
+        d3, w3, mv3, K3, clk3, _ = timed_sampler(pkg, torch, dist, world, data2, params2, lab2, args.chains, chain0, args,
+                                                 max(args.moving_warmup, 0), max(args.moving_steps, 1), local_rank)
+        moving = {"value": world * args.chains * args.moving_steps / d3, "unit": "chain-sweeps/s", "ms_per_step": d3 / args.moving_steps * 1e3,
+                  "moves_per_sweep": mv3, "K_final_chain0": K3, "steps": args.moving_steps, "warmup": args.moving_warmup, "clocks": clk3,
+                  "config": {"workload": f"generatemixture(N={args.n}, K={args.K}; alpha={args.K}, sigma={args.moving_sigma}, dim={args.dim}) seed {args.seed}, "
+                                         f"maxK={args.moving_maxK}, {args.chains} chains per GPU, init true labels, {args.moving_warmup} untimed sweeps first",
+                             "why_maxK": "at sigma = 0.25 the model opens several hundred clusters at this n; the sampler holds at most 128 live "
+                                         "clusters per chain, so the run uses the reference's own cap parameter"},
+                  "note": "per sweep the chain moves ~2 % of the points and its split-merge proposals involve clusters of thousands of points: the "
+                          "restricted Gibbs scans (sequential, O(members) per move) dominate"}
+        del data2
 
     # ---- end-to-end through the public API with HOST buffers (upload D, build, run, read results back) ----
     e2e = None
@@ -262,7 +368,8 @@ def main():
         d2h = sum(sum(v.nbytes for v in o.values()) for o in outs)
         e2e = {"value": world * args.chains * steps / float(et[0]), "unit": "chain-sweeps/s",
                "h2d_bytes_per_step": int(h2d / steps), "d2h_bytes_per_step": int(d2h / steps),
-               "includes": "upload of D from pinned host memory, logD / fixed-point build, block-sum init, sampling, readback of all samples; one untimed warm-up pass of the same path first"}
+               "includes": "upload of D from pinned host memory, logD / fixed-point build, per-chain sum initialisation, sampling, readback of all samples; one untimed warm-up pass of the same path first"}
+        del outs
 
     if rank != 0:
         if world > 1:
@@ -271,21 +378,34 @@ def main():
     peak, peak_src = measured_peaks()
     b_scan = 16.0 * args.n * (args.n - 1)                         # algorithmic bytes per chain-sweep
     per_launch_bytes = b_scan * args.chains
-    achieved = per_launch_bytes / (dev_s / steps) / 1e9
+    step_s = dev_s / steps
+    achieved = per_launch_bytes / step_s / 1e9
+    prof = profile_numbers().get(f"k_chain_inc:{args.n}:{args.chains}", {})
+    traffic = prof.get("dram_bytes")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profile_traffic(args.n), "kernel": "k_chain", "peak_source": peak_src + " (of measured)",
+                "traffic": traffic, "kernel": "k_chain_inc", "peak_source": peak_src + " (of measured)",
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "note": "algorithmic bytes = chains x 16 n (n-1) per sweep (full scan only); chains that walk the same rows share them through L2, so DRAM traffic can be far below the algorithmic bytes"}
+                "dram_frac": (traffic / step_s / 1e9 / peak) if traffic else None,
+                "fp64_pipe_frac": prof.get("fp64_pipe_frac"), "issue_active_frac": prof.get("issue_active_frac"),
+                "note": "algorithmic bytes = chains x 16 n (n-1) per sweep: what a scan that reads every row costs (SURVEY 8d).  This kernel does "
+                        "not read the rows: each chain keeps the sums of every row by cluster (exact integers) and a Gibbs step reads one 16-byte "
+                        "entry per live cluster; only a move streams a row.  frac > 1 therefore measures the work avoided, dram_frac is the real "
+                        "DRAM utilisation (ncu bytes / step time / peak), and the binding resources are instruction issue and the fp64 pipe "
+                        "(fp64_pipe_frac, issue_active_frac: ncu, profiles/)"}
     cpu = None
     if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
         fields = {k: getattr(params, k) for k in params._fields}
         v, ms, sample = cpu_reference(args, X, lab, fields, args.cpu_steps, 0, cores, D=Dh)
         cpu = {"value": v, "unit": "chain-sweeps/s", "cores": cores, "kind": "port", "sample": sample}
+    post = None
+    if not args.no_post and world == 1:
+        post = post_block(pkg, args, data, lab)
     line = {"metric": "Gibbs+SM chain-sweeps/sec", "value": value, "unit": "chain-sweeps/s", "n_gpus": world, "steps": steps, "warmup": W,
-            "ms_per_step": dev_s / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (exact i64 fixed-point cluster sums)", "data": "synthetic", "config": config,
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": steps, "roofline": roofline, "cpu_baseline": cpu,
+            "moves_per_sweep": moves, "strong": strong, "moving": moving, "post": post,
             "wall_ms_per_step": wall_s / steps * 1e3, "K_final_chain0": Kfinal}
     emit(line)
     if world > 1:

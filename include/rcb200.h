@@ -130,8 +130,12 @@ int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* label
  * out: nchains x 16 int64.  Only librcb200_stats.so carries the clock reads; the default library returns the
  * move / rebuild counts and zeros for the cycle slots. */
 int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out);
-/* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the slot capacity overflowed.           */
+/* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the chain needed more than slot_cap simultaneously live
+ * clusters and stopped there (the reference allows up to n, src/types.jl:135, src/mcmc.jl:199).
+ * rc_sampler_run fails with RC_ERR_SLOTS only when EVERY chain stopped; otherwise the healthy chains' results are
+ * valid and rc_sampler_overflowed tells how many chains to skip.                                 */
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain);
+int64_t rc_sampler_overflowed(const rc_sampler* s);
 /* Posterior co-clustering counts of the device-resident samples of chains [chain0, chain0+nch):
  * sum(adjacencymatrix.(clusts)) (src/mcmc.jl:560, src/utils.jl:59-63) as exact int32 counts in a
  * DEVICE buffer of n*n int32 (e.g. a torch tensor's data_ptr, so the caller can all-reduce it

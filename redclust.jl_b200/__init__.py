@@ -10,6 +10,6 @@ The directory name contains a dot, so it is loaded under the module name `redclu
 """
 from .host import (MCMCOptionsList, PriorHyperparamsList, MCMCData, MCMCState, MCMCResult, Sampler, runsampler,
                    getpointestimate, binderloss, infodist, adjacencymatrix, sortlabels, makematrix, uppertriangle,
-                   generatemixture, prettytime, prettynumber, evaluateclustering, summarise, params_from_labels, pair_stats, psm, psm_sharded, mpel_loss_sums, mpel_loss_sums_sharded, cyclic_rows, assemble_cyclic_rows, init_rp, ArgumentError)
+                   generatemixture, prettytime, prettynumber, evaluateclustering, summarise, params_from_labels, pair_stats, psm, psm_counts_dev, psm_sharded, mpel_loss_sums, mpel_loss_sums_sharded, cyclic_rows, assemble_cyclic_rows, init_rp, ArgumentError)
 from ._lib import RCError, LIB_PATH
 from .prior import fitprior, fitprior2, sampledist, sampleK, kmedoids, kmedoids_device, kmeans

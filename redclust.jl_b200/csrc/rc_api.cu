@@ -32,6 +32,7 @@ struct rc_sampler {
   int64_t nchains, chain_offset, numsamples;
   uint64_t seed;
   int cap, tiles, npad_max, G;
+  int nsm;                     // SMs of the device
   int device;                  // copied from the data handle: the sampler may be destroyed after it
   int64_t n;
   size_t smem;
@@ -53,6 +54,7 @@ struct rc_sampler {
   uint8_t *r_acc, *sm_acc, *sm_split;
   // progress
   int64_t iters_done;
+  int64_t overflowed;          // chains stopped by the slot capacity so far
   double dev_seconds;
   bool W_ready;
   bool shared_init;            // every chain starts from the same labels: the block sums are built once and copied
@@ -292,7 +294,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   s->shared_init = nchains > 1;
   for (int64_t c = 1; c < nchains && s->shared_init; ++c) s->shared_init = memcmp(lab.data(), lab.data() + c * n, (size_t)n) == 0;
   s->d = d; s->device = d->device; s->n = d->n; s->opt = *opt; s->par = *par; s->nchains = nchains; s->chain_offset = chain_offset; s->seed = seed;
-  s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem; s->G = G;
+  s->nsm = nsm; s->cap = cap; s->tiles = tiles; s->npad_max = (int)npad; s->smem = smem; s->G = G;
   s->numsamples = (opt->numiters - opt->burnin) / opt->thin;   // floor((numiters - burnin) / thin), types.jl:55
   const size_t NS = (size_t)std::max<int64_t>(s->numsamples, 1);
 #define TRY(x) do { st = (x); if (st) { rc_sampler_destroy(s); return st; } } while (0)
@@ -349,7 +351,8 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRY(dalloc(&s->sm_acc, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
   TRY(dalloc(&s->sm_split, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
 #undef TRY
-  cudaMemcpy(s->labels, lab.data(), lab.size(), cudaMemcpyHostToDevice);
+#define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc_set_error("sampler setup: CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); rc_sampler_destroy(s); return RC_ERR_CUDA; } } while (0)
+  TRYC(cudaMemcpy(s->labels, lab.data(), lab.size(), cudaMemcpyHostToDevice));
   // Column order of the streamed matrix.  The row reduction is fastest when the members of a cluster are contiguous
   // columns (few (tile, label) runs, little padding, conflict-free shared-memory gathers).  When the initial labels
   // of chain 0 are scattered over the points, the sampler streams its own copy of DL whose columns are sorted by those
@@ -370,9 +373,10 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
       std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return lab[a] < lab[b]; });
       for (int64_t c = 0; c < n; ++c) { pt[c] = (unsigned short)idx[c]; pos[idx[c]] = (unsigned short)c; }
       if (dalloc(&s->DLp, (size_t)n * n) == RC_OK && dalloc(&s->colpos, (size_t)n) == RC_OK && dalloc(&s->colpt, (size_t)n) == RC_OK) {
-        cudaMemcpy(s->colpos, pos.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice);
-        cudaMemcpy(s->colpt, pt.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice);
-        k_permute_cols<<<148 * 16, 256>>>(d->DL, n, s->colpt, s->DLp);
+        TRYC(cudaMemcpy(s->colpos, pos.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(s->colpt, pt.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice));
+        k_permute_cols<<<nsm * 16, 256>>>(d->DL, n, s->colpt, s->DLp);
+        TRYC(cudaGetLastError());
         if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] columns of the streamed matrix sorted by the initial labels (%lld label changes along the points, %lld clusters)\n", (long long)changes, (long long)distinct);
       } else {                                   // not enough memory for the copy: stream the data's own matrix
         rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt);
@@ -381,16 +385,17 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
       }
     }
   }
-  cudaMemcpy(s->sizes, sizes.data(), sizes.size() * sizeof(int), cudaMemcpyHostToDevice);
-  cudaMemcpy(s->r, init_r, sizeof(double) * nchains, cudaMemcpyHostToDevice);
-  cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice);
-  cudaMemset(s->status, 0, sizeof(int) * nchains);
-  cudaMemset(s->stats, 0, sizeof(long long) * 16 * nchains);
-  cudaMemset(s->r_acc, 0, (size_t)nchains * opt->numiters);
-  cudaMemset(s->sm_acc, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1));
-  cudaMemset(s->sm_split, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1));
-  cudaStreamCreate(&s->stream);
-  cudaEventCreate(&s->e0); cudaEventCreate(&s->e1);
+  TRYC(cudaMemcpy(s->sizes, sizes.data(), sizes.size() * sizeof(int), cudaMemcpyHostToDevice));
+  TRYC(cudaMemcpy(s->r, init_r, sizeof(double) * nchains, cudaMemcpyHostToDevice));
+  TRYC(cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice));
+  TRYC(cudaMemset(s->status, 0, sizeof(int) * nchains));
+  TRYC(cudaMemset(s->stats, 0, sizeof(long long) * 16 * nchains));
+  TRYC(cudaMemset(s->r_acc, 0, (size_t)nchains * opt->numiters));
+  TRYC(cudaMemset(s->sm_acc, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
+  TRYC(cudaMemset(s->sm_split, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
+  TRYC(cudaStreamCreate(&s->stream));
+  TRYC(cudaEventCreate(&s->e0)); TRYC(cudaEventCreate(&s->e1));
+#undef TRYC
   rc_launch_tables(s->par, (int)n, s->LGA, s->LGZ, s->LOGN, s->stream);
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) { rc_set_error("sampler setup failed: %s", cudaGetErrorString(e)); rc_sampler_destroy(s); return RC_ERR_CUDA; }
@@ -426,9 +431,9 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
     const size_t per = (size_t)s->cap * s->cap;
     RC_CUDA(cudaMemsetAsync(s->WD, 0, sizeof(rc_i128) * per, s->stream));
     RC_CUDA(cudaMemsetAsync(s->WL, 0, sizeof(rc_i128) * per, s->stream));
-    k_initw_shared<<<148 * 8, 256, sizeof(unsigned long long) * 2 * s->cap, s->stream>>>(s->DLp ? s->DLp : s->d->DL, (int)s->n, s->labels, s->cap, s->WD, s->WL, s->colpt);
-    k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WD, per, s->nchains);
-    k_replicate_w<<<148 * 4, 256, 0, s->stream>>>(s->WL, per, s->nchains);
+    k_initw_shared<<<s->nsm * 8, 256, sizeof(unsigned long long) * 2 * s->cap, s->stream>>>(s->DLp ? s->DLp : s->d->DL, (int)s->n, s->labels, s->cap, s->WD, s->WL, s->colpt);
+    k_replicate_w<<<s->nsm * 4, 256, 0, s->stream>>>(s->WD, per, s->nchains);
+    k_replicate_w<<<s->nsm * 4, 256, 0, s->stream>>>(s->WL, per, s->nchains);
     RC_CUDA(cudaGetLastError());
     kp.init_W = 0;
   }
@@ -443,13 +448,19 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters) {
   s->iters_done = it1;
   s->W_ready = true;
   s->mirror.valid = false;
+  // A chain that needed more than slot_cap live clusters has stopped (rc_sampler_chain_status reports it); the other
+  // chains are unaffected and their results stay readable.  The call fails only when no healthy chain is left.
   std::vector<int> status((size_t)s->nchains);
   RC_CUDA(cudaMemcpy(status.data(), s->status, sizeof(int) * s->nchains, cudaMemcpyDeviceToHost));
+  int64_t bad = 0, firstbad = -1;
   for (int64_t c = 0; c < s->nchains; ++c)
-    if (status[c]) {
-      rc_set_error("chain %lld needed more than slot_cap = %d simultaneously live clusters", (long long)c, s->cap);
-      return RC_ERR_SLOTS;
-    }
+    if (status[c]) { if (firstbad < 0) firstbad = c; ++bad; }
+  s->overflowed = bad;
+  if (bad == s->nchains) {
+    rc_set_error("chain %lld needed more than slot_cap = %d simultaneously live clusters (%lld of %lld chains stopped)", (long long)firstbad,
+                 s->cap, (long long)bad, (long long)s->nchains);
+    return RC_ERR_SLOTS;
+  }
   return RC_OK;
 }
 
@@ -566,6 +577,8 @@ int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out) {
   RC_CUDA(cudaMemcpy(out, s->stats, sizeof(long long) * 16 * s->nchains, cudaMemcpyDeviceToHost));
   return RC_OK;
 }
+
+int64_t rc_sampler_overflowed(const rc_sampler* s) { return s ? s->overflowed : 0; }
 
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_chain_status: bad handle or chain"); return RC_ERR_ARG; }

@@ -220,6 +220,14 @@ class Sampler:
     def run(self, iters=-1):
         check(lib().rc_sampler_run(self._h, iters))
 
+    def chain_status(self, chain=0):
+        """0, or RC_ERR_SLOTS (-5) when the chain needed more than slot_cap simultaneously live clusters and stopped."""
+        return int(lib().rc_sampler_chain_status(self._h, chain))
+
+    def overflowed(self):
+        """Number of chains stopped by the slot capacity (run() raises only when every chain stopped)."""
+        return int(lib().rc_sampler_overflowed(self._h))
+
     def progress(self):
         a, b = C.c_int64(), C.c_double()
         check(lib().rc_sampler_progress(self._h, C.byref(a), C.byref(b)))
@@ -349,6 +357,14 @@ def runsampler(data, options=None, params=None, init=None, verbose=True, nchains
         print("Computing summary statistics and diagnostics.")
     results = []
     for c in range(nchains):
+        if smp.overflowed() and smp.chain_status(c) != 0:
+            # the chain needed more than slot_cap live clusters (the reference allows up to n, src/mcmc.jl:199): its
+            # trace is incomplete, the other chains are unaffected
+            import warnings
+            warnings.warn(f"chain {c} needed more than slot_cap = {slot_cap or 128} simultaneously live clusters and was stopped; "
+                          "its result is None (raise slot_cap, or set maxK in the hyperparameters)")
+            results.append(None)
+            continue
         s = smp.samples(c)
         psm = smp.psm(c, 1) if options.numsamples > 0 else np.full((n, n), np.nan)   # mcmc.jl:560
         results.append(_result_from(s, options, params, psm, runtime))
@@ -424,6 +440,13 @@ def mpel_loss_sums(labels, loss, device=0):
     best = C.c_int64()
     check(lib().rc_mpel(ptr(L), L.shape[0], L.shape[1], _LOSS[loss], device, ptr(sums), C.byref(best)))
     return sums, best.value
+
+
+def psm_counts_dev(labels, counts_ptr, device=0):
+    """Exact co-clustering counts (mcmc.jl:560, not divided) of host label vectors (S x n) into a caller DEVICE buffer of
+    n x n int32 (e.g. a torch tensor's data_ptr()): one rank's share of a PSM whose samples are sharded over GPUs."""
+    L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
+    check(lib().rc_psm_counts_dev(ptr(L), L.shape[0], L.shape[1], device, C.c_void_p(counts_ptr)))
 
 
 def psm_sharded(labels, group=None, device=None, total=None):

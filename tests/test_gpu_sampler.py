@@ -137,6 +137,32 @@ def test_slot_overflow_is_reported(pkg, golden):
     assert e.value.status == -5
 
 
+def test_slot_overflow_stops_only_the_chain_that_overflowed(pkg, orc, golden):
+    """With several chains the run succeeds as long as one chain is healthy; rc_sampler_chain_status names the stopped
+    ones and the healthy chains still match the oracle bit for bit."""
+    D, lab = golden[1]["distance_matrix"], golden[1]["cluster_labels"]
+    params = pkg.params_from_labels(D, lab)
+    opts = pkg.MCMCOptionsList(numiters=40, burnin=0, thin=1)
+    nch = 6
+    rp = [pkg.init_rp(params, 2, c) for c in range(nch)]
+    for cap in (10, 11, 12, 13, 14):
+        smp = pkg.Sampler(pkg.MCMCData(D), opts, params, np.tile(lab, (nch, 1)), [x[0] for x in rp], [x[1] for x in rp], seed=2, slot_cap=cap)
+        try:
+            smp.run(-1)
+        except pkg.RCError as e:
+            assert e.status == -5 and smp.overflowed() == nch
+            continue
+        st = [smp.chain_status(c) for c in range(nch)]
+        assert sum(1 for x in st if x) == smp.overflowed() < nch
+        if 0 < smp.overflowed():
+            for c in range(nch):
+                if st[c] == 0:
+                    ref = orc.run_chain(D, orc.Options(40, 0, 1, 5, 1), oparams(orc, params), lab, rp[c][0], rp[c][1], seed=2, chain=c)
+                    assert_same(smp.samples(c), ref, smp.state(c))
+            return
+    pytest.skip("no slot capacity in 10..14 stopped some but not all of the chains")
+
+
 @pytest.mark.parametrize("G", [1, 2])
 def test_chains_per_cta_share_rows(pkg, orc, golden, monkeypatch, G):
     """G chains of a CTA consume the same staged row tiles; 3 chains leave a ragged last CTA for G = 2."""
