@@ -345,7 +345,7 @@ def main():
             d2 = pkg.MCMCData(Dp.numpy(), device=local_rank); t.append(time.perf_counter())
             s2 = pkg.Sampler(d2, o2, params, labs, r0, p0, seed=args.seed, chain_offset=chain0, slot_cap=args.slot_cap); t.append(time.perf_counter())
             s2.run(-1); t.append(time.perf_counter())
-            outs = [s2.samples(c) for c in range(args.chains)]
+            outs = [s2.samples_all()]                      # every chain's samples, traces and acceptances on the host
             barrier(); t.append(time.perf_counter())
             dev = s2.progress()[1]
             s2.close()

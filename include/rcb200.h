@@ -115,10 +115,16 @@ int32_t rc_sampler_run(rc_sampler* s, int64_t iters);
  * MCMCResult.runtime / mean_iter_time, src/mcmc.jl:536,586-587.                                */
 int32_t rc_sampler_progress(const rc_sampler* s, int64_t* iters_done, double* device_seconds);
 int64_t rc_sampler_numsamples(const rc_sampler* s);
+int64_t rc_sampler_n(const rc_sampler* s);
+int64_t rc_sampler_nchains(const rc_sampler* s);
 /* Recorded samples of one chain (src/mcmc.jl:546-554): labels numsamples x n (sortlabels'd,
  * 1-based), K, r, p, loglik, logposterior.  Any pointer may be NULL.                          */
 int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* labels, int64_t* K,
                                 double* r, double* p, double* loglik, double* logposterior);
+/* The same for EVERY chain in one call (labels nchains x numsamples x n, traces nchains x numsamples, acceptances
+ * nchains x numiters [x numMH]): one device-to-host copy per array, labels widened by all host threads.            */
+int32_t rc_sampler_copy_all(const rc_sampler* s, int64_t* labels, int64_t* K, double* r, double* p, double* loglik,
+                            double* logposterior, uint8_t* r_acc, uint8_t* sm_acc, uint8_t* sm_split);
 /* r_acceptances (numiters), splitmerge_acceptances / splitmerge_splits (numiters*numMH):
  * src/mcmc.jl:538-543.                                                                         */
 int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t* r_acc,
@@ -165,6 +171,28 @@ int32_t rc_mpel(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32
 int32_t rc_mpel_rows_dev(const int64_t* labels, int64_t S, int64_t n, int32_t loss, int32_t device, int64_t row_first,
                          int64_t row_stride, int64_t nrows, void* M_rows_dev);
 int32_t rc_mpel_finish_dev(const void* M_upper_dev, int64_t S, int32_t device, double* loss_sums, int64_t* best);
+
+/* ---- multi-GPU exchange steps -------------------------------------------------------
+ * One process per GPU.  The sampler needs no collective (independent chains: chain_offset above).  The three steps
+ * that exchange data run over an NCCL communicator owned by an rc_comm handle: rank 0 calls rc_comm_unique_id, the
+ * launcher (torch.distributed, MPI, Julia Distributed, ...) hands the 128 bytes to every rank, every rank calls
+ * rc_comm_init.  NCCL is resolved at run time (libnccl.so.2), so the library loads without it.
+ *   rc_comm_data_from_points  MCMCData(points), src/types.jl:159-162: row blocks of pairwise(Euclidean()) + all-gather
+ *   rc_comm_sampler_psm       src/mcmc.jl:560 over the chains of every rank: int32 counts + ONE all-reduce + divide
+ *   rc_comm_psm               the same for host label vectors sharded over the ranks (S_local of them on this rank)
+ *   rc_comm_mpel              src/pointestimate.jl:49-57 with the candidate rows dealt cyclically + all-gather
+ * psm_out (host, n x n fp64) and counts_dev_out (device, n x n int32) may each be NULL.  Results are bit-equal to the
+ * single-GPU entry points.                                                                              */
+typedef struct rc_comm rc_comm;
+int32_t rc_comm_unique_id(uint8_t* id128);
+int32_t rc_comm_init(const uint8_t* id128, int32_t rank, int32_t world, int32_t device, rc_comm** out);
+int32_t rc_comm_info(const rc_comm* c, int32_t* rank, int32_t* world);
+void rc_comm_destroy(rc_comm* c);
+int32_t rc_comm_allreduce_i32(rc_comm* c, void* buf_dev, int64_t count);
+int32_t rc_comm_data_from_points(rc_comm* c, const double* X, int64_t dim, int64_t n, rc_data** out);
+int32_t rc_comm_sampler_psm(rc_comm* c, const rc_sampler* s, double* psm_out, void* counts_dev_out);
+int32_t rc_comm_psm(rc_comm* c, const int64_t* labels, int64_t S_local, int64_t n, double* psm_out, void* counts_dev_out);
+int32_t rc_comm_mpel(rc_comm* c, const int64_t* labels, int64_t S, int64_t n, int32_t loss, double* loss_sums, int64_t* best);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ The directory name contains a dot, so it is loaded under the module name `redclu
   prior.py     host-side fitprior / k-medoids (caller of the hot path)
   julia/       the `ccall` twin of host.py for a Julia host
 """
-from .host import (MCMCOptionsList, PriorHyperparamsList, MCMCData, MCMCState, MCMCResult, Sampler, runsampler,
+from .host import (Comm, MCMCOptionsList, PriorHyperparamsList, MCMCData, MCMCState, MCMCResult, Sampler, runsampler,
                    getpointestimate, binderloss, infodist, adjacencymatrix, sortlabels, makematrix, uppertriangle,
                    generatemixture, prettytime, prettynumber, evaluateclustering, summarise, params_from_labels, pair_stats, psm, psm_counts_dev, psm_sharded, mpel_loss_sums, mpel_loss_sums_sharded, cyclic_rows, assemble_cyclic_rows, init_rp, ArgumentError)
 from ._lib import RCError, LIB_PATH

@@ -55,7 +55,10 @@ SIGNATURES = {
     "rc_sampler_run": (C.c_int32, [_vp, C.c_int64]),
     "rc_sampler_progress": (C.c_int32, [_vp, _P(C.c_int64), _P(C.c_double)]),
     "rc_sampler_numsamples": (C.c_int64, [_vp]),
+    "rc_sampler_n": (C.c_int64, [_vp]),
+    "rc_sampler_nchains": (C.c_int64, [_vp]),
     "rc_sampler_copy_samples": (C.c_int32, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rc_sampler_copy_all": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rc_sampler_copy_acceptances": (C.c_int32, [_vp, C.c_int64, _vp, _vp, _vp]),
     "rc_sampler_copy_state": (C.c_int32, [_vp, C.c_int64, _vp, _P(C.c_double), _P(C.c_double)]),
     "rc_sampler_chain_status": (C.c_int32, [_vp, C.c_int64]),
@@ -70,6 +73,15 @@ SIGNATURES = {
     "rc_mpel": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _P(C.c_int64)]),
     "rc_mpel_rows_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "rc_mpel_finish_dev": (C.c_int32, [_vp, C.c_int64, C.c_int32, _vp, _P(C.c_int64)]),
+    "rc_comm_unique_id": (C.c_int32, [_vp]),
+    "rc_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _P(_vp)]),
+    "rc_comm_info": (C.c_int32, [_vp, _P(C.c_int32), _P(C.c_int32)]),
+    "rc_comm_destroy": (None, [_vp]),
+    "rc_comm_allreduce_i32": (C.c_int32, [_vp, _vp, C.c_int64]),
+    "rc_comm_data_from_points": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, _P(_vp)]),
+    "rc_comm_sampler_psm": (C.c_int32, [_vp, _vp, _vp, _vp]),
+    "rc_comm_psm": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "rc_comm_mpel": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, _vp, _P(C.c_int64)]),
 }
 
 

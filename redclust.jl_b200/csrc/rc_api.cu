@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <thread>
 #include "rc_sampler.cuh"
 
 static thread_local char g_err[512] = "";
@@ -537,6 +538,58 @@ int32_t rc_sampler_copy_samples(const rc_sampler* s, int64_t chain, int64_t* lab
   return RC_OK;
 }
 
+// Every chain's recorded outputs at once: ONE device-to-host copy per array into a pinned staging buffer, then the label
+// bytes are widened to the int64 the reference's API returns (Vector{Int}) by all host threads.  Layouts: labels
+// nchains x numsamples x n; K, r, p, loglik, logposterior nchains x numsamples; r_acc nchains x numiters; sm_* nchains x
+// numiters*numMH.  Any pointer may be NULL.
+static void* pinned_staging(size_t bytes) {
+  static void* buf = nullptr; static size_t cap = 0;     // grow-only, process lifetime (one reader at a time per process)
+  if (bytes > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr; cap = 0;
+    if (cudaMallocHost(&buf, bytes) != cudaSuccess) { (void)cudaGetLastError(); buf = nullptr; return nullptr; }
+    cap = bytes;
+  }
+  return buf;
+}
+int32_t rc_sampler_copy_all(const rc_sampler* s, int64_t* labels, int64_t* K, double* r, double* p, double* loglik,
+                            double* logposterior, uint8_t* r_acc, uint8_t* sm_acc, uint8_t* sm_split) {
+  if (!s) { rc_set_error("rc_sampler_copy_all: null handle"); return RC_ERR_ARG; }
+  RC_CUDA(cudaSetDevice(s->device));
+  const size_t Cn = (size_t)s->nchains, S = (size_t)s->numsamples, n = (size_t)s->n;
+  const size_t ni = (size_t)s->opt.numiters, nm = ni * (size_t)s->opt.numMH;
+  if (S) {
+    if (labels) {
+      const size_t total = Cn * S * n;
+      uint8_t* st = (uint8_t*)pinned_staging(total);
+      std::vector<uint8_t> fallback;
+      if (!st) { fallback.resize(total); st = fallback.data(); }
+      RC_CUDA(cudaMemcpy(st, s->out_labels, total, cudaMemcpyDeviceToHost));
+      const unsigned nth = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nth; ++t)
+        th.emplace_back([=]() {
+          const size_t b = total * t / nth, e = total * (t + 1) / nth;
+          for (size_t i = b; i < e; ++i) labels[i] = st[i];
+        });
+      for (auto& x : th) x.join();
+    }
+    if (K) {
+      std::vector<int> tmp(Cn * S);
+      RC_CUDA(cudaMemcpy(tmp.data(), s->out_K, sizeof(int) * Cn * S, cudaMemcpyDeviceToHost));
+      for (size_t t = 0; t < Cn * S; ++t) K[t] = tmp[t];
+    }
+    if (r) RC_CUDA(cudaMemcpy(r, s->out_r, sizeof(double) * Cn * S, cudaMemcpyDeviceToHost));
+    if (p) RC_CUDA(cudaMemcpy(p, s->out_p, sizeof(double) * Cn * S, cudaMemcpyDeviceToHost));
+    if (loglik) RC_CUDA(cudaMemcpy(loglik, s->out_ll, sizeof(double) * Cn * S, cudaMemcpyDeviceToHost));
+    if (logposterior) RC_CUDA(cudaMemcpy(logposterior, s->out_lp, sizeof(double) * Cn * S, cudaMemcpyDeviceToHost));
+  }
+  if (r_acc && ni) RC_CUDA(cudaMemcpy(r_acc, s->r_acc, Cn * ni, cudaMemcpyDeviceToHost));
+  if (sm_acc && nm) RC_CUDA(cudaMemcpy(sm_acc, s->sm_acc, Cn * nm, cudaMemcpyDeviceToHost));
+  if (sm_split && nm) RC_CUDA(cudaMemcpy(sm_split, s->sm_split, Cn * nm, cudaMemcpyDeviceToHost));
+  return RC_OK;
+}
+
 int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t* r_acc, uint8_t* sm_acc, uint8_t* sm_split) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_copy_acceptances: bad handle or chain"); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(s->device));
@@ -615,6 +668,9 @@ int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels,
   RC_CUDA(e);
   return RC_OK;
 }
+
+int64_t rc_sampler_n(const rc_sampler* s) { return s ? s->n : 0; }
+int64_t rc_sampler_nchains(const rc_sampler* s) { return s ? s->nchains : 0; }
 
 // internal accessors used by rc_post.cu
 const uint8_t* rc_sampler_dev_labels(const rc_sampler* s, int64_t* S, int64_t* n, int64_t* nchains, int* device) {

@@ -25,6 +25,9 @@ void rc_dev_free(void* p);
     }                                                                                          \
   } while (0)
 
+// int32 co-clustering counts on the device -> host fp64 counts / denom (rc_post.cu)
+int rc_counts_to_host_psm(const int* counts, size_t total, double denom, double* out);
+
 // ---- 128-bit two's complement accumulators (block totals of the fixed-point images) ------------
 struct rc_i128 {
   unsigned long long lo;

@@ -264,7 +264,7 @@ __global__ void k_colsum_upper(const double* __restrict__ U, int64_t S, double* 
 
 // D2H of the counts as int32 through two pinned staging buffers; host threads turn each chunk into counts / denom
 // (fp64) while the next chunk is in flight -- half the PCIe bytes of an fp64 copy and no pageable-memory bounce.
-static int counts_to_host_psm(const int* counts, size_t total, double denom, double* out) {
+int rc_counts_to_host_psm(const int* counts, size_t total, double denom, double* out) {
   const size_t CH = (size_t)8 << 20;                       // entries per chunk (32 MB)
   int* stage[2] = {nullptr, nullptr};
   cudaStream_t st; cudaEvent_t ev[2];
@@ -320,7 +320,7 @@ int32_t rc_sampler_psm(const rc_sampler* s, int64_t chain0, int64_t nch, double*
   int* counts = nullptr;
   RC_CUDA(cudaMalloc(&counts, sizeof(int) * (size_t)n * n));
   int st = rc_sampler_psm_counts_dev(s, chain0, nch, counts);
-  if (!st) st = counts_to_host_psm(counts, (size_t)n * n, (double)(nch * S), psm_out);   // ./ numsamples (0/0 = NaN if no samples)
+  if (!st) st = rc_counts_to_host_psm(counts, (size_t)n * n, (double)(nch * S), psm_out);   // ./ numsamples (0/0 = NaN if no samples)
   cudaFree(counts);
   return st;
 }
@@ -414,7 +414,7 @@ int32_t rc_psm(const int64_t* labels, int64_t S, int64_t n, int32_t device, doub
   if (cudaMalloc(&counts, sizeof(int) * (size_t)n * n) != cudaSuccess) { cudaFree(dL); rc_set_error("out of device memory"); return RC_ERR_CUDA; }
   st = psm_counts_device(dL, S, n, counts);
   const double t2 = now();
-  if (!st) st = counts_to_host_psm(counts, (size_t)n * n, (double)S, psm_out);
+  if (!st) st = rc_counts_to_host_psm(counts, (size_t)n * n, (double)S, psm_out);
   cudaFree(dL); cudaFree(counts);
   if (verbose) fprintf(stderr, "[rcb200] rc_psm: relabel %.3f s, upload + counts %.3f s, download + divide %.3f s\n", t1 - t0, t2 - t1, now() - t2);
   return st;

@@ -85,6 +85,52 @@ class PriorHyperparamsList:
         return "PriorHyperparamsList(" + ", ".join(f"{k}={getattr(self, k)!r}" for k in self._fields) + ")"
 
 
+class Comm:
+    """The NCCL communicator of the three exchange steps (rc_comm_* of include/rcb200.h): one per process, one process
+    per GPU.  torch.distributed (or anything else) is only the launcher that hands rank 0's 128-byte id to the others."""
+
+    _cache = {}
+
+    def __init__(self, unique_id, rank, world, device):
+        self._h = C.c_void_p()
+        self.rank, self.world, self.device = rank, world, device
+        idb = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        check(lib().rc_comm_init(ptr(idb), rank, world, device, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id():
+        idb = np.zeros(128, np.uint8)
+        check(lib().rc_comm_unique_id(ptr(idb)))
+        return idb.tobytes()
+
+    @classmethod
+    def from_torch(cls, group=None, device=None):
+        """Communicator over the ranks of a torch.distributed process group (cached per group and device); a world of
+        one without an initialised process group."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.cuda.current_device() if device is None else device
+        key = (id(group), dev)
+        if key in cls._cache:
+            return cls._cache[key]
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            box = [cls.unique_id() if rank == 0 else None]
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=group)
+            c = cls(box[0], rank, world, dev)
+        else:
+            c = cls(cls.unique_id(), 0, 1, dev)
+        cls._cache[key] = c
+        return c
+
+    def close(self):
+        L = getattr(_lib, "_lib", None)
+        if getattr(self, "_h", None) and L is not None:
+            L.rc_comm_destroy(self._h)
+            self._h = None
+
+
 class MCMCData:
     """Device-resident dissimilarity matrix (D, log D and their fixed-point images)."""
 
@@ -115,28 +161,16 @@ class MCMCData:
         return obj
 
     @classmethod
-    def from_points_sharded(cls, points, group=None, device=None):
-        """MCMCData(points) with the distance build split over the ranks of a torch.distributed process group
-        (SURVEY 8e): rank r computes a block of rows, one all_gather (NCCL) gives every GPU the whole matrix, which
-        stays on the device.  Bit-equal to from_points on one GPU.  Without a process group: this rank builds all rows."""
-        import torch
-        import torch.distributed as dist
+    def from_points_sharded(cls, points, group=None, device=None, comm=None):
+        """MCMCData(points) with the distance build split over the ranks: rank r computes a block of rows,
+        one ncclAllGather gives every GPU the whole matrix, which stays on the device (rc_comm_data_from_points).
+        Bit-equal to from_points on one GPU."""
+        comm = comm or Comm.from_torch(group, device)
         P = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
-        n, dim = P.shape
-        dev = torch.cuda.current_device() if device is None else device
-        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        rank = dist.get_rank(group) if world > 1 else 0
-        per = (n + world - 1) // world                                 # equal blocks (the last one is padded)
-        full = torch.zeros((world * per, n), dtype=torch.float64, device=torch.device("cuda", dev))
-        row0 = min(rank * per, n); nrows = min(per, n - row0)
-        mine = full[rank * per:(rank + 1) * per]
-        check(lib().rc_distm_rows_dev(ptr(P), dim, n, row0, nrows, dev, C.c_void_p(mine.data_ptr())))
-        if world > 1:
-            dist.all_gather_into_tensor(full, mine.clone(), group=group)
         obj = cls.__new__(cls)
         obj._h = C.c_void_p()
-        obj.device = dev
-        check(lib().rc_data_from_dist_dev(C.c_void_p(full.data_ptr()), n, dev, C.byref(obj._h)))
+        obj.device = comm.device
+        check(lib().rc_comm_data_from_points(comm._h, ptr(P), P.shape[1], P.shape[0], C.byref(obj._h)))
         obj.n = int(lib().rc_data_n(obj._h))
         return obj
 
@@ -246,6 +280,17 @@ class Sampler:
         check(lib().rc_sampler_copy_acceptances(self._h, chain, ptr(out["r_acc"]), ptr(out["sm_acc"]), ptr(out["sm_split"])))
         return out
 
+    def samples_all(self):
+        """The recorded outputs of every chain in one call: dict of arrays with a leading chain axis."""
+        S, n, Cn = int(lib().rc_sampler_numsamples(self._h)), self.data.n, self.nchains
+        ni, nm = self.options.numiters, self.options.numiters * self.options.numMH
+        out = dict(labels=np.empty((Cn, S, n), np.int64), K=np.empty((Cn, S), np.int64), r=np.empty((Cn, S)), p=np.empty((Cn, S)),
+                   loglik=np.empty((Cn, S)), logposterior=np.empty((Cn, S)), r_acc=np.zeros((Cn, ni), np.uint8),
+                   sm_acc=np.zeros((Cn, nm), np.uint8), sm_split=np.zeros((Cn, nm), np.uint8))
+        check(lib().rc_sampler_copy_all(self._h, ptr(out["labels"]), ptr(out["K"]), ptr(out["r"]), ptr(out["p"]), ptr(out["loglik"]),
+                                        ptr(out["logposterior"]), ptr(out["r_acc"]), ptr(out["sm_acc"]), ptr(out["sm_split"])))
+        return out
+
     def state(self, chain=0):
         lab = np.zeros(self.data.n, np.int64)
         r, p = C.c_double(), C.c_double()
@@ -271,21 +316,14 @@ class Sampler:
         nch = self.nchains - chain0 if nch is None else nch
         check(lib().rc_sampler_psm_counts_dev(self._h, chain0, nch, C.c_void_p(counts_ptr)))
 
-    def psm_allreduce(self, group=None, device=None):
+    def psm_allreduce(self, group=None, device=None, comm=None):
         """PSM over the samples of every rank (mcmc.jl:560 across chain shards): per-rank exact int32 co-clustering
-        counts stay on the device, ONE all_reduce(SUM) of the n x n matrix (NCCL over NVLink) combines them, then a
-        single divide by the global number of samples.  Without an initialised process group it is this rank's PSM."""
-        import torch
-        import torch.distributed as dist
-        n = self.data.n
-        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        counts = torch.empty((n, n), dtype=torch.int32, device=dev)
-        self.psm_counts_dev(counts.data_ptr())
-        total = torch.tensor([self.nchains * int(lib().rc_sampler_numsamples(self._h))], dtype=torch.int64, device=dev)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-        return (counts.to(torch.float64) / total.to(torch.float64)).cpu().numpy()
+        counts stay on the device, ONE ncclAllReduce(sum) of the n x n matrix combines them, then a single divide by
+        the global number of samples (rc_comm_sampler_psm)."""
+        comm = comm or Comm.from_torch(group, self.data.device if device is None else device)
+        out = np.empty((self.data.n, self.data.n))
+        check(lib().rc_comm_sampler_psm(comm._h, self._h, ptr(out), None))
+        return out
 
     def close(self):
         L = getattr(_lib, "_lib", None)
@@ -449,23 +487,16 @@ def psm_counts_dev(labels, counts_ptr, device=0):
     check(lib().rc_psm_counts_dev(ptr(L), L.shape[0], L.shape[1], device, C.c_void_p(counts_ptr)))
 
 
-def psm_sharded(labels, group=None, device=None, total=None):
-    """PSM of label vectors that are sharded over the ranks of a torch.distributed process group (BASELINE
-    configs[4]): `labels` is THIS rank's S_r x n share; exact int32 counts per rank on the device, one all_reduce(SUM)
-    of the n x n matrix (NCCL), one divide by the global number of samples.  Every rank returns the full PSM."""
-    import torch
-    import torch.distributed as dist
+def psm_sharded(labels, group=None, device=None, total=None, comm=None):
+    """PSM of label vectors that are sharded over the ranks (BASELINE configs[4]): `labels` is THIS rank's
+    S_r x n share; exact int32 counts per rank on the device, one ncclAllReduce(sum) of the n x n matrix, one divide by
+    the global number of samples (rc_comm_psm).  Every rank returns the full PSM."""
+    comm = comm or Comm.from_torch(group, device)
     L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
     S, n = L.shape
-    dev = torch.cuda.current_device() if device is None else device
-    tdev = torch.device("cuda", dev)
-    counts = torch.empty((n, n), dtype=torch.int32, device=tdev)
-    check(lib().rc_psm_counts_dev(ptr(L), S, n, dev, C.c_void_p(counts.data_ptr())))
-    tot = torch.tensor([S], dtype=torch.int64, device=tdev)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    return (counts.to(torch.float64) / tot.to(torch.float64)).cpu().numpy()
+    out = np.empty((n, n))
+    check(lib().rc_comm_psm(comm._h, ptr(L), S, n, ptr(out), None))
+    return out
 
 
 def cyclic_rows(rank, world, S):
@@ -481,30 +512,15 @@ def assemble_cyclic_rows(allrows, S):
     return allrows.permute(1, 0, 2).reshape(per * world, cols)[:S].contiguous()
 
 
-def mpel_loss_sums_sharded(labels, loss, group=None, device=None):
-    """mpel_loss_sums with the candidate samples split over the ranks of a torch.distributed process group:
-    rank r evaluates rows r, r + world, ... of the upper triangle of the pairwise loss matrix (cyclic, so the ranks
-    do equal work), one all_gather (NCCL) assembles it on every GPU, the column sums run in ascending row order --
-    bit-equal to the single-GPU result."""
-    import torch
-    import torch.distributed as dist
+def mpel_loss_sums_sharded(labels, loss, group=None, device=None, comm=None):
+    """mpel_loss_sums with the candidate samples split over the ranks: rank r evaluates rows r, r + world,
+    ... of the upper triangle of the pairwise loss matrix (cyclic, so the ranks do equal work), one ncclAllGather
+    assembles it on every GPU, the column sums run in ascending row order -- bit-equal to the single-GPU result
+    (rc_comm_mpel)."""
+    comm = comm or Comm.from_torch(group, device)
     L = np.ascontiguousarray(np.asarray(labels, dtype=np.int64))
-    S, n = L.shape
-    dev = torch.cuda.current_device() if device is None else device
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    per = (S + world - 1) // world
-    tdev = torch.device("cuda", dev)
-    mine = torch.zeros((per, S), dtype=torch.float64, device=tdev)
-    check(lib().rc_mpel_rows_dev(ptr(L), S, n, _LOSS[loss], dev, rank, world, per, C.c_void_p(mine.data_ptr())))
-    if world > 1:
-        flat = torch.empty((world * per, S), dtype=torch.float64, device=tdev)       # rank-major blocks
-        dist.all_gather_into_tensor(flat, mine, group=group)
-        upper = assemble_cyclic_rows(flat.view(world, per, S), S)
-    else:
-        upper = mine[:S].contiguous()
-    sums = np.zeros(S); best = C.c_int64()
-    check(lib().rc_mpel_finish_dev(C.c_void_p(upper.data_ptr()), S, dev, ptr(sums), C.byref(best)))
+    sums = np.zeros(L.shape[0]); best = C.c_int64()
+    check(lib().rc_comm_mpel(comm._h, ptr(L), L.shape[0], L.shape[1], _LOSS[loss], ptr(sums), C.byref(best)))
     return sums, int(best.value)
 
 

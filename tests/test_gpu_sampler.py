@@ -106,6 +106,10 @@ def test_multichain_n1000(pkg, orc):
     res, smp = run_both(pkg, orc, D, lab, params, 12, 2, 2, 5, 1, seed=77, nchains=4)
     for got, ref, st in res:
         assert_same(got, ref, st)
+    allc = smp.samples_all()                               # one-call read-back of every chain == the per-chain reads
+    for c, (got, _, _) in enumerate(res):
+        for k in got:
+            assert np.array_equal(allc[k][c], got[k]), k
     # PSM counts of the device-resident samples are exact integers
     S = res[0][1]["labels"].shape[0]
     psm = smp.psm(0, 4)

@@ -75,5 +75,36 @@ for loss in ("binder", "VI"):
         ok = np.array_equal(s1, sums) and b1 == best
         print(f"world={world} MPEL {loss} over {S.shape[0]} samples: sharded {dt * 1e3:.1f} ms; equal to one GPU: {ok}", flush=True)
         assert ok
+# BASELINE configs[4]-shaped PSM: n x n int32 counts of S samples sharded over the ranks, one ncclAllReduce (10 GB at
+# n = 50 000).  RCB200_VERBOSE=1 prints the all-reduce time and bandwidth from inside the library.
+if len(sys.argv) > 4:
+    nb, Sb = int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 2000
+    gb = np.random.default_rng(9)
+    base = np.sort(gb.integers(1, 81, size=nb))
+    mine = np.tile(base, (Sb // world, 1))
+    gr = np.random.default_rng(100 + rank)
+    flip = gr.random(mine.shape) < 0.1
+    mine[flip] = gr.integers(1, 91, size=int(flip.sum()))
+    comm = pkg.Comm.from_torch()
+    cnt = torch.zeros((nb, nb), dtype=torch.int32, device="cuda")
+    from redclust_jl_b200._lib import lib, check, ptr
+    import ctypes as C
+    for rep in range(2):
+        torch.cuda.synchronize(); dist.barrier()
+        t = time.perf_counter()
+        check(lib().rc_comm_psm(comm._h, ptr(np.ascontiguousarray(mine)), mine.shape[0], nb, None, C.c_void_p(cnt.data_ptr())))
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t
+    # bit-equality: rows of the reduced counts against a direct comparison over ALL ranks' samples
+    allS = [None] * world
+    dist.all_gather_object(allS, mine[:, :0].shape[0])
+    rows = np.random.default_rng(1).choice(nb, size=8, replace=False)
+    part = np.stack([(mine == mine[:, [i]]).sum(0) for i in rows]).astype(np.int64)
+    tp = torch.from_numpy(part).cuda(); dist.all_reduce(tp)
+    ok = bool((cnt[torch.from_numpy(rows).cuda()].to(torch.int64) == tp).all())
+    if rank == 0:
+        print(f"world={world} configs[4]-shaped PSM n={nb} S={mine.shape[0] * world} (sharded): counts + all-reduce {dt * 1e3:.1f} ms; "
+              f"8 sampled rows equal to direct label comparison over all ranks: {ok}", flush=True)
+    assert ok
 dist.barrier()
 dist.destroy_process_group()
