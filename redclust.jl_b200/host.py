@@ -19,6 +19,8 @@ task-local RNG)."""
 import ctypes as C
 import math
 import time
+import os
+
 import numpy as np
 
 from . import _lib
@@ -659,6 +661,63 @@ def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None,
     occ = _oracle_coclustering(pts, K, alpha, radius, sigma, g, device) if want else None
     return dict(points=[pts[i] for i in range(N)], distancematrix=data.D, clusts=clusts.astype(np.int64), probs=probs,
                 oracle_coclustering=occ, data=data)
+
+
+class _NpzDatasets:
+    """The package's own copy of the example data sets behind the interface of an open HDF5 file
+    (handle["example1"]["points"], keys(), close())."""
+
+    def __init__(self, path):
+        self._z = np.load(path)
+
+    def keys(self):
+        return sorted({k.split("/")[0] for k in self._z.files})
+
+    def __getitem__(self, group):
+        if group not in self.keys():
+            raise KeyError(group)
+        z = self._z
+
+        class _G:
+            def keys(self_):
+                return sorted(k.split("/")[1] for k in z.files if k.startswith(group + "/"))
+
+            def __getitem__(self_, name):
+                return z[f"{group}/{name}"]
+        return _G()
+
+    def close(self):
+        self._z.close()
+
+
+def example_datasets(path=None):
+    """example_datasets() (example_data.jl:33-35): a read-only handle to the example data sets of the main paper; close
+    it when done.  `path` (or the environment variable REDCLUST_EXAMPLE_DATA) names an HDF5 file of the reference's
+    layout -- RedClust.jl's own data/example_datasets.h5 -- which is read by the package's minimal HDF5 reader
+    (h5min.py); without it the package's own copy of the same arrays is opened.  Datasets come back in HDF5 dimension
+    order (a Julia dim x N matrix as N x dim)."""
+    path = path or os.environ.get("REDCLUST_EXAMPLE_DATA")
+    if path:
+        from .h5min import H5File
+        return H5File(path)
+    return _NpzDatasets(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "example_datasets.npz"))
+
+
+def example_dataset(n, path=None):
+    """example_dataset(n) (example_data.jl:56-71): the n-th simulated example of the main paper (generated by the
+    reference with seed 44, K = 10, N = 100, sigma = 0.25 / 0.2 / 0.18, dim = 10 / 50 / 10) as a dict with the fields of
+    the reference's named tuple: points (list of N vectors), distmatrix, clusts, probs, oracle_coclustering."""
+    if n not in (1, 2, 3):
+        raise ArgumentError("n must be 1, 2, or 3.")
+    f = example_datasets(path)
+    try:
+        eg = f["example" + str(n)]
+        x = np.asarray(eg["points"])                                   # N x dim here = Julia's dim x N, column i = point i
+        return dict(points=[x[i].copy() for i in range(x.shape[0])], distmatrix=np.asarray(eg["distance_matrix"]),
+                    clusts=np.asarray(eg["cluster_labels"]).astype(np.int64), probs=np.asarray(eg["cluster_weights"]),
+                    oracle_coclustering=np.asarray(eg["oracle_coclustering_probabilities"]))
+    finally:
+        f.close()
 
 
 def pair_stats(data, labels):

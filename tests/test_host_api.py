@@ -144,3 +144,31 @@ def test_reference_utils_cases(pkg):
              7205: "2 hrs 5 s", 7265: "2 hrs 1 min 5 s", 7325: "2 hrs 2 mins 5 s", 24 * 3600: "1 day", 2 * 24 * 3600: "2 days"}
     for t, want in cases.items():
         assert pkg.prettytime(t) == want, (t, pkg.prettytime(t), want)
+
+
+def test_example_dataset_reader(pkg, golden):
+    """example_dataset(n) / example_datasets() (example_data.jl:33-71): the package copy, and -- where the reference's
+    own HDF5 file is present (the build container) -- the same arrays through the minimal HDF5 reader."""
+    for n in (1, 2, 3):
+        d = pkg.example_dataset(n)
+        assert len(d["points"]) == 100 and d["points"][0].shape == golden[n]["points"][0].shape
+        assert np.array_equal(np.stack(d["points"]), golden[n]["points"])
+        assert np.array_equal(d["distmatrix"], golden[n]["distance_matrix"])
+        assert np.array_equal(d["clusts"], golden[n]["cluster_labels"]) and d["clusts"].dtype == np.int64
+        assert abs(d["probs"].sum() - 1) < 1e-12
+        assert np.array_equal(d["oracle_coclustering"], golden[n]["oracle_coclustering_probabilities"])
+    with pytest.raises(pkg.ArgumentError):
+        pkg.example_dataset(4)
+    f = pkg.example_datasets()
+    assert f.keys() == ["example1", "example2", "example3"]
+    assert "distance_matrix" in f["example2"].keys()
+    f.close()
+    ref = "/root/reference/data/example_datasets.h5"
+    if os.path.exists(ref):
+        h = pkg.example_datasets(ref)
+        assert h.keys() == ["example1", "example2", "example3"]
+        for n in (1, 2, 3):
+            for name in golden[n]:
+                assert np.array_equal(h[f"example{n}"][name], golden[n][name]), (n, name)
+        h.close()
+        assert np.array_equal(pkg.example_dataset(3, path=ref)["distmatrix"], golden[3]["distance_matrix"])
