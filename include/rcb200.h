@@ -93,6 +93,11 @@ int32_t rc_data_copy_row(const rc_data* d, int64_t i, double* row_out);
 int32_t rc_kmedoids(const rc_data* d, int64_t k, const int64_t* init_medoids, int64_t maxiter, int64_t* assignments,
                     int64_t* medoids, double* totalcost, int32_t* converged, int64_t* iterations);
 int32_t rc_pair_stats(const rc_data* d, const int64_t* labels, int64_t* rows_out);
+/* sample_rp(clustsizes, options, params): src/mcmc.jl:592-636, called by fitprior at src/prior.jl:80 -- the (r, p)-only
+ * chain on fixed cluster sizes (sample_r / sample_p of src/mcmc.jl:94-155; initial r ~ Gamma(eta, scale sigma) as
+ * written at :617).  r_out / p_out: numsamples values; r_acc_out (numiters bytes) may be NULL.                      */
+int32_t rc_sample_rp(const int64_t* clustsizes, int64_t nsizes, const rc_options* opt, const rc_params* par, uint64_t seed,
+                     int32_t device, double* r_out, double* p_out, uint8_t* r_acc_out);
 void rc_data_destroy(rc_data* d);
 
 /* ---- runsampler ------------------------------------------------------------------------ */

@@ -353,3 +353,13 @@ def draws(kind, a, b, count, seed=0):
     out = np.zeros(count)
     lib().rco_draws(C.c_int(k), C.c_double(a), C.c_double(b), C.c_uint64(seed), C.c_int64(count), _p(out, C.c_double))
     return out
+
+
+def sample_rp(clustsizes, options, params, seed=0):
+    """mcmc.jl:592-636 on the CPU: dict(r, p, r_acc)."""
+    cs = np.ascontiguousarray(clustsizes, dtype=np.int64)
+    S = numsamples(options)
+    out = dict(r=np.zeros(S), p=np.zeros(S), r_acc=np.zeros(options.numiters, np.uint8))
+    lib().rco_sample_rp(_p(cs, C.c_int64), C.c_int64(cs.size), C.byref(options), C.byref(params), C.c_uint64(seed),
+                        _p(out["r"], C.c_double), _p(out["p"], C.c_double), _p(out["r_acc"], C.c_uint8))
+    return out

@@ -590,6 +590,26 @@ double rco_time_chains(const double* D, int64_t n, const rc_options* O, const rc
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// sample_rp, mcmc.jl:592-636: the (r, p)-only chain on fixed cluster sizes (fitprior, prior.jl:80).
+void rco_sample_rp(const int64_t* clustsizes, int64_t nsizes, const rc_options* O, const rc_params* P, uint64_t seed,
+                   double* out_r, double* out_p, uint8_t* r_acc) {
+  std::vector<int64_t> labels;                                       // C = clustsizes[findall(clustsizes .> 0)]  (:613)
+  int64_t k = 0;
+  for (int64_t t = 0; t < nsizes; ++t)
+    if (clustsizes[t] > 0) { ++k; for (int64_t q = 0; q < clustsizes[t]; ++q) labels.push_back(k); }
+  const uint64_t key = rc_chain_key(seed, 0);
+  const double r0 = rc_gamma_mt(P->eta, key, 0, RC_SITE_INIT, 2) * P->sigma;   // :617 rand(Gamma(eta, sigma)): scale sigma
+  const double p0 = rc_beta(P->u, P->v, key, 0);                                // :618
+  State s = make_state(labels.data(), (int64_t)labels.size(), r0, p0);
+  int64_t j = 0;
+  for (int64_t i = 1; i <= O->numiters; ++i) {
+    bool ra = sample_r(s, *P, key, (uint32_t)i);                                 // :623
+    sample_p(s, *P, key, (uint32_t)i);                                           // :625
+    if (r_acc) r_acc[i - 1] = ra;
+    if (i > O->burnin && (i - O->burnin) % O->thin == 0) { out_r[j] = s.r; out_p[j] = s.p; ++j; }
+  }
+}
+
 // ---- probes for tests/test_oracle_pins.py ----------------------------------------------------------------
 // `iters` full Gibbs scans (mcmc.jl:158-256) at FIXED (r, p): the Markov chain on partitions whose exact transition
 // matrix the test builds from an independent numpy statement of the conditionals.  states: iters x n, sortlabels'd.

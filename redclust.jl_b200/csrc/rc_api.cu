@@ -672,6 +672,45 @@ int32_t rc_loglik(const rc_data* d, const rc_params* par, const int64_t* labels,
 int64_t rc_sampler_n(const rc_sampler* s) { return s ? s->n : 0; }
 int64_t rc_sampler_nchains(const rc_sampler* s) { return s ? s->nchains : 0; }
 
+// sample_rp(clustsizes, options, params) (mcmc.jl:592-636): the (r, p)-only chain of fitprior (prior.jl:80) on the device.
+int32_t rc_sample_rp(const int64_t* clustsizes, int64_t nsizes, const rc_options* opt, const rc_params* par, uint64_t seed, int32_t device,
+                     double* r_out, double* p_out, uint8_t* r_acc_out) {
+  if (!clustsizes || !opt || !par || !r_out || !p_out || nsizes < 1) { rc_set_error("rc_sample_rp: null pointer or no cluster sizes"); return RC_ERR_ARG; }
+  int st = validate_options(opt);
+  if (st) return st;
+  if (!(par->proposalsd_r > 0)) { rc_set_error("invalid hyperparameters (proposalsd_r <= 0)"); return RC_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { (void)cudaGetLastError(); rc_set_error("no CUDA device available (librcb200 has no CPU fallback)"); return RC_ERR_CUDA; }
+  RC_CUDA(cudaSetDevice(device));
+  std::vector<int> C;                                  // C = clustsizes[findall(clustsizes .> 0)]  (:613)
+  long long n = 0;
+  for (int64_t k = 0; k < nsizes; ++k) if (clustsizes[k] > 0) { C.push_back((int)clustsizes[k]); n += clustsizes[k]; }
+  if (C.empty()) { rc_set_error("rc_sample_rp: every cluster is empty"); return RC_ERR_ARG; }
+  const int K = (int)C.size();
+  const int64_t S = (opt->numiters - opt->burnin) / opt->thin;
+  int* dsz = nullptr; double *terms = nullptr, *dr = nullptr, *dp = nullptr; uint8_t* dacc = nullptr;
+  cudaError_t e = cudaMalloc(&dsz, sizeof(int) * K);
+  if (e == cudaSuccess) e = cudaMalloc(&terms, sizeof(double) * 2 * K);
+  if (e == cudaSuccess) e = cudaMalloc(&dr, sizeof(double) * std::max<int64_t>(S, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&dp, sizeof(double) * std::max<int64_t>(S, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&dacc, (size_t)opt->numiters);
+  if (e == cudaSuccess) e = cudaMemcpy(dsz, C.data(), sizeof(int) * K, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc_kparams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.n = (int)n; kp.P = *par; kp.numiters = opt->numiters; kp.burnin = opt->burnin; kp.thin = opt->thin; kp.numsamples = S;
+    kp.seed = seed; kp.chain_offset = 0;
+    rc_launch_sample_rp(kp, dsz, K, terms, dr, dp, dacc, 0);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess && S > 0) e = cudaMemcpy(r_out, dr, sizeof(double) * S, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && S > 0) e = cudaMemcpy(p_out, dp, sizeof(double) * S, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && r_acc_out) e = cudaMemcpy(r_acc_out, dacc, (size_t)opt->numiters, cudaMemcpyDeviceToHost);
+  cudaFree(dsz); cudaFree(terms); cudaFree(dr); cudaFree(dp); cudaFree(dacc);
+  RC_CUDA(e);
+  return RC_OK;
+}
+
 // internal accessors used by rc_post.cu
 const uint8_t* rc_sampler_dev_labels(const rc_sampler* s, int64_t* S, int64_t* n, int64_t* nchains, int* device) {
   if (S) *S = s->numsamples;

@@ -2926,6 +2926,36 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   }
 }
 
+// sample_rp (mcmc.jl:592-636): the (r, p)-only chain fitprior runs on the cluster sizes of its notional clustering
+// (prior.jl:80).  One warp; update_r / update_p are the sampler's own (mcmc.jl:80-155); the initial r is drawn with
+// SCALE sigma (mcmc.jl:617: rand(Gamma(eta, sigma)), where runsampler uses 1/sigma -- reproduced as written).
+__global__ void __launch_bounds__(32) k_sample_rp(const __grid_constant__ rc_kparams kp, int* sizes, int K, double* terms, double* out_r,
+                                                  double* out_p, uint8_t* out_acc) {
+  __shared__ Scal sc;
+  Ctx c;
+  c.n = kp.n; c.cap = K; c.kp = &kp; c.sizes = sizes; c.sc = &sc; c.terms = terms;
+  c.ctid = threadIdx.x; c.cwarp = 0; c.lane = threadIdx.x; c.nthr = 32; c.nwarp = 1; c.barid = 1;
+  c.key = rc_chain_key(kp.seed, (unsigned long long)kp.chain_offset);
+  if (threadIdx.x == 0) {
+    const rc_params& P = kp.P;
+    sc.r = rc_gamma_mt(P.eta, c.key, 0, RC_SITE_INIT, 2) * P.sigma;
+    sc.p = rc_beta(P.u, P.v, c.key, 0);
+    sc.K = K; sc.status = 0;
+  }
+  __syncwarp();
+  long long j = 0;
+  for (long long iter = 1; iter <= kp.numiters; ++iter) {
+    const bool ra = update_r(c, (unsigned)iter);
+    if (threadIdx.x == 0) {
+      update_p(c, (unsigned)iter);
+      if (out_acc) out_acc[iter - 1] = ra ? 1 : 0;
+      if (iter > kp.burnin && (iter - kp.burnin) % kp.thin == 0 && j < kp.numsamples) { out_r[j] = sc.r; out_p[j] = sc.p; ++j; }
+    }
+    j = __shfl_sync(0xffffffffu, j, 0);
+    __syncwarp();
+  }
+}
+
 __global__ void k_tables(rc_params P, int n, double* LGA, double* LGZ, double* LOGN) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n + 1; s += gridDim.x * blockDim.x) {
     const double sd = (double)s;
@@ -2984,6 +3014,10 @@ int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st) {
   cudaFuncSetAttribute(k_chain_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_chain_inc<<<kp.nchains, nthr, smem, st>>>(kp);
+}
+
+void rc_launch_sample_rp(const rc_kparams& kp, int* sizes, int K, double* terms, double* out_r, double* out_p, uint8_t* out_acc, cudaStream_t st) {
+  k_sample_rp<<<1, 32, 0, st>>>(kp, sizes, K, terms, out_r, out_p, out_acc);
 }
 
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st) {

@@ -67,4 +67,5 @@ bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
 size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap);
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st);
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st);
+void rc_launch_sample_rp(const rc_kparams& kp, int* sizes, int K, double* terms, double* out_r, double* out_p, uint8_t* out_acc, cudaStream_t st);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);
