@@ -70,6 +70,12 @@ int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t dev
  * from a complete matrix that already lives on the device (src/types.jl:148-162 across GPUs). */
 int32_t rc_distm_rows_dev(const double* X, int64_t dim, int64_t n, int64_t row0, int64_t nrows, int32_t device, void* D_rows_dev);
 int32_t rc_data_from_dist_dev(const void* D_dev, int64_t n, int32_t device, rc_data** out);
+/* The oracle co-clustering matrix of generatemixture (src/utils.jl:130-143) for given points and Dirichlet draws:
+ * out[i][j] = (1 / numiters) sum_t (P_t' P_t)[i][j], P_t[k][i] = W[t][k] N(x_i; radius e_k, sigma^2 I) normalised over k.
+ * X: n x dim row-major, W: numiters x K, out: n x n, all host fp64.  The stacked posteriors of a chunk of draws form one
+ * Gram product on the FP64 tensor cores (the kernel of the distance build).                                          */
+int32_t rc_oracle_coclustering(const double* X, int64_t dim, int64_t n, int64_t K, double radius, double sigma, const double* W,
+                               int64_t numiters, int32_t device, double* out);
 int64_t rc_data_n(const rc_data* d);
 /* data.D and data.logD back to the host as n x n fp64. */
 int32_t rc_data_copy_dist(const rc_data* d, double* D_out);

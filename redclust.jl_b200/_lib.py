@@ -41,6 +41,7 @@ SIGNATURES = {
     "rc_data_from_points": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int32, _P(_vp)]),
     "rc_distm_rows_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _vp]),
     "rc_data_from_dist_dev": (C.c_int32, [_vp, C.c_int64, C.c_int32, _P(_vp)]),
+    "rc_oracle_coclustering": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double, _vp, C.c_int64, C.c_int32, _vp]),
     "rc_data_n": (C.c_int64, [_vp]),
     "rc_data_copy_dist": (C.c_int32, [_vp, _vp]),
     "rc_data_copy_logdist": (C.c_int32, [_vp, _vp]),

@@ -73,7 +73,11 @@ cudaError_t rc_dev_malloc(void** p, size_t bytes) {
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
+      // The device's default pool is process-global: freed handle memory is kept for the next handle up to this bound
+      // (RCB200_POOL_KEEP_GB, default 32) and handed back to the driver beyond it, so that other allocators in the
+      // process (PyTorch's cudaMalloc cache) are not starved by a destroyed sampler's tens of gigabytes.
+      unsigned long long keep = 32ull << 30;
+      if (const char* e = getenv("RCB200_POOL_KEEP_GB")) keep = (unsigned long long)atoll(e) << 30;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     configured[dev] = true;

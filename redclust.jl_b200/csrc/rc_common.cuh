@@ -10,9 +10,9 @@
 
 // ---- error plumbing ----------------------------------------------------------------------------
 void rc_set_error(const char* fmt, ...);
-// Device memory of the long-lived handles comes from the device's stream-ordered pool with an unlimited release
-// threshold: a destroyed handle's gigabytes are reused by the next one instead of going back to the driver
-// (RCB200_NO_POOL=1: plain cudaMalloc / cudaFree).
+// Device memory of the long-lived handles comes from the device's stream-ordered pool with a bounded release
+// threshold (32 GB, RCB200_POOL_KEEP_GB): a destroyed handle's gigabytes are reused by the next one instead of going back
+// to the driver (RCB200_NO_POOL=1: plain cudaMalloc / cudaFree).
 cudaError_t rc_dev_malloc(void** p, size_t bytes);
 void rc_dev_free(void* p);
 #define RC_CUDA(call)                                                                          \
@@ -25,6 +25,8 @@ void rc_dev_free(void* p);
     }                                                                                          \
   } while (0)
 
+// pairwise Euclidean distances on the FP64 tensor cores (rc_gram.cu): X_dev n x dim row-major -> rows [row0, row0 + nrows) in D_dev (nrows x n)
+int rc_distm_dmma(const double* X_dev, int64_t dim, int64_t n, int64_t row0, int64_t nrows, double* D_dev);
 // int32 co-clustering counts on the device -> host fp64 counts / denom (rc_post.cu)
 int rc_counts_to_host_psm(const int* counts, size_t total, double denom, double* out);
 

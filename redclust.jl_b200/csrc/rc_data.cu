@@ -170,7 +170,9 @@ int finish_data(rc_data* d) {
   RC_CUDA(rc_dev_malloc((void**)&maxbits, 2 * sizeof(unsigned long long)));
   RC_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
   RC_CUDA(cudaMemset(maxbits, 0, 2 * sizeof(unsigned long long)));
-  const int grid = 148 * 8;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+  const int grid = nsm * 8;
   (void)cudaGetLastError();   // drop any stale error of an unrelated earlier call
   k_scan<<<grid, 256>>>(d->D, n, flags, maxbits);
   RC_CUDA(cudaGetLastError());
@@ -180,7 +182,9 @@ int finish_data(rc_data* d) {
   rc_dev_free(flags); rc_dev_free(maxbits);
   if (hflags[0]) { rc_set_error("D must be symmetric."); return RC_ERR_NOTSYM; }
   if (hflags[1]) {
-    rc_set_error("D must have finite entries and strictly positive off-diagonal dissimilarities (log D must be finite).");
+    rc_set_error("D must have finite entries and strictly positive off-diagonal dissimilarities: log D must be finite for the "
+                 "fixed-point image the sampler streams (the reference accepts a zero and carries log D = -Inf, src/types.jl:155). "
+                 "Remove duplicate observations or add a small jitter to them.");
     return RC_ERR_DOMAIN;
   }
   double mD, mL;
@@ -290,9 +294,13 @@ int32_t rc_data_from_points(const double* X, int64_t dim, int64_t n, int32_t dev
   cudaMemcpy(dX, X, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice);
   k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
   const unsigned nb = (unsigned)((n + DT - 1) / DT);
+  // Default: the Gram blocks on the FP64 tensor cores (rc_gram.cu, <= 1e-10 relative to the reference's fixture).
+  // RCB200_DISTM=exact: the ascending-coordinate kernel whose operation order is the oracle's (bit-equal to it);
+  // RCB200_DISTM=dmma32: round 1's 32 x 32-tile DMMA kernel (kept for comparison).
   const char* mode = getenv("RCB200_DISTM");
-  if (mode && !strcmp(mode, "dmma")) k_distm_dmma<<<dim3(nb, nb), 128>>>(dX, sq, dim, n, d->D);
-  else k_distm<<<dim3(nb, nb), 256>>>(dX, sq, dim, n, d->D);
+  if (mode && !strcmp(mode, "exact")) k_distm<<<dim3(nb, nb), 256>>>(dX, sq, dim, n, d->D);
+  else if (mode && !strcmp(mode, "dmma32")) k_distm_dmma<<<dim3(nb, nb), 128>>>(dX, sq, dim, n, d->D);
+  else if (rc_distm_dmma(dX, dim, n, 0, n, d->D) != RC_OK) { cudaFree(dX); cudaFree(sq); rc_data_destroy(d); return RC_ERR_CUDA; }
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(dX); cudaFree(sq);
   if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); rc_data_destroy(d); return RC_ERR_CUDA; }
@@ -314,8 +322,11 @@ int32_t rc_distm_rows_dev(const double* X, int64_t dim, int64_t n, int64_t row0,
     rc_set_error("out of device memory for the points"); cudaFree(dX); cudaFree(sq); return RC_ERR_CUDA;
   }
   cudaMemcpy(dX, X, sizeof(double) * (size_t)n * dim, cudaMemcpyHostToDevice);
-  k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
-  k_distm_rows<<<dim3((unsigned)((n + DT - 1) / DT), (unsigned)((nrows + DT - 1) / DT)), 256>>>(dX, sq, dim, n, row0, nrows, (double*)D_rows_dev);
+  const char* mode = getenv("RCB200_DISTM");            // same choice as rc_data_from_points: the row block equals its rows bit for bit
+  if (mode && (!strcmp(mode, "exact") || !strcmp(mode, "dmma32"))) {
+    k_sqnorm<<<(unsigned)((n + 255) / 256), 256>>>(dX, dim, n, sq);
+    k_distm_rows<<<dim3((unsigned)((n + DT - 1) / DT), (unsigned)((nrows + DT - 1) / DT)), 256>>>(dX, sq, dim, n, row0, nrows, (double*)D_rows_dev);
+  } else if (rc_distm_dmma(dX, dim, n, row0, nrows, (double*)D_rows_dev) != RC_OK) { cudaFree(dX); cudaFree(sq); return RC_ERR_CUDA; }
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(dX); cudaFree(sq);
   if (e != cudaSuccess) { rc_set_error("distance kernel failed: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }

@@ -611,32 +611,23 @@ def summarise(clusts, truth, io=None, device=0):
     print(f"Normalised Mutual Information : {t['nmi']}", file=out)
 
 
-def _oracle_coclustering(pts, K, alpha, radius, sigma, g, device, numiters=5000, batch=64):
+def _oracle_coclustering(pts, K, alpha, radius, sigma, g, device, numiters=5000):
     """utils.jl:130-143: average over 5000 Dirichlet draws w of P' P, P[j, i] = w_j N(x_i; c_j, sigma^2 I) normalised
-    over j.  The K x N log-densities are fixed; a batch of draws is one (N x BK)(BK x N) fp64 GEMM on the device
-    (torch.matmul -> cuBLAS: a plain library GEMM)."""
-    import torch
-    dev = torch.device("cuda", device)
-    X = torch.from_numpy(np.ascontiguousarray(pts)).to(dev)
+    over j.  The draws come from the host generator; the posteriors and the Gram products (chunks of draws stacked into
+    one n x (B K) operand, FP64 tensor cores) run in librcb200 (rc_oracle_coclustering)."""
+    X = np.ascontiguousarray(np.asarray(pts, dtype=np.float64))
     N, dim = X.shape
-    C = torch.zeros((K, dim), dtype=torch.float64, device=dev)
-    C[torch.arange(K), torch.arange(K)] = radius
-    d2 = (X * X).sum(1)[None, :] - 2.0 * (C @ X.T) + (C * C).sum(1)[:, None]                  # K x N
-    logpdf = -d2 / (2.0 * sigma * sigma)                                                       # the common factor cancels
-    W = torch.from_numpy(g.dirichlet(np.full(K, float(alpha)), size=numiters)).to(dev)         # numiters x K
-    acc = torch.zeros((N, N), dtype=torch.float64, device=dev)
-    for b0 in range(0, numiters, batch):
-        lw = torch.log(W[b0:b0 + batch])[:, :, None] + logpdf[None, :, :]                      # B x K x N
-        P = torch.softmax(lw, dim=1).reshape(-1, N)                                            # (B K) x N
-        acc += P.T @ P
-    return (acc / numiters).cpu().numpy()
+    W = np.ascontiguousarray(g.dirichlet(np.full(K, float(alpha)), size=numiters))             # numiters x K
+    out = np.empty((N, N))
+    check(lib().rc_oracle_coclustering(ptr(X), dim, N, K, float(radius), float(sigma), ptr(W), numiters, device, ptr(out)))
+    return out
 
 
 def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None, device=0, oracle=None):
     """generatemixture(N, K; α, dim, radius, σ, rng) (utils.jl:101-147): Dirichlet weights, sorted labels,
     simplex-vertex centres, isotropic normal points, Euclidean distance matrix (built on the GPU), and the oracle
-    co-clustering matrix (utils.jl:130-143; by default only for N <= 4000, where it costs nothing -- it is not consumed
-    by the sampler; oracle=True / False forces it)."""
+    co-clustering matrix (utils.jl:130-143, always computed as in the reference -- about a second at N = 10 000;
+    oracle=False skips it, it is not consumed by the sampler)."""
     alpha = K if alpha is None else alpha
     dim = K if dim is None else dim
     if N < 1:
@@ -657,7 +648,7 @@ def generatemixture(N, K, alpha=None, dim=None, radius=1.0, sigma=0.1, rng=None,
     pts = g.normal(0.0, sigma, size=(N, dim))
     pts[np.arange(N), clusts - 1] += radius
     data = MCMCData.from_points(pts, device=device)
-    want = (N <= 4000) if oracle is None else bool(oracle)
+    want = True if oracle is None else bool(oracle)
     occ = _oracle_coclustering(pts, K, alpha, radius, sigma, g, device) if want else None
     return dict(points=[pts[i] for i in range(N)], distancematrix=data.D, clusts=clusts.astype(np.int64), probs=probs,
                 oracle_coclustering=occ, data=data)

@@ -3,14 +3,18 @@
 # This is the Julia twin of redclust.jl_b200/host.py: it keeps RedClust.jl's API surface
 # (MCMCData / MCMCOptionsList / PriorHyperparamsList / runsampler / MCMCResult / getpointestimate,
 # /root/reference/src/RedClust.jl:32-66) and replaces the bodies of the hot-path functions by calls into the
-# sm_100a library.  Julia is not installed in the build image, so this file is exercised only where Julia exists;
-# the same ABI is exercised by the Python mirror in the test-suite.  Drop it next to RedClust.jl's src/ and
-# `include` it after types.jl (it reuses RedClust's own MCMCOptionsList / PriorHyperparamsList / MCMCResult).
+# sm_100a library.
+#
+# STATUS: EXPERIMENTAL, NEVER EXECUTED.  Julia is not installed in the build image or on the GPU boxes, so this file
+# has been read against the reference and against include/rcb200.h but not run; the same ABI is exercised by the Python
+# mirror in the test-suite.  Use it with RedClust.jl installed: `include("RedClustB200.jl"); using .RedClustB200`
+# (it reuses RedClust's own MCMCOptionsList / PriorHyperparamsList / MCMCResult types).
 module RedClustB200
 
+import RedClust
+import Clustering
 using RedClust: MCMCOptionsList, PriorHyperparamsList, MCMCResult, MCMCState, ClustLabelVector, fitprior
 using RedClust: iac_ess_acf, sortlabels
-using Clustering: kmedoids
 using StatsBase: mean_and_var, mean
 import Libdl
 
@@ -31,6 +35,27 @@ rc_params(p::PriorHyperparamsList) = rc_params(p.δ1, p.δ2, p.α, p.β, p.ζ, p
 lasterror() = unsafe_string(ccall((:rc_last_error, LIB[]), Cstring, ()))
 check(st::Integer) = st == 0 ? nothing : error(lasterror())      # ErrorException, as error(...) in src/types.jl
 
+"""
+NCCL communicator of the exchange steps (rc_comm_* of include/rcb200.h), one per process / GPU.  Rank 0 calls
+`comm_unique_id()`, the launcher (Distributed, MPI.jl, ...) hands the 128 bytes to every rank, every rank builds `Comm`.
+"""
+mutable struct Comm
+    handle::Ptr{Cvoid}
+    rank::Int; world::Int; device::Int
+    function Comm(id::Vector{UInt8}, rank::Integer, world::Integer; device::Integer = 0)
+        length(id) == 128 || error("the NCCL unique id has 128 bytes")
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve id check(ccall((:rc_comm_init, LIB[]), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), id, rank, world, device, h))
+        x = new(h[], rank, world, device)
+        finalizer(c -> ccall((:rc_comm_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), c.handle), x)
+    end
+end
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:rc_comm_unique_id, LIB[]), Int32, (Ptr{UInt8},), id))
+    return id
+end
+
 "Device-resident MCMCData (src/types.jl:145-162)."
 mutable struct MCMCData
     handle::Ptr{Cvoid}
@@ -44,11 +69,16 @@ mutable struct MCMCData
         x = new(h[], size(Dm, 1))
         finalizer(d -> ccall((:rc_data_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.handle), x)
     end
-    function MCMCData(pnts::AbstractVector{<:AbstractVector{<:Float64}}; device::Integer = 0)
+    function MCMCData(pnts::AbstractVector{<:AbstractVector{<:Float64}}; device::Integer = 0, comm::Union{Comm,Nothing} = nothing)
         X = [pnts[i][j] for j in 1:length(pnts[1]), i in 1:length(pnts)]      # dim x n, makematrix (src/utils.jl:154-156)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        GC.@preserve X check(ccall((:rc_data_from_points, LIB[]), Int32, (Ptr{Float64}, Int64, Int64, Int32, Ref{Ptr{Cvoid}}),
-                                   X, size(X, 1), size(X, 2), device, h))
+        if isnothing(comm)
+            GC.@preserve X check(ccall((:rc_data_from_points, LIB[]), Int32, (Ptr{Float64}, Int64, Int64, Int32, Ref{Ptr{Cvoid}}),
+                                       X, size(X, 1), size(X, 2), device, h))
+        else                                                                   # row blocks over the ranks + ncclAllGather
+            GC.@preserve X check(ccall((:rc_comm_data_from_points, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                                       comm.handle, X, size(X, 1), size(X, 2), h))
+        end
         x = new(h[], size(X, 2))
         finalizer(d -> ccall((:rc_data_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.handle), x)
     end
@@ -56,7 +86,6 @@ end
 function Base.getproperty(d::MCMCData, s::Symbol)
     if s === :D || s === :logD
         out = Matrix{Float64}(undef, d.n, d.n)
-        f = s === :D ? :rc_data_copy_dist : :rc_data_copy_logdist
         check(s === :D ? ccall((:rc_data_copy_dist, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(d, :handle), out) :
                          ccall((:rc_data_copy_logdist, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(d, :handle), out))
         return out
@@ -72,7 +101,8 @@ Same contract as RedClust.runsampler (src/mcmc.jl:501-590); the iteration loop r
 """
 function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList(),
                     params::Union{PriorHyperparamsList,Nothing} = nothing, init::Union{MCMCState,Nothing} = nothing;
-                    verbose = true, nchains::Integer = 1, seed::UInt64 = rand(UInt64), slot_cap::Integer = 0)
+                    verbose = true, nchains::Integer = 1, seed::UInt64 = rand(UInt64), slot_cap::Integer = 0,
+                    comm::Union{Comm,Nothing} = nothing, chain_offset::Integer = isnothing(comm) ? 0 : comm.rank * nchains)
     if isnothing(params)
         params = fitprior(data.D, "k-medoids", true; verbose = verbose)                      # :516-518
     end
@@ -81,11 +111,11 @@ function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList()
     labels = Matrix{Int64}(undef, n, nchains); r0 = Vector{Float64}(undef, nchains); p0 = similar(r0)
     if isnothing(init)                                                                       # :519-527
         k0 = params.maxK > 0 ? min(params.maxK, params.K_initial) : params.K_initial
-        lab0 = kmedoids(data.D, k0; maxiter = 1000).assignments
+        lab0 = Clustering.kmedoids(data.D, k0; maxiter = 1000).assignments
         for c in 1:nchains
             labels[:, c] .= lab0
             r = Ref(0.0); p = Ref(0.0)
-            check(ccall((:rc_init_rp, LIB[]), Int32, (Ref{rc_params}, UInt64, Int64, Ref{Float64}, Ref{Float64}), cp, seed, c - 1, r, p))
+            check(ccall((:rc_init_rp, LIB[]), Int32, (Ref{rc_params}, UInt64, Int64, Ref{Float64}, Ref{Float64}), cp, seed, chain_offset + c - 1, r, p))
             r0[c] = r[]; p0[c] = p[]
         end
     else
@@ -97,7 +127,7 @@ function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList()
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve labels r0 p0 check(ccall((:rc_sampler_create, LIB[]), Int32,
         (Ptr{Cvoid}, Ref{rc_options}, Ref{rc_params}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, UInt64, Int32, Ref{Ptr{Cvoid}}),
-        data.handle, co, cp, nchains, 0, labels, r0, p0, seed, slot_cap, h))
+        data.handle, co, cp, nchains, chain_offset, labels, r0, p0, seed, slot_cap, h))
     s = h[]
     try
         check(ccall((:rc_sampler_run, LIB[]), Int32, (Ptr{Cvoid}, Int64), s, -1))
@@ -105,8 +135,21 @@ function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList()
         check(ccall((:rc_sampler_progress, LIB[]), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Float64}), s, iters, secs))
         S = options.numsamples
         results = MCMCResult[]
+        # PSM over the chains of EVERY rank (src/mcmc.jl:560 across chain shards): int32 counts + one ncclAllReduce
+        psm_all = nothing
+        if !isnothing(comm)
+            psm_all = Matrix{Float64}(undef, n, n)
+            check(ccall((:rc_comm_sampler_psm, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}), comm.handle, s, psm_all, C_NULL))
+        end
         for c in 0:(nchains - 1)
-            res = MCMCResult(RedClustDataShim(n), options, params)
+            if ccall((:rc_sampler_chain_status, LIB[]), Int32, (Ptr{Cvoid}, Int64), s, c) != 0
+                @warn "chain $(c + 1) needed more than slot_cap simultaneously live clusters and was stopped; it is skipped"
+                continue
+            end
+            # MCMCResult's only constructor takes a RedClust.MCMCData and reads size(data.D, 1) (src/types.jl:225-247):
+            # build it on a 1 x 1 matrix and size the two point-indexed fields here
+            res = MCMCResult(RedClust.MCMCData(zeros(1, 1)), options, params)
+            res.clusts = [Vector{Int}(undef, n) for _ in 1:S]
             lab = Matrix{Int64}(undef, n, S)
             racc = Vector{UInt8}(undef, options.numiters); sacc = Vector{UInt8}(undef, options.numiters * options.numMH); sspl = similar(sacc)
             GC.@preserve lab check(ccall((:rc_sampler_copy_samples, LIB[]), Int32,
@@ -117,9 +160,13 @@ function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList()
                 res.clusts[j] .= @view lab[:, j]
             end
             res.r_acceptances .= racc .!= 0; res.splitmerge_acceptances .= sacc .!= 0; res.splitmerge_splits .= sspl .!= 0
-            psm = Matrix{Float64}(undef, n, n)
-            check(ccall((:rc_sampler_psm, LIB[]), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), s, c, 1, psm))   # :560
-            res.posterior_coclustering = psm
+            if isnothing(psm_all)
+                psm = Matrix{Float64}(undef, n, n)
+                check(ccall((:rc_sampler_psm, LIB[]), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), s, c, 1, psm))   # :560
+                res.posterior_coclustering = psm
+            else
+                res.posterior_coclustering = psm_all
+            end
             res.K_iac, res.K_ess, res.K_acf = iac_ess_acf(res.K); res.K_mean, res.K_variance = mean_and_var(res.K)   # :564-573
             res.r_iac, res.r_ess, res.r_acf = iac_ess_acf(res.r); res.r_mean, res.r_variance = mean_and_var(res.r)
             res.p_iac, res.p_ess, res.p_acf = iac_ess_acf(res.p); res.p_mean, res.p_variance = mean_and_var(res.p)
@@ -134,10 +181,6 @@ function runsampler(data::MCMCData, options::MCMCOptionsList = MCMCOptionsList()
     end
 end
 
-# MCMCResult's constructor only reads size(data.D, 1) (src/types.jl:225-227)
-struct RedClustDataShim; n::Int; end
-Base.getproperty(d::RedClustDataShim, s::Symbol) = s === :D ? zeros(getfield(d, :n), 0) : getfield(d, s)
-
 "MPEL search of getpointestimate (src/pointestimate.jl:34-59) on the GPU; loss in (\"binder\", \"omARI\", \"VI\", \"ID\")."
 function mpel(clusts::Vector{ClustLabelVector}, loss::String; device::Integer = 0)
     code = Dict("binder" => 0, "omARI" => 1, "VI" => 2, "ID" => 3)[loss]
@@ -150,7 +193,7 @@ function mpel(clusts::Vector{ClustLabelVector}, loss::String; device::Integer = 
 end
 
 "Clustering.kmedoids(dissM, k) on the resident matrix (src/prior.jl:55-71, src/mcmc.jl:519-527); init: 1-based medoids."
-function kmedoids(data::MCMCData, k::Integer, init::Vector{Int}; maxiter::Integer = 1000)
+function kmedoids_device(data::MCMCData, k::Integer, init::Vector{Int}; maxiter::Integer = 1000)
     n = getfield(data, :n)
     assign = Vector{Int64}(undef, n); med = Vector{Int64}(undef, k)
     cost = Ref{Float64}(0); conv = Ref{Int32}(0); its = Ref{Int64}(0)
@@ -172,6 +215,18 @@ function pairstats(data::MCMCData, labels::Vector{Int})
     nA = Int(t[5]); nB = n * (n - 1) ÷ 2 - nA
     return (nA = nA, sA = Float64(t[1] / big(2)^qD[]), lA = Float64(t[2] / big(2)^qL[]),
             nB = nB, sB = Float64((t[3] - t[1]) / big(2)^qD[]), lB = Float64((t[4] - t[2]) / big(2)^qL[]))
+end
+
+"sample_rp(clustsizes, options, params) (src/mcmc.jl:592-636) on the device: the (r, p)-only chain of fitprior."
+function sample_rp(clustsizes::Vector{Int}, options::MCMCOptionsList = MCMCOptionsList(), params::PriorHyperparamsList = PriorHyperparamsList();
+                   seed::UInt64 = rand(UInt64), device::Integer = 0)
+    S = options.numsamples
+    r = Vector{Float64}(undef, S); p = Vector{Float64}(undef, S)
+    cs = Int64.(clustsizes)
+    GC.@preserve cs check(ccall((:rc_sample_rp, LIB[]), Int32,
+        (Ptr{Int64}, Int64, Ref{rc_options}, Ref{rc_params}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
+        cs, length(cs), rc_options(options), rc_params(params), seed, device, r, p, C_NULL))
+    return (r = r, p = p)
 end
 
 function getpointestimate(samples::MCMCResult; method::String = "MAP", loss::Union{String,Function} = "VI")

@@ -15,12 +15,18 @@ class ArgumentError(ValueError):
 
 
 # ---- third-party pieces restated (Clustering.jl kmeans / kmedoids, Distributions.fit_mle) -----------
+def _gen(rng):
+    """One random stream per call tree: a Generator is used as is (fitprior threads a single one through the elbow scan,
+    the notional clustering and sample_rp), an int seeds a new one, None draws fresh entropy."""
+    return rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+
+
 def _kmpp_seed(row, n, k, g):
     """k-medoids++ style seeding (Clustering.jl's default :kmpp); row(i) returns row i of the dissimilarity matrix."""
     med = [int(g.integers(n))]
     mind = np.array(row(med[0]), dtype=np.float64)
     for _ in range(1, k):
-        w = mind ** 2
+        w = mind                      # Clustering.jl's kmpp-by-costs weights a point by its cost itself (squares are k-means')
         tot = w.sum()
         nxt = int(g.choice(n, p=w / tot)) if tot > 0 else int(g.integers(n))
         med.append(nxt)
@@ -34,7 +40,7 @@ def kmedoids_device(data, k, maxiter=1000, rng=None, init_medoids=None):
     import ctypes as C
     from ._lib import lib, check, ptr
     n = data.n
-    g = np.random.default_rng(0 if rng is None else rng)
+    g = _gen(rng)
     if init_medoids is None:
         def row(i):
             out = np.empty(n)
@@ -56,7 +62,7 @@ def kmedoids(D, k, maxiter=1000, rng=None):
         return kmedoids_device(D, k, maxiter=maxiter, rng=rng)
     D = np.asarray(D)
     n = D.shape[0]
-    g = np.random.default_rng(0 if rng is None else rng)
+    g = _gen(rng)
     med = _kmpp_seed(lambda i: D[i], n, k, g)
     converged = False
     assign = np.argmin(D[med], axis=0)
@@ -80,7 +86,7 @@ def kmeans(X, k, maxiter=1000, rng=None):
     X = np.asarray(X, dtype=np.float64)
     P = X.T
     n = P.shape[0]
-    g = np.random.default_rng(0 if rng is None else rng)
+    g = _gen(rng)
     cent = [P[int(g.integers(n))]]
     d2 = ((P - cent[0]) ** 2).sum(1)
     for _ in range(1, k):
@@ -186,32 +192,29 @@ def _trunc_logcdf_ratio(r, cand, sd):
     return norm.logcdf(r / sd) - norm.logcdf(cand / sd)
 
 
-def sample_rp(clustsizes, numiters=5000, burnin=None, thin=1, params=None, rng=None):
-    """mcmc.jl:592-636: (r, p)-only chain for fixed cluster sizes (default hyperparameters when called from
-    fitprior: eta = sigma = u = v = 1, proposalsd_r = 1)."""
-    g = np.random.default_rng(0 if rng is None else rng)
+def sample_rp(clustsizes, numiters=5000, burnin=None, thin=1, params=None, rng=None, device=0):
+    """sample_rp(clustsizes, options, params) (mcmc.jl:592-636): the (r, p)-only chain for fixed cluster sizes, run on
+    the device by rc_sample_rp (one warp on the sampler's own sample_r / sample_p; default hyperparameters when called
+    from fitprior: eta = sigma = u = v = 1, proposalsd_r = 1).  `rng`: an int seed, a numpy Generator (one draw seeds the
+    device stream) or None (fresh entropy)."""
+    from .host import MCMCOptionsList, PriorHyperparamsList
+    from ._lib import lib, check, ptr
+    import ctypes as C
     burnin = int(math.floor(0.2 * numiters)) if burnin is None else burnin
-    eta = sigma = u = v = sd = 1.0
-    if params is not None:
-        eta, sigma, u, v, sd = params.eta, params.sigma, params.u, params.v, params.proposalsd_r
-    C = np.asarray([c for c in clustsizes if c > 0], dtype=np.float64)
-    n, K = C.sum(), len(C)
-    r = g.gamma(eta, sigma)          # quirk Q6: scale sigma here (mcmc.jl:617)
-    p = g.beta(u, v)
-    rs, ps = [], []
-    from scipy.stats import truncnorm, norm
-    for i in range(1, numiters + 1):
-        cand = truncnorm.rvs((0 - r) / sd, np.inf, loc=r, scale=sd, random_state=g)
-        l1mp = math.log1p(-p) if p < 1 else -np.inf
-        lpc = (eta - 1) * math.log(cand) + K * (cand * l1mp - gammaln(cand)) - cand * sigma + gammaln(C - 1 + cand).sum()
-        lpr = (eta - 1) * math.log(r) + K * (r * l1mp - gammaln(r)) - r * sigma + gammaln(C - 1 + r).sum()
-        lratio = norm.logcdf(cand / sd) - norm.logcdf(r / sd)     # log pdf ratio of the two truncated normals
-        if math.log(g.random()) < min(0.0, lpc - lpr - lratio):
-            r = cand
-        p = g.beta(n - K + u, r * K + v)
-        if i > burnin and (i - burnin) % thin == 0:
-            rs.append(r); ps.append(p)
-    return dict(r=np.array(rs), p=np.array(ps))
+    opts = MCMCOptionsList(numiters=numiters, burnin=burnin, thin=thin)
+    params = PriorHyperparamsList() if params is None else params
+    if isinstance(rng, np.random.Generator):
+        seed = int(rng.integers(0, 2 ** 63 - 1))
+    elif rng is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 63 - 1))
+    else:
+        seed = int(rng)
+    cs = np.ascontiguousarray(np.asarray(clustsizes, dtype=np.int64))
+    S = opts.numsamples
+    out = dict(r=np.zeros(S), p=np.zeros(S), r_acc=np.zeros(numiters, np.uint8))
+    o, q = opts._c(), params._c()
+    check(lib().rc_sample_rp(ptr(cs), cs.size, C.byref(o), C.byref(q), C.c_uint64(seed), device, ptr(out["r"]), ptr(out["p"]), ptr(out["r_acc"])))
+    return out
 
 
 def _prepare(data, algo, diss, Kmin, Kmax, device):
@@ -251,6 +254,7 @@ def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, 
     """fitprior(data, algo, diss = false; Kmin, Kmax, verbose) -> PriorHyperparamsList   (prior.jl:22-128)."""
     from .host import PriorHyperparamsList, pair_stats
     x, N, dev, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
+    rng = _gen(rng)                                   # one stream for the elbow scan, the notional clustering and sample_rp
     if verbose:
         print("Fitting prior hyperparameters")
     clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)      # k-medoids runs on the device-resident matrix
@@ -290,6 +294,7 @@ def fitprior2(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0,
     the device.  (The reference clusters for every k in 1:N and then uses Kmin:Kmax; only that range is computed.)"""
     from .host import PriorHyperparamsList, pair_stats
     x, N, dev, Kmax = _prepare(data, algo, diss, Kmin, Kmax, device)
+    rng = _gen(rng)                                   # one stream for the elbow scan, the notional clustering and sample_rp
     if verbose:
         print("Fitting prior hyperparameters")
     clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)

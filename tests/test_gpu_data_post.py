@@ -5,7 +5,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_distance_matrix_golden_and_oracle(pkg, orc, golden):
+def test_distance_matrix_golden_and_oracle(pkg, orc, golden, monkeypatch):
+    monkeypatch.setenv("RCB200_DISTM", "exact")                                # the ascending-coordinate kernel: the oracle's operation order
     for k in (1, 2, 3):
         pts, ref = golden[k]["points"], golden[k]["distance_matrix"]
         data = pkg.MCMCData.from_points(pts)
@@ -117,10 +118,24 @@ def test_statistical_agreement_with_independent_streams(pkg, orc, golden):
     assert np.abs(gpsm - opsm).mean() < 0.03
 
 
-def test_distance_matrix_fp64_tensor_core_path(pkg, orc, golden, monkeypatch):
-    """RCB200_DISTM=dmma: Gram block on the FP64 tensor cores (mma.sync m8n8k4 f64).  Different summation order than
-    the oracle, so 1e-10 relative (north-star tolerance); symmetry and zero diagonal stay exact."""
-    monkeypatch.setenv("RCB200_DISTM", "dmma")
+@pytest.mark.parametrize("mode", [None, "dmma32"])
+def test_distance_matrix_fp64_tensor_core_path(pkg, orc, golden, monkeypatch, mode):
+    """The default distance build: Gram blocks on the FP64 tensor cores (mma.sync m8n8k4 f64 -> DMMA, 128 x 128 tiles;
+    "dmma32": round 1's small-tile kernel).  Different summation order than the oracle, so 1e-10 relative (north-star
+    tolerance) against the reference's fixture and the oracle; symmetry and zero diagonal stay exact; sizes that are
+    not multiples of the tile or of the staged chunk."""
+    if mode:
+        monkeypatch.setenv("RCB200_DISTM", mode)
+    else:
+        monkeypatch.delenv("RCB200_DISTM", raising=False)
+    for n, dim in ((1, 3), (7, 1), (129, 16), (300, 5), (257, 130)):
+        X = np.random.default_rng(n).normal(size=(n, dim))
+        D = pkg.MCMCData.from_points(X).D if n > 1 else None
+        if n > 1:
+            ref = orc.distm(X)
+            off = ~np.eye(n, dtype=bool)
+            assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+            assert (np.abs(D[off] - ref[off]) / ref[off]).max() < 1e-10
     for k in (1, 2, 3):
         pts, ref = golden[k]["points"], golden[k]["distance_matrix"]
         D = pkg.MCMCData.from_points(pts).D
@@ -306,7 +321,7 @@ def test_reference_datagen_cases(pkg):
     from redclust_jl_b200.host import _oracle_coclustering
     X = np.asarray(pnts)
     g = np.random.default_rng(9)
-    got = _oracle_coclustering(X, K, 10.0, 1.0, sig, np.random.default_rng(9), 0, numiters=3, batch=2)
+    got = _oracle_coclustering(X, K, 10.0, 1.0, sig, np.random.default_rng(9), 0, numiters=3)
     W = g.dirichlet(np.full(K, 10.0), size=3)
     C = np.eye(K, dim)
     ref = np.zeros((N, N))
@@ -315,3 +330,49 @@ def test_reference_datagen_cases(pkg):
         P = pdf / pdf.sum(0, keepdims=True)
         ref += P.T @ P
     assert np.allclose(got, ref / 3, rtol=1e-10, atol=1e-14)
+
+
+def test_sample_rp_matches_oracle(pkg, orc):
+    """sample_rp (mcmc.jl:592-636, the (r, p)-only chain of fitprior) on the device: bit-identical to the oracle's
+    restatement on the same structured stream, with the default and with fitted hyperparameters."""
+    from redclust_jl_b200.prior import sample_rp
+    sizes = [10, 0, 12, 9, 11, 0, 58]
+    for params, kw in ((None, dict(eta=1.0, sigma=1.0, u=1.0, v=1.0, proposalsd_r=1.0)),
+                       (pkg.PriorHyperparamsList(eta=4.0, sigma=2.0, u=2.0, v=20.0), dict(eta=4.0, sigma=2.0, u=2.0, v=20.0))):
+        got = sample_rp(sizes, numiters=600, burnin=100, thin=3, params=params, rng=17)
+        ref = orc.sample_rp(sizes, orc.Options(600, 100, 3, 5, 1), orc.make_params(**kw), seed=17)
+        assert len(got["r"]) == 166
+        for k in ("r", "p", "r_acc"):
+            assert np.array_equal(got[k], ref[k]), k
+        assert np.all(got["r"] > 0) and np.all((got["p"] > 0) & (got["p"] < 1)) and 0 < got["r_acc"].mean() < 1
+
+
+def test_generatemixture_oracle_coclustering(pkg, golden):
+    """generatemixture's oracle co-clustering matrix (utils.jl:130-143) on the FP64 tensor cores: (i) against a direct
+    numpy evaluation with the same Dirichlet draws, (ii) against the matrix the reference ships for the same points in
+    data/example_datasets.h5 (5000 different draws there: Monte Carlo error only)."""
+    import ctypes as C
+    from redclust_jl_b200._lib import lib, check, ptr
+    g = np.random.default_rng(3)
+    for k, sigma in ((1, 0.25), (3, 0.18)):
+        pts, cc = golden[k]["points"], golden[k]["oracle_coclustering_probabilities"]
+        n, dim = pts.shape
+        K, T = 10, 700
+        W = np.ascontiguousarray(g.dirichlet(np.full(K, 10.0), size=T))
+        out = np.zeros((n, n))
+        check(lib().rc_oracle_coclustering(ptr(np.ascontiguousarray(pts)), dim, n, K, 1.0, sigma, ptr(W), T, 0, ptr(out)))
+        centres = np.eye(K, dim)
+        d2 = ((pts[:, None, :] - centres[None, :, :]) ** 2).sum(-1)                   # n x K
+        ref = np.zeros((n, n))
+        for t in range(T):
+            P = W[t][None, :] * np.exp(-d2 / (2 * sigma * sigma))
+            P /= P.sum(1, keepdims=True)
+            ref += P @ P.T
+        ref /= T
+        assert np.allclose(out, ref, rtol=1e-10, atol=1e-13)
+        assert np.array_equal(out, out.T)
+        assert np.abs(out - cc).max() < 0.05 and np.abs(out - cc).mean() < 0.005
+    mix = pkg.generatemixture(300, 6, alpha=6, sigma=0.2, dim=8, rng=5)
+    occ = mix["oracle_coclustering"]
+    same = mix["clusts"][:, None] == mix["clusts"][None, :]
+    assert occ.shape == (300, 300) and np.array_equal(occ, occ.T) and occ[same].mean() > occ[~same].mean() + 0.3

@@ -115,12 +115,10 @@ def test_fitprior_and_kmedoids_host(pkg, golden):
     D = golden[1]["distance_matrix"]
     r = pkg.kmedoids(D, 10)
     assert r["assignments"].min() == 1 and r["assignments"].max() == 10 and r["converged"]
-    from redclust_jl_b200.prior import detectknee, gamma_mle_shape, sample_rp, sampleK, sampledist
+    from redclust_jl_b200.prior import detectknee, gamma_mle_shape, sampleK, sampledist
     assert detectknee([1, 2, 3, 4, 5], [10, 4, 2, 1.5, 1.2])[0] == 2
     x = np.random.default_rng(0).gamma(5.0, 2.0, 20000)
     assert abs(gamma_mle_shape(x) - 5.0) < 0.2
-    t = sample_rp([10, 12, 9, 11], numiters=300)
-    assert len(t["r"]) == 240 and np.all(t["r"] > 0) and np.all((t["p"] > 0) & (t["p"] < 1))
     p = pkg.PriorHyperparamsList(eta=4.0, sigma=2.0, u=2.0, v=20.0, alpha=10.0, beta=5.0, delta1=3.0)
     assert sampleK(p, 5, 30).shape == (5,) and sampledist(p, "intracluster", 4).shape == (4,)
     with pytest.raises(ValueError):
