@@ -153,6 +153,10 @@ int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out);
  * valid and rc_sampler_overflowed tells how many chains to skip.                                 */
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain);
 int64_t rc_sampler_overflowed(const rc_sampler* s);
+/* Diagnostic (no reference equivalent): the sampler keeps, per chain, the sums of every row of D / log D by cluster and
+ * the cluster-by-cluster block sums incrementally (exact integers).  This rebuilds both from the current labels and
+ * counts the 64-bit words that differ -- 0 / 0 unless an update was lost; -1 / -1 in streaming mode.                */
+int32_t rc_sampler_check_sums(const rc_sampler* s, int64_t* mismatches_S, int64_t* mismatches_W);
 /* Posterior co-clustering counts of the device-resident samples of chains [chain0, chain0+nch):
  * sum(adjacencymatrix.(clusts)) (src/mcmc.jl:560, src/utils.jl:59-63) as exact int32 counts in a
  * DEVICE buffer of n*n int32 (e.g. a torch tensor's data_ptr, so the caller can all-reduce it

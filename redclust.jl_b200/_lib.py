@@ -65,6 +65,7 @@ SIGNATURES = {
     "rc_sampler_copy_state": (C.c_int32, [_vp, C.c_int64, _vp, _P(C.c_double), _P(C.c_double)]),
     "rc_sampler_chain_status": (C.c_int32, [_vp, C.c_int64]),
     "rc_sampler_overflowed": (C.c_int64, [_vp]),
+    "rc_sampler_check_sums": (C.c_int32, [_vp, _P(C.c_int64), _P(C.c_int64)]),
     "rc_sampler_copy_stats": (C.c_int32, [_vp, _vp]),
     "rc_sampler_psm_counts_dev": (C.c_int32, [_vp, C.c_int64, C.c_int64, _vp]),
     "rc_sampler_psm": (C.c_int32, [_vp, C.c_int64, C.c_int64, _vp]),

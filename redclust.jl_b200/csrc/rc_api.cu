@@ -43,7 +43,7 @@ struct rc_sampler {
   rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
-  double2* sc2;                // incremental mode: [nchains][cap][inc_nthr] scratch of the scan
+  double2* Cc; unsigned *Vv, *epochs;   // incremental mode: cached per-slot terms, their epochs, the slots' epochs
   longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
@@ -175,7 +175,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.sc2 = s->sc2;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -221,7 +221,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
-  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S); rc_dev_free(s->sc2);
+  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S); rc_dev_free(s->Cc); rc_dev_free(s->Vv); rc_dev_free(s->epochs);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -312,7 +312,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   // re-reduces every row against the labels (no per-chain matrix; needed when nchains * cap * n * 16 B does not fit).
   {
     const char* env = getenv("RCB200_SCAN");
-    const size_t needS = sizeof(longlong2) * (size_t)nchains * cap * n;
+    const size_t needS = (sizeof(longlong2) + sizeof(double2) + sizeof(unsigned)) * (size_t)nchains * cap * n;   // row sums + cached terms + their epochs
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
     bool want = !opt_loglik_only && needS <= freeb / 10 * 6;
@@ -337,7 +337,10 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     if (getenv("RCB200_VERBOSE")) fprintf(stderr, "[rcb200] scan mode: %s (S needs %.2f GB, %.2f GB free), %d threads per chain, %zu B shared memory (%d split-merge members)\n", s->inc ? "incremental" : "streaming", needS / 1e9, freeb / 1e9, nthr, s->inc_smem, s->inc_mcap);
   }
   s->terms_stride = (size_t)std::max(cap * cap, 8192);
-  if (s->inc) { TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->sc2, (size_t)nchains * cap * s->inc_nthr)); }
+  if (s->inc) {
+    TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->Cc, (size_t)nchains * cap * n)); TRY(dalloc(&s->Vv, (size_t)nchains * cap * n));
+    TRY(dalloc(&s->epochs, (size_t)nchains * cap));
+  }
   TRY(dalloc(&s->T, (opt->numMH > 0 && !s->inc) ? (size_t)nchains * n * cap : 1));
   if (opt->numMH > 1) {
     TRY(dalloc(&s->WDbak, (size_t)nchains * cap * cap)); TRY(dalloc(&s->WLbak, (size_t)nchains * cap * cap));
@@ -394,6 +397,11 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRYC(cudaMemcpy(s->r, init_r, sizeof(double) * nchains, cudaMemcpyHostToDevice));
   TRYC(cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice));
   TRYC(cudaMemset(s->status, 0, sizeof(int) * nchains));
+  if (s->inc) {
+    TRYC(cudaMemset(s->Vv, 0, sizeof(unsigned) * (size_t)nchains * cap * n));          // no cached entry is valid
+    std::vector<unsigned> ones((size_t)nchains * cap, 1u);
+    TRYC(cudaMemcpy(s->epochs, ones.data(), sizeof(unsigned) * ones.size(), cudaMemcpyHostToDevice));
+  }
   TRYC(cudaMemset(s->stats, 0, sizeof(long long) * 16 * nchains));
   TRYC(cudaMemset(s->r_acc, 0, (size_t)nchains * opt->numiters));
   TRYC(cudaMemset(s->sm_acc, 0, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
@@ -636,6 +644,22 @@ int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out) {
 }
 
 int64_t rc_sampler_overflowed(const rc_sampler* s) { return s ? s->overflowed : 0; }
+
+// Invariant check of the incremental scan mode: rebuilds every chain's row sums S and block sums W from its current
+// labels and counts the 64-bit words that differ from the incrementally maintained ones (both must be 0).  In streaming
+// mode there is nothing to compare: both counts are returned as -1.
+int32_t rc_sampler_check_sums(const rc_sampler* s, int64_t* mismatches_S, int64_t* mismatches_W) {
+  if (!s || !mismatches_S || !mismatches_W) { rc_set_error("rc_sampler_check_sums: null pointer"); return RC_ERR_ARG; }
+  *mismatches_S = -1; *mismatches_W = -1;
+  if (!s->inc || !s->W_ready) return RC_OK;
+  RC_CUDA(cudaSetDevice(s->device));
+  rc_kparams kp;
+  fill_kparams(s, kp);
+  long long a = 0, b = 0;
+  if (rc_inc_check(kp, &a, &b, s->stream)) { rc_set_error("rc_sampler_check_sums: rebuild failed (out of memory?)"); return RC_ERR_CUDA; }
+  *mismatches_S = a; *mismatches_W = b;
+  return RC_OK;
+}
 
 int32_t rc_sampler_chain_status(const rc_sampler* s, int64_t chain) {
   if (!s || chain < 0 || chain >= s->nchains) { rc_set_error("rc_sampler_chain_status: bad handle or chain"); return RC_ERR_ARG; }

@@ -155,7 +155,9 @@ struct Ctx {
   uint8_t* live;          // incremental mode (shared memory): live slots, ascending
   double* tabs;           // incremental mode (shared memory): [6][cap] lgamma(alpha + delta1 s), lgamma(zeta + delta2 s), prior term at the slot's size / at size - 1
   int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
-  double2* sc2;           // incremental mode (global): [cap][nthr] per-slot terms of the rows of a batch
+  double2* Cc;            // incremental mode (global): [cap][n] cached per-slot terms, see inc_eval_row
+  unsigned* Vv;           // incremental mode (global): [cap][n] slot epoch of each cached entry
+  unsigned* ep;           // incremental mode (shared memory): [cap] current epoch of every slot
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
   longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
@@ -1470,6 +1472,20 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
       const int stepi = warp * RC_RS_B + st;           // step within the batch
       const int pos = pos0 + stepi;
       const bool on = stepi < nb;
+      if (nwact <= 2 && warp >= nwact && mt <= 1024) {
+        // Short runs: a move is likely within the next few steps, and its update gathers the mover's row at every member
+        // column (DRAM latency on the critical path).  The warps that sit this batch out pull those entries towards L2
+        // for the first steps of the batch while the evaluating warps are busy.
+        const int npf = min(nb, 4);
+        const int nidle = (NW - nwact) * 32, me = (warp - nwact) * 32 + lane;
+        for (int q = me; q < mt; q += nidle) {
+          const int xq = c.Slist[q];
+          for (int u = 0; u < npf; ++u) {
+            const longlong2* pr = c.DL + (size_t)c.Slist[pos0 + u] * c.n + xq;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+          }
+        }
+      }
       int y = 0, cur = 0, cnew = 0, k = 0;
       double lt = 0.0;
       if (on) {
@@ -1881,6 +1897,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
         const int y = c.Slist[q], from = c.origM[q], to = c.lab[y];
         if (from != to) inc_update_S(c, y, from, to);
       }
+      for (int s2 = tid; s2 < cap; s2 += c.nthr) c.ep[s2] += 1;            // cached per-slot terms: all stale
     }
   } else {
     // restore the labels of the members (the proposal lived in place)
@@ -1921,9 +1938,8 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 // ------------------------------------------------------------------------------------------------
 
 // One row of the scan, evaluated by ONE thread (lane = row: the 32 lanes of a warp hold 32 consecutive rows, so the loads
-// of S[k][i .. i+31] are one 512-byte segment and no lane idles on an absent candidate).  Per-slot terms go through a
-// per-chain scratch column (sc[k * RB], L1 / L2' then the log-probability) because they are needed again once the
-// canonical sum L2_i is known.  Returns the chosen slot, or -2 when a new cluster is a candidate and no slot is free.
+// of S[k][i .. i+31] are one 512-byte segment and no lane idles on an absent candidate).  Returns the chosen slot, or -2
+// when a new cluster is a candidate and no slot is free.
 #define RC_INC_WARPROWS 128   // batches of at most this many expected rows are evaluated one row per warp
 #define RC_NZMAX 37.0   // Gumbel noise -log(-log u) <= 36.74 for every 53-bit u < 1: candidates further than this below the leader cannot win
 // What a row evaluation reads, passed BY VALUE: inc_eval_row is deliberately not inlined (its register allocation stays
@@ -1940,12 +1956,20 @@ struct RowCtx {
   const Scal* sc;
   const rc_kparams* kp;
   unsigned long long key;
+  double2* Cc;               // [cap][n] cached per-slot terms (L1, L2') of every point attached elsewhere, see inc_eval_row
+  unsigned* Vv;              // [cap][n] epoch of the slot at which the cached entry was computed (0: never)
+  const unsigned* ep;        // [cap] current epoch of every slot (shared memory)
 };
 __device__ __forceinline__ double inc_noise(const RowCtx& c, unsigned it, int i, int kk) {          // utils.jl:4-5
   const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
   return -rc_log(-rc_log((kk & 1) ? dr.u1 : dr.u0));
 }
-__device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, double2* __restrict__ sc, int RB) {
+// Per-slot terms are CACHED across sweeps: L1 and L2' of (slot k, point i) depend only on S[k][i] and the size of k, i.e.
+// on cluster k alone, which carries an epoch that is bumped whenever it gains or loses a point.  An entry whose stored
+// epoch equals the slot's is what a fresh evaluation would give (same formula, same inputs, same bits); anything else is
+// recomputed and stored.  The point's own slot (evaluated with the point detached) is never cached.  A chain at
+// equilibrium therefore spends two logarithms per row instead of two per (row, cluster).
+__device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int n = c.n, cap = c.cap;
@@ -1961,21 +1985,30 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, dou
   if (hasnew && e < 0) return -2;
   const longlong2* __restrict__ Si = c.S + i;
   const double* __restrict__ tabs = c.tabs;
-  // ---- pass 1: per-slot terms (:206-242), four slots at a time: the four loads of S are in flight together and the
-  //      eight logarithms interleave ----
+  // ---- pass 1: per-slot terms (:206-242), four slots at a time (loads in flight together, logarithms interleaved);
+  //      cached entries of unchanged clusters are kept, the others are recomputed and stored ----
+  double2* __restrict__ Ci = c.Cc + i;
+  unsigned* __restrict__ Vi = c.Vv + i;
+  double2 ownv = make_double2(0.0, 0.0);
   for (int idx0 = 0; idx0 < nlive; idx0 += 4) {
     int k[4];
-    longlong2 sv[4];
+    unsigned tag[4], epk[4];
+    bool need[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       k[u] = idx0 + u < nlive ? (int)c.live[idx0 + u] : -1;
       if (k[u] == li && single) k[u] = -1;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sv[u] = k[u] >= 0 ? Si[(size_t)k[u] * n] : make_longlong2(0, 0);
+    for (int u = 0; u < 4; ++u) { tag[u] = (k[u] >= 0 && k[u] != li) ? Vi[(size_t)k[u] * n] : 0u; epk[u] = k[u] >= 0 ? c.ep[k[u]] : 0u; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) need[u] = k[u] >= 0 && (k[u] == li || tag[u] != epk[u]);
+    longlong2 sv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sv[u] = need[u] ? Si[(size_t)k[u] * n] : make_longlong2(0, 0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (k[u] < 0) continue;
+      if (!need[u]) continue;
       const bool own = k[u] == li;
       if (own) { sv[u].x -= self.x; sv[u].y -= self.y; }                    // :193-194 detach i
       const int szs = c.sizes[k[u]] - (own ? 1 : 0);
@@ -1987,9 +2020,11 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, dou
       const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
       const double L1 = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
       const double L2p = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-      sc[(size_t)k[u] * RB] = make_double2(L1, L2p);
+      if (own) ownv = make_double2(L1, L2p);
+      else { Ci[(size_t)k[u] * n] = make_double2(L1, L2p); Vi[(size_t)k[u] * n] = epk[u]; }
     }
   }
+  auto terms = [&](int k) -> double2 { return k == li ? ownv : Ci[(size_t)k * n]; };
   // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
   //      xor-butterfly tree over the 32 classes (16, 8, 4, 2, 1) as lane 0 of a warp would evaluate it ----
   double L2i = 0.0;
@@ -2014,7 +2049,7 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, dou
 #pragma unroll
               for (int w = 0; w < RC_NS; ++w) {
                 const int k = r + 32 * w;
-                if (k < cap && c.sizes[k] > 0 && !(single && k == li)) a += sc[(size_t)k * RB].y;
+                if (k < cap && c.sizes[k] > 0 && !(single && k == li)) a += terms(k).y;
               }
               t1 = b16 == 0 ? a : t1 + a;
             }
@@ -2030,7 +2065,7 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i, dou
   }
   // log-probability of live slot k (:244-247) from the stored terms -- evaluated identically wherever it is needed
   auto logprob = [&](int k) -> double {
-    const double2 v = sc[(size_t)k * RB];
+    const double2 v = terms(k);
     const double L2 = L2i - v.y;
     return (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + (v.x + (P.repulsion ? L2 : copysign(0.0, L2)));
   };
@@ -2295,6 +2330,7 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
       c.tabs[5 * cap + s] = c.LPR[sz > 1 ? sz - 1 : 1];
     }
   }
+  if (only_a >= 0 && lane == 0) { c.ep[only_a] += 1; c.ep[only_b] += 1; }       // clusters a and b changed: their cached terms are stale
   if (lane == 0) { sh->nlive = base; sh->e0 = e0; sh->narrow = (base == 0 || c.live[base - 1] < 64) && (e0 >= 0 && e0 < 64); }
   __syncwarp();
 }
@@ -2306,10 +2342,9 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   if (tid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; sh->nmoves = 0; }
   if (c.cwarp == 0) inc_build_tables(c);
   csync(c);
-  double2* const sc = c.sc2 + tid;
   RowCtx rc;
   rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.live = c.live;
-  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key;
+  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.Vv = c.Vv; rc.ep = c.ep;
   int batch = 0, i0 = 0;
   // Rows per batch follow the observed run length between moves.  Long runs: one row per THREAD (throughput: no lane
   // idles, coalesced loads).  Short runs (nrows <= RC_INC_WARPROWS): one row per WARP (latency: a row's slots are spread
@@ -2334,7 +2369,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     } else {
       const int i = i0 + tid;
       if (tid < nrows && i < n) {
-        const int cnew = inc_eval_row(rc, it, i, sc, NT);
+        const int cnew = inc_eval_row(rc, it, i);
         c.res[tid] = cnew;
         if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], tid);
       }
@@ -2419,7 +2454,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, tabs, res, mAB, mDG, mL2s, total; };
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, tabs, res, ep, mAB, mDG, mL2s, total; };
 __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   IncLayout L;
   size_t o = 0;
@@ -2436,6 +2471,7 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   L.live = take(cap);
   L.tabs = take(sizeof(double) * 6 * cap);
   L.res = take(sizeof(int) * 512);
+  L.ep = take(sizeof(unsigned) * cap);
   L.mAB = take(sizeof(longlong4) * mcap);
   L.mDG = take(sizeof(longlong2) * mcap);
   L.mL2s = take(sizeof(double2) * mcap);
@@ -2465,6 +2501,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.live = smem + L.live;
     c.tabs = reinterpret_cast<double*>(smem + L.tabs);
     c.res = reinterpret_cast<int*>(smem + L.res);
+    c.ep = reinterpret_cast<unsigned*>(smem + L.ep);
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2480,7 +2517,8 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   c.WL = kp.WL + (size_t)ch * cap * cap;
   c.T = nullptr;
   c.S = kp.S + (size_t)ch * cap * n;
-  c.sc2 = kp.sc2 + (size_t)ch * cap * blockDim.x;
+  c.Cc = kp.Cc + (size_t)ch * cap * n;
+  c.Vv = kp.Vv + (size_t)ch * cap * n;
   c.WDbak = kp.WDbak ? kp.WDbak + (size_t)ch * cap * cap : nullptr;
   c.WLbak = kp.WLbak ? kp.WLbak + (size_t)ch * cap * cap : nullptr;
   c.labbak = kp.labbak ? kp.labbak + (size_t)ch * n : nullptr;
@@ -2498,7 +2536,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   const int tid = c.ctid, nt = c.nthr;
 
   for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
-  for (int s = tid; s < cap; s += nt) c.sizes[s] = kp.sizes[(size_t)chain * cap + s];
+  for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.ep[s] = kp.epochs[(size_t)chain * cap + s]; }
   if (tid == 0) {
     Scal& s = *c.sc;
     s.r = kp.r[chain]; s.p = kp.p[chain];
@@ -2553,6 +2591,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
           const int from = c.lab[j], to = c.labbak[j];
           if (from != to) inc_update_S(c, j, from, to);
         }
+        for (int s2 = tid; s2 < cap; s2 += nt) c.ep[s2] += 1;    // cached per-slot terms: all stale
         csync(c);
         for (int j = tid; j < n; j += nt) c.lab[j] = c.labbak[j];
         for (int s = tid; s < cap; s += nt) c.sizes[s] = c.szbak[s];
@@ -2585,7 +2624,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   }
   csync(c);
   for (int j = tid; j < n; j += nt) kp.labels[(size_t)chain * n + j] = c.lab[j];
-  for (int s = tid; s < cap; s += nt) kp.sizes[(size_t)chain * cap + s] = c.sizes[s];
+  for (int s = tid; s < cap; s += nt) { kp.sizes[(size_t)chain * cap + s] = c.sizes[s]; kp.epochs[(size_t)chain * cap + s] = c.ep[s]; }
   if (tid == 0) { kp.r[chain] = c.sc->r; kp.p[chain] = c.sc->p; kp.status[chain] = c.sc->status; }
 }
 
@@ -2707,7 +2746,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.tabs = nullptr; c.res = nullptr; c.sc2 = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.Vv = nullptr; c.ep = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
@@ -3011,6 +3050,37 @@ int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st
   k_initw_from_S<<<dim3(kp.cap, kp.nchains), 256, 0, st>>>(kp.S, kp.n, kp.labels, kp.sizes, kp.cap, kp.WD, kp.WL);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
+// Self-check of the incrementally maintained sums (compute-sanitizer is not available on the target pool, so the
+// invariant is checked directly): rebuild S and W of every chain from its labels into scratch and count the entries
+// that differ from the maintained ones.  Exact integers: any lost or doubled update shows up as a mismatch.
+__global__ void k_count_diff(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, size_t words,
+                             unsigned long long* __restrict__ ndiff) {
+  unsigned long long local = 0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < words; t += (size_t)gridDim.x * blockDim.x) local += a[t] != b[t];
+  if (local) atomicAdd(ndiff, local);
+}
+int rc_inc_check(const rc_kparams& kp, long long* mismatches_S, long long* mismatches_W, cudaStream_t st) {
+  const size_t per = (size_t)kp.cap * kp.n, perW = (size_t)kp.cap * kp.cap;
+  longlong2* S2 = nullptr; rc_i128 *WD2 = nullptr, *WL2 = nullptr; unsigned long long* nd = nullptr;
+  if (cudaMalloc(&S2, sizeof(longlong2) * per * kp.nchains) != cudaSuccess || cudaMalloc(&WD2, sizeof(rc_i128) * perW * kp.nchains) != cudaSuccess ||
+      cudaMalloc(&WL2, sizeof(rc_i128) * perW * kp.nchains) != cudaSuccess || cudaMalloc(&nd, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaFree(S2); cudaFree(WD2); cudaFree(WL2); cudaFree(nd); return 1;
+  }
+  rc_kparams k2 = kp;
+  k2.S = S2; k2.WD = WD2; k2.WL = WL2;
+  int rc = rc_launch_inc_init(k2, false, st);
+  cudaMemsetAsync(nd, 0, 2 * sizeof(unsigned long long), st);
+  // W: only the entries (k <= t) of live slots are maintained / rebuilt; dead slots hold zeros in both
+  k_count_diff<<<1024, 256, 0, st>>>((const unsigned long long*)kp.S, (const unsigned long long*)S2, per * kp.nchains * 2, nd);
+  k_count_diff<<<256, 256, 0, st>>>((const unsigned long long*)kp.WD, (const unsigned long long*)WD2, perW * kp.nchains * 2, nd + 1);
+  k_count_diff<<<256, 256, 0, st>>>((const unsigned long long*)kp.WL, (const unsigned long long*)WL2, perW * kp.nchains * 2, nd + 1);
+  unsigned long long h[2] = {0, 0};
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaMemcpy(h, nd, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+  cudaFree(S2); cudaFree(WD2); cudaFree(WL2); cudaFree(nd);
+  *mismatches_S = (long long)h[0]; *mismatches_W = (long long)h[1];
+  return rc;
+}
+
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st) {
   cudaFuncSetAttribute(k_chain_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_chain_inc<<<kp.nchains, nthr, smem, st>>>(kp);

@@ -47,7 +47,9 @@ struct rc_kparams {
   longlong2* DG;        // [nchains][n+2]  diagonal entries DL[x][x] of the split-merge members
   double* terms;        // [nchains][terms_stride]  log-likelihood terms / reduction scratch
   size_t terms_stride;  // max(cap*cap, 8192) doubles
-  double2* sc2;         // [nchains][cap][threads per chain]  incremental mode: per-slot terms of the rows of a batch
+  double2* Cc;          // [nchains][cap][n]  incremental mode: cached per-slot terms (L1, L2') of every (slot, point)
+  unsigned* Vv;         // [nchains][cap][n]  slot epoch at which each cached entry was computed (0: never)
+  unsigned* epochs;     // [nchains][cap]     current epoch of every slot (>= 1)
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
@@ -66,6 +68,7 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
 bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
 size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap);
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st);
+int rc_inc_check(const rc_kparams& kp, long long* mismatches_S, long long* mismatches_W, cudaStream_t st);
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st);
 void rc_launch_sample_rp(const rc_kparams& kp, int* sizes, int K, double* terms, double* out_r, double* out_p, uint8_t* out_acc, cudaStream_t st);
 void rc_launch_tables(const rc_params& P, int n, double* LGA, double* LGZ, double* LOGN, cudaStream_t st);

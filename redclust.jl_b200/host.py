@@ -260,6 +260,13 @@ class Sampler:
         """0, or RC_ERR_SLOTS (-5) when the chain needed more than slot_cap simultaneously live clusters and stopped."""
         return int(lib().rc_sampler_chain_status(self._h, chain))
 
+    def check_sums(self):
+        """(mismatching words of the row sums, of the block sums) after rebuilding both from the labels: (0, 0) when the
+        incremental scan mode kept them exact, (-1, -1) in streaming mode."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().rc_sampler_check_sums(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def overflowed(self):
         """Number of chains stopped by the slot capacity (run() raises only when every chain stopped)."""
         return int(lib().rc_sampler_overflowed(self._h))

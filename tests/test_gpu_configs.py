@@ -40,6 +40,7 @@ def replay(pkg, orc, n, K, dim, sigma, nchains, iters, burnin, thin, seed, mode=
         if mode:
             os.environ.pop("RCB200_SCAN") if old is None else os.environ.__setitem__("RCB200_SCAN", old)
     smp.run(-1)
+    assert smp.check_sums() in ((0, 0), (-1, -1))
     refs = oracle_chains(orc, D, (iters, burnin, thin, 5, 1), oparams(orc, params), lab, rp, seed, range(nchains))
     moved = 0
     for c in range(nchains):

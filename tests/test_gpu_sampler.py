@@ -18,6 +18,7 @@ def run_both(pkg, orc, D, labels, params, numiters, burnin, thin, numGibbs, numM
     rp = [pkg.init_rp(params, seed, c) for c in range(nchains)]
     smp = pkg.Sampler(data, opts, params, labs, [x[0] for x in rp], [x[1] for x in rp], seed=seed, slot_cap=slot_cap)
     smp.run(-1)
+    assert smp.check_sums() in ((0, 0), (-1, -1))            # incrementally maintained sums == a rebuild from the labels
     out = []
     for c in range(nchains):
         got = smp.samples(c)
