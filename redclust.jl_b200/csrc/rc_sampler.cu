@@ -153,6 +153,7 @@ struct Ctx {
   int mcap;               // incremental mode: members of a split-merge step whose AB / DG / L2s fit the shared-memory scratch
   longlong4* mAB; longlong2* mDG; double2* mL2s;   // that scratch
   uint8_t* live;          // incremental mode (shared memory): live slots, ascending
+  uint8_t* rank;          // incremental mode (shared memory): [cap] number of live slots below each slot
   double* tabs;           // incremental mode (shared memory): [6][cap] lgamma(alpha + delta1 s), lgamma(zeta + delta2 s), prior term at the slot's size / at size - 1
   int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
   double2* Cc;            // incremental mode (global): [cap][n] cached per-slot terms, see inc_eval_row
@@ -1937,11 +1938,19 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 //   streaming kernel's and the oracle's.
 // ------------------------------------------------------------------------------------------------
 
-// One row of the scan, evaluated by ONE thread (lane = row: the 32 lanes of a warp hold 32 consecutive rows, so the loads
-// of S[k][i .. i+31] are one 512-byte segment and no lane idles on an absent candidate).  Returns the chosen slot, or -2
-// when a new cluster is a candidate and no slot is free.
-#define RC_INC_WARPROWS 128   // batches of at most this many expected rows are evaluated one row per warp
+// One row of the scan is evaluated by a GROUP of G adjacent lanes (G = 4: 8 rows per warp, slots < 64; G = 8: 4 rows per
+// warp, slots < 128).  Lane g of the group owns the slots k = g + G j, j = 0..15, and keeps their terms in registers, so
+// every term is loaded once, all of a lane's loads are in flight together, and a batch of nthr / G consecutive rows costs
+// one memory round trip plus a few hundred instructions -- short enough for a chain that moves, wide enough (the whole
+// CTA works on consecutive rows: one 128-byte segment per slot and 8 rows) for one that does not.
+//
+// Per-slot terms are CACHED across sweeps: L1 and L2' of (slot k, point i) depend only on S[k][i] and the size of k, i.e.
+// on cluster k alone, which carries an epoch that is bumped whenever it gains or loses a point.  An entry whose stored
+// epoch equals the slot's is what a fresh evaluation would give (same formula, same inputs, same bits); anything else is
+// recomputed and stored.  The point's own slot (evaluated with the point detached) is never cached.  A chain at
+// equilibrium therefore spends two logarithms per row instead of two per (row, cluster).
 #define RC_NZMAX 37.0   // Gumbel noise -log(-log u) <= 36.74 for every 53-bit u < 1: candidates further than this below the leader cannot win
+#define RC_NP 16        // slots per lane of a row group
 // What a row evaluation reads, passed BY VALUE: inc_eval_row is deliberately not inlined (its register allocation stays
 // its own) and a reference to the kernel's Ctx would force that whole structure into local memory.
 struct RowCtx {
@@ -1950,13 +1959,13 @@ struct RowCtx {
   const longlong2* S;
   const uint8_t* lab;
   const int* sizes;
-  const uint8_t* live;
+  const uint8_t* rank;       // [cap] number of live slots below each slot (chain state)
   const double* tabs;
   const IncShared* inc;
   const Scal* sc;
   const rc_kparams* kp;
   unsigned long long key;
-  double2* Cc;               // [cap][n] cached per-slot terms (L1, L2') of every point attached elsewhere, see inc_eval_row
+  double2* Cc;               // [cap][n] cached per-slot terms (L1, L2') of every point attached elsewhere
   unsigned* Vv;              // [cap][n] epoch of the slot at which the cached entry was computed (0: never)
   const unsigned* ep;        // [cap] current epoch of every slot (shared memory)
 };
@@ -1964,16 +1973,16 @@ __device__ __forceinline__ double inc_noise(const RowCtx& c, unsigned it, int i,
   const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
   return -rc_log(-rc_log((kk & 1) ? dr.u1 : dr.u0));
 }
-// Per-slot terms are CACHED across sweeps: L1 and L2' of (slot k, point i) depend only on S[k][i] and the size of k, i.e.
-// on cluster k alone, which carries an epoch that is bumped whenever it gains or loses a point.  An entry whose stored
-// epoch equals the slot's is what a fresh evaluation would give (same formula, same inputs, same bits); anything else is
-// recomputed and stored.  The point's own slot (evaluated with the point detached) is never cached.  A chain at
-// equilibrium therefore spends two logarithms per row instead of two per (row, cluster).
+// Returns the chosen slot (the same value in the G lanes of the row's group), or -2 when a new cluster is a candidate
+// and no slot is free.  All G lanes of a group call it with the same i; groups are independent of each other.
+template <int G>
 __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int n = c.n, cap = c.cap;
   const IncShared* sh = c.inc;
+  const int lane = threadIdx.x & 31, g = lane & (G - 1), gbase = lane & ~(G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
   const int nlive = sh->nlive;
   const int li = c.lab[i];
   const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
@@ -1983,329 +1992,173 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   if (single && (e < 0 || li < e)) e = li;                                  // findfirst(clustsizes .== 0), :199
   const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
   if (hasnew && e < 0) return -2;
-  const longlong2* __restrict__ Si = c.S + i;
   const double* __restrict__ tabs = c.tabs;
-  // ---- pass 1: per-slot terms (:206-242), four slots at a time (loads in flight together, logarithms interleaved);
-  //      cached entries of unchanged clusters are kept, the others are recomputed and stored ----
-  double2* __restrict__ Ci = c.Cc + i;
-  unsigned* __restrict__ Vi = c.Vv + i;
-  double2 ownv = make_double2(0.0, 0.0);
-  for (int idx0 = 0; idx0 < nlive; idx0 += 4) {
-    int k[4];
-    unsigned tag[4], epk[4];
-    bool need[4];
+  // ---- the lane's slots: liveness (i detached), cached terms or row sums, all loads up front ----
+  unsigned live = 0u, fresh = 0u;                                           // bit j: slot g + G j is a live candidate / must be recomputed
+  unsigned tag[RC_NP];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      k[u] = idx0 + u < nlive ? (int)c.live[idx0 + u] : -1;
-      if (k[u] == li && single) k[u] = -1;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { tag[u] = (k[u] >= 0 && k[u] != li) ? Vi[(size_t)k[u] * n] : 0u; epk[u] = k[u] >= 0 ? c.ep[k[u]] : 0u; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) need[u] = k[u] >= 0 && (k[u] == li || tag[u] != epk[u]);
-    longlong2 sv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) sv[u] = need[u] ? Si[(size_t)k[u] * n] : make_longlong2(0, 0);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!need[u]) continue;
-      const bool own = k[u] == li;
-      if (own) { sv[u].x -= self.x; sv[u].y -= self.y; }                    // :193-194 detach i
-      const int szs = c.sizes[k[u]] - (own ? 1 : 0);
-      const double szd = (double)szs;
-      const double lgA = own ? tabs[3 * cap + k[u]] : tabs[k[u]];
-      const double lgZ = own ? tabs[4 * cap + k[u]] : tabs[cap + k[u]];
-      const double sD = rc_dequant(sv[u].x, c.qD), sL = rc_dequant(sv[u].y, c.qL);
-      const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-      const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-      const double L1 = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-      const double L2p = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-      if (own) ownv = make_double2(L1, L2p);
-      else { Ci[(size_t)k[u] * n] = make_double2(L1, L2p); Vi[(size_t)k[u] * n] = epk[u]; }
-    }
+  for (int j = 0; j < RC_NP; ++j) {
+    const int k = g + G * j;
+    const bool lv = k < cap && c.sizes[k] - (k == li ? 1 : 0) > 0;
+    live |= (lv ? 1u : 0u) << j;
+    tag[j] = (lv && k != li) ? c.Vv[(size_t)k * n + i] : 0u;
   }
-  auto terms = [&](int k) -> double2 { return k == li ? ownv : Ci[(size_t)k * n]; };
-  // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
-  //      xor-butterfly tree over the 32 classes (16, 8, 4, 2, 1) as lane 0 of a warp would evaluate it ----
-  double L2i = 0.0;
-  {
-    double t5 = 0.0;
+  double va[RC_NP], vb[RC_NP];                                              // (L1, L2') -- or the raw row sums until they are evaluated
 #pragma unroll
-    for (int b1 = 0; b1 < 2; ++b1) {
-      double t4 = 0.0;
-#pragma unroll
-      for (int b2 = 0; b2 < 2; ++b2) {
-        double t3 = 0.0;
-#pragma unroll
-        for (int b4 = 0; b4 < 2; ++b4) {
-          double t2 = 0.0;
-#pragma unroll
-          for (int b8 = 0; b8 < 2; ++b8) {
-            double t1 = 0.0;
-#pragma unroll
-            for (int b16 = 0; b16 < 2; ++b16) {
-              const int r = b1 + 2 * b2 + 4 * b4 + 8 * b8 + 16 * b16;
-              double a = 0.0;
-#pragma unroll
-              for (int w = 0; w < RC_NS; ++w) {
-                const int k = r + 32 * w;
-                if (k < cap && c.sizes[k] > 0 && !(single && k == li)) a += terms(k).y;
-              }
-              t1 = b16 == 0 ? a : t1 + a;
-            }
-            t2 = b8 == 0 ? t1 : t2 + t1;
-          }
-          t3 = b4 == 0 ? t2 : t3 + t2;
-        }
-        t4 = b2 == 0 ? t3 : t4 + t3;
+  for (int j = 0; j < RC_NP; ++j) {
+    const int k = g + G * j;
+    va[j] = 0.0; vb[j] = 0.0;
+    if ((live >> j) & 1u) {
+      if (k != li && tag[j] == c.ep[k]) { const double2 t = c.Cc[(size_t)k * n + i]; va[j] = t.x; vb[j] = t.y; }
+      else {
+        const longlong2 t = c.S[(size_t)k * n + i];
+        va[j] = __longlong_as_double(t.x); vb[j] = __longlong_as_double(t.y);
+        fresh |= 1u << j;
       }
-      t5 = b1 == 0 ? t4 : t5 + t4;
     }
-    L2i = t5;
   }
-  // log-probability of live slot k (:244-247) from the stored terms -- evaluated identically wherever it is needed
-  auto logprob = [&](int k) -> double {
-    const double2 v = terms(k);
-    const double L2 = L2i - v.y;
-    return (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + (v.x + (P.repulsion ? L2 : copysign(0.0, L2)));
-  };
-  // ---- pass 2: minimum of the log-probabilities and the leader ----
+  // ---- per-slot terms (:206-242) of the slots that have no valid cached entry (always the point's own slot) ----
+#pragma unroll
+  for (int j = 0; j < RC_NP; ++j) {
+    if (!((fresh >> j) & 1u)) continue;
+    const int k = g + G * j;
+    const bool own = k == li;
+    long long sx = __double_as_longlong(va[j]), sy = __double_as_longlong(vb[j]);
+    if (own) { sx -= self.x; sy -= self.y; }                                // :193-194 detach i
+    const int szs = c.sizes[k] - (own ? 1 : 0);
+    const double szd = (double)szs;
+    const double lgA = own ? tabs[3 * cap + k] : tabs[k];
+    const double lgZ = own ? tabs[4 * cap + k] : tabs[cap + k];
+    const double sD = rc_dequant(sx, c.qD), sL = rc_dequant(sy, c.qL);
+    const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+    const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+    va[j] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+    vb[j] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+    if (!own) { c.Cc[(size_t)k * n + i] = make_double2(va[j], vb[j]); c.Vv[(size_t)k * n + i] = c.ep[k]; }
+  }
+  // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
+  //      xor-butterfly tree over the 32 classes (16, 8, 4, 2, 1).  A lane owns the classes g + G q entirely, so the tree
+  //      levels with offset >= G are local and the last log2(G) levels are shuffles inside the group ----
+  double L2i;
+  {
+    constexpr int NQ = 32 / G;                                              // classes per lane; class q has the slots j = q, q + NQ, ...
+    double a[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      a[q] = 0.0;
+#pragma unroll
+      for (int j = q; j < RC_NP; j += NQ)
+        if ((live >> j) & 1u) a[q] += vb[j];
+    }
+#pragma unroll
+    for (int h = NQ / 2; h >= 1; h >>= 1)                                   // class offsets 16, 8, ... down to G
+#pragma unroll
+      for (int q = 0; q < h; ++q) a[q] = a[q] + a[q + h];
+    double t = a[0];
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) t = t + __shfl_xor_sync(gmask, t, off);
+    L2i = t;
+  }
+  // ---- log-probabilities (:244-247), their minimum, the leader ----
   const double r = c.sc->r, log1mp = c.sc->log1mp;
+  unsigned have = live;
+  const bool ownsnew = hasnew && (e & (G - 1)) == g;
+  const int jnew = e / G;
   bool anynan = false;
   double mn = RC_INF, toplp = -RC_INF;
-  int topkk = -1, topk = -1;
-#pragma unroll 4
-  for (int idx = 0; idx < nlive; ++idx) {
-    const int k = c.live[idx];
-    if (k == li && single) continue;
-    const double lp = logprob(k);
-    if (rc_isnan(lp)) anynan = true;
+  int topj = -1;
+#pragma unroll
+  for (int j = 0; j < RC_NP; ++j) {
+    const int k = g + G * j;
+    if ((live >> j) & 1u) {
+      const double L2 = L2i - vb[j];
+      va[j] = (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + (va[j] + (P.repulsion ? L2 : copysign(0.0, L2)));
+    } else if (ownsnew && j == jnew) {                                      // :228-230 new cluster
+      const double L2 = L2i - 0.0;
+      va[j] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
+      have |= 1u << j;
+    } else continue;
+    if (rc_isnan(va[j])) anynan = true;
     else {
-      if (lp < mn) mn = lp;
-      if (lp > toplp) { toplp = lp; topkk = idx - ((single && k > li) ? 1 : 0); topk = k; }
+      if (va[j] < mn) mn = va[j];
+      if (va[j] > toplp) { toplp = va[j]; topj = j; }
     }
   }
-  double lpnew = 0.0;
-  if (hasnew) {                                                             // :228-230 new cluster
-    const double L2 = L2i - 0.0;
-    lpnew = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
-    if (rc_isnan(lpnew)) anynan = true;
-    else {
-      if (lpnew < mn) mn = lpnew;
-      if (lpnew > toplp) { toplp = lpnew; topkk = Ki; topk = e; }
-    }
+  // group-wide minimum / NaN flag / leader (highest log-probability; ties: lowest lane, then lowest j)
+  int toplane = topj >= 0 ? g : -1;
+#pragma unroll
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    const double om = __shfl_xor_sync(gmask, mn, off);
+    const int on = __shfl_xor_sync(gmask, (int)anynan, off);
+    const double ot = __shfl_xor_sync(gmask, toplp, off);
+    const int oj = __shfl_xor_sync(gmask, topj, off), ol = __shfl_xor_sync(gmask, toplane, off);
+    if (om < mn) mn = om;
+    anynan = anynan || on != 0;
+    if (ol >= 0 && (toplane < 0 || ot > toplp || (ot == toplp && (ol < toplane || (ol == toplane && oj < topj))))) { toplp = ot; topj = oj; toplane = ol; }
   }
   if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
+  // candidate index of the lane's slot j (position among the candidates in ascending slot order, new cluster last)
+  auto cand_index = [&](int j) -> int {
+    const int k = g + G * j;
+    if (!((live >> j) & 1u)) return Ki;
+    return (int)c.rank[k] - ((single && k > li) ? 1 : 0);
+  };
   // ---- Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties ----
-  if (!anynan && mn > -RC_INF && mn < RC_INF && toplp < RC_INF && topkk >= 0) {
+  double bg = 0.0; int bkk = 0x7fffffff, bslot = -1; bool bnan = false;    // the lane's best candidate
+  const bool fast = !anynan && mn > -RC_INF && mn < RC_INF && toplp < RC_INF && toplane >= 0;     // uniform over the group
+  if (fast) {
     // every shifted log-probability is finite: a candidate whose value plus the largest possible noise stays below the
     // leader's exact value cannot be the arg-max, so its noise is never drawn (same result, far fewer logarithms)
-    double best = inc_noise(c, it, i, topkk) + (toplp - mn);
-    int bestkk = topkk, bestk = topk;
-    int ck0 = -1, ck1 = -1, ck2 = -1, ckk0 = 0, ckk1 = 0, ckk2 = 0;
-    double clp0 = 0.0, clp1 = 0.0, clp2 = 0.0;
-    int nc = 0;
-    auto contender = [&](int k, int kk, double lpm) {
-      if (nc == 0) { ck0 = k; ckk0 = kk; clp0 = lpm; }
-      else if (nc == 1) { ck1 = k; ckk1 = kk; clp1 = lpm; }
-      else if (nc == 2) { ck2 = k; ckk2 = kk; clp2 = lpm; }
-      ++nc;
-    };
-#pragma unroll 4
-    for (int idx = 0; idx < nlive; ++idx) {
-      const int k = c.live[idx];
-      if ((k == li && single) || k == topk) continue;
-      const double lpm = logprob(k) - mn;
-      if (lpm + RC_NZMAX >= best) contender(k, idx - ((single && k > li) ? 1 : 0), lpm);
+    double gtop = 0.0;
+    if (g == toplane) {
+      bkk = cand_index(topj);
+      bg = inc_noise(c, it, i, bkk) + (toplp - mn);
+      bslot = g + G * topj;
+      gtop = bg;
     }
-    if (hasnew && topk != e) {
-      const double lpm = lpnew - mn;
-      if (lpm + RC_NZMAX >= best) contender(e, Ki, lpm);
-    }
-    if (nc <= 3) {
-      if (nc > 0) { const double g = inc_noise(c, it, i, ckk0) + clp0; if (g > best || (g == best && ckk0 < bestkk)) { best = g; bestkk = ckk0; bestk = ck0; } }
-      if (nc > 1) { const double g = inc_noise(c, it, i, ckk1) + clp1; if (g > best || (g == best && ckk1 < bestkk)) { best = g; bestkk = ckk1; bestk = ck1; } }
-      if (nc > 2) { const double g = inc_noise(c, it, i, ckk2) + clp2; if (g > best || (g == best && ckk2 < bestkk)) { best = g; bestkk = ckk2; bestk = ck2; } }
-      return bestk;
-    }
-  }
-  // general path (NaN / infinities among the log-probabilities, or more than three contenders): every candidate in
-  // index order, NaN is maximal for argmax and the first NaN wins
-  {
-    int bestk = -1; double bv = 0.0;
-    bool first = true;
-    for (int idx = 0; idx <= nlive; ++idx) {
-      int k, kk; double lp;
-      if (idx < nlive) {
-        k = c.live[idx];
-        if (k == li && single) continue;
-        kk = idx - ((single && k > li) ? 1 : 0);
-        lp = logprob(k);
-      } else {
-        if (!hasnew) break;
-        k = e; kk = Ki; lp = lpnew;
-      }
-      const double g = inc_noise(c, it, i, kk) + (lp - mn);
-      if (first) { bestk = k; bv = g; first = false; if (rc_isnan(g)) break; continue; }
-      if (rc_isnan(g)) { bestk = k; break; }
-      if (g > bv) { bestk = k; bv = g; }
-    }
-    return bestk;
-  }
-}
-
-// The same row evaluated by a WARP (lane = slot, rounds of 32 slots): used while the chain moves often and the batches
-// are short -- the per-slot work of a row is spread over the lanes, so a batch of nwarp rows costs the latency of ~NSR
-// slots instead of all of them.  Same arithmetic as inc_eval_row; the canonical vecsum is the warp butterfly itself.
-template <int NSR>
-__device__ __noinline__ int inc_eval_row_warp(const RowCtx c, unsigned it, int i) {
-  const rc_kparams& kp = *c.kp;
-  const rc_params& P = kp.P;
-  const int n = c.n, cap = c.cap, lane = threadIdx.x & 31;
-  const unsigned ltmask = (1u << lane) - 1u;
-  const int li = c.lab[i];
-  const longlong2 self = __ldg(c.DL + (size_t)i * n + i);
-  int sz[NSR];
-  unsigned occ[NSR];
-  long long bd[NSR], bl[NSR];
+    gtop = __shfl_sync(gmask, gtop, gbase + toplane);
 #pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    const int s = w * 32 + lane;
-    sz[w] = s < cap ? c.sizes[s] : 0;
-    occ[w] = __ballot_sync(0xffffffffu, sz[w] - (s == li ? 1 : 0) > 0);      // occupancy with i detached (:193-202)
-    bd[w] = 0; bl[w] = 0;
-    if ((occ[w] >> lane) & 1u) { const longlong2 t = c.S[(size_t)s * n + i]; bd[w] = t.x; bl[w] = t.y; }
-  }
-  int Ki = 0, e = -1, nw = 0;
-#pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    Ki += __popc(occ[w]);
-    if (occ[w]) nw = w + 1;
-    const int lim = cap - w * 32;
-    const unsigned capmask = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
-    const unsigned emp = ~occ[w] & capmask;
-    if (e < 0 && emp) e = w * 32 + __ffs(emp) - 1;                          // findfirst(clustsizes .== 0)
-  }
-  const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
-  if (hasnew && e < 0) return -2;                                           // (the caller picks NSR so that every slot is covered)
-  if (hasnew && (e >> 5) + 1 > nw) nw = (e >> 5) + 1;
-  int kk[NSR];
-  bool have[NSR];
-  {
-    int base = 0;
-#pragma unroll
-    for (int w = 0; w < NSR; ++w) {
-      const int s = w * 32 + lane;
-      const bool live = (occ[w] >> lane) & 1u;
-      have[w] = live || (hasnew && s == e);
-      kk[w] = live ? base + __popc(occ[w] & ltmask) : Ki;
-      base += __popc(occ[w]);
-    }
-  }
-  double L1[NSR], L2p[NSR], pr[NSR];
-  double acc = 0.0;
-#pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    L1[w] = 0.0; L2p[w] = 0.0; pr[w] = 0.0;
-    if (w < nw) {
-      const int s = w * 32 + lane;
-      if ((occ[w] >> lane) & 1u) {
-        const bool own = s == li;
-        if (own) { bd[w] -= self.x; bl[w] -= self.y; }                      // :193-194 detach i
-        const double lgA = own ? c.tabs[3 * cap + s] : c.tabs[s];
-        const double lgZ = own ? c.tabs[4 * cap + s] : c.tabs[cap + s];
-        pr[w] = own ? c.tabs[5 * cap + s] : c.tabs[2 * cap + s];
-        const double szd = (double)(sz[w] - (own ? 1 : 0));
-        const double sD = rc_dequant(bd[w], c.qD), sL = rc_dequant(bl[w], c.qL);
-        const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-        const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-        L1[w] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-        L2p[w] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-        acc += L2p[w];                                                      // vecsum: lane-wise ascending slots
+    for (int j = 0; j < RC_NP; ++j) {
+      if (!((have >> j) & 1u) || (g == toplane && j == topj)) continue;
+      const double lpm = va[j] - mn;
+      if (lpm + RC_NZMAX >= gtop) {
+        const int kk = cand_index(j);
+        const double gg = inc_noise(c, it, i, kk) + lpm;
+        if (bslot < 0 || gg > bg || (gg == bg && kk < bkk)) { bg = gg; bkk = kk; bslot = g + G * j; }
       }
     }
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);   // :243 canonical butterfly
-  const double L2i = acc;
-  const double r = c.sc->r, log1mp = c.sc->log1mp;
-  double lp[NSR];
-  bool anynan = false;
-  double mn = RC_INF;
-#pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    lp[w] = 0.0;
-    if (w < nw) {
-      if ((occ[w] >> lane) & 1u) {
-        const double L2 = L2i - L2p[w];
-        lp[w] = pr[w] + (L1[w] + (P.repulsion ? L2 : copysign(0.0, L2)));
-      } else if (have[w]) {                                                 // :228-230 new cluster
-        const double L2 = L2i - 0.0;
-        lp[w] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
-      }
-      if (have[w]) {
-        if (rc_isnan(lp[w])) anynan = true;
-        else if (lp[w] < mn) mn = lp[w];
-      }
-    }
-  }
-  mn = warp_min_f64(mn);
-  anynan = __any_sync(0xffffffffu, anynan);
-  if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
-  // Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties
-  double g[NSR];
-  double gbest = -RC_INF;
-  bool gnan = false;
-#pragma unroll
-  for (int w = 0; w < NSR; ++w) {
-    g[w] = -RC_INF;
-    if (w < nw && have[w]) {
-      g[w] = inc_noise(c, it, i, kk[w]) + (lp[w] - mn);
-      if (rc_isnan(g[w])) gnan = true;
-      else if (g[w] > gbest) gbest = g[w];
-    }
-  }
-  int cnew;
-  if (!__any_sync(0xffffffffu, gnan)) {
-    gbest = warp_max_f64(gbest);
-    int kbest = 0x7fffffff, sbest = -1;
-#pragma unroll
-    for (int w = 0; w < NSR; ++w)
-      if (w < nw && have[w] && g[w] == gbest && kk[w] < kbest) { kbest = kk[w]; sbest = w * 32 + lane; }
-    const int kmin = __reduce_min_sync(0xffffffffu, kbest);
-    const unsigned who = __ballot_sync(0xffffffffu, kbest == kmin && sbest >= 0);
-    cnew = __shfl_sync(0xffffffffu, sbest, __ffs(who) - 1);
   } else {
-    // NaN is maximal for argmax and the first NaN wins
-    double bg = 0.0; int bk = 0x7fffffff, bs = -1; bool bnan = false;
+    // general path (NaN / infinities among the log-probabilities): every candidate draws its noise; NaN is maximal for
+    // argmax and the first NaN (lowest candidate index) wins
 #pragma unroll
-    for (int w = 0; w < NSR; ++w) {
-      if (!(w < nw && have[w])) continue;
-      const bool gn = rc_isnan(g[w]);
+    for (int j = 0; j < RC_NP; ++j) {
+      if (!((have >> j) & 1u)) continue;
+      const int kk = cand_index(j);
+      const double gg = inc_noise(c, it, i, kk) + (va[j] - mn);
+      const bool gn = rc_isnan(gg);
       bool better;
-      if (bs < 0) better = true;
-      else if (gn) better = !bnan || kk[w] < bk;
+      if (bslot < 0) better = true;
+      else if (gn) better = !bnan || kk < bkk;
       else if (bnan) better = false;
-      else better = g[w] > bg || (g[w] == bg && kk[w] < bk);
-      if (better) { bg = g[w]; bk = kk[w]; bs = w * 32 + lane; bnan = gn; }
+      else better = gg > bg || (gg == bg && kk < bkk);
+      if (better) { bg = gg; bkk = kk; bslot = g + G * j; bnan = gn; }
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const double og = __shfl_xor_sync(0xffffffffu, bg, off);
-      const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
-      const int os = __shfl_xor_sync(0xffffffffu, bs, off);
-      const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, off);
-      bool better;
-      if (os < 0) better = false;
-      else if (bs < 0) better = true;
-      else if (on) better = !bnan || ok < bk;
-      else if (bnan) better = false;
-      else better = og > bg || (og == bg && ok < bk);
-      if (better) { bg = og; bk = ok; bs = os; bnan = on != 0; }
-    }
-    cnew = bs;
   }
-  return cnew;
+#pragma unroll
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    const double og = __shfl_xor_sync(gmask, bg, off);
+    const int ok = __shfl_xor_sync(gmask, bkk, off);
+    const int os = __shfl_xor_sync(gmask, bslot, off);
+    const int on = __shfl_xor_sync(gmask, (int)bnan, off);
+    bool better;
+    if (os < 0) better = false;
+    else if (bslot < 0) better = true;
+    else if (on) better = !bnan || ok < bkk;
+    else if (bnan) better = false;
+    else better = og > bg || (og == bg && ok < bkk);
+    if (better) { bg = og; bkk = ok; bslot = os; bnan = on != 0; }
+  }
+  return bslot;
 }
 
 // (Re)build the chain's slot tables in shared memory from the sizes: the live list, the first empty slot and the
@@ -2322,6 +2175,7 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
     const unsigned m = __ballot_sync(0xffffffffu, live);
     const unsigned em = __ballot_sync(0xffffffffu, s < cap && sz == 0);
     if (live) c.live[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)s;
+    if (s < cap) c.rank[s] = (uint8_t)(base + __popc(m & ((1u << lane) - 1u)));      // live slots below s
     base += __popc(m);
     if (e0 < 0 && em) e0 = w * 32 + __ffs(em) - 1;
     if (s < cap && (only_a < 0 || s == only_a || s == only_b)) {
@@ -2335,7 +2189,7 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
   __syncwarp();
 }
 
-// The full scan (mcmc.jl:192-253) in batches of up to nthr consecutive rows.
+// The full scan (mcmc.jl:192-253) in batches of up to nthr / G consecutive rows (G lanes per row).
 __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   IncShared* sh = c.inc;
   const int n = c.n, cap = c.cap, NT = c.nthr, tid = c.ctid, lane = c.lane;
@@ -2343,43 +2197,34 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   if (c.cwarp == 0) inc_build_tables(c);
   csync(c);
   RowCtx rc;
-  rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.live = c.live;
+  rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.rank = c.rank;
   rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.Vv = c.Vv; rc.ep = c.ep;
   int batch = 0, i0 = 0;
-  // Rows per batch follow the observed run length between moves.  Long runs: one row per THREAD (throughput: no lane
-  // idles, coalesced loads).  Short runs (nrows <= RC_INC_WARPROWS): one row per WARP (latency: a row's slots are spread
-  // over the lanes), `streak` counting the rows that stood since the last move.
-  int nrows = sh->hint > 0 ? min(NT, sh->hint) : NT, streak = 0;
-  const int NW = c.nwarp;
+  // Rows per batch follow the observed run length between moves (rows behind a move are evaluated again).
+  int nrows = sh->hint > 0 ? sh->hint : NT, streak = 0;
   while (i0 < n) {
     const int slot3 = batch % 3;
     if (tid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
     ++batch;
-    const bool warpmode = nrows <= RC_INC_WARPROWS;
-    const int nb = warpmode ? NW : nrows;                                  // rows of this batch
-    if (warpmode) {
-      const int i = i0 + c.cwarp;
-      if (i < n) {
-        const int cnew = sh->narrow ? inc_eval_row_warp<2>(rc, it, i) : inc_eval_row_warp<RC_NS>(rc, it, i);
-        if (lane == 0) {
-          c.res[c.cwarp] = cnew;
-          if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], c.cwarp);
+    const bool narrow = sh->narrow != 0;                                    // every candidate slot below 64: 4 lanes per row, else 8
+    const int G = narrow ? 4 : 8;
+    const int nb = min(nrows, NT / G);                                      // rows of this batch
+    {
+      const int row = tid / G, i = i0 + row;
+      if (row < nb && i < n) {
+        const int cnew = narrow ? inc_eval_row<4>(rc, it, i) : inc_eval_row<8>(rc, it, i);
+        if ((tid & (G - 1)) == 0) {
+          c.res[row] = cnew;
+          if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], row);
         }
-      }
-    } else {
-      const int i = i0 + tid;
-      if (tid < nrows && i < n) {
-        const int cnew = inc_eval_row(rc, it, i);
-        c.res[tid] = cnew;
-        if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], tid);
       }
     }
     csync(c);
     const int F = sh->first[slot3];
     if (F == RC_INC_NONE) {                                                 // nobody moved: the whole batch stands
       i0 += nb;
-      if (warpmode) { streak += nb; if (streak >= nrows) { nrows = min(NT, nrows * 2); streak = 0; } }
-      else nrows = min(NT, nrows * 2);
+      streak += nb;
+      if (streak >= nrows) { nrows = min(NT, nrows * 2); streak = 0; }
       continue;
     }
     const int mi = i0 + F, b = c.res[F];
@@ -2441,7 +2286,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     csync(c);
     if (tid == 0) st_add(c, ST_BULK_PATCH, RC_CLOCK() - tu0);               // (incremental mode: cycles in the move updates)
     i0 = mi + 1;
-    nrows = min(NT, max(32, (2 * (streak + F + 1) + 31) & ~31));
+    nrows = min(NT, max(8, (2 * (streak + F + 1) + 7) & ~7));
     streak = 0;
   }
   csync(c);
@@ -2454,7 +2299,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, tabs, res, ep, mAB, mDG, mL2s, total; };
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, rank, tabs, res, ep, mAB, mDG, mL2s, total; };
 __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   IncLayout L;
   size_t o = 0;
@@ -2469,6 +2314,7 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   L.clist = take(cap);
   L.lab = take(n);
   L.live = take(cap);
+  L.rank = take(cap);
   L.tabs = take(sizeof(double) * 6 * cap);
   L.res = take(sizeof(int) * 512);
   L.ep = take(sizeof(unsigned) * cap);
@@ -2499,6 +2345,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.mDG = reinterpret_cast<longlong2*>(smem + L.mDG);
     c.mL2s = reinterpret_cast<double2*>(smem + L.mL2s);
     c.live = smem + L.live;
+    c.rank = smem + L.rank;
     c.tabs = reinterpret_cast<double*>(smem + L.tabs);
     c.res = reinterpret_cast<int*>(smem + L.res);
     c.ep = reinterpret_cast<unsigned*>(smem + L.ep);
@@ -2746,7 +2593,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.Vv = nullptr; c.ep = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.Vv = nullptr; c.ep = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
