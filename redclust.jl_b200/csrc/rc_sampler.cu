@@ -1489,6 +1489,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
       }
       int y = 0, cur = 0, cnew = 0, k = 0;
       double lt = 0.0;
+      long long trx = tr0;
       if (on) {
         y = c.Slist[pos];
         const longlong2 self = c.DG[pos];
@@ -1514,6 +1515,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
             X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
           }
         }
+        trx = RC_CLOCK();
         const unsigned qm = 0xfu << quad;
         const double L2pA = __shfl_sync(qm, X, quad), L2pB = __shfl_sync(qm, X, quad + 1);
         const double L1A = __shfl_sync(qm, X, quad + 2), L1B = __shfl_sync(qm, X, quad + 3);
@@ -1556,6 +1558,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
           atomicMin(&sh->first[slot3], warp * RC_RS_B + sf);
         }
       }
+      const long long trb = RC_CLOCK();
       csync(c);
       const long long tr1 = RC_CLOCK();
       const int F = sh->first[slot3];
@@ -1596,7 +1599,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
         }
         csync(c);
       }
-      if (c.ctid == 0) { st_add(c, ST_DEC_WAIT, tr1 - tr0); st_add(c, ST_DEC_WORK, RC_CLOCK() - tr1); st_add(c, ST_BULK_WAIT_CONSUMED, 1); st_add(c, ST_BULK_WAIT_FULL, F != RC_INC_NONE); }
+      if (c.ctid == 0) { st_add(c, ST_BULK_ROWS, trx - tr0); st_add(c, ST_BULK_REDUCE, trb - trx); st_add(c, ST_DEC_WAIT, tr1 - tr0); st_add(c, ST_DEC_WORK, RC_CLOCK() - tr1); st_add(c, ST_BULK_WAIT_CONSUMED, 1); st_add(c, ST_BULK_WAIT_FULL, F != RC_INC_NONE); }
       pos0 += nvalid;
     }
   }
