@@ -377,21 +377,22 @@ def main():
         return
     peak, peak_src = measured_peaks()
     b_scan = 16.0 * args.n * (args.n - 1)                         # algorithmic bytes per chain-sweep
-    per_launch_bytes = b_scan * args.chains
     step_s = dev_s / steps
-    achieved = per_launch_bytes / step_s / 1e9
+    per_launch_bytes = b_scan * args.chains * steps               # the timed launch advances every chain by K sweeps
+    achieved = per_launch_bytes / dev_s / 1e9
     prof = profile_numbers().get(f"k_chain_inc:{args.n}:{args.chains}", {})
-    traffic = prof.get("dram_bytes")
+    traffic = prof["dram_bytes_per_sweep"] * steps if "dram_bytes_per_sweep" in prof else None     # per launch = K sweeps
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_chain_inc", "peak_source": peak_src + " (of measured)",
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "dram_frac": (traffic / step_s / 1e9 / peak) if traffic else None,
+                "dram_frac": (traffic / steps / step_s / 1e9 / peak) if traffic else None,
                 "fp64_pipe_frac": prof.get("fp64_pipe_frac"), "issue_active_frac": prof.get("issue_active_frac"),
                 "note": "algorithmic bytes = chains x 16 n (n-1) per sweep: what a scan that reads every row costs (SURVEY 8d).  This kernel does "
                         "not read the rows: each chain keeps the sums of every row by cluster (exact integers) and a Gibbs step reads one 16-byte "
                         "entry per live cluster; only a move streams a row.  frac > 1 therefore measures the work avoided, dram_frac is the real "
-                        "DRAM utilisation (ncu bytes / step time / peak), and the binding resources are instruction issue and the fp64 pipe "
-                        "(fp64_pipe_frac, issue_active_frac: ncu, profiles/)"}
+                        "DRAM utilisation (ncu bytes / step time / peak); the kernel is bound by latency -- the sequential dependence of the "
+                        "restricted Gibbs scans (one warp) and of the batches of the full scan -- not by a pipe: fp64_pipe_frac and "
+                        "issue_active_frac are ncu's (profiles/r02_kchaininc_summary.md)"}
     cpu = None
     if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
