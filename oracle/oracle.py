@@ -17,6 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LOCK = __import__("threading").Lock()          # the tests call the oracle from a thread pool: build / load once
 
 
 class Options(C.Structure):
@@ -42,7 +43,11 @@ def build(force=False):
 
 def lib():
     global _LIB
-    if _LIB is None:
+    if _LIB is not None:
+        return _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
         L = C.CDLL(build())
         dp = C.POINTER(C.c_double)
         L.rco_run.restype = C.c_int

@@ -238,8 +238,11 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   if (st) return st;
   const int64_t n = d->n;
   if (opt->numMH > 0 && n < 2) { rc_set_error("split-merge needs at least 2 observations."); return RC_ERR_ARG; }
+  // slot capacity: 128 by default; the incremental kernel takes up to 255 (byte labels), the streaming kernel up to 128
+  const bool force_stream = getenv("RCB200_SCAN") && !strcmp(getenv("RCB200_SCAN"), "stream");
+  const int capmax = (opt_loglik_only || force_stream) ? RC_MAXCAP : RC_MAXCAP_INC;
   int cap = slot_cap == 0 ? RC_MAXCAP : slot_cap;
-  if (cap < 2 || cap > RC_MAXCAP) { rc_set_error("slot_cap must be in 2..%d", RC_MAXCAP); return RC_ERR_ARG; }
+  if (cap < 2 || cap > capmax) { rc_set_error("slot_cap must be in 2..%d", capmax); return RC_ERR_ARG; }
   if (par->maxK < 0 || !(par->proposalsd_r > 0)) { rc_set_error("invalid hyperparameters (maxK < 0 or proposalsd_r <= 0)"); return RC_ERR_ARG; }
   const int tiles = (int)((n + RC_W - 1) / RC_W);
   // permutation length: every (tile, slot) run is padded by at most 7 entries.  The worst case (all slots live in
@@ -247,7 +250,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   // 32 slots' worth per tile) and a chain whose runs need more stops with RC_ERR_SLOTS.
   const int64_t npad_full = (((n + 7) & ~7LL) + 7LL * tiles * cap + 7) & ~7LL;
   const int64_t npad_min = (((n + 7) & ~7LL) + 7LL * tiles * std::min(cap, 32) + 7) & ~7LL;
-  if (npad_min > 65528) { rc_set_error("n = %lld is too large for the shared-memory resident chain state", (long long)n); return RC_ERR_ARG; }
+  if (n > 65535) { rc_set_error("n = %lld: the sampler indexes points with 16 bits (n <= 65535)", (long long)n); return RC_ERR_ARG; }
   RC_CUDA(cudaSetDevice(d->device));
   int maxsmem = 0, nsm = 0;
   RC_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
@@ -257,7 +260,10 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   int G = 0, forceG = 0;
   int64_t npad = 0;
   if (const char* e = getenv("RCB200_CHAINS_PER_CTA")) forceG = atoi(e);   // test hook
+  // (geometry of the STREAMING kernel: labels and the column permutation of a chain live in shared memory, which bounds
+  // n at about 26 000; the incremental kernel has no such bound -- stream_ok records whether streaming is possible)
   for (int g : {1, 2}) {
+    if (npad_min > 65528 || cap > RC_MAXCAP) break;
     if (forceG && g != forceG) continue;
     int64_t np = std::min<int64_t>(npad_full, 65528);
     while (np > npad_min && rc_sampler_smem_bytes((int)n, cap, tiles, (int)np, g) > (size_t)maxsmem) np -= 64;
@@ -268,13 +274,14 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     const int per_sm = std::max<int>(1, std::min<int>((int)((size_t)maxsmem / sm), 2048 / (RC_NTHR * g + 64)));
     if (ctas <= (int64_t)nsm * per_sm) break;
   }
-  if (G == 0) {
-    rc_set_error("chain state needs %zu bytes of shared memory (> %d available): reduce n or slot_cap",
-                 rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad_min, 1), maxsmem);
+  const bool stream_ok = G != 0;
+  if (!stream_ok && (opt_loglik_only || force_stream)) {
+    rc_set_error("the streaming kernel keeps a chain's labels and column permutation in shared memory: n = %lld with slot_cap = %d does not fit "
+                 "(%d bytes available); use the incremental scan mode", (long long)n, cap, maxsmem);
     return RC_ERR_ARG;
   }
-  const size_t smem = rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G);
-  if (getenv("RCB200_VERBOSE"))
+  const size_t smem = stream_ok ? rc_sampler_smem_bytes((int)n, cap, tiles, (int)npad, G) : 0;
+  if (getenv("RCB200_VERBOSE") && stream_ok)
     fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld (full %lld) G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles,
             (long long)npad, (long long)npad_full, G, smem, maxsmem, (long long)nchains);
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
@@ -316,6 +323,12 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
     bool want = !opt_loglik_only && needS <= freeb / 10 * 6;
+    if (!stream_ok && !want) {
+      rc_set_error("n = %lld, slot_cap = %d: the streaming kernel does not fit shared memory and the incremental mode's per-chain sums (%.1f GB) do not fit the device",
+                   (long long)n, cap, needS / 1e9);
+      rc_sampler_destroy(s); return RC_ERR_ARG;
+    }
+    if (cap > RC_MAXCAP && !want) { rc_set_error("slot_cap = %d > %d needs the incremental scan mode, whose per-chain sums (%.1f GB) do not fit the device", cap, RC_MAXCAP, needS / 1e9); rc_sampler_destroy(s); return RC_ERR_ARG; }
     if (env && !strcmp(env, "stream")) want = false;
     if (env && !strcmp(env, "inc") && !opt_loglik_only) want = true;
     s->inc = want;
@@ -351,7 +364,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRY(dalloc(&s->NZ, opt->numMH > 0 ? (size_t)nchains * (opt->numGibbs + 1) * n : 1));
   TRY(dalloc(&s->LPR, (size_t)nchains * (n + 2))); TRY(dalloc(&s->DG, (size_t)nchains * (n + 2)));
   TRY(dalloc(&s->stats, (size_t)nchains * 16)); TRY(dalloc(&s->gridbar, 1));
-  s->coresident = rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * s->terms_stride));
+  s->coresident = stream_ok && rc_chain_kernel_coresident((int)nchains, smem, G, d->device); TRY(dalloc(&s->terms, (size_t)nchains * s->terms_stride));
   TRY(dalloc(&s->out_labels, (size_t)nchains * NS * n)); TRY(dalloc(&s->out_K, (size_t)nchains * NS));
   TRY(dalloc(&s->out_r, (size_t)nchains * NS)); TRY(dalloc(&s->out_p, (size_t)nchains * NS));
   TRY(dalloc(&s->out_ll, (size_t)nchains * NS)); TRY(dalloc(&s->out_lp, (size_t)nchains * NS));

@@ -103,7 +103,7 @@ struct IncShared {
   int nmoves;
   int nlive, e0;     // live slots of the chain's state and its first empty slot (-1: none), see inc_build_tables
   int hint;          // rows per batch the previous scan ended with (0: none yet)
-  int narrow;        // every live slot and the first empty slot lie below 64: the warp evaluator runs two rounds instead of four
+  int narrow;        // lanes per row of the scan (4 / 8 / 16: every live slot and the first empty slot lie below 64 / 128 / 256)
   int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
   double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
 };
@@ -2188,7 +2188,11 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
     }
   }
   if (only_a >= 0 && lane == 0) { c.ep[only_a] += 1; c.ep[only_b] += 1; }       // clusters a and b changed: their cached terms are stale
-  if (lane == 0) { sh->nlive = base; sh->e0 = e0; sh->narrow = (base == 0 || c.live[base - 1] < 64) && (e0 >= 0 && e0 < 64); }
+  if (lane == 0) {
+    sh->nlive = base; sh->e0 = e0;
+    const int hi = max(base > 0 ? (int)c.live[base - 1] : 0, e0 >= 0 ? e0 : cap - 1);   // highest slot a row of the scan can meet
+    sh->narrow = hi < 64 ? 4 : (hi < 128 ? 8 : 16);
+  }
   __syncwarp();
 }
 
@@ -2209,13 +2213,12 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     const int slot3 = batch % 3;
     if (tid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
     ++batch;
-    const bool narrow = sh->narrow != 0;                                    // every candidate slot below 64: 4 lanes per row, else 8
-    const int G = narrow ? 4 : 8;
+    const int G = sh->narrow;                                               // lanes per row: 4 / 8 / 16 when every candidate slot is below 64 / 128 / 256
     const int nb = min(nrows, NT / G);                                      // rows of this batch
     {
       const int row = tid / G, i = i0 + row;
       if (row < nb && i < n) {
-        const int cnew = narrow ? inc_eval_row<4>(rc, it, i) : inc_eval_row<8>(rc, it, i);
+        const int cnew = G == 4 ? inc_eval_row<4>(rc, it, i) : (G == 8 ? inc_eval_row<8>(rc, it, i) : inc_eval_row<16>(rc, it, i));
         if ((tid & (G - 1)) == 0) {
           c.res[row] = cnew;
           if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], row);
@@ -2237,10 +2240,10 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     if (c.cwarp == 0) {
       // ---- the point moved (:250-252): block sums from row mi's sums over the live slots, then labels, sizes, tables ----
       const longlong2 self = __ldg(c.DL + (size_t)mi * n + mi);
-      long long bd[RC_NS], bl[RC_NS];
-      bool live[RC_NS];
+      long long bd[RC_NSI], bl[RC_NSI];
+      bool live[RC_NSI];
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < RC_NSI; ++w) {
         const int s = w * 32 + lane;
         bd[w] = 0; bl[w] = 0;
         live[w] = s < cap && c.sizes[s] - (s == a ? 1 : 0) > 0;
@@ -2248,7 +2251,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
       }
       __syncwarp();
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < RC_NSI; ++w) {
         const int s = w * 32 + lane;
         if (s >= cap) continue;
         if (s == a) {
@@ -2265,7 +2268,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
       }
       __syncwarp();
 #pragma unroll
-      for (int w = 0; w < RC_NS; ++w) {
+      for (int w = 0; w < RC_NSI; ++w) {
         const int s = w * 32 + lane;
         if (s >= cap) continue;
         if (s == b) {

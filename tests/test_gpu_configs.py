@@ -147,3 +147,22 @@ def test_config4_mpel_S512(pkg, orc, loss):
     got, best = pkg.mpel_loss_sums(L, loss)
     assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
     assert abs(ref[best] - ref.min()) <= 1e-10 * max(1.0, abs(ref.min()))
+
+
+def test_more_than_128_live_clusters(pkg, orc):
+    """The incremental scan mode takes up to 255 simultaneously live clusters (byte labels; the streaming kernel stops at
+    128, the reference at n): sigma = 0.25 at n = 2000 opens well over 128 clusters within four sweeps -- every sweep
+    bit-identical to the oracle, 16 lanes per row once a slot beyond 127 is live."""
+    X, lab = mixture(2000, 20, 50, 0.25, 44)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab)
+    opts = pkg.MCMCOptionsList(numiters=4, burnin=0, thin=1, numGibbs=5, numMH=1)
+    rp = [pkg.init_rp(params, 3, c) for c in range(2)]
+    smp = pkg.Sampler(data, opts, params, np.tile(lab, (2, 1)), [x[0] for x in rp], [x[1] for x in rp], seed=3, slot_cap=255)
+    smp.run(-1)
+    assert smp.check_sums() == (0, 0)
+    refs = oracle_chains(orc, D, (4, 0, 1, 5, 1), oparams(orc, params), lab, rp, 3, range(2))
+    for c in range(2):
+        assert_same(smp.samples(c), refs[c], smp.state(c))
+    assert max(int(r["K"].max()) for r in refs) > 128
