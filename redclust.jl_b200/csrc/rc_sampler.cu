@@ -1996,6 +1996,9 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
   if (hasnew && e < 0) return -2;
   const double* __restrict__ tabs = c.tabs;
+  // the point's own slot is always evaluated from its row sum: that load starts now, under the epoch round trip
+  longlong2 own_s = make_longlong2(0, 0);
+  if (!single && (li & (G - 1)) == g) own_s = c.S[(size_t)li * n + i];
   // ---- the lane's slots: liveness (i detached), cached terms or row sums, all loads up front ----
   unsigned live = 0u, fresh = 0u;                                           // bit j: slot g + G j is a live candidate / must be recomputed
   unsigned tag[RC_NP];
@@ -2014,7 +2017,7 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
     if ((live >> j) & 1u) {
       if (k != li && tag[j] == c.ep[k]) { const double2 t = c.Cc[(size_t)k * n + i]; va[j] = t.x; vb[j] = t.y; }
       else {
-        const longlong2 t = c.S[(size_t)k * n + i];
+        const longlong2 t = k == li ? own_s : c.S[(size_t)k * n + i];
         va[j] = __longlong_as_double(t.x); vb[j] = __longlong_as_double(t.y);
         fresh |= 1u << j;
       }
@@ -2215,6 +2218,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     ++batch;
     const int G = sh->narrow;                                               // lanes per row: 4 / 8 / 16 when every candidate slot is below 64 / 128 / 256
     const int nb = min(nrows, NT / G);                                      // rows of this batch
+    const long long te0 = RC_CLOCK();
     {
       const int row = tid / G, i = i0 + row;
       if (row < nb && i < n) {
@@ -2225,6 +2229,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
         }
       }
     }
+    if (tid == 0) st_add(c, ST_REBUILDS, RC_CLOCK() - te0);                 // (incremental mode: cycles of thread 0 in the row evaluations)
     csync(c);
     const int F = sh->first[slot3];
     if (F == RC_INC_NONE) {                                                 // nobody moved: the whole batch stands
