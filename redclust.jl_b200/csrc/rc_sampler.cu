@@ -102,6 +102,8 @@ struct IncShared {
   int mv_i, mv_a, mv_b;
   int nmoves;
   int nlive, e0;     // live slots of the chain's state and its first empty slot (-1: none), see inc_build_tables
+  int sfirst[3];     // the scan's own rotating slots (the restricted scans use first[] and may run beside it)
+  int dry_stop;      // row at which the scan that ran beside the restricted scans stopped (first row that moves; n: none)
   int hint;          // rows per batch the previous scan ended with (0: none yet)
   int narrow;        // lanes per row of the scan (4 / 8 / 16: every live slot and the first empty slot lie below 64 / 128 / 256)
   int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
@@ -121,6 +123,8 @@ struct Ctx {
   const rc_kparams* kp;
   // shared memory (per chain)
   uint8_t* lab;
+  uint8_t* labL;          // the labels a split-merge step works on in place (launch state): the chain's own array, or -- incremental mode
+                          // with one proposal per iteration -- a copy, so that the scan can run beside the restricted scans
   unsigned short* perm;
   unsigned short* runStart;
   unsigned char* bscratch[2];   // build_perm scratch (run counters + chunk slot masks): aliases the row-sum buffers
@@ -1238,7 +1242,7 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
         const longlong4 ab = c.AB[pos];
         const double2 l2s = c.L2s[pos];
         const double2 nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
-        cur = c.lab[y];
+        cur = c.labL[y];
         // sums over the candidates with y detached (:303-304)
         const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
         const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
@@ -1298,7 +1302,7 @@ __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, i
       if (sfirst >= 0) {                                                                            // :344-345
         const int ym = __shfl_sync(0xffffffffu, y, 4 * sfirst);
         const int curm = __shfl_sync(0xffffffffu, cur, 4 * sfirst), newm = __shfl_sync(0xffffffffu, cnew, 4 * sfirst);
-        if (lane == 0) { c.lab[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
+        if (lane == 0) { c.labL[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
         // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
         const longlong2* row = c.DL + (size_t)ym * c.n;
         const bool a2b = curm == ca;
@@ -1347,7 +1351,7 @@ __device__ void member_sums_gather(const Ctx& c, int nS, int ca, int cb, int c1,
     for (int q2 = lane; q2 < mt; q2 += 32) {
       const int y = c.Slist[q2];
       const longlong2 e = __ldg(row + cpos(c, y));
-      const int l = c.lab[y];
+      const int l = c.labL[y];
       if (l == ca) { v[0] += e.x; v[1] += e.y; } else if (l == cb) { v[2] += e.x; v[3] += e.y; }
     }
     if (c.S) {                                    // incremental mode: the sums over an untouched cluster are already in S
@@ -1405,7 +1409,7 @@ __device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, in
 #pragma unroll 4
     for (int q2 = 0; q2 < mt; ++q2) {
       const int y = c.Slist[q2];                               // uniform over the team
-      const bool isA = c.lab[y] == ca;
+      const bool isA = c.labL[y] == ca;
       const longlong2* row = c.DL + (size_t)y * n;
       const longlong2 ea = oa ? __ldg(row + xa) : make_longlong2(0, 0);
       const longlong2 eb = ob ? __ldg(row + xb) : make_longlong2(0, 0);
@@ -1496,7 +1500,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
         const longlong4 ab = c.AB[pos];
         const double2 l2s = c.L2s[pos];
         const double2 nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
-        cur = c.lab[y];
+        cur = c.labL[y];
         // sums over the candidates with y detached (:303-304)
         const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
         const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
@@ -1569,7 +1573,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
       if (F != RC_INC_NONE) {                                                                       // :344-345
         const int fw = F / RC_RS_B;
         const int ym = sh->rs_cand[fw][0], curm = sh->rs_cand[fw][1], newm = sh->rs_cand[fw][2];
-        if (c.ctid == 0) { c.lab[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
+        if (c.ctid == 0) { c.labL[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
         // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
         const longlong2* row = c.DL + (size_t)ym * c.n;
         const bool a2b = curm == ca;
@@ -1607,6 +1611,8 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
   csync(c);
 }
 
+__device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry);
+
 // One split-merge proposal (mcmc.jl:372-474) on the current LOCAL state of sample_labels!.  Returns accept through
 // c.sc->itmp[1], split through itmp[2].  With commit == false the state is unchanged on return.  With commit == true
 // (more proposals follow in this iteration, numMH > 1) an accepted proposal becomes the local state (:470): labels,
@@ -1625,7 +1631,11 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   long long i1 = rc_randint(dr.u0, n), i2 = rc_randint(dr.u1, n - 1);
   if (i2 == i1) i2 = n;
   const int pi = (int)i1 - 1, pj = (int)i2 - 1;
-  const int ci = c.lab[pi], cj = c.lab[pj];
+  if (c.labL != c.lab) {                       // the proposal lives in its own copy of the labels (see the restricted scans below)
+    for (int k = tid; k < n; k += c.nthr) c.labL[k] = c.lab[k];
+    csync(c);
+  }
+  const int ci = c.labL[pi], cj = c.labL[pj];
   csync(c);
   if (tid == 0) { c.sc->itmp[1] = 0; c.sc->itmp[2] = 0; }
   if (P.maxK > 0 && ci == cj && K >= P.maxK) { csync(c); return; }          // :384-386
@@ -1634,7 +1644,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     const int chunk = (n + c.nthr - 1) / c.nthr;
     const int b = tid * chunk, e = min(n, b + chunk);
     int cntm = 0;
-    for (int k = b; k < e; ++k) cntm += ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj);
+    for (int k = b; k < e; ++k) cntm += ((c.labL[k] == ci || c.labL[k] == cj) && k != pi && k != pj);
     int incl = cntm;
     for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
     if (lane == 31) c.itmp[warp] = incl;
@@ -1643,7 +1653,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     for (int w = 0; w < warp; ++w) woff += c.itmp[w];
     int o = woff + incl - cntm;
     for (int k = b; k < e; ++k)
-      if ((c.lab[k] == ci || c.lab[k] == cj) && k != pi && k != pj) { c.Slist[o] = (unsigned short)k; c.origM[o] = c.lab[k]; ++o; }
+      if ((c.labL[k] == ci || c.labL[k] == cj) && k != pi && k != pj) { c.Slist[o] = (unsigned short)k; c.origM[o] = c.labL[k]; ++o; }
     if (tid == c.nthr - 1) c.sc->itmp[3] = woff + incl;
     csync(c);
   }
@@ -1654,7 +1664,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   if (c.S && nS + 2 <= c.mcap) { c.AB = c.mAB; c.DG = c.mDG; c.L2s = c.mL2s; }
   auto unswap = [&]() { c.AB = gAB; c.DG = gDG; c.L2s = gL2s; };
   if (tid == 0) { c.Slist[nS] = (unsigned short)pi; c.origM[nS] = (uint8_t)ci; c.Slist[nS + 1] = (unsigned short)pj; c.origM[nS + 1] = (uint8_t)cj; }
-  // launch state (:393-408), in place in c.lab / c.szL
+  // launch state (:393-408), in place in c.labL / c.szL
   for (int s = tid; s < cap; s += c.nthr) c.szL[s] = c.sizes[s];
   const bool split = ci == cj;
   int ca = ci;
@@ -1671,7 +1681,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     csync(c);
     ca = c.sc->itmp[4];
     if (ca < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; csync(c); unswap(); return; }
-    if (tid == 0) c.lab[pi] = (uint8_t)ca;
+    if (tid == 0) c.labL[pi] = (uint8_t)ca;
   }
   const int cb = cj;
   csync(c);
@@ -1681,7 +1691,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
       const int k = c.Slist[pos];
       const double u = rc_draw1(c.key, it, RC_SITE_SM_LAUNCH, mh, (uint32_t)pos, 0);
       const int cn = rc_randint(u, 2) == 1 ? ca : cb;
-      c.lab[k] = (uint8_t)cn;
+      c.labL[k] = (uint8_t)cn;
       na += cn == ca; nb += cn == cb;
     }
     for (int off = 16; off; off >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, off); nb += __shfl_xor_sync(0xffffffffu, nb, off); }
@@ -1706,7 +1716,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     // block sums of the proposed state)
     build_perm<false>(c);
     if (c.sc->status) {                                      // does not fit: undo the in-place launch labels and stop the chain
-      for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
+      for (int q = tid; q < nS + 2; q += c.nthr) c.labL[c.Slist[q]] = c.origM[q];
       csync(c);
       unswap();
       return;
@@ -1753,7 +1763,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     csync(c);
     const bool need1 = c1 != ca && c1 != cb, need2 = c2 != ca && c2 != cb;
     for (int k = tid; k < n; k += c.nthr) {
-      const int l = c.lab[k];
+      const int l = c.labL[k];
       if (need1 && l == c1) CL1[atomicAdd(&c.itmp[8], 1)] = (unsigned short)k;
       else if (need2 && l == c2) CL2[atomicAdd(&c.itmp[9], 1)] = (unsigned short)k;
     }
@@ -1770,7 +1780,24 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   }
   csync(c);
   const long long tm1 = RC_CLOCK();
-  if (c.S) restricted_scans_team(c, nS, ca, cb, c1, c2, split);               // :411-414, :419 / :454-455
+  if (c.S && c.labL != c.lab && c.nthr >= 512 && nS + 2 <= 1024) {           // (a CTA that has its SM to itself; large member sets need every thread)
+    // The restricted scans are a chain of dependent steps that keeps one or two warps busy.  With one proposal per
+    // iteration the full scan that follows does not depend on them unless the proposal is accepted (quirk Q1: then the
+    // scan is discarded), so the rest of the CTA runs it now, DRY: it commits nothing and stops at the first row that
+    // would move its point.  Labels, sizes, S and W are only read by both sides (the proposal's labels are a copy).
+    // Measured: -11 % per iteration with one chain per SM (512 threads); with two chains per SM the two sides compete
+    // for the same issue slots and the sum gets slower (+8 %), so the 256-thread configuration does not do this.
+    const int TA = max(64, (c.nthr / 4) & ~31);
+    if (tid < TA) {
+      Ctx cA = c;
+      cA.nthr = TA; cA.nwarp = TA / 32; cA.barid = 2;
+      restricted_scans_team(cA, nS, ca, cb, c1, c2, split);                  // :411-414, :419 / :454-455
+    } else {
+      Ctx cB = c;
+      cB.ctid = tid - TA; cB.cwarp = cB.ctid >> 5; cB.nthr = c.nthr - TA; cB.nwarp = cB.nthr / 32; cB.barid = 3;
+      inc_full_scan(cB, it, 0, true);
+    }
+  } else if (c.S) restricted_scans_team(c, nS, ca, cb, c1, c2, split);
   else if (warp == 0) restricted_scans(c, nS, ca, cb, c1, c2, split);
   csync(c);
   const long long tm2 = RC_CLOCK();
@@ -1793,11 +1820,11 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
         if (t != ca && t != cb && c.sizes[t] > 0)
           for (int q = 0; q < nS + 2; ++q) {
             const int x = c.Slist[q];
-            if (c.lab[x] == ca) { const longlong2 v = c.S[(size_t)t * n + x]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+            if (c.labL[x] == ca) { const longlong2 v = c.S[(size_t)t * n + x]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
           }
       } else {
         for (int q = 0; q < nS + 2; ++q)
-          if (c.lab[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+          if (c.labL[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
       }
       rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
     }
@@ -1806,7 +1833,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     rc_i128 acc[4];
     for (int h = 0; h < 4; ++h) { acc[h].lo = 0; acc[h].hi = 0; }
     for (int q = tid; q < nS + 2; q += c.nthr)
-      if (c.lab[c.Slist[q]] == ca) {
+      if (c.labL[c.Slist[q]] == ca) {
         const longlong4 ab = c.AB[q];
         rc_add128(acc[0], ab.x); rc_add128(acc[1], ab.y); rc_add128(acc[2], ab.z); rc_add128(acc[3], ab.w);
       }
@@ -1893,19 +1920,19 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
       c.sc->K = split ? K + 1 : K - 1;
     }
     if (!split)
-      for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = (uint8_t)cj;     // :436-445 (split: labels are final in place)
+      for (int q = tid; q < nS + 2; q += c.nthr) c.labL[c.Slist[q]] = (uint8_t)cj;     // :436-445 (split: labels are final in place)
     for (int s = tid; s < cap; s += c.nthr) c.sizes[s] = c.szL[s];
     if (c.S) {                                  // incremental mode: the row sums follow the members that changed slot
       csync(c);
       for (int q = 0; q < nS + 2; ++q) {
-        const int y = c.Slist[q], from = c.origM[q], to = c.lab[y];
+        const int y = c.Slist[q], from = c.origM[q], to = c.labL[y];
         if (from != to) inc_update_S(c, y, from, to);
       }
       for (int s2 = tid; s2 < cap; s2 += c.nthr) c.ep[s2] += 1;            // cached per-slot terms: all stale
     }
   } else {
     // restore the labels of the members (the proposal lived in place)
-    for (int q = tid; q < nS + 2; q += c.nthr) c.lab[c.Slist[q]] = c.origM[q];
+    for (int q = tid; q < nS + 2; q += c.nthr) c.labL[c.Slist[q]] = c.origM[q];
   }
   csync(c);
   unswap();
@@ -2199,22 +2226,25 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
   __syncwarp();
 }
 
-// The full scan (mcmc.jl:192-253) in batches of up to nthr / G consecutive rows (G lanes per row).
-__device__ void inc_full_scan(const Ctx& c, unsigned it) {
+// The full scan (mcmc.jl:192-253) from row istart in batches of up to nthr / G consecutive rows (G lanes per row), by the
+// team described by c (the whole CTA, or the warps that have nothing to do during the restricted scans).
+// dry: nothing is committed -- the scan stops at the first row that would move its point (or overflow) and leaves that
+// row in dry_stop; every row before it stands exactly as the sequential scan would leave it (it does not move).
+__device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
   IncShared* sh = c.inc;
   const int n = c.n, cap = c.cap, NT = c.nthr, tid = c.ctid, lane = c.lane;
-  if (tid == 0) { sh->first[0] = RC_INC_NONE; sh->first[1] = RC_INC_NONE; sh->first[2] = RC_INC_NONE; sh->nmoves = 0; }
+  if (tid == 0) { sh->sfirst[0] = RC_INC_NONE; sh->sfirst[1] = RC_INC_NONE; sh->sfirst[2] = RC_INC_NONE; if (!dry) sh->nmoves = 0; else sh->dry_stop = n; }
   if (c.cwarp == 0) inc_build_tables(c);
   csync(c);
   RowCtx rc;
   rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.rank = c.rank;
   rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.Vv = c.Vv; rc.ep = c.ep;
-  int batch = 0, i0 = 0;
+  int batch = 0, i0 = istart;
   // Rows per batch follow the observed run length between moves (rows behind a move are evaluated again).
   int nrows = sh->hint > 0 ? sh->hint : NT, streak = 0;
   while (i0 < n) {
     const int slot3 = batch % 3;
-    if (tid == 0) sh->first[(batch + 1) % 3] = RC_INC_NONE;
+    if (tid == 0) sh->sfirst[(batch + 1) % 3] = RC_INC_NONE;
     ++batch;
     const int G = sh->narrow;                                               // lanes per row: 4 / 8 / 16 when every candidate slot is below 64 / 128 / 256
     const int nb = min(nrows, NT / G);                                      // rows of this batch
@@ -2225,13 +2255,13 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
         const int cnew = G == 4 ? inc_eval_row<4>(rc, it, i) : (G == 8 ? inc_eval_row<8>(rc, it, i) : inc_eval_row<16>(rc, it, i));
         if ((tid & (G - 1)) == 0) {
           c.res[row] = cnew;
-          if (cnew != (int)c.lab[i]) atomicMin(&sh->first[slot3], row);
+          if (cnew != (int)c.lab[i]) atomicMin(&sh->sfirst[slot3], row);
         }
       }
     }
     if (tid == 0) st_add(c, ST_REBUILDS, RC_CLOCK() - te0);                 // (incremental mode: cycles of thread 0 in the row evaluations)
     csync(c);
-    const int F = sh->first[slot3];
+    const int F = sh->sfirst[slot3];
     if (F == RC_INC_NONE) {                                                 // nobody moved: the whole batch stands
       i0 += nb;
       streak += nb;
@@ -2239,6 +2269,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
       continue;
     }
     const int mi = i0 + F, b = c.res[F];
+    if (dry) { if (tid == 0) sh->dry_stop = mi; break; }                    // the committing scan resumes here
     if (b < 0) { if (tid == 0) c.sc->status = RC_ERR_SLOTS; break; }        // slot capacity exhausted at row mi
     const int a = c.lab[mi];
     const long long tu0 = RC_CLOCK();
@@ -2301,6 +2332,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
     streak = 0;
   }
   csync(c);
+  if (dry) return;
   if (c.cwarp == 0) {                                                       // :254
     int K = 0;
     for (int s = lane; s < cap; s += 32) K += c.sizes[s] > 0;
@@ -2310,7 +2342,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it) {
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, live, rank, tabs, res, ep, mAB, mDG, mL2s, total; };
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, labL, live, rank, tabs, res, ep, mAB, mDG, mL2s, total; };
 __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   IncLayout L;
   size_t o = 0;
@@ -2324,6 +2356,7 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   L.itmp = take(sizeof(int) * (cap > 64 ? cap : 64));
   L.clist = take(cap);
   L.lab = take(n);
+  L.labL = take(n);
   L.live = take(cap);
   L.rank = take(cap);
   L.tabs = take(sizeof(double) * 6 * cap);
@@ -2369,6 +2402,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.itmp = reinterpret_cast<int*>(smem + L.itmp);
     c.clist = smem + L.clist;
     c.lab = smem + L.lab;
+    c.labL = (kp.numMH == 1 && blockDim.x >= 512) ? smem + L.labL : c.lab;   // one proposal per iteration: the proposal works on a copy (scan beside the restricted scans)
   }
   const int ch = chain;
   c.WD = kp.WD + (size_t)ch * cap * cap;
@@ -2413,6 +2447,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     csync(c);
     if (c.sc->status != 0) break;                                            // the chain stopped (slot capacity)
     bool do_scan = true;
+    if (tid == 0) c.inc->dry_stop = 0;
     if (c.cwarp == 0) {
       const bool ra = update_r(c, it);                                       // mcmc.jl:538
       if (tid == 0) {
@@ -2458,7 +2493,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
       csync(c);
     }
     const long long ts0 = RC_CLOCK();
-    if (do_scan) inc_full_scan(c, it);
+    if (do_scan) inc_full_scan(c, it, c.inc->dry_stop, false);         // (rows before dry_stop were scanned beside the restricted scans and stand)
     const long long ts1 = RC_CLOCK();
     if (tid == 0) st_add(c, ST_SCAN_TOTAL, ts1 - ts0);
     csync(c);
@@ -2627,6 +2662,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
     c.itmp = reinterpret_cast<int*>(base + L.itmp);
     c.clist = base + L.clist;
     c.lab = base + L.lab;
+    c.labL = c.lab;
   }
   const int ch = valid ? chain : 0;
   c.WD = kp.WD + (size_t)ch * cap * cap;
