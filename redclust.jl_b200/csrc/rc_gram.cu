@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) k_gram128(const double* __restrict__ A
 // ---- epilogues -------------------------------------------------------------------------------------------------------
 struct EpiDistImpl : EpiDist {
   int64_t row0, nrows;     // row block [row0, row0 + nrows) of the matrix held by D (row0 = 0, nrows = n for the whole matrix)
-  __device__ __forceinline__ void store(const double* T, int64_t i0, int64_t j0, bool diag, bool sym, int tid) const {
+  __device__ __forceinline__ void store(double* T, int64_t i0, int64_t j0, bool diag, bool sym, int tid) const {
     // rows of the tile: thread t handles column t % 128 of rows t / 128, t / 128 + 2, ...
     const int c = tid & (GT - 1);
 #pragma unroll 8
@@ -130,21 +130,22 @@ struct EpiDistImpl : EpiDist {
       double v = 0.0;
       if (i != j) { const double w = sq[i] + sq[j] - 2 * T[(size_t)r * GTP + c]; v = sqrt(w > 0.0 ? w : 0.0); }
       D[il * n + j] = v;
+      T[(size_t)r * GTP + c] = v;                                            // the mirror image below copies it (one square root per pair)
     }
     if (diag || !sym) return;
+    __syncthreads();
     // the mirror image: row j0 + c of D, columns i0 + r (r fastest across the threads: column reads of T, pitch 129)
     const int r = tid & (GT - 1);
 #pragma unroll 8
     for (int cc = tid >> 7; cc < GT; cc += 2) {
       const int64_t i = i0 + r, j = j0 + cc;
       if (i >= n || j >= n) continue;
-      const double w = sq[i] + sq[j] - 2 * T[(size_t)r * GTP + cc];
-      D[j * n + i] = sqrt(w > 0.0 ? w : 0.0);
+      D[j * n + i] = T[(size_t)r * GTP + cc];
     }
   }
 };
 struct EpiAccumImpl : EpiAccum {
-  __device__ __forceinline__ void store(const double* T, int64_t i0, int64_t j0, bool diag, bool sym, int tid) const {
+  __device__ __forceinline__ void store(double* T, int64_t i0, int64_t j0, bool diag, bool sym, int tid) const {
     const int c = tid & (GT - 1);
     for (int r = tid >> 7; r < GT; r += 2) {
       const int64_t i = i0 + r, j = j0 + c;

@@ -26,3 +26,8 @@ cnt = torch.empty((n2, n2), dtype=torch.int32, device="cuda")
 for rep in range(2):
     torch.cuda.synchronize(); t = time.perf_counter(); pkg.psm_counts_dev(L2, cnt.data_ptr()); torch.cuda.synchronize()
     print(f"psm_counts_dev n={n2} S={S2}: {time.perf_counter() - t:.2f} s", flush=True)
+# MPEL at the configs[4] scale: S = 10 000 candidate samples of n = 50 000 (5e7 pairs of contingency tables)
+if len(sys.argv) > 1 and sys.argv[1] == "mpel":
+    for loss in ("binder", "VI"):
+        t = time.perf_counter(); sums, best = pkg.mpel_loss_sums(L2, loss); dt = time.perf_counter() - t
+        print(f"getpointestimate(MPEL, {loss}) search n={n2} S={S2}: {dt:.2f} s ({S2 * (S2 - 1) / 2 / dt:.3e} pairs/s), best sample {best}, loss sum {sums[best]:.6g}", flush=True)
