@@ -190,8 +190,12 @@ def post_block(pkg, args, data, lab):
 
     # distance build (MCMCData(points), types.jl:159-162) at the bench size
     X, _ = synth(args.n, args.K, args.dim, args.sigma, args.K, args.seed)
-    pkg.MCMCData.from_points(X)
-    t = time.perf_counter(); pkg.MCMCData.from_points(X); out["distm_s"] = time.perf_counter() - t
+    keep = [pkg.MCMCData.from_points(X)]            # warm: first-use allocations of the pool stay out of the timing
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter(); keep.append(pkg.MCMCData.from_points(X)); ts.append(time.perf_counter() - t)
+    out["distm_s"] = min(ts); out["distm_first_s"] = ts[0]
+    del keep
     out["distm"] = f"MCMCData(points) n={args.n} dim={args.dim}: upload, Euclidean distances, checks, logD and fixed-point images"
     # PSM of host label vectors into a host fp64 matrix (mcmc.jl:560)
     n1, S1 = 10000, 2000
@@ -205,8 +209,11 @@ def post_block(pkg, args, data, lab):
         L2 = samples(S2, n2, 90)
         cnt = torch.empty((n2, n2), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
-        t = time.perf_counter(); pkg.psm_counts_dev(L2, cnt.data_ptr()); torch.cuda.synchronize()
-        out["psm_c4_s"] = time.perf_counter() - t
+        ts = []
+        for _ in range(2):                           # the first call pays the staging buffers' first allocation
+            t = time.perf_counter(); pkg.psm_counts_dev(L2, cnt.data_ptr()); torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t)
+        out["psm_c4_s"] = ts[1]; out["psm_c4_first_s"] = ts[0]
         out["psm_c4"] = f"psm_counts_dev n={n2} S={S2} (BASELINE configs[4]): host labels -> device int32 counts (relabel, upload, transpose, tcgen05 one-hot counts)"
         del cnt
         # MPEL search over candidate samples (pointestimate.jl:34-59)
