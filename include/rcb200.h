@@ -99,6 +99,17 @@ int32_t rc_data_copy_row(const rc_data* d, int64_t i, double* row_out);
 int32_t rc_kmedoids(const rc_data* d, int64_t k, const int64_t* init_medoids, int64_t maxiter, int64_t* assignments,
                     int64_t* medoids, double* totalcost, int32_t* converged, int64_t* iterations);
 int32_t rc_pair_stats(const rc_data* d, const int64_t* labels, int64_t* rows_out);
+/* rc_kmeans: Clustering.kmeans(x, k; maxiter) as called at src/prior.jl:63-69 (algo = "k-means": elbow scan and notional
+ * clustering on the points).  X: n x dim row-major host points.  Seeding: the k points init_idx (0-based) when given, else
+ * k-means++ driven by the k uniforms u01 (u01[0] picks the first centre uniformly, u01[t] the t-th in proportion to the
+ * squared distance to the nearest centre so far).  Lloyd iterations (nearest centre, first minimum on ties; centre = mean
+ * of its members, an empty cluster keeps its centre) until no label changes or the objective moves by less than tol
+ * (Clustering.jl's criterion; its default tol is 1e-6) or maxiter updates were made.  All sums run in a fixed order: the
+ * result is a function of the arguments alone.  assignments: n, 1-based; centers (may be NULL): k x dim row-major;
+ * totalcost = sum of squared distances to the assigned centres.                                                       */
+int32_t rc_kmeans(const double* X, int64_t n, int64_t dim, int64_t k, const int64_t* init_idx, const double* u01, int64_t maxiter,
+                  double tol, int32_t device, int64_t* assignments, double* centers, double* totalcost, int32_t* converged,
+                  int64_t* iterations);
 /* sample_rp(clustsizes, options, params): src/mcmc.jl:592-636, called by fitprior at src/prior.jl:80 -- the (r, p)-only
  * chain on fixed cluster sizes (sample_r / sample_p of src/mcmc.jl:94-155; initial r ~ Gamma(eta, scale sigma) as
  * written at :617).  r_out / p_out: numsamples values; r_acc_out (numiters bytes) may be NULL.                      */

@@ -368,3 +368,30 @@ def sample_rp(clustsizes, options, params, seed=0):
     lib().rco_sample_rp(_p(cs, C.c_int64), C.c_int64(cs.size), C.byref(options), C.byref(params), C.c_uint64(seed),
                         _p(out["r"], C.c_double), _p(out["p"], C.c_double), _p(out["r_acc"], C.c_uint8))
     return out
+
+
+def kmeans_lloyd(X, init, maxiter=1000, tol=1e-6):
+    """Lloyd iterations of Clustering.kmeans from the given seeds (numpy; checker of rc_kmeans): X n x dim points, init 0-based
+    seed points.  Nearest centre (first minimum), centre = mean of members (an empty cluster keeps its centre), stop when no
+    label changes or the objective moves by less than tol.  Returns 1-based assignments, centres (k x dim), cost, converged, iterations."""
+    P = np.asarray(X, dtype=np.float64)
+    cent = P[np.asarray(init)].copy()
+    k = cent.shape[0]
+
+    def assign_pass():
+        d = ((P[:, None, :] - cent[None, :, :]) ** 2).sum(2)
+        a = np.argmin(d, axis=1)
+        return a, float(d[np.arange(P.shape[0]), a].sum())
+    a, obj = assign_pass()
+    conv, it = False, 0
+    while not conv and it < maxiter:
+        it += 1
+        for c in range(k):
+            m = a == c
+            if m.any():
+                cent[c] = P[m].mean(0)
+        na, nobj = assign_pass()
+        if k == 1 or np.array_equal(na, a) or abs(nobj - obj) < tol:
+            conv = True
+        a, obj = na, nobj
+    return a + 1, cent, obj, conv, it

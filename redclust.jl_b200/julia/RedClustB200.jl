@@ -204,6 +204,18 @@ function kmedoids_device(data::MCMCData, k::Integer, init::Vector{Int}; maxiter:
     return (assignments = assign, medoids = med .+ 1, totalcost = cost[], converged = conv[] != 0, iterations = its[])
 end
 
+"Clustering.kmeans(x, k; maxiter) on the device (src/prior.jl:63-69): x is dim x n (a point per column, the C side's n x dim row-major)."
+function kmeans_device(x::Matrix{Float64}, k::Integer; maxiter::Integer = 1000, tol::Float64 = 1e-6, device::Integer = 0)
+    dim, n = size(x)
+    u = rand(k)
+    assign = Vector{Int64}(undef, n); cent = Matrix{Float64}(undef, dim, k)
+    cost = Ref{Float64}(0); conv = Ref{Int32}(0); its = Ref{Int64}(0)
+    GC.@preserve x u check(ccall((:rc_kmeans, LIB[]), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Float64, Int32, Ptr{Int64}, Ptr{Float64}, Ref{Float64}, Ref{Int32}, Ref{Int64}),
+        x, n, dim, k, C_NULL, u, maxiter, tol, device, assign, cent, cost, conv, its))
+    return (assignments = assign, centers = cent, totalcost = cost[], converged = conv[] != 0, iterations = its[])
+end
+
 "Counts, sums and log-sums of the within / between cluster dissimilarities (A and B of src/prior.jl:73-75)."
 function pairstats(data::MCMCData, labels::Vector{Int})
     n = getfield(data, :n)

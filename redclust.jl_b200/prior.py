@@ -2,16 +2,16 @@
 (/root/reference/src/prior.jl:22-367, src/mcmc.jl:592-636 sample_rp).  SURVEY.md section 8(f) rank 1, the caller
 of the hot path.  The O(n^2) parts run on the device-resident matrix behind MCMCData (prior.jl:51,180): the
 distance build, k-medoids (rc_kmedoids) and the within / between sufficient statistics of the Gamma fits
-(rc_pair_stats).  k-means (points, O(n K dim)) and the O(K) fits stay on the host; k-means / k-medoids are
-third-party Clustering.jl code in the reference and are restated here."""
+(rc_pair_stats), k-means on the points (rc_kmeans) and the (r, p) chain (rc_sample_rp).  The O(K) fits stay on the host;
+k-means / k-medoids are third-party Clustering.jl code in the reference and are restated here."""
 import math
 import warnings
+from functools import partial
 import numpy as np
 from scipy.special import digamma, polygamma, gammaln, betaln
 
 
-class ArgumentError(ValueError):
-    pass
+from .host import ArgumentError          # Julia's ArgumentError, one class for the package
 
 
 # ---- third-party pieces restated (Clustering.jl kmeans / kmedoids, Distributions.fit_mle) -----------
@@ -54,63 +54,33 @@ def kmedoids_device(data, k, maxiter=1000, rng=None, init_medoids=None):
     return dict(assignments=assign, medoids=med, totalcost=cost.value, converged=bool(conv.value), iterations=its.value)
 
 
-def kmedoids(D, k, maxiter=1000, rng=None):
-    """Clustering.kmedoids(D, k; maxiter): alternate assignment / medoid update from a random seeding.
-    D: host matrix (numpy path below) or a device-resident MCMCData (GPU path)."""
+def kmedoids(D, k, maxiter=1000, rng=None, device=0):
+    """Clustering.kmedoids(D, k; maxiter): alternate assignment / medoid update from a k-medoids++ seeding, on the device.
+    D: a device-resident MCMCData, or a host matrix (uploaded into one first)."""
     from .host import MCMCData
-    if isinstance(D, MCMCData):
-        return kmedoids_device(D, k, maxiter=maxiter, rng=rng)
-    D = np.asarray(D)
-    n = D.shape[0]
-    g = _gen(rng)
-    med = _kmpp_seed(lambda i: D[i], n, k, g)
-    converged = False
-    assign = np.argmin(D[med], axis=0)
-    for _ in range(maxiter):
-        newmed = med.copy()
-        for c in range(k):
-            mem = np.where(assign == c)[0]
-            if mem.size:
-                newmed[c] = mem[np.argmin(D[np.ix_(mem, mem)].sum(0))]
-        newassign = np.argmin(D[newmed], axis=0)
-        if np.array_equal(newmed, med) and np.array_equal(newassign, assign):
-            converged = True
-            break
-        med, assign = newmed, newassign
-    cost = float(D[med[assign], np.arange(n)].sum())
-    return dict(assignments=(assign + 1).astype(np.int64), medoids=med, totalcost=cost, converged=converged)
+    if not isinstance(D, MCMCData):
+        D = MCMCData(np.ascontiguousarray(np.asarray(D, dtype=np.float64)), device=device)
+    return kmedoids_device(D, k, maxiter=maxiter, rng=rng)
 
 
-def kmeans(X, k, maxiter=1000, rng=None):
-    """Clustering.kmeans(X, k; maxiter) with X dim x n (columns are observations), k-means++ seeding."""
-    X = np.asarray(X, dtype=np.float64)
-    P = X.T
-    n = P.shape[0]
-    g = _gen(rng)
-    cent = [P[int(g.integers(n))]]
-    d2 = ((P - cent[0]) ** 2).sum(1)
-    for _ in range(1, k):
-        tot = d2.sum()
-        nxt = int(g.choice(n, p=d2 / tot)) if tot > 0 else int(g.integers(n))
-        cent.append(P[nxt])
-        d2 = np.minimum(d2, ((P - P[nxt]) ** 2).sum(1))
-    cent = np.array(cent)
-    assign = np.zeros(n, np.int64)
-    converged = False
-    for it in range(maxiter):
-        dist = ((P[:, None, :] - cent[None, :, :]) ** 2).sum(2) if n * k <= 4_000_000 else \
-            (P ** 2).sum(1)[:, None] + (cent ** 2).sum(1)[None, :] - 2 * P @ cent.T
-        newassign = np.argmin(dist, axis=1)
-        if it > 0 and np.array_equal(newassign, assign):
-            converged = True
-            break
-        assign = newassign
-        for c in range(k):
-            mem = assign == c
-            if mem.any():
-                cent[c] = P[mem].mean(0)
-    cost = float(((P - cent[assign]) ** 2).sum())
-    return dict(assignments=(assign + 1).astype(np.int64), centers=cent.T, totalcost=cost, converged=converged)
+def kmeans(X, k, maxiter=1000, rng=None, init=None, tol=1e-6, device=0):
+    """Clustering.kmeans(X, k; maxiter) with X dim x n (columns are observations), on the device (librcb200 rc_kmeans):
+    k-means++ seeding driven by k uniforms of `rng` (or the 0-based points `init`), Lloyd iterations until no label
+    changes or the objective moves by less than tol (Clustering.jl's default 1e-6).  centers: dim x k."""
+    import ctypes as C
+    from ._lib import lib, check, ptr
+    P = np.ascontiguousarray(np.asarray(X, dtype=np.float64).T)           # n x dim, a point per row
+    n, dim = P.shape
+    if not 1 <= k <= n:
+        raise ArgumentError("Number of clusters must satisfy 1 ≤ k ≤ n")
+    idx = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.int64))
+    u = None if init is not None else np.ascontiguousarray(_gen(rng).random(k))
+    assign = np.zeros(n, np.int64); cent = np.zeros((k, dim))
+    cost, conv, its = C.c_double(), C.c_int32(), C.c_int64()
+    check(lib().rc_kmeans(ptr(P), n, dim, k, ptr(idx), ptr(u), maxiter, float(tol), device, ptr(assign), ptr(cent),
+                          C.byref(cost), C.byref(conv), C.byref(its)))
+    return dict(assignments=assign, centers=np.ascontiguousarray(cent.T), totalcost=cost.value, converged=bool(conv.value),
+                iterations=its.value)
 
 
 def gamma_shape_from_stats(mx, mlx):
@@ -257,7 +227,7 @@ def fitprior(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0, 
     rng = _gen(rng)                                   # one stream for the elbow scan, the notional clustering and sample_rp
     if verbose:
         print("Fitting prior hyperparameters")
-    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)      # k-medoids runs on the device-resident matrix
+    clustfn, inp = (partial(kmeans, device=device), x) if algo == "k-means" else (kmedoids, dev)   # both on the device
     objective = np.zeros(Kmax - Kmin + 1)
     for k in range(1, Kmax - Kmin + 2):            # quirk Q11: clusters with k = loop index (prior.jl:63-64)
         t = clustfn(inp, k, maxiter=1000, rng=rng)
@@ -297,7 +267,7 @@ def fitprior2(data, algo, diss=False, Kmin=1, Kmax=None, verbose=True, device=0,
     rng = _gen(rng)                                   # one stream for the elbow scan, the notional clustering and sample_rp
     if verbose:
         print("Fitting prior hyperparameters")
-    clustfn, inp = (kmeans, x) if algo == "k-means" else (kmedoids, dev)
+    clustfn, inp = (partial(kmeans, device=device), x) if algo == "k-means" else (kmedoids, dev)
     ks = list(range(Kmin, Kmax + 1))
     objective = np.zeros(len(ks))
     stats = []

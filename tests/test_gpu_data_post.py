@@ -376,3 +376,54 @@ def test_generatemixture_oracle_coclustering(pkg, golden):
     occ = mix["oracle_coclustering"]
     same = mix["clusts"][:, None] == mix["clusts"][None, :]
     assert occ.shape == (300, 300) and np.array_equal(occ, occ.T) and occ[same].mean() > occ[~same].mean() + 0.3
+
+
+@pytest.mark.gpu
+def test_kmeans_device_matches_lloyd_restatement(pkg, orc, golden):
+    """rc_kmeans (fitprior's elbow scan with algo = "k-means", prior.jl:63-69) against the numpy Lloyd iterations from the
+    same seeds: same labels, centres and objective to 1e-10; a fixed point of both steps; k-means++ seeding reproducible."""
+    rng = np.random.default_rng(11)
+    for n_ex, k in ((1, 4), (2, 7), (3, 12)):
+        P = np.ascontiguousarray(golden[n_ex]["points"])                  # n x dim
+        init = rng.choice(P.shape[0], size=k, replace=False)
+        got = pkg.kmeans(P.T, k, init=init)
+        a, cent, cost, conv, its = orc.kmeans_lloyd(P, init)
+        assert np.array_equal(got["assignments"], a) and got["converged"] == conv and got["iterations"] == its
+        assert np.allclose(got["centers"].T, cent, rtol=1e-10, atol=1e-12) and abs(got["totalcost"] - cost) <= 1e-10 * cost
+    # larger, well separated mixture: converged result is a fixed point and recovers the truth
+    g = np.random.default_rng(5)
+    K, n, dim = 20, 5000, 30
+    mu = g.normal(size=(K, dim)) * 10
+    z = g.integers(0, K, n)
+    X = mu[z] + 0.3 * g.normal(size=(n, dim))
+    r = pkg.kmeans(X.T, K, rng=7)
+    r2 = pkg.kmeans(X.T, K, rng=7)
+    assert r["converged"] and np.array_equal(r["assignments"], r2["assignments"]) and r["totalcost"] == r2["totalcost"]
+    C = r["centers"].T
+    d = ((X[:, None, :] - C[None]) ** 2).sum(2)
+    assert np.array_equal(np.argmin(d, 1) + 1, r["assignments"])
+    for c in range(K):
+        m = r["assignments"] == c + 1
+        if m.any():
+            assert np.allclose(C[c], X[m].mean(0), rtol=1e-10, atol=1e-12)
+    assert abs(r["totalcost"] - d.min(1).sum()) <= 1e-10 * r["totalcost"]
+    # k-means++ from the same uniforms never does worse than 3 x the truth's own cost here, and k = 1 / k = n are exact
+    truth_cost = ((X - np.stack([X[z == c].mean(0) for c in range(K)])[z]) ** 2).sum()
+    assert r["totalcost"] < 3 * truth_cost
+    one = pkg.kmeans(X.T, 1, rng=0)
+    assert np.all(one["assignments"] == 1) and np.allclose(one["centers"][:, 0], X.mean(0), rtol=1e-10)
+    small = X[:50]
+    alln = pkg.kmeans(small.T, 50, rng=1)
+    assert alln["totalcost"] < 1e-18 * 50 or len(set(alln["assignments"])) >= 45
+    with pytest.raises(pkg.ArgumentError):
+        pkg.kmeans(small.T, 51)
+
+
+@pytest.mark.gpu
+def test_kmedoids_host_matrix_runs_on_device(pkg, golden):
+    D = golden[1]["distance_matrix"]
+    r = pkg.kmedoids(D, 10, rng=0)
+    assert r["assignments"].min() == 1 and r["assignments"].max() == 10 and r["converged"]
+    data = pkg.MCMCData(D)
+    r2 = pkg.kmedoids(data, 10, rng=0)
+    assert np.array_equal(r["assignments"], r2["assignments"]) and r["totalcost"] == r2["totalcost"]
