@@ -98,6 +98,10 @@ int32_t rc_data_copy_row(const rc_data* d, int64_t i, double* row_out);
  * totals are the sufficient statistics of the Gamma fits to A and B (src/prior.jl:73-110). */
 int32_t rc_kmedoids(const rc_data* d, int64_t k, const int64_t* init_medoids, int64_t maxiter, int64_t* assignments,
                     int64_t* medoids, double* totalcost, int32_t* converged, int64_t* iterations);
+/* rc_kmedoids_seed: Clustering.jl's default seeding of kmedoids (:kmpp on the costs) on the resident matrix, driven by k
+ * uniforms: u01[0] picks the first medoid uniformly, u01[t] the t-th in proportion to the dissimilarity to the nearest
+ * medoid so far.  medoids_out: k, 0-based -- the init_medoids of rc_kmedoids.                                        */
+int32_t rc_kmedoids_seed(const rc_data* d, int64_t k, const double* u01, int64_t* medoids_out);
 int32_t rc_pair_stats(const rc_data* d, const int64_t* labels, int64_t* rows_out);
 /* rc_kmeans: Clustering.kmeans(x, k; maxiter) as called at src/prior.jl:63-69 (algo = "k-means": elbow scan and notional
  * clustering on the points).  X: n x dim row-major host points.  Seeding: the k points init_idx (0-based) when given, else

@@ -48,6 +48,7 @@ SIGNATURES = {
     "rc_data_scales": (C.c_int32, [_vp, _P(C.c_int32), _P(C.c_int32)]),
     "rc_data_copy_row": (C.c_int32, [_vp, C.c_int64, _vp]),
     "rc_kmeans": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, C.c_double, C.c_int32, _vp, _vp, _P(C.c_double), _P(C.c_int32), _P(C.c_int64)]),
+    "rc_kmedoids_seed": (C.c_int32, [_vp, C.c_int64, _vp, _vp]),
     "rc_kmedoids": (C.c_int32, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _P(C.c_double), _P(C.c_int32), _P(C.c_int64)]),
     "rc_pair_stats": (C.c_int32, [_vp, _vp, _vp]),
     "rc_sample_rp": (C.c_int32, [_vp, C.c_int64, _P(rc_options), _P(rc_params), C.c_uint64, C.c_int32, _vp, _vp, _vp]),

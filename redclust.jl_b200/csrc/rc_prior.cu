@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) k_kmn_seed_dist(const double* __restrict_
 // the chosen point becomes centre t
 __global__ void __launch_bounds__(128) k_kmn_seed_pick(const double* __restrict__ mind, const double* __restrict__ partial, int nb, int64_t n,
                                                       double u, int fixed, const double* __restrict__ Xr, int64_t dim, double* __restrict__ C, int t,
-                                                      int* __restrict__ pick) {
+                                                      int* __restrict__ pick, int* __restrict__ picks) {
   __shared__ int sel;
   if (threadIdx.x == 0) {
     int64_t j = fixed;
@@ -186,9 +186,25 @@ __global__ void __launch_bounds__(128) k_kmn_seed_pick(const double* __restrict_
       if (j >= n) j = n - 1;
     }
     sel = (int)j; *pick = (int)j;
+    if (picks) picks[t] = (int)j;
   }
   __syncthreads();
   for (int64_t d = threadIdx.x; d < dim; d += blockDim.x) C[(size_t)t * dim + d] = Xr[(size_t)sel * dim + d];
+}
+// k-medoids++ seeding step on the resident matrix: dissimilarity to the newest medoid (its row of D), running minimum,
+// per-block totals (Clustering.jl's kmpp on costs: a point is drawn in proportion to its cost itself)
+__global__ void __launch_bounds__(128) k_km_seed_dist(const double* __restrict__ D, int64_t n, const int* __restrict__ pick, int first,
+                                                     double* __restrict__ mind, double* __restrict__ partial) {
+  __shared__ double red[4];
+  const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  double v = 0.0;
+  if (j < n) {
+    v = D[(size_t)(*pick) * n + j];
+    if (!first) v = fmin(v, mind[j]);
+    mind[j] = v;
+  }
+  const double tot = kmn_block_sum(j < n ? v : 0.0, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 // assignment: nearest centre (first minimum), the point's cost, per-block totals of the costs; out[nb] != 0 when a label
 // changed.  Block = 32 points x 8 centre groups: thread (x, y) scans the centres 8 y .. 8 y + 7, 8 (y + 8) .. for point x
@@ -280,6 +296,25 @@ int32_t rc_data_copy_row(const rc_data* d, int64_t i, double* row_out) {
   return RC_OK;
 }
 
+int32_t rc_kmedoids_seed(const rc_data* d, int64_t k, const double* u01, int64_t* medoids_out) {
+  if (!d || !u01 || !medoids_out || k < 1 || k > d->n) { rc_set_error("rc_kmedoids_seed: bad arguments (need 1 <= k <= n)"); return RC_ERR_ARG; }
+  const int64_t n = d->n;
+  RC_CUDA(cudaSetDevice(d->device));
+  const int nb = (int)((n + 127) / 128);
+  Scratch S;
+  double *mind, *partial; int *pick, *picks;
+  if (S.get(&mind, n) || S.get(&partial, nb) || S.get(&pick, 1) || S.get(&picks, k)) { rc_set_error("rc_kmedoids_seed: out of device memory"); return RC_ERR_CUDA; }
+  for (int64_t t = 0; t < k; ++t) {
+    const int fixed = t == 0 ? (int)fmin((double)(n - 1), u01[0] * (double)n) : -1;
+    k_kmn_seed_pick<<<1, 128>>>(mind, partial, nb, n, u01[t], fixed, nullptr, 0, nullptr, (int)t, pick, picks);
+    if (t + 1 < k) k_km_seed_dist<<<nb, 128>>>(d->D, n, pick, t == 0, mind, partial);
+  }
+  std::vector<int> h((size_t)k);
+  RC_CUDA(cudaMemcpy(h.data(), picks, sizeof(int) * k, cudaMemcpyDeviceToHost));
+  for (int64_t t = 0; t < k; ++t) medoids_out[t] = h[t];
+  return RC_OK;
+}
+
 int32_t rc_kmedoids(const rc_data* d, int64_t k, const int64_t* init_medoids, int64_t maxiter, int64_t* assignments,
                     int64_t* medoids, double* totalcost, int32_t* converged, int64_t* iterations) {
   if (!d || !init_medoids || !assignments || !medoids || k < 1 || k > d->n || maxiter < 0) {
@@ -366,7 +401,7 @@ int32_t rc_kmeans(const double* X, int64_t n, int64_t dim, int64_t k, const int6
   // seeding: the given points, or k-means++ (first centre uniform, then proportional to the squared distance to the nearest centre)
   for (int64_t t = 0; t < k; ++t) {
     const int fixed = init_idx ? (int)init_idx[t] : (t == 0 ? (int)fmin((double)(n - 1), u01[0] * (double)n) : -1);
-    k_kmn_seed_pick<<<1, 128>>>(mind, out, nb, n, init_idx ? 0.0 : u01[t], fixed, Xr, dim, C, (int)t, pick);
+    k_kmn_seed_pick<<<1, 128>>>(mind, out, nb, n, init_idx ? 0.0 : u01[t], fixed, Xr, dim, C, (int)t, pick, nullptr);
     if (!init_idx && t + 1 < k) k_kmn_seed_dist<<<nb, 128>>>(Xt, Xr, n, dim, pick, t == 0, mind, out);
   }
   RC_CUDA(cudaMemset(assign, 0xff, sizeof(int) * n));

@@ -204,6 +204,13 @@ function kmedoids_device(data::MCMCData, k::Integer, init::Vector{Int}; maxiter:
     return (assignments = assign, medoids = med .+ 1, totalcost = cost[], converged = conv[] != 0, iterations = its[])
 end
 
+"k-medoids++ seeding on the resident matrix (Clustering.jl's default init of kmedoids): 1-based medoids for kmedoids_device."
+function kmedoids_seed(data::MCMCData, k::Integer)
+    u = rand(k); med = Vector{Int64}(undef, k)
+    GC.@preserve u check(ccall((:rc_kmedoids_seed, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}), getfield(data, :handle), k, u, med))
+    return Int.(med .+ 1)
+end
+
 "Clustering.kmeans(x, k; maxiter) on the device (src/prior.jl:63-69): x is dim x n (a point per column, the C side's n x dim row-major)."
 function kmeans_device(x::Matrix{Float64}, k::Integer; maxiter::Integer = 1000, tol::Float64 = 1e-6, device::Integer = 0)
     dim, n = size(x)

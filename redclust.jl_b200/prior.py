@@ -21,19 +21,6 @@ def _gen(rng):
     return rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
 
 
-def _kmpp_seed(row, n, k, g):
-    """k-medoids++ style seeding (Clustering.jl's default :kmpp); row(i) returns row i of the dissimilarity matrix."""
-    med = [int(g.integers(n))]
-    mind = np.array(row(med[0]), dtype=np.float64)
-    for _ in range(1, k):
-        w = mind                      # Clustering.jl's kmpp-by-costs weights a point by its cost itself (squares are k-means')
-        tot = w.sum()
-        nxt = int(g.choice(n, p=w / tot)) if tot > 0 else int(g.integers(n))
-        med.append(nxt)
-        mind = np.minimum(mind, row(nxt))
-    return np.array(med, dtype=np.int64)
-
-
 def kmedoids_device(data, k, maxiter=1000, rng=None, init_medoids=None):
     """Clustering.kmedoids on a device-resident MCMCData (librcb200 rc_kmedoids): same seeding and iteration as
     kmedoids(), the O(n^2) medoid updates run on the GPU over the exact fixed-point image of D."""
@@ -41,12 +28,10 @@ def kmedoids_device(data, k, maxiter=1000, rng=None, init_medoids=None):
     from ._lib import lib, check, ptr
     n = data.n
     g = _gen(rng)
-    if init_medoids is None:
-        def row(i):
-            out = np.empty(n)
-            check(lib().rc_data_copy_row(data._h, int(i), ptr(out)))
-            return out
-        init_medoids = _kmpp_seed(row, n, k, g)
+    if init_medoids is None:                          # k-medoids++ on the device, driven by k uniforms of the host stream
+        u = np.ascontiguousarray(g.random(k))
+        init_medoids = np.zeros(k, np.int64)
+        check(lib().rc_kmedoids_seed(data._h, k, ptr(u), ptr(init_medoids)))
     init = np.ascontiguousarray(np.asarray(init_medoids, dtype=np.int64))
     assign = np.zeros(n, np.int64); med = np.zeros(k, np.int64)
     cost, conv, its = C.c_double(), C.c_int32(), C.c_int64()

@@ -427,3 +427,32 @@ def test_kmedoids_host_matrix_runs_on_device(pkg, golden):
     data = pkg.MCMCData(D)
     r2 = pkg.kmedoids(data, 10, rng=0)
     assert np.array_equal(r["assignments"], r2["assignments"]) and r["totalcost"] == r2["totalcost"]
+
+
+@pytest.mark.gpu
+def test_kmedoids_seeding_on_device(pkg, golden):
+    """rc_kmedoids_seed: the first medoid is point floor(u0 n); medoid t is the first point whose cumulative cost (distance to
+    the nearest medoid so far) exceeds u_t x the total -- checked against numpy cumulative sums of the same rows."""
+    import ctypes as C
+    from redclust_jl_b200._lib import lib, check, ptr
+    D = golden[2]["distance_matrix"]
+    data = pkg.MCMCData(D)
+    n, k = D.shape[0], 9
+    u = np.random.default_rng(4).random(k)
+    med = np.zeros(k, np.int64)
+    check(lib().rc_kmedoids_seed(data._h, k, ptr(u), ptr(med)))
+    assert med[0] == int(u[0] * n) and len(set(med.tolist())) == k
+    mind = D[med[0]].copy()
+    for t in range(1, k):
+        cum = np.cumsum(mind); target = u[t] * cum[-1]; j = med[t]
+        assert cum[j] >= target * (1 - 1e-12) and (j == 0 or cum[j - 1] <= target * (1 + 1e-12)) and mind[j] > 0
+        mind = np.minimum(mind, D[j])
+    # the draw follows the weights: far points are preferred
+    hits = np.zeros(n)
+    g = np.random.default_rng(0)
+    for _ in range(300):
+        uu = np.array([0.0, g.random()]); m2 = np.zeros(2, np.int64)
+        check(lib().rc_kmedoids_seed(data._h, 2, ptr(uu), ptr(m2)))
+        hits[m2[1]] += 1
+    w = D[0] / D[0].sum()
+    assert abs((hits / 300 * D[0]).sum() - (w * D[0]).sum()) < 0.25 * (w * D[0]).sum()
