@@ -49,6 +49,7 @@ struct rc_sampler {
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
   size_t inc_smem, terms_stride;
   int inc_mcap;                // split-merge members whose running sums fit the chain's shared memory
+  int ovl_min_thr, rs_team;    // scan beside the restricted scans: from this many threads per chain on, with this many on the restricted scans
   longlong2* DLp;              // copy of the data's DL with label-sorted columns (null: the data's own matrix is streamed)
   unsigned short *colpos, *colpt;   // [n] point -> column and column -> point of DLp
   uint8_t* out_labels; int* out_K; double *out_r, *out_p, *out_ll, *out_lp;
@@ -175,7 +176,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -335,6 +336,11 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     int nthr = nchains <= nsm ? 512 : (nchains <= 2 * nsm ? 256 : 256);
     if (const char* e = getenv("RCB200_INC_THREADS")) nthr = std::max(32, std::min(512, atoi(e) / 32 * 32));
     s->inc_nthr = nthr;
+    // The scan runs beside the restricted scans (dry, on a copy of the labels) when there is one proposal per iteration:
+    // measured at n = 10^4 / 50 clusters, 256 threads with 64 on the restricted scans +12 % (256 chains), 512 with 128 +11 %.
+    s->ovl_min_thr = 256; s->rs_team = nthr >= 512 ? 128 : 64;
+    if (const char* e = getenv("RCB200_OVERLAP_MIN_THREADS")) s->ovl_min_thr = atoi(e);
+    if (const char* e = getenv("RCB200_RS_TEAM")) s->rs_team = std::max(32, atoi(e) / 32 * 32);
     {
       // shared memory per chain: the fixed part plus as many split-merge members (64 B each) as fit next to the other
       // CTAs of the SM (two chains per SM when there are more chains than SMs)

@@ -96,6 +96,7 @@ struct CtaShared {
 
 // Incremental mode (k_chain_inc): hand-off block of the chain's team.
 #define RC_INC_MAXW 16               // warps per chain, at most
+#define RC_RS_MAXW 8                 // warps that evaluate a batch of the restricted scans, at most
 struct IncShared {
   int first[3];      // lowest warp / step of a batch that needs a commit (three rotating slots, see inc_scan_rows)
   int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
@@ -106,7 +107,9 @@ struct IncShared {
   int dry_stop;      // row at which the scan that ran beside the restricted scans stopped (first row that moves; n: none)
   int hint;          // rows per batch the previous scan ended with (0: none yet)
   int narrow;        // lanes per row of the scan (4 / 8 / 16: every live slot and the first empty slot lie below 64 / 128 / 256)
-  int rs_cand[RC_INC_MAXW][4];          // restricted scans: per warp {item, its slot, its new slot} of the warp's first moving step
+  int rs_mv[RC_INC_MAXW][8];            // restricted scans: per warp the moves of its eight steps, in step order: item << 1 | (1: ca -> cb)
+  int rs_nm[RC_INC_MAXW];               // ... and how many
+  double rs_win[RC_RS_MAXW][6][16];     // ... per evaluating warp: LGA / LGZ / LPR at the sixteen sizes its steps can see ({A, B} x 3 tables)
   double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
 };
 #define RC_INC_NONE 0x7fffffff
@@ -218,6 +221,17 @@ __device__ __forceinline__ void bsync(const Ctx& c) { asm volatile("bar.sync %0,
 // a team is either the whole chain (RC_NTHR threads, csync) or its bulk warps (RC_BW*32 threads, bsync)
 template <bool BULK> __device__ __forceinline__ void tsync(const Ctx& c) { if (BULK) bsync(c); else csync(c); }
 
+// sum of a 128-bit value over the lanes of a warp (every lane gets the total)
+__device__ __forceinline__ rc_i128 warp_sum128(rc_i128 v) {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    rc_i128 o;
+    o.lo = __shfl_xor_sync(0xffffffffu, v.lo, off);
+    o.hi = __shfl_xor_sync(0xffffffffu, v.hi, off);
+    rc_add128(v, o);
+  }
+  return v;
+}
 __device__ __forceinline__ int tri(int k, int t, int cap) { return k < t ? k * cap + t : t * cap + k; }
 __device__ __forceinline__ long long shfl_up_ll(long long v, int off) { return __shfl_up_sync(0xffffffffu, v, off); }
 __device__ __forceinline__ long long shfl_xor_ll(long long v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
@@ -1212,6 +1226,9 @@ __device__ void build_lpr(const Ctx& c) {
 // the rest is evaluated again after the move has been applied.  Every committed step sees exactly the inputs of the
 // sequential scan, so the results are the same bits.
 #define RC_RS_B 8
+#ifndef RC_RS_PF
+#define RC_RS_PF 4      // steps of a short batch whose rows the idle warps pull towards L2
+#endif
 __device__ void restricted_scans(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
@@ -1445,9 +1462,13 @@ __device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, in
   }
 }
 
-// restricted_scans for the whole team: every warp evaluates eight consecutive steps (as restricted_scans does), so a
-// batch covers 8 * nwarp steps; the steps up to and including the first one that moves its item are committed, the move
-// is applied to the running candidate sums of all members by all threads, and the scan continues behind it.
+// restricted_scans for the whole team: every warp evaluates eight consecutive steps (a quad of lanes per step, as
+// restricted_scans does) and resolves them among themselves -- each quad holds the matrix entries between its item and
+// the items of the warp's earlier steps, so when an earlier step moves its item the later quads correct their sums in
+// registers and decide again, in step order.  A warp's eight steps are therefore final given the state at the start of
+// the batch.  A batch covers 8 * nwact steps: the warps up to and including the first one with a move are committed, that
+// warp's moves (up to eight) are applied to the running candidate sums of all members by all threads with one round of
+// gathers, and the scan continues behind them.
 __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int c1, int c2, bool split) {
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
@@ -1461,9 +1482,11 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
   const bool c1dyn = (c1 == ca || c1 == cb), c2dyn = (c2 == ca || c2 == cb);
   const int st = lane >> 2, role = lane & 3, quad = lane & ~3;
   const bool isA = (role & 1) == 0;
+  const unsigned qm = 0xfu << quad;
   double ltp = 0.0;                                   // accumulated by thread 0 in step order
   int batch = 0;
-  int nwact = NW;                                     // warps that evaluate a batch: follows the observed run length between moves
+  const int NWE = min(NW, RC_RS_MAXW);
+  int nwact = NWE;                                    // warps that evaluate a batch: follows the observed run length between moves
   for (int g = 0; g <= numGibbs; ++g) {
     const bool last = g == numGibbs;
     const bool forced = last && !split;
@@ -1478,10 +1501,10 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
       const int pos = pos0 + stepi;
       const bool on = stepi < nb;
       if (nwact <= 2 && warp >= nwact && mt <= 1024) {
-        // Short runs: a move is likely within the next few steps, and its update gathers the mover's row at every member
-        // column (DRAM latency on the critical path).  The warps that sit this batch out pull those entries towards L2
-        // for the first steps of the batch while the evaluating warps are busy.
-        const int npf = min(nb, 4);
+        // Short runs: moves are likely within the next few steps, and their update gathers the movers' rows at every
+        // member column (DRAM latency on the critical path).  The warps that sit this batch out pull those entries
+        // towards L2 for the first steps of the batch while the evaluating warps are busy.
+        const int npf = min(nb, RC_RS_PF);
         const int nidle = (NW - nwact) * 32, me = (warp - nwact) * 32 + lane;
         for (int q = me; q < mt; q += nidle) {
           const int xq = c.Slist[q];
@@ -1494,110 +1517,145 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
       int y = 0, cur = 0, cnew = 0, k = 0;
       double lt = 0.0;
       long long trx = tr0;
-      if (on) {
-        y = c.Slist[pos];
-        const longlong2 self = c.DG[pos];
-        const longlong4 ab = c.AB[pos];
-        const double2 l2s = c.L2s[pos];
-        const double2 nz = forced ? make_double2(0.0, 0.0) : c.NZ[(size_t)g * nS + pos];
-        cur = c.labL[y];
-        // sums over the candidates with y detached (:303-304)
-        const long long sAd = ab.x - (cur == ca ? self.x : 0), sAl = ab.y - (cur == ca ? self.y : 0);
-        const long long sBd = ab.z - (cur == cb ? self.x : 0), sBl = ab.w - (cur == cb ? self.y : 0);
-        const int szA = c.szL[ca] - (cur == ca ? 1 : 0), szB = c.szL[cb] - (cur == cb ? 1 : 0);
-        // roles 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)} -- one logarithm each
-        double X;
-        {
-          const int szs = isA ? szA : szB;
-          const double szd = (double)szs;
-          const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
-          if ((role & 2) == 0) {                                                                    // :313-319, 327-330
-            const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-            X = kp.LGZ[szs] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
-          } else {                                                                                  // :307-312, 321-326
-            const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-            X = kp.LGA[szs] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+      if (warp < nwact) {                                // (uniform per warp)
+        // the size-indexed tables at the sizes this warp's steps can see (start-of-batch size - 8 .. + 7), into shared memory:
+        // a step that is decided again after an earlier step moved must not wait for global memory
+        double (*win)[16] = sh->rs_win[warp];
+        const int loA = c.szL[ca] - 8, loB = c.szL[cb] - 8;
+        double wv[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int idx = lane + 32 * u, tb = idx >> 4, off = idx & 15;
+          const int sz = min(max(((tb & 1) ? loB : loA) + off, 0), c.n);
+          wv[u] = tb < 2 ? kp.LGA[sz] : (tb < 4 ? kp.LGZ[sz] : c.LPR[sz]);
+        }
+        long long sAd = 0, sAl = 0, sBd = 0, sBl = 0;
+        int szA = 0, szB = 0, forcedto = 0;
+        double2 l2s = make_double2(0.0, 0.0), nz = make_double2(0.0, 0.0);
+        longlong2 e0 = make_longlong2(0, 0), e1 = make_longlong2(0, 0);
+        if (on) {
+          y = c.Slist[pos];
+          // entries between this step's item and the items of the warp's earlier steps (role r holds steps r and r + 4)
+          const longlong2* row = c.DL + (size_t)y * c.n;
+          if (role < st) e0 = __ldg(row + c.Slist[pos - st + role]);
+          if (role + 4 < st) e1 = __ldg(row + c.Slist[pos - st + role + 4]);
+          const longlong2 self = c.DG[pos];
+          const longlong4 ab = c.AB[pos];
+          l2s = c.L2s[pos];
+          if (!forced) nz = c.NZ[(size_t)g * nS + pos]; else forcedto = c.origM[pos];
+          cur = c.labL[y];
+          // sums over the candidates with y detached (:303-304)
+          sAd = ab.x - (cur == ca ? self.x : 0); sAl = ab.y - (cur == ca ? self.y : 0);
+          sBd = ab.z - (cur == cb ? self.x : 0); sBl = ab.w - (cur == cb ? self.y : 0);
+          szA = c.szL[ca] - (cur == ca ? 1 : 0); szB = c.szL[cb] - (cur == cb ? 1 : 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) { const int idx = lane + 32 * u; win[idx >> 4][idx & 15] = wv[u]; }     // (after every load of the step is in flight)
+        __syncwarp();
+        // one step's decision from its current sums (the four lanes of the quad: one logarithm each)
+        auto decide = [&]() {
+          // roles 0..3: {L2'(ca), L2'(cb), L1(ca), L1(cb)}
+          double X;
+          {
+            const int szs = isA ? szA : szB;
+            const double szd = (double)szs;
+            const double sD = rc_dequant(isA ? sAd : sBd, c.qD), sL = rc_dequant(isA ? sAl : sBl, c.qL);
+            if ((role & 2) == 0) {                                                                    // :313-319, 327-330
+              const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+              X = win[2 + (isA ? 0 : 1)][szs - (isA ? loA : loB)] - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+            } else {                                                                                  // :307-312, 321-326
+              const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+              X = win[isA ? 0 : 1][szs - (isA ? loA : loB)] + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+            }
           }
-        }
+          const double L2pA = __shfl_sync(qm, X, quad), L2pB = __shfl_sync(qm, X, quad + 1);
+          const double L1A = __shfl_sync(qm, X, quad + 2), L1B = __shfl_sync(qm, X, quad + 3);
+          const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
+          const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
+          const double L2i = L2p1 + L2p2;                                                             // :331 (quirk Q2)
+          const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                            // :332-334
+          double lp0 = win[4][szA - loA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));          // :335
+          double lp1 = win[5][szB - loB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
+          if (!forced) {                                                                              // :336-338
+            double mn = lp0;
+            if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+            lp0 -= mn; lp1 -= mn;
+            const double g0 = nz.x + lp0, g1 = nz.y + lp1;
+            k = 0;
+            if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
+            cnew = k == 0 ? ca : cb;
+          } else {                                                                                    // :339-342
+            cnew = forcedto;
+            k = (ca == cnew) ? 0 : 1;
+          }
+          if (last) {                                                                                 // :347-351
+            double mn = lp0;                                                                          // quirk Q3
+            if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
+            lp0 += mn; lp1 += mn;
+            double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
+            const double den = p0 + p1;
+            p0 /= den; p1 /= den;
+            lt = rc_log(k == 0 ? p0 : p1);
+          }
+        };
+        if (on) decide();
         trx = RC_CLOCK();
-        const unsigned qm = 0xfu << quad;
-        const double L2pA = __shfl_sync(qm, X, quad), L2pB = __shfl_sync(qm, X, quad + 1);
-        const double L1A = __shfl_sync(qm, X, quad + 2), L1B = __shfl_sync(qm, X, quad + 3);
-        const double L2p1 = c1dyn ? (c1 == ca ? L2pA : L2pB) : l2s.x;
-        const double L2p2 = c2dyn ? (c2 == ca ? L2pA : L2pB) : l2s.y;
-        const double L2i = L2p1 + L2p2;                                                             // :331 (quirk Q2)
-        const double L2a = L2i - L2pA, L2b = L2i - L2pB;                                            // :332-334
-        double lp0 = c.LPR[szA] + (L1A + (P.repulsion ? L2a : copysign(0.0, L2a)));                 // :335
-        double lp1 = c.LPR[szB] + (L1B + (P.repulsion ? L2b : copysign(0.0, L2b)));
-        if (!forced) {                                                                              // :336-338
-          double mn = lp0;
-          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-          lp0 -= mn; lp1 -= mn;
-          const double g0 = nz.x + lp0, g1 = nz.y + lp1;
-          k = 0;
-          if (!rc_isnan(g0)) { if (rc_isnan(g1) || g1 > g0) k = 1; }
-          cnew = k == 0 ? ca : cb;
-        } else {                                                                                    // :339-342
-          cnew = c.origM[pos];
-          k = (ca == cnew) ? 0 : 1;
+        // resolve the warp's steps in order: a step that moves its item changes the sums of the steps behind it (:344-345)
+        unsigned pend = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur);     // steps that move their item, as decided so far
+        while (pend) {
+          const int l0 = __ffs(pend) - 1, s2 = l0 >> 2;                                  // the earliest one is final
+          const int a2b = __shfl_sync(0xffffffffu, cur == ca ? 1 : 0, l0);
+          if (on && st > s2) {
+            const longlong2 mine = (s2 >> 2) ? e1 : e0;
+            const int src = quad + (s2 & 3);
+            const long long ex = __shfl_sync(qm, mine.x, src), ey = __shfl_sync(qm, mine.y, src);
+            if (a2b) { sAd -= ex; sAl -= ey; sBd += ex; sBl += ey; szA -= 1; szB += 1; }
+            else { sAd += ex; sAl += ey; sBd -= ex; sBl -= ey; szA += 1; szB -= 1; }
+            decide();
+          }
+          pend = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur && st > s2);
         }
-        if (last) {                                                                                 // :347-351
-          double mn = lp0;                                                                          // quirk Q3
-          if (!rc_isnan(mn)) { if (rc_isnan(lp1) || lp1 < mn) mn = lp1; }
-          lp0 += mn; lp1 += mn;
-          double p0 = rc_exp(lp0), p1 = rc_exp(lp1);
-          const double den = p0 + p1;
-          p0 /= den; p1 /= den;
-          lt = rc_log(k == 0 ? p0 : p1);
-          if (role == 0) sh->ltbuf[par][stepi] = lt;
-        }
-      }
-      __syncwarp();
-      // the warp's first step that moves its item
-      const unsigned mv = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur);
-      if (mv) {
-        const int sf = (__ffs(mv) - 1) >> 2;
-        if (lane == 4 * sf) {
-          sh->rs_cand[warp][0] = y; sh->rs_cand[warp][1] = cur; sh->rs_cand[warp][2] = cnew;
-          atomicMin(&sh->first[slot3], warp * RC_RS_B + sf);
+        if (last && on && role == 0) sh->ltbuf[par][stepi] = lt;
+        // the warp's moves, in step order
+        const unsigned mv = __ballot_sync(0xffffffffu, on && role == 0 && cnew != cur);
+        if (mv) {
+          if (on && role == 0 && cnew != cur) sh->rs_mv[warp][__popc(mv & ((1u << lane) - 1))] = (y << 1) | (cur == ca ? 1 : 0);
+          if (lane == 0) { sh->rs_nm[warp] = __popc(mv); atomicMin(&sh->first[slot3], warp); }
         }
       }
       const long long trb = RC_CLOCK();
       csync(c);
       const long long tr1 = RC_CLOCK();
-      const int F = sh->first[slot3];
-      const int nvalid = F == RC_INC_NONE ? nb : F + 1;
-      nwact = F == RC_INC_NONE ? min(NW, nwact * 2) : max(1, min(NW, (2 * nvalid + RC_RS_B - 1) / RC_RS_B));
+      const int F = sh->first[slot3];                                                               // first warp with moves
+      const int nvalid = F == RC_INC_NONE ? nb : min(nb, (F + 1) * RC_RS_B);
+      nwact = F == RC_INC_NONE ? min(NWE, nwact * 2) : max(1, min(NWE, F + 1));
       if (last && c.ctid == 0)
         for (int q = 0; q < nvalid; ++q) ltp += sh->ltbuf[par][q];                                  // in step order, as the scan adds them
-      if (F != RC_INC_NONE) {                                                                       // :344-345
-        const int fw = F / RC_RS_B;
-        const int ym = sh->rs_cand[fw][0], curm = sh->rs_cand[fw][1], newm = sh->rs_cand[fw][2];
-        if (c.ctid == 0) { c.labL[ym] = (uint8_t)newm; c.szL[curm] -= 1; c.szL[newm] += 1; }
-        // every member's candidate sums follow the move (D is symmetric: DL[q][y] == DL[y][q])
-        const longlong2* row = c.DL + (size_t)ym * c.n;
-        const bool a2b = curm == ca;
-        {
-          const int nt = c.nthr;
-          int q = c.ctid;
-          for (; q + 3 * nt < mt; q += 4 * nt) {                 // four members per thread in flight: the gathers are DRAM latency
-            int xq[4]; longlong2 e[4]; longlong4 t[4];
+      if (F != RC_INC_NONE) {
+        const int nm = sh->rs_nm[F];
+        if (c.ctid == 0)
+          for (int m = 0; m < nm; ++m) {
+            const int v = sh->rs_mv[F][m];
+            const bool a2b = v & 1;
+            c.labL[v >> 1] = (uint8_t)(a2b ? cb : ca);
+            c.szL[ca] += a2b ? -1 : 1; c.szL[cb] += a2b ? 1 : -1;
+          }
+        // every member's candidate sums follow the moves (D is symmetric: DL[q][y] == DL[y][q]); four rows in flight
+        for (int m0 = 0; m0 < nm; m0 += 4) {
+          int mvv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xq[u] = c.Slist[q + u * nt];
+          for (int u = 0; u < 4; ++u) mvv[u] = m0 + u < nm ? sh->rs_mv[F][m0 + u] : -1;
+          for (int q = c.ctid; q < mt; q += c.nthr) {
+            const int xq = c.Slist[q];
+            longlong2 e[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { e[u] = __ldg(row + xq[u]); t[u] = c.AB[q + u * nt]; }
+            for (int u = 0; u < 4; ++u) e[u] = mvv[u] >= 0 ? __ldg(c.DL + (size_t)(mvv[u] >> 1) * c.n + xq) : make_longlong2(0, 0);
+            longlong4 t = c.AB[q];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (a2b) { t[u].x -= e[u].x; t[u].y -= e[u].y; t[u].z += e[u].x; t[u].w += e[u].y; }
-              else { t[u].x += e[u].x; t[u].y += e[u].y; t[u].z -= e[u].x; t[u].w -= e[u].y; }
-              c.AB[q + u * nt] = t[u];
+              if (mvv[u] & 1) { t.x -= e[u].x; t.y -= e[u].y; t.z += e[u].x; t.w += e[u].y; }       // (an absent move has a zero entry)
+              else { t.x += e[u].x; t.y += e[u].y; t.z -= e[u].x; t.w -= e[u].y; }
             }
-          }
-          for (; q < mt; q += nt) {
-            const longlong2 e = __ldg(row + c.Slist[q]);
-            longlong4 t = c.AB[q];
-            if (a2b) { t.x -= e.x; t.y -= e.y; t.z += e.x; t.w += e.y; }
-            else { t.x += e.x; t.y += e.y; t.z -= e.x; t.w -= e.y; }
             c.AB[q] = t;
           }
         }
@@ -1780,14 +1838,15 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   }
   csync(c);
   const long long tm1 = RC_CLOCK();
-  if (c.S && c.labL != c.lab && c.nthr >= 512 && nS + 2 <= 1024) {           // (a CTA that has its SM to itself; large member sets need every thread)
+  if (c.S && c.labL != c.lab && nS + 2 <= 1024) {           // (large member sets need every thread)
     // The restricted scans are a chain of dependent steps that keeps one or two warps busy.  With one proposal per
     // iteration the full scan that follows does not depend on them unless the proposal is accepted (quirk Q1: then the
     // scan is discarded), so the rest of the CTA runs it now, DRY: it commits nothing and stops at the first row that
     // would move its point.  Labels, sizes, S and W are only read by both sides (the proposal's labels are a copy).
-    // Measured: -11 % per iteration with one chain per SM (512 threads); with two chains per SM the two sides compete
-    // for the same issue slots and the sum gets slower (+8 %), so the 256-thread configuration does not do this.
-    const int TA = max(64, (c.nthr / 4) & ~31);
+    // The restricted scans resolve the moves of eight steps inside one warp, so a small team (kp.rs_team: 64 of 256 threads,
+    // 128 of 512) runs them as fast as the whole CTA would.  Measured at n = 10^4, 50 clusters: +12 % chain-sweeps/s with two
+    // chains per SM (256 threads each), +11 % with one (512 threads).
+    const int TA = min(kp.rs_team, c.nthr / 2);
     if (tid < TA) {
       Ctx cA = c;
       cA.nthr = TA; cA.nwarp = TA / 32; cA.barid = 2;
@@ -1814,19 +1873,27 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     }
     // block sums of the proposed state: rows a (= new slot ca) and b (= cb)
     rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);   // [rowA_D | rowA_L | rowB_D | rowB_L] x cap
-    for (int t = tid; t < cap; t += c.nthr) {
-      rc_i128 sd, sl; sd.lo = 0; sd.hi = 0; sl.lo = 0; sl.hi = 0;
-      if (c.S) {                               // the slots other than ca / cb are untouched clusters: their sums are in S
-        if (t != ca && t != cb && c.sizes[t] > 0)
-          for (int q = 0; q < nS + 2; ++q) {
+    if (c.S) {
+      // the slots other than ca / cb are untouched clusters: their sums over the members that ended in ca are entries of S.
+      // A warp per slot, the members over its lanes.
+      for (int t = warp; t < cap; t += c.nwarp) {
+        rc_i128 sd, sl; sd.lo = 0; sd.hi = 0; sl.lo = 0; sl.hi = 0;
+        if (t != ca && t != cb && c.sizes[t] > 0) {
+          for (int q = lane; q < nS + 2; q += 32) {
             const int x = c.Slist[q];
             if (c.labL[x] == ca) { const longlong2 v = c.S[(size_t)t * n + x]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
           }
-      } else {
+          sd = warp_sum128(sd); sl = warp_sum128(sl);
+        }
+        if (lane == 0) { rows[0 * cap + t] = sd; rows[1 * cap + t] = sl; }
+      }
+    } else {
+      for (int t = tid; t < cap; t += c.nthr) {
+        rc_i128 sd, sl; sd.lo = 0; sd.hi = 0; sl.lo = 0; sl.hi = 0;
         for (int q = 0; q < nS + 2; ++q)
           if (c.labL[c.Slist[q]] == ca) { const longlong2 v = c.T[(size_t)q * cap + t]; rc_add128(sd, v.x); rc_add128(sl, v.y); }
+        rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
       }
-      rows[0 * cap + t] = sd; rows[1 * cap + t] = sl;
     }
     // within / cross sums from the running candidate sums of the final state:
     //   aa = sum_{x in a_F} sum_{y in a_F} DL[x][y],  ab = sum_{x in a_F} sum_{y in b_F} DL[x][y]
@@ -1837,13 +1904,16 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
         const longlong4 ab = c.AB[q];
         rc_add128(acc[0], ab.x); rc_add128(acc[1], ab.y); rc_add128(acc[2], ab.z); rc_add128(acc[3], ab.w);
       }
-    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch [c.nthr][4]
-    for (int h = 0; h < 4; ++h) red128[tid * 4 + h] = acc[h];
+    rc_i128* red128 = reinterpret_cast<rc_i128*>(c.terms);    // scratch [c.nwarp][4]
+    for (int h = 0; h < 4; ++h) {
+      const rc_i128 w = warp_sum128(acc[h]);
+      if (lane == 0) red128[warp * 4 + h] = w;
+    }
     csync(c);
     if (tid == 0) {
       rc_i128 tot[4];
       for (int h = 0; h < 4; ++h) { tot[h].lo = 0; tot[h].hi = 0; }
-      for (int w = 0; w < c.nthr; ++w)
+      for (int w = 0; w < c.nwarp; ++w)
         for (int h = 0; h < 4; ++h) rc_add128(tot[h], red128[w * 4 + h]);
       const rc_i128 aaD = tot[0], aaL = tot[1], xD = tot[2], xL = tot[3];
       rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
@@ -2402,7 +2472,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.itmp = reinterpret_cast<int*>(smem + L.itmp);
     c.clist = smem + L.clist;
     c.lab = smem + L.lab;
-    c.labL = (kp.numMH == 1 && blockDim.x >= 512) ? smem + L.labL : c.lab;   // one proposal per iteration: the proposal works on a copy (scan beside the restricted scans)
+    c.labL = (kp.numMH == 1 && kp.ovl_min_thr > 0 && (int)blockDim.x >= kp.ovl_min_thr) ? smem + L.labL : c.lab;   // one proposal per iteration: the proposal works on a copy (scan beside the restricted scans)
   }
   const int ch = chain;
   c.WD = kp.WD + (size_t)ch * cap * cap;

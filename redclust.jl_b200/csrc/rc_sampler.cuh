@@ -51,6 +51,8 @@ struct rc_kparams {
   unsigned* Vv;         // [nchains][cap][n]  slot epoch at which each cached entry was computed (0: never)
   unsigned* epochs;     // [nchains][cap]     current epoch of every slot (>= 1)
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
+  int ovl_min_thr;      // the scan runs beside the restricted scans when the chain has at least this many threads (0: never)
+  int rs_team;          // ... and this many of them run the restricted scans
   // outputs
   uint8_t* out_labels;  // [nchains][numsamples][n]  sortlabels'd, 1-based
   int* out_K;           // [nchains][numsamples]
