@@ -1418,20 +1418,23 @@ __device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, in
   const rc_kparams& kp = *c.kp;
   const rc_params& P = kp.P;
   const int mt = nS + 2, n = c.n;
+  // Only the smaller launch side is gathered: the members are exactly the clusters ca and cb of the chain's state (a split's
+  // new slot ca is empty there), so both sides together are S[ca][x] + S[cb][x] and the other side is the difference.
+  const bool gA = c.szL[ca] <= c.szL[cb];
+  const int side = gA ? ca : cb;
   for (int q0 = 0; q0 < mt; q0 += 2 * c.nthr) {
     const int qa = q0 + c.ctid, qb = q0 + c.nthr + c.ctid;
     const bool oa = qa < mt, ob = qb < mt;
     const int xa = oa ? (int)c.Slist[qa] : 0, xb = ob ? (int)c.Slist[qb] : 0;
-    long long va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+    long long va[2] = {0, 0}, vb[2] = {0, 0};
 #pragma unroll 4
     for (int q2 = 0; q2 < mt; ++q2) {
       const int y = c.Slist[q2];                               // uniform over the team
-      const bool isA = c.labL[y] == ca;
+      if (c.labL[y] != side) continue;
       const longlong2* row = c.DL + (size_t)y * n;
       const longlong2 ea = oa ? __ldg(row + xa) : make_longlong2(0, 0);
       const longlong2 eb = ob ? __ldg(row + xb) : make_longlong2(0, 0);
-      if (isA) { va[0] += ea.x; va[1] += ea.y; vb[0] += eb.x; vb[1] += eb.y; }
-      else { va[2] += ea.x; va[3] += ea.y; vb[2] += eb.x; vb[3] += eb.y; }
+      va[0] += ea.x; va[1] += ea.y; vb[0] += eb.x; vb[1] += eb.y;
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -1439,7 +1442,10 @@ __device__ void member_sums_inc(const Ctx& c, int nS, int ca, int cb, int c1, in
       if (!(h ? ob : oa)) continue;
       const int x = h ? xb : xa;
       const long long* v = h ? vb : va;
-      longlong4 ab; ab.x = v[0]; ab.y = v[1]; ab.z = v[2]; ab.w = v[3];
+      const longlong2 ta = c.S[(size_t)ca * n + x], tb = c.S[(size_t)cb * n + x];
+      const long long od = ta.x + tb.x - v[0], ol = ta.y + tb.y - v[1];
+      longlong4 ab;
+      if (gA) { ab.x = v[0]; ab.y = v[1]; ab.z = od; ab.w = ol; } else { ab.x = od; ab.y = ol; ab.z = v[0]; ab.w = v[1]; }
       c.AB[q] = ab;
       c.DG[q] = __ldg(c.DL + (size_t)x * n + x);
       if (q < nS) {
@@ -1645,18 +1651,30 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
           int mvv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) mvv[u] = m0 + u < nm ? sh->rs_mv[F][m0 + u] : -1;
-          for (int q = c.ctid; q < mt; q += c.nthr) {
-            const int xq = c.Slist[q];
-            longlong2 e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) e[u] = mvv[u] >= 0 ? __ldg(c.DL + (size_t)(mvv[u] >> 1) * c.n + xq) : make_longlong2(0, 0);
-            longlong4 t = c.AB[q];
+          for (int q = c.ctid; q < mt; q += 2 * c.nthr) {
+            const int q1 = q + c.nthr;
+            const bool o1 = q1 < mt;
+            const int xq = c.Slist[q], xq1 = o1 ? (int)c.Slist[q1] : 0;
+            longlong2 e[4], f[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (mvv[u] & 1) { t.x -= e[u].x; t.y -= e[u].y; t.z += e[u].x; t.w += e[u].y; }       // (an absent move has a zero entry)
-              else { t.x += e[u].x; t.y += e[u].y; t.z -= e[u].x; t.w -= e[u].y; }
+              const longlong2* row = c.DL + (size_t)(mvv[u] >> 1) * c.n;
+              e[u] = mvv[u] >= 0 ? __ldg(row + xq) : make_longlong2(0, 0);
+              f[u] = (mvv[u] >= 0 && o1) ? __ldg(row + xq1) : make_longlong2(0, 0);
+            }
+            longlong4 t = c.AB[q], t1 = o1 ? c.AB[q1] : longlong4{0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (mvv[u] & 1) {                                                                       // (an absent move has zero entries)
+                t.x -= e[u].x; t.y -= e[u].y; t.z += e[u].x; t.w += e[u].y;
+                t1.x -= f[u].x; t1.y -= f[u].y; t1.z += f[u].x; t1.w += f[u].y;
+              } else {
+                t.x += e[u].x; t.y += e[u].y; t.z -= e[u].x; t.w -= e[u].y;
+                t1.x += f[u].x; t1.y += f[u].y; t1.z -= f[u].x; t1.w -= f[u].y;
+              }
             }
             c.AB[q] = t;
+            if (o1) c.AB[q1] = t1;
           }
         }
         csync(c);
