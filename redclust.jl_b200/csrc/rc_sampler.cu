@@ -2087,9 +2087,26 @@ struct RowCtx {
   unsigned* Vv;              // [cap][n] epoch of the slot at which the cached entry was computed (0: never)
   const unsigned* ep;        // [cap] current epoch of every slot (shared memory)
 };
-__device__ __forceinline__ double inc_noise(const RowCtx& c, unsigned it, int i, int kk) {          // utils.jl:4-5
-  const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
+// Out of line on purpose: a row evaluation is unrolled over the lane's slots, and these two bodies (a Philox block and two
+// logarithms each) are reached by a few slots per row only -- sixteen inlined copies of each made the evaluator larger than
+// the instruction cache (ncu: 15 % of the kernel's stall samples were instruction fetches at exactly these branches).
+__device__ __noinline__ double inc_noise_ool(unsigned long long key, unsigned it, int i, int kk) {  // utils.jl:4-5
+  const rc_draw dr = rc_draw2(key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
   return -rc_log(-rc_log((kk & 1) ? dr.u1 : dr.u0));
+}
+__device__ __forceinline__ double inc_noise(const RowCtx& c, unsigned it, int i, int kk) { return inc_noise_ool(c.key, it, i, kk); }
+// per-slot terms (L1, L2') of one (slot, point) from its row sum and size (:206-242)
+__device__ __noinline__ double2 inc_terms_ool(const rc_kparams* kpp, long long sx, long long sy, int szs, double lgA, double lgZ, int qD, int qL) {
+  const rc_kparams& kp = *kpp;
+  const rc_params& P = kp.P;
+  const double szd = (double)szs;
+  const double sD = rc_dequant(sx, qD), sL = rc_dequant(sy, qL);
+  const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
+  const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
+  double2 o;
+  o.x = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
+  o.y = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+  return o;
 }
 // Returns the chosen slot (the same value in the G lanes of the row's group), or -2 when a new cluster is a candidate
 // and no slot is free.  All G lanes of a group call it with the same i; groups are independent of each other.
@@ -2147,14 +2164,10 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
     long long sx = __double_as_longlong(va[j]), sy = __double_as_longlong(vb[j]);
     if (own) { sx -= self.x; sy -= self.y; }                                // :193-194 detach i
     const int szs = c.sizes[k] - (own ? 1 : 0);
-    const double szd = (double)szs;
     const double lgA = own ? tabs[3 * cap + k] : tabs[k];
     const double lgZ = own ? tabs[4 * cap + k] : tabs[cap + k];
-    const double sD = rc_dequant(sx, c.qD), sL = rc_dequant(sy, c.qL);
-    const double a_i = P.alpha + P.delta1 * szd, b_i = P.beta + sD;
-    const double z_i = P.zeta + P.delta2 * szd, g_i = P.gamma + sD;
-    va[j] = lgA + kp.abratio - a_i * rc_log(b_i) + (P.delta1 - 1) * sL - szd * kp.lgd1;
-    vb[j] = lgZ - z_i * rc_log(g_i) + kp.zgratio + (P.delta2 - 1) * sL - szd * kp.lgd2;
+    const double2 tv = inc_terms_ool(c.kp, sx, sy, szs, lgA, lgZ, c.qD, c.qL);
+    va[j] = tv.x; vb[j] = tv.y;
     if (!own) { c.Cc[(size_t)k * n + i] = make_double2(va[j], vb[j]); c.Vv[(size_t)k * n + i] = c.ep[k]; }
   }
   // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
