@@ -43,7 +43,8 @@ struct rc_sampler {
   rc_i128 *WD, *WL, *WDbak, *WLbak; uint8_t* labbak; int* szbak; longlong2* T; unsigned short* Slist;
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
-  double2* Cc; unsigned *Vv, *epochs;   // incremental mode: cached per-slot terms, their epochs, the slots' epochs
+  double2* Cc; unsigned *Vv, *epochs;   // incremental mode: cached per-slot terms, per-point / per-slot change counts that validate them
+  int tw_smem;
   longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
@@ -176,7 +177,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs; kp.tw_smem = s->tw_smem;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -320,7 +321,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   // re-reduces every row against the labels (no per-chain matrix; needed when nchains * cap * n * 16 B does not fit).
   {
     const char* env = getenv("RCB200_SCAN");
-    const size_t needS = (sizeof(longlong2) + sizeof(double2) + sizeof(unsigned)) * (size_t)nchains * cap * n;   // row sums + cached terms + their epochs
+    const size_t needS = (sizeof(longlong2) + sizeof(double2)) * (size_t)nchains * cap * n;   // row sums + cached terms
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
     bool want = !opt_loglik_only && needS <= freeb / 10 * 6;
@@ -344,12 +345,16 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     {
       // shared memory per chain: the fixed part plus as many split-merge members (64 B each) as fit next to the other
       // CTAs of the SM (two chains per SM when there are more chains than SMs)
-      const size_t base = rc_sampler_inc_smem_bytes((int)n, cap, 0);
       const size_t budget = nchains <= nsm ? (size_t)maxsmem : ((size_t)maxsmem + 1024) / 2 - 1024;
+      // the per-point validity counts of the cached terms (4 B per point) go to shared memory when at least 512 split-merge
+      // members still fit beside them: the row evaluation then knows which entries are valid without a trip to memory
+      s->tw_smem = rc_sampler_inc_smem_bytes((int)n, cap, 512, 1) <= budget ? 1 : 0;
+      if (const char* e = getenv("RCB200_TW_SMEM")) s->tw_smem = atoi(e) != 0 && rc_sampler_inc_smem_bytes((int)n, cap, 0, 1) <= budget;
+      const size_t base = rc_sampler_inc_smem_bytes((int)n, cap, 0, s->tw_smem);
       int mcap = base < budget ? (int)((budget - base) / 64) : 0;
       mcap = std::min<int>(mcap, (int)n + 2) / 8 * 8;
       s->inc_mcap = std::max(mcap, 0);
-      s->inc_smem = rc_sampler_inc_smem_bytes((int)n, cap, s->inc_mcap);
+      s->inc_smem = rc_sampler_inc_smem_bytes((int)n, cap, s->inc_mcap, s->tw_smem);
       if (s->inc_smem > (size_t)maxsmem) { s->inc_mcap = 0; s->inc_smem = base; }
     }
     if (s->inc && s->inc_smem > (size_t)maxsmem) s->inc = false;
@@ -357,8 +362,8 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   }
   s->terms_stride = (size_t)std::max(cap * cap, 8192);
   if (s->inc) {
-    TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->Cc, (size_t)nchains * cap * n)); TRY(dalloc(&s->Vv, (size_t)nchains * cap * n));
-    TRY(dalloc(&s->epochs, (size_t)nchains * cap));
+    TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->Cc, (size_t)nchains * cap * n)); TRY(dalloc(&s->Vv, (size_t)nchains * n));
+    TRY(dalloc(&s->epochs, (size_t)nchains * (cap + 1)));
   }
   TRY(dalloc(&s->T, (opt->numMH > 0 && !s->inc) ? (size_t)nchains * n * cap : 1));
   if (opt->numMH > 1) {
@@ -417,8 +422,8 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRYC(cudaMemcpy(s->p, init_p, sizeof(double) * nchains, cudaMemcpyHostToDevice));
   TRYC(cudaMemset(s->status, 0, sizeof(int) * nchains));
   if (s->inc) {
-    TRYC(cudaMemset(s->Vv, 0, sizeof(unsigned) * (size_t)nchains * cap * n));          // no cached entry is valid
-    std::vector<unsigned> ones((size_t)nchains * cap, 1u);
+    TRYC(cudaMemset(s->Vv, 0, sizeof(unsigned) * (size_t)nchains * n));                // no cached entry is valid
+    std::vector<unsigned> ones((size_t)nchains * (cap + 1), 1u);
     TRYC(cudaMemcpy(s->epochs, ones.data(), sizeof(unsigned) * ones.size(), cudaMemcpyHostToDevice));
   }
   TRYC(cudaMemset(s->stats, 0, sizeof(long long) * 16 * nchains));

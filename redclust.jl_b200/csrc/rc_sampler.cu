@@ -102,6 +102,7 @@ struct IncShared {
   int ev;            // what that warp found: 1 move, 2 a slot beyond this instantiation is needed, 3 slot capacity exhausted
   int mv_i, mv_a, mv_b;
   int nmoves;
+  unsigned clk;      // number of changes of the chain's state so far (moves of the scan, committed proposals): the clock of the cached terms
   int nlive, e0;     // live slots of the chain's state and its first empty slot (-1: none), see inc_build_tables
   int sfirst[3];     // the scan's own rotating slots (the restricted scans use first[] and may run beside it)
   int dry_stop;      // row at which the scan that ran beside the restricted scans stopped (first row that moves; n: none)
@@ -164,8 +165,8 @@ struct Ctx {
   double* tabs;           // incremental mode (shared memory): [6][cap] lgamma(alpha + delta1 s), lgamma(zeta + delta2 s), prior term at the slot's size / at size - 1
   int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
   double2* Cc;            // incremental mode (global): [cap][n] cached per-slot terms, see inc_eval_row
-  unsigned* Vv;           // incremental mode (global): [cap][n] slot epoch of each cached entry
-  unsigned* ep;           // incremental mode (shared memory): [cap] current epoch of every slot
+  unsigned* tw;           // incremental mode (shared memory when it fits, else global): [n] change count at which point x's cached entries were last made valid
+  unsigned* tchg;         // incremental mode (shared memory): [cap] change count at which each slot last gained or lost a point
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
   uint8_t* origM;         // their labels in the chain's state
   longlong4* AB;          // [n+2] running sums of each member's row over the two candidate clusters {aD, aL, bD, bL}
@@ -2016,7 +2017,10 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
         const int y = c.Slist[q], from = c.origM[q], to = c.labL[y];
         if (from != to) inc_update_S(c, y, from, to);
       }
-      for (int s2 = tid; s2 < cap; s2 += c.nthr) c.ep[s2] += 1;            // cached per-slot terms: all stale
+      const unsigned m = c.inc->clk + 1;                                    // cached per-slot terms: all stale
+      csync(c);
+      for (int s2 = tid; s2 < cap; s2 += c.nthr) c.tchg[s2] = m;
+      if (tid == 0) c.inc->clk = m;
     }
   } else {
     // restore the labels of the members (the proposal lived in place)
@@ -2063,10 +2067,13 @@ __device__ void record_labels(const Ctx& c, uint8_t* out) {
 // CTA works on consecutive rows: one 128-byte segment per slot and 8 rows) for one that does not.
 //
 // Per-slot terms are CACHED across sweeps: L1 and L2' of (slot k, point i) depend only on S[k][i] and the size of k, i.e.
-// on cluster k alone, which carries an epoch that is bumped whenever it gains or loses a point.  An entry whose stored
-// epoch equals the slot's is what a fresh evaluation would give (same formula, same inputs, same bits); anything else is
-// recomputed and stored.  The point's own slot (evaluated with the point detached) is never cached.  A chain at
-// equilibrium therefore spends two logarithms per row instead of two per (row, cluster).
+// on cluster k alone.  The chain counts its state changes (clk: moves of the scan, committed proposals); every slot
+// remembers the count at which it last gained or lost a point (tchg[k]) and every point the count at which its row was
+// last evaluated (tw[i]) -- an evaluation leaves the entry of EVERY live slot of that point valid (kept or recomputed and
+// stored).  Entry (k, i) is therefore what a fresh evaluation would give (same formula, same inputs, same bits) exactly
+// when tchg[k] <= tw[i]; anything else is recomputed.  The point's own slot (evaluated with the point detached) is never
+// cached.  A chain at equilibrium spends two logarithms per row instead of two per (row, cluster), and validity costs
+// one 4-byte count per point (shared memory when it fits) instead of a tag per entry.
 #define RC_NZMAX 37.0   // Gumbel noise -log(-log u) <= 36.74 for every 53-bit u < 1: candidates further than this below the leader cannot win
 #define RC_NP 16        // slots per lane of a row group
 // What a row evaluation reads, passed BY VALUE: inc_eval_row is deliberately not inlined (its register allocation stays
@@ -2084,8 +2091,8 @@ struct RowCtx {
   const rc_kparams* kp;
   unsigned long long key;
   double2* Cc;               // [cap][n] cached per-slot terms (L1, L2') of every point attached elsewhere
-  unsigned* Vv;              // [cap][n] epoch of the slot at which the cached entry was computed (0: never)
-  const unsigned* ep;        // [cap] current epoch of every slot (shared memory)
+  unsigned* tw;              // [n] change count at which the point's cached entries were last all valid (0: never)
+  const unsigned* tchg;      // [cap] change count at which each slot last changed (shared memory)
 };
 // Out of line on purpose: a row evaluation is unrolled over the lane's slots, and these two bodies (a Philox block and two
 // logarithms each) are reached by a few slots per row only -- sixteen inlined copies of each made the evaluator larger than
@@ -2133,27 +2140,28 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   if (!single && (li & (G - 1)) == g) own_s = c.S[(size_t)li * n + i];
   // ---- the lane's slots: liveness (i detached), cached terms or row sums, all loads up front ----
   unsigned live = 0u, fresh = 0u;                                           // bit j: slot g + G j is a live candidate / must be recomputed
-  unsigned tag[RC_NP];
+  const unsigned twi = c.tw[i], clk = sh->clk;
 #pragma unroll
   for (int j = 0; j < RC_NP; ++j) {
     const int k = g + G * j;
     const bool lv = k < cap && c.sizes[k] - (k == li ? 1 : 0) > 0;
     live |= (lv ? 1u : 0u) << j;
-    tag[j] = (lv && k != li) ? c.Vv[(size_t)k * n + i] : 0u;
   }
   double va[RC_NP], vb[RC_NP];                                              // (L1, L2') -- or the raw row sums until they are evaluated
 #pragma unroll
   for (int j = 0; j < RC_NP; ++j) {
     const int k = g + G * j;
-    va[j] = 0.0; vb[j] = 0.0;
-    if ((live >> j) & 1u) {
-      if (k != li && tag[j] == c.ep[k]) { const double2 t = c.Cc[(size_t)k * n + i]; va[j] = t.x; vb[j] = t.y; }
-      else {
-        const longlong2 t = k == li ? own_s : c.S[(size_t)k * n + i];
-        va[j] = __longlong_as_double(t.x); vb[j] = __longlong_as_double(t.y);
-        fresh |= 1u << j;
-      }
-    }
+    // one 16-byte load per live slot, without a branch (all of the lane's loads are in flight together): the cached terms
+    // when slot k has not changed since they were made, else its row sum
+    const bool lv = (live >> j) & 1u, own = k == li;
+    const bool hit = lv && !own && c.tchg[k] <= twi;
+    const size_t idx = (size_t)k * n + i;
+    const longlong2* src = hit ? reinterpret_cast<const longlong2*>(c.Cc + idx) : c.S + idx;
+    longlong2 t = make_longlong2(0, 0);
+    if (lv && !own) t = *src;
+    if (own) t = own_s;
+    va[j] = __longlong_as_double(t.x); vb[j] = __longlong_as_double(t.y);
+    if (lv && !hit) fresh |= 1u << j;
   }
   // ---- per-slot terms (:206-242) of the slots that have no valid cached entry (always the point's own slot) ----
 #pragma unroll
@@ -2168,8 +2176,9 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
     const double lgZ = own ? tabs[4 * cap + k] : tabs[cap + k];
     const double2 tv = inc_terms_ool(c.kp, sx, sy, szs, lgA, lgZ, c.qD, c.qL);
     va[j] = tv.x; vb[j] = tv.y;
-    if (!own) { c.Cc[(size_t)k * n + i] = make_double2(va[j], vb[j]); c.Vv[(size_t)k * n + i] = c.ep[k]; }
+    if (!own) c.Cc[(size_t)k * n + i] = make_double2(va[j], vb[j]);
   }
+  if (g == 0 && twi != clk) c.tw[i] = clk;                                  // every live slot's entry of this point is valid as of now
   // ---- vecsum(L2', C_i) in the canonical order (:243): slot s in class s % 32, ascending within a class, then the
   //      xor-butterfly tree over the 32 classes (16, 8, 4, 2, 1).  A lane owns the classes g + G q entirely, so the tree
   //      levels with offset >= G are local and the last log2(G) levels are shuffles inside the group ----
@@ -2318,7 +2327,7 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
       c.tabs[5 * cap + s] = c.LPR[sz > 1 ? sz - 1 : 1];
     }
   }
-  if (only_a >= 0 && lane == 0) { c.ep[only_a] += 1; c.ep[only_b] += 1; }       // clusters a and b changed: their cached terms are stale
+  if (only_a >= 0 && lane == 0) { const unsigned m = ++sh->clk; c.tchg[only_a] = m; c.tchg[only_b] = m; }   // clusters a and b changed: their cached terms are stale
   if (lane == 0) {
     sh->nlive = base; sh->e0 = e0;
     const int hi = max(base > 0 ? (int)c.live[base - 1] : 0, e0 >= 0 ? e0 : cap - 1);   // highest slot a row of the scan can meet
@@ -2339,7 +2348,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
   csync(c);
   RowCtx rc;
   rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.rank = c.rank;
-  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.Vv = c.Vv; rc.ep = c.ep;
+  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.tw = c.tw; rc.tchg = c.tchg;
   int batch = 0, i0 = istart;
   // Rows per batch follow the observed run length between moves (rows behind a move are evaluated again).
   int nrows = sh->hint > 0 ? sh->hint : NT, streak = 0;
@@ -2443,8 +2452,8 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
   csync(c);
 }
 
-struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, labL, live, rank, tabs, res, ep, mAB, mDG, mL2s, total; };
-__host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
+struct IncLayout { size_t partial, sc, inc, red, sizes, szL, itmp, clist, lab, labL, live, rank, tabs, res, ep, tw, mAB, mDG, mL2s, total; };
+__host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap, int tw_smem) {
   IncLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t p = o; o += (bytes + 15) & ~(size_t)15; return p; };
@@ -2463,6 +2472,7 @@ __host__ __device__ inline IncLayout inc_layout(int n, int cap, int mcap) {
   L.tabs = take(sizeof(double) * 6 * cap);
   L.res = take(sizeof(int) * 512);
   L.ep = take(sizeof(unsigned) * cap);
+  L.tw = take(tw_smem ? sizeof(unsigned) * n : 0);
   L.mAB = take(sizeof(longlong4) * mcap);
   L.mDG = take(sizeof(longlong2) * mcap);
   L.mL2s = take(sizeof(double2) * mcap);
@@ -2484,7 +2494,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   c.dummy = 0; c.stage_bytes = 0; c.stages = nullptr; c.cta = nullptr; c.chain0 = nullptr; c.chain_stride = 0; c.ss_off = 0;
   c.perm = nullptr; c.runStart = nullptr; c.bscratch[0] = nullptr; c.bscratch[1] = nullptr; c.tileStart = nullptr; c.ss = nullptr;
   {
-    const IncLayout L = inc_layout(n, cap, kp.inc_mcap);
+    const IncLayout L = inc_layout(n, cap, kp.inc_mcap, kp.tw_smem);
     c.mcap = kp.inc_mcap;
     c.mAB = reinterpret_cast<longlong4*>(smem + L.mAB);
     c.mDG = reinterpret_cast<longlong2*>(smem + L.mDG);
@@ -2493,7 +2503,8 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.rank = smem + L.rank;
     c.tabs = reinterpret_cast<double*>(smem + L.tabs);
     c.res = reinterpret_cast<int*>(smem + L.res);
-    c.ep = reinterpret_cast<unsigned*>(smem + L.ep);
+    c.tchg = reinterpret_cast<unsigned*>(smem + L.ep);
+    c.tw = kp.tw_smem ? reinterpret_cast<unsigned*>(smem + L.tw) : kp.Vv + (size_t)chain * n;
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2511,7 +2522,6 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   c.T = nullptr;
   c.S = kp.S + (size_t)ch * cap * n;
   c.Cc = kp.Cc + (size_t)ch * cap * n;
-  c.Vv = kp.Vv + (size_t)ch * cap * n;
   c.WDbak = kp.WDbak ? kp.WDbak + (size_t)ch * cap * cap : nullptr;
   c.WLbak = kp.WLbak ? kp.WLbak + (size_t)ch * cap * cap : nullptr;
   c.labbak = kp.labbak ? kp.labbak + (size_t)ch * n : nullptr;
@@ -2529,7 +2539,9 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   const int tid = c.ctid, nt = c.nthr;
 
   for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
-  for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.ep[s] = kp.epochs[(size_t)chain * cap + s]; }
+  for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.tchg[s] = kp.epochs[(size_t)chain * (cap + 1) + s]; }
+  if (kp.tw_smem) for (int j = tid; j < n; j += nt) c.tw[j] = kp.Vv[(size_t)chain * n + j];
+  if (tid == 0) c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap];
   if (tid == 0) {
     Scal& s = *c.sc;
     s.r = kp.r[chain]; s.p = kp.p[chain];
@@ -2585,7 +2597,10 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
           const int from = c.lab[j], to = c.labbak[j];
           if (from != to) inc_update_S(c, j, from, to);
         }
-        for (int s2 = tid; s2 < cap; s2 += nt) c.ep[s2] += 1;    // cached per-slot terms: all stale
+        const unsigned m = c.inc->clk + 1;                       // cached per-slot terms: all stale
+        csync(c);
+        for (int s2 = tid; s2 < cap; s2 += nt) c.tchg[s2] = m;
+        if (tid == 0) c.inc->clk = m;
         csync(c);
         for (int j = tid; j < n; j += nt) c.lab[j] = c.labbak[j];
         for (int s = tid; s < cap; s += nt) c.sizes[s] = c.szbak[s];
@@ -2618,7 +2633,9 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   }
   csync(c);
   for (int j = tid; j < n; j += nt) kp.labels[(size_t)chain * n + j] = c.lab[j];
-  for (int s = tid; s < cap; s += nt) { kp.sizes[(size_t)chain * cap + s] = c.sizes[s]; kp.epochs[(size_t)chain * cap + s] = c.ep[s]; }
+  for (int s = tid; s < cap; s += nt) { kp.sizes[(size_t)chain * cap + s] = c.sizes[s]; kp.epochs[(size_t)chain * (cap + 1) + s] = c.tchg[s]; }
+  if (kp.tw_smem) for (int j = tid; j < n; j += nt) kp.Vv[(size_t)chain * n + j] = c.tw[j];
+  if (tid == 0) kp.epochs[(size_t)chain * (cap + 1) + cap] = c.inc->clk;
   if (tid == 0) { kp.r[chain] = c.sc->r; kp.p[chain] = c.sc->p; kp.status[chain] = c.sc->status; }
 }
 
@@ -2740,7 +2757,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.Vv = nullptr; c.ep = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.tw = nullptr; c.tchg = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);
@@ -3029,7 +3046,7 @@ void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream
   }
 }
 
-size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap) { return inc_layout(n, cap, mcap).total; }
+size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap, int tw_smem) { return inc_layout(n, cap, mcap, tw_smem).total; }
 
 // Incremental mode: (re)build S (and W) of every chain from the labels, then one launch of k_chain_inc.
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st) {

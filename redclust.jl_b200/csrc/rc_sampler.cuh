@@ -48,8 +48,9 @@ struct rc_kparams {
   double* terms;        // [nchains][terms_stride]  log-likelihood terms / reduction scratch
   size_t terms_stride;  // max(cap*cap, 8192) doubles
   double2* Cc;          // [nchains][cap][n]  incremental mode: cached per-slot terms (L1, L2') of every (slot, point)
-  unsigned* Vv;         // [nchains][cap][n]  slot epoch at which each cached entry was computed (0: never)
-  unsigned* epochs;     // [nchains][cap]     current epoch of every slot (>= 1)
+  unsigned* Vv;         // [nchains][n]       change count at which each point's cached entries were last all valid (0: never)
+  unsigned* epochs;     // [nchains][cap + 1] change count at which each slot last changed (>= 1), then the chain's change count
+  int tw_smem;          // the per-point counts of a chain live in shared memory during a launch
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   int ovl_min_thr;      // the scan runs beside the restricted scans when the chain has at least this many threads (0: never)
   int rs_team;          // ... and this many of them run the restricted scans
@@ -68,7 +69,7 @@ struct rc_kparams {
 size_t rc_sampler_smem_bytes(int n, int cap, int tiles, int npad_max, int G);
 void rc_launch_chain_kernel(const rc_kparams& kp, size_t smem, int G, cudaStream_t st);
 bool rc_chain_kernel_coresident(int nchains, size_t smem, int G, int device);
-size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap);
+size_t rc_sampler_inc_smem_bytes(int n, int cap, int mcap, int tw_smem);
 int rc_launch_inc_init(const rc_kparams& kp, bool shared_labels, cudaStream_t st);
 int rc_inc_check(const rc_kparams& kp, long long* mismatches_S, long long* mismatches_W, cudaStream_t st);
 void rc_launch_chain_inc(const rc_kparams& kp, size_t smem, int nthr, cudaStream_t st);
