@@ -244,3 +244,38 @@ def test_points_in_random_order(pkg, orc):
     res, smp = run_both(pkg, orc, D, init, params, 5, 0, 1, 5, 1, seed=13, nchains=3)
     for got, ref, st in res:
         assert_same(got, ref, st)
+
+
+@pytest.mark.parametrize("env", [
+    dict(RCB200_INC_THREADS="256"),                                                       # the bench configuration: 64 threads on the restricted scans
+    dict(RCB200_INC_THREADS="256", RCB200_RS_TEAM="32"),
+    dict(RCB200_INC_THREADS="256", RCB200_OVERLAP_MIN_THREADS="0"),                       # scan after the restricted scans
+    dict(RCB200_INC_THREADS="256", RCB200_TW_SMEM="0"),                                   # validity counts of the cached terms in global memory
+    dict(RCB200_INC_THREADS="512", RCB200_RS_TEAM="256"),
+    dict(RCB200_INC_THREADS="128"),
+    dict(RCB200_INC_THREADS="64", RCB200_OVERLAP_MIN_THREADS="64", RCB200_RS_TEAM="32"),
+])
+def test_team_shapes_are_bit_identical(pkg, orc, monkeypatch, env):
+    """The incremental kernel's team shapes (threads per chain, threads on the restricted scans, scan beside or after them,
+    where the cached terms' validity counts live) change the schedule, never a bit: a chain that moves points, splits and
+    merges (loose mixture, wrong initial labels), three chains, against the oracle; the maintained sums equal a rebuild."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("RCB200_SCAN", "inc")
+    X, lab = mixture(700, 9, 12, 0.45, 21)
+    g = np.random.default_rng(3)
+    init = lab.copy()
+    flip = g.random(lab.size) < 0.3
+    init[flip] = g.integers(1, 10, size=int(flip.sum()))
+    init = (np.unique(init, return_inverse=True)[1] + 1).astype(np.int64)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab, maxK=40)          # (the loose mixture would open hundreds of clusters)
+    res, smp = run_both(pkg, orc, D, init, params, 25, 0, 1, 5, 1, seed=5, nchains=3)
+    assert smp.check_sums() == (0, 0)
+    moved = 0
+    for got, ref, st in res:
+        assert_same(got, ref, st)
+        moved += int((np.diff(ref["labels"].astype(np.int64), axis=0) != 0).sum())
+    splits = sum(int(r[1]["sm_split"].sum()) for r in res)
+    assert moved > 200 and 0 < splits < 75                       # the run moved points and proposed both splits and merges
