@@ -334,7 +334,7 @@ def main():
                   "moves_per_sweep": mv3, "K_final_chain0": K3, "steps": args.moving_steps, "warmup": args.moving_warmup, "clocks": clk3,
                   "config": {"workload": f"generatemixture(N={args.n}, K={args.K}; alpha={args.K}, sigma={args.moving_sigma}, dim={args.dim}) seed {args.seed}, "
                                          f"maxK={args.moving_maxK}, {args.chains} chains per GPU, init true labels, {args.moving_warmup} untimed sweeps first",
-                             "why_maxK": "at sigma = 0.25 the model opens several hundred clusters at this n; the sampler holds at most 128 live "
+                             "why_maxK": "at sigma = 0.25 the model opens several hundred clusters at this n; the sampler holds at most 255 live "
                                          "clusters per chain, so the run uses the reference's own cap parameter"},
                   "note": "per sweep the chain moves ~2 % of the points and its split-merge proposals involve clusters of thousands of points: the "
                           "restricted Gibbs scans (sequential, O(members) per move) dominate"}
