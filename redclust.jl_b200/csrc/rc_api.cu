@@ -45,6 +45,7 @@ struct rc_sampler {
   long long* stats; unsigned* gridbar; bool coresident;
   double2* Cc; unsigned *Vv, *epochs;   // incremental mode: cached per-slot terms, per-point / per-slot change counts that validate them
   int tw_smem;
+  void* Rs;                    // row summaries of the incremental scan (nchains x n x 32 B)
   longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
   int inc_nthr;                // threads per chain (= per CTA) of k_chain_inc
@@ -177,7 +178,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs; kp.tw_smem = s->tw_smem;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs; kp.tw_smem = s->tw_smem; kp.Rs = (RowSum*)s->Rs;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -223,7 +224,7 @@ void rc_sampler_destroy(rc_sampler* s) {
   rc_dev_free(s->stats); rc_dev_free(s->gridbar);
   rc_dev_free(s->out_labels); rc_dev_free(s->out_K); rc_dev_free(s->out_r); rc_dev_free(s->out_p); rc_dev_free(s->out_ll); rc_dev_free(s->out_lp);
   rc_dev_free(s->r_acc); rc_dev_free(s->sm_acc); rc_dev_free(s->sm_split);
-  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S); rc_dev_free(s->Cc); rc_dev_free(s->Vv); rc_dev_free(s->epochs);
+  rc_dev_free(s->DLp); rc_dev_free(s->colpos); rc_dev_free(s->colpt); rc_dev_free(s->S); rc_dev_free(s->Cc); rc_dev_free(s->Vv); rc_dev_free(s->epochs); rc_dev_free(s->Rs);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -364,6 +365,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   if (s->inc) {
     TRY(dalloc(&s->S, (size_t)nchains * cap * n)); TRY(dalloc(&s->Cc, (size_t)nchains * cap * n)); TRY(dalloc(&s->Vv, (size_t)nchains * n));
     TRY(dalloc(&s->epochs, (size_t)nchains * (cap + 1)));
+    { char* rs = nullptr; TRY(dalloc(&rs, (size_t)nchains * n * 32)); s->Rs = rs; }
   }
   TRY(dalloc(&s->T, (opt->numMH > 0 && !s->inc) ? (size_t)nchains * n * cap : 1));
   if (opt->numMH > 1) {
@@ -423,6 +425,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRYC(cudaMemset(s->status, 0, sizeof(int) * nchains));
   if (s->inc) {
     TRYC(cudaMemset(s->Vv, 0, sizeof(unsigned) * (size_t)nchains * n));                // no cached entry is valid
+    TRYC(cudaMemset(s->Rs, 0, (size_t)nchains * n * 32));                               // no row summary is valid (stamp 0)
     std::vector<unsigned> ones((size_t)nchains * (cap + 1), 1u);
     TRYC(cudaMemcpy(s->epochs, ones.data(), sizeof(unsigned) * ones.size(), cudaMemcpyHostToDevice));
   }

@@ -108,12 +108,28 @@ struct IncShared {
   int dry_stop;      // row at which the scan that ran beside the restricted scans stopped (first row that moves; n: none)
   int hint;          // rows per batch the previous scan ended with (0: none yet)
   int narrow;        // lanes per row of the scan (4 / 8 / 16: every live slot and the first empty slot lie below 64 / 128 / 256)
+  int fa[3], fm[3];  // row summaries (see RowSum): first row of a batch its summary does not decide / first decided row that moves
+  int mksum;         // the last committed scan moved at most two points: rows keep summaries and are tried against them first
+  int nfast_dry;     // rows the dry part of the current pass decided by their summaries
+  int scanfast;      // at least half the rows of the last complete pass were: the scan is short, nothing is gained by running it beside the restricted scans
+  int tabs_ok;       // every live slot's size-dependent prior term is finite ...
+  double maxtab;     // ... and this is their maximum (at the slot's size and at size - 1)
   int rs_mv[RC_INC_MAXW][8];            // restricted scans: per warp the moves of its eight steps, in step order: item << 1 | (1: ca -> cb)
   int rs_nm[RC_INC_MAXW];               // ... and how many
   double rs_win[RC_RS_MAXW][6][16];     // ... per evaluating warp: LGA / LGZ / LPR at the sixteen sizes its steps can see ({A, B} x 3 tables)
   double ltbuf[2][RC_INC_MAXW * 8];     // restricted scans: log transition probabilities of a batch's steps (last scan)
 };
 #define RC_INC_NONE 0x7fffffff
+
+// Summary of a row's last full evaluation (incremental mode, one per point and chain): the leading slot T, its term c_T and
+// the largest term c_2 among the other live slots, where the log-probability of slot k is tab_k + c_k with tab_k the only part
+// that depends on (r, p), and the repulsion total L2i (the new-cluster candidate is A(r, p) + L2i).  While the chain's state
+// has not changed (stamp == clk) every c_k is bit for bit what a fresh evaluation would compute, so
+//   tab_T + c_T - (max_k tab_k + c_2) > 41   and   tab_T + c_T - (A + L2i) > 41
+// prove that slot T wins the Gumbel-max whatever the noise is (noise lies in [-3.61, 36.74] for every 53-bit uniform > 0;
+// the leader's own uniform is drawn and checked to be > 0): the row is decided without being evaluated.
+// (struct RowSum { double cT, c2, L2i; int T; unsigned stamp; } is declared in rc_sampler.cuh)
+#define RC_SUM_MARGIN 41.0
 
 struct Ctx {
   int n, cap, tiles;
@@ -165,6 +181,7 @@ struct Ctx {
   double* tabs;           // incremental mode (shared memory): [6][cap] lgamma(alpha + delta1 s), lgamma(zeta + delta2 s), prior term at the slot's size / at size - 1
   int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
   double2* Cc;            // incremental mode (global): [cap][n] cached per-slot terms, see inc_eval_row
+  RowSum* Rs;             // incremental mode (global): [n] row summaries
   unsigned* tw;           // incremental mode (shared memory when it fits, else global): [n] change count at which point x's cached entries were last made valid
   unsigned* tchg;         // incremental mode (shared memory): [cap] change count at which each slot last gained or lost a point
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
@@ -1857,7 +1874,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   }
   csync(c);
   const long long tm1 = RC_CLOCK();
-  if (c.S && c.labL != c.lab && nS + 2 <= 1024) {           // (large member sets need every thread)
+  if (c.S && c.labL != c.lab && nS + 2 <= 1024 && !c.inc->scanfast) {   // (large member sets need every thread; a scan decided by its row summaries is too short to matter)
     // The restricted scans are a chain of dependent steps that keeps one or two warps busy.  With one proposal per
     // iteration the full scan that follows does not depend on them unless the proposal is accepted (quirk Q1: then the
     // scan is discarded), so the rest of the CTA runs it now, DRY: it commits nothing and stops at the first row that
@@ -2091,6 +2108,7 @@ struct RowCtx {
   const rc_kparams* kp;
   unsigned long long key;
   double2* Cc;               // [cap][n] cached per-slot terms (L1, L2') of every point attached elsewhere
+  RowSum* Rs;                // [n] row summaries (written when inc->mksum)
   unsigned* tw;              // [n] change count at which the point's cached entries were last all valid (0: never)
   const unsigned* tchg;      // [cap] change count at which each slot last changed (shared memory)
 };
@@ -2208,14 +2226,15 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   const bool ownsnew = hasnew && (e & (G - 1)) == g;
   const int jnew = e / G;
   bool anynan = false;
-  double mn = RC_INF, toplp = -RC_INF;
+  double mn = RC_INF, toplp = -RC_INF, topc = 0.0;
   int topj = -1;
 #pragma unroll
   for (int j = 0; j < RC_NP; ++j) {
     const int k = g + G * j;
     if ((live >> j) & 1u) {
       const double L2 = L2i - vb[j];
-      va[j] = (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + (va[j] + (P.repulsion ? L2 : copysign(0.0, L2)));
+      vb[j] = va[j] + (P.repulsion ? L2 : copysign(0.0, L2));               // c_k: everything but the (r, p)-dependent prior term
+      va[j] = (k == li ? tabs[5 * cap + k] : tabs[2 * cap + k]) + vb[j];
     } else if (ownsnew && j == jnew) {                                      // :228-230 new cluster
       const double L2 = L2i - 0.0;
       va[j] = (kp.LOGN[Ki + 1] + r * log1mp) + (0.0 + (P.repulsion ? L2 : copysign(0.0, L2)));
@@ -2224,7 +2243,7 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
     if (rc_isnan(va[j])) anynan = true;
     else {
       if (va[j] < mn) mn = va[j];
-      if (va[j] > toplp) { toplp = va[j]; topj = j; }
+      if (va[j] > toplp) { toplp = va[j]; topj = j; topc = vb[j]; }
     }
   }
   // group-wide minimum / NaN flag / leader (highest log-probability; ties: lowest lane, then lowest j)
@@ -2235,9 +2254,10 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
     const int on = __shfl_xor_sync(gmask, (int)anynan, off);
     const double ot = __shfl_xor_sync(gmask, toplp, off);
     const int oj = __shfl_xor_sync(gmask, topj, off), ol = __shfl_xor_sync(gmask, toplane, off);
+    const double oc = __shfl_xor_sync(gmask, topc, off);
     if (om < mn) mn = om;
     anynan = anynan || on != 0;
-    if (ol >= 0 && (toplane < 0 || ot > toplp || (ot == toplp && (ol < toplane || (ol == toplane && oj < topj))))) { toplp = ot; topj = oj; toplane = ol; }
+    if (ol >= 0 && (toplane < 0 || ot > toplp || (ot == toplp && (ol < toplane || (ol == toplane && oj < topj))))) { toplp = ot; topj = oj; toplane = ol; topc = oc; }
   }
   if (anynan) mn = RC_NAN;                                                  // Julia minimum propagates NaN
   // candidate index of the lane's slot j (position among the candidates in ascending slot order, new cluster last)
@@ -2249,6 +2269,20 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   // ---- Gumbel-max (utils.jl:2-6): argmax of noise + shifted log-probability, first index wins ties ----
   double bg = 0.0; int bkk = 0x7fffffff, bslot = -1; bool bnan = false;    // the lane's best candidate
   const bool fast = !anynan && mn > -RC_INF && mn < RC_INF && toplp < RC_INF && toplane >= 0;     // uniform over the group
+  if (fast && sh->mksum && !single) {
+    // row summary (RowSum): the leader when it is a live slot, its term, the largest term among the other live slots
+    double c2 = -RC_INF;
+#pragma unroll
+    for (int j = 0; j < RC_NP; ++j)
+      if (((live >> j) & 1u) && !(g == toplane && j == topj) && vb[j] > c2) c2 = vb[j];
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) { const double o = __shfl_xor_sync(gmask, c2, off); if (o > c2) c2 = o; }
+    const int leadlive = __shfl_sync(gmask, (g == toplane) ? (int)((live >> topj) & 1u) : 0, gbase + toplane);
+    if (g == 0) {
+      RowSum rs; rs.cT = topc; rs.c2 = c2; rs.L2i = L2i; rs.T = toplane + G * topj; rs.stamp = leadlive ? clk : 0u;
+      c.Rs[i] = rs;
+    }
+  }
   if (fast) {
     // every shifted log-probability is finite: a candidate whose value plus the largest possible noise stays below the
     // leader's exact value cannot be the arg-max, so its noise is never drawn (same result, far fewer logarithms)
@@ -2334,6 +2368,19 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
     sh->narrow = hi < 64 ? 4 : (hi < 128 ? 8 : 16);
   }
   __syncwarp();
+  {
+    // the row summaries' bound: the largest prior term over the live slots (at the slot's size and at size - 1), all finite
+    double mx = -RC_INF; bool ok = true;
+    for (int s = lane; s < cap; s += 32)
+      if (c.sizes[s] > 0) {
+        const double t2 = c.tabs[2 * cap + s], t5 = c.tabs[5 * cap + s];
+        if (!(t2 > -RC_INF && t2 < RC_INF && t5 > -RC_INF && t5 < RC_INF)) ok = false;       // (false for NaN too)
+        else mx = fmax(mx, fmax(t2, t5));
+      }
+    for (int off = 16; off; off >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off)); ok = __shfl_xor_sync(0xffffffffu, (int)ok, off) && ok; }
+    if (lane == 0) { sh->maxtab = mx; sh->tabs_ok = ok ? 1 : 0; }
+  }
+  __syncwarp();
 }
 
 // The full scan (mcmc.jl:192-253) from row istart in batches of up to nthr / G consecutive rows (G lanes per row), by the
@@ -2343,40 +2390,87 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
 __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
   IncShared* sh = c.inc;
   const int n = c.n, cap = c.cap, NT = c.nthr, tid = c.ctid, lane = c.lane;
-  if (tid == 0) { sh->sfirst[0] = RC_INC_NONE; sh->sfirst[1] = RC_INC_NONE; sh->sfirst[2] = RC_INC_NONE; if (!dry) sh->nmoves = 0; else sh->dry_stop = n; }
+  if (tid == 0) {
+    sh->sfirst[0] = RC_INC_NONE; sh->sfirst[1] = RC_INC_NONE; sh->sfirst[2] = RC_INC_NONE;
+    sh->fa[0] = RC_INC_NONE; sh->fa[1] = RC_INC_NONE; sh->fa[2] = RC_INC_NONE; sh->fm[0] = RC_INC_NONE; sh->fm[1] = RC_INC_NONE; sh->fm[2] = RC_INC_NONE;
+    if (!dry) sh->nmoves = 0; else sh->dry_stop = n;
+  }
   if (c.cwarp == 0) inc_build_tables(c);
   csync(c);
   RowCtx rc;
   rc.n = n; rc.cap = cap; rc.qD = c.qD; rc.qL = c.qL; rc.DL = c.DL; rc.S = c.S; rc.lab = c.lab; rc.sizes = c.sizes; rc.rank = c.rank;
-  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.tw = c.tw; rc.tchg = c.tchg;
+  rc.tabs = c.tabs; rc.inc = c.inc; rc.sc = c.sc; rc.kp = c.kp; rc.key = c.key; rc.Cc = c.Cc; rc.tw = c.tw; rc.tchg = c.tchg; rc.Rs = c.Rs;
   int batch = 0, i0 = istart;
   // Rows per batch follow the observed run length between moves (rows behind a move are evaluated again).
   int nrows = sh->hint > 0 ? sh->hint : NT, streak = 0;
+  int skipA = 0;                                                            // batches to go before the summaries are tried again
+  long long nfast = 0;
   while (i0 < n) {
     const int slot3 = batch % 3;
-    if (tid == 0) sh->sfirst[(batch + 1) % 3] = RC_INC_NONE;
+    if (tid == 0) { const int nx = (batch + 1) % 3; sh->sfirst[nx] = RC_INC_NONE; sh->fa[nx] = RC_INC_NONE; sh->fm[nx] = RC_INC_NONE; }
     ++batch;
-    const int G = sh->narrow;                                               // lanes per row: 4 / 8 / 16 when every candidate slot is below 64 / 128 / 256
-    const int nb = min(nrows, NT / G);                                      // rows of this batch
-    const long long te0 = RC_CLOCK();
-    {
-      const int row = tid / G, i = i0 + row;
-      if (row < nb && i < n) {
-        const int cnew = G == 4 ? inc_eval_row<4>(rc, it, i) : (G == 8 ? inc_eval_row<8>(rc, it, i) : inc_eval_row<16>(rc, it, i));
-        if ((tid & (G - 1)) == 0) {
-          c.res[row] = cnew;
-          if (cnew != (int)c.lab[i]) atomicMin(&sh->sfirst[slot3], row);
+    int F = RC_INC_NONE;
+    bool fromA = false;
+    if (sh->mksum && sh->tabs_ok && skipA == 0) {
+      // ---- rows decided by their summaries (RowSum), one thread per row ----
+      const int nbA = min(NT, n - i0);
+      if (tid < nbA) {
+        const int i = i0 + tid;
+        const RowSum rs = c.Rs[i];
+        int r = -3;                                                         // undecided
+        if (rs.stamp == sh->clk) {
+          const rc_kparams& kp = *c.kp;
+          const rc_params& P = kp.P;
+          const int li = c.lab[i], T = rs.T;
+          const int Ki = sh->nlive;
+          const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;       // :198 (the point's own cluster survives: not single)
+          if (c.sizes[li] > 1 && !(hasnew && sh->e0 < 0)) {
+            const double lpT = (T == li ? c.tabs[5 * cap + T] : c.tabs[2 * cap + T]) + rs.cT;
+            const double bound = sh->maxtab + rs.c2;
+            const double lpnew = (kp.LOGN[Ki + 1] + c.sc->r * c.sc->log1mp) + (0.0 + (P.repulsion ? rs.L2i : copysign(0.0, rs.L2i)));
+            if (lpT - bound > RC_SUM_MARGIN && (!hasnew || lpT - lpnew > RC_SUM_MARGIN) && lpT < RC_INF && lpT > -RC_INF) {
+              const int kk = (int)c.rank[T];                                 // the leader's own uniform must be > 0 (else its noise is -Inf)
+              const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
+              if (((kk & 1) ? dr.u1 : dr.u0) > 0.0) r = T;
+            }
+          }
+        }
+        c.res[tid] = r;
+        if (r == -3) atomicMin(&sh->fa[slot3], tid);
+        else if (r != (int)c.lab[i]) atomicMin(&sh->fm[slot3], tid);
+      }
+      csync(c);
+      const int U = min(sh->fa[slot3], nbA), M = sh->fm[slot3];
+      if (M < U) { F = M; fromA = true; nfast += M; }                        // a decided row moves its point: committed below like any move
+      else {
+        i0 += U; nfast += U;                                                // the rows before U stand
+        skipA = U == 0 ? 4 : 0;
+        if (U == nbA) continue;
+      }
+    } else if (skipA > 0) --skipA;
+    if (!fromA) {
+      const int G = sh->narrow;                                             // lanes per row: 4 / 8 / 16 when every candidate slot is below 64 / 128 / 256
+      const int nb = min(nrows, NT / G);                                    // rows of this batch
+      const long long te0 = RC_CLOCK();
+      {
+        const int row = tid / G, i = i0 + row;
+        if (row < nb && i < n) {
+          const int cnew = G == 4 ? inc_eval_row<4>(rc, it, i) : (G == 8 ? inc_eval_row<8>(rc, it, i) : inc_eval_row<16>(rc, it, i));
+          if ((tid & (G - 1)) == 0) {
+            c.res[row] = cnew;
+            if (cnew != (int)c.lab[i]) atomicMin(&sh->sfirst[slot3], row);
+          }
         }
       }
-    }
-    if (tid == 0) st_add(c, ST_REBUILDS, RC_CLOCK() - te0);                 // (incremental mode: cycles of thread 0 in the row evaluations)
-    csync(c);
-    const int F = sh->sfirst[slot3];
-    if (F == RC_INC_NONE) {                                                 // nobody moved: the whole batch stands
-      i0 += nb;
-      streak += nb;
-      if (streak >= nrows) { nrows = min(NT, nrows * 2); streak = 0; }
-      continue;
+      if (tid == 0) st_add(c, ST_REBUILDS, RC_CLOCK() - te0);               // (incremental mode: cycles of thread 0 in the row evaluations)
+      csync(c);
+      F = sh->sfirst[slot3];
+      if (F == RC_INC_NONE) {                                               // nobody moved: the whole batch stands
+        i0 += nb;
+        streak += nb;
+        if (streak >= nrows) { nrows = min(NT, nrows * 2); streak = 0; }
+        continue;
+      }
     }
     const int mi = i0 + F, b = c.res[F];
     if (dry) { if (tid == 0) sh->dry_stop = mi; break; }                    // the committing scan resumes here
@@ -2442,12 +2536,19 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
     streak = 0;
   }
   csync(c);
+#ifdef RC_NO_STATS
+  if (tid == 0) st_add(c, ST_BULK_ROWS, nfast);                             // (default library: rows decided by their summaries)
+#endif
+  if (tid == 0) {
+    if (dry) sh->nfast_dry = (int)nfast;
+    else { sh->scanfast = 2 * ((istart > 0 ? sh->nfast_dry : 0) + nfast) >= n ? 1 : 0; sh->nfast_dry = 0; }
+  }
   if (dry) return;
   if (c.cwarp == 0) {                                                       // :254
     int K = 0;
     for (int s = lane; s < cap; s += 32) K += c.sizes[s] > 0;
     for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
-    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); sh->hint = nrows; }
+    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); sh->hint = nrows; sh->mksum = sh->nmoves <= 2 ? 1 : 0; }
   }
   csync(c);
 }
@@ -2505,6 +2606,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.res = reinterpret_cast<int*>(smem + L.res);
     c.tchg = reinterpret_cast<unsigned*>(smem + L.ep);
     c.tw = kp.tw_smem ? reinterpret_cast<unsigned*>(smem + L.tw) : kp.Vv + (size_t)chain * n;
+    c.Rs = kp.Rs + (size_t)chain * n;
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2541,7 +2643,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
   for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.tchg[s] = kp.epochs[(size_t)chain * (cap + 1) + s]; }
   if (kp.tw_smem) for (int j = tid; j < n; j += nt) c.tw[j] = kp.Vv[(size_t)chain * n + j];
-  if (tid == 0) c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap];
+  if (tid == 0) { c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap]; c.inc->mksum = 1; c.inc->tabs_ok = 0; c.inc->maxtab = 0.0; c.inc->nfast_dry = 0; c.inc->scanfast = 0; }
   if (tid == 0) {
     Scal& s = *c.sc;
     s.r = kp.r[chain]; s.p = kp.p[chain];
@@ -2757,7 +2859,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.tw = nullptr; c.tchg = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.tw = nullptr; c.tchg = nullptr; c.Rs = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);

@@ -8,6 +8,7 @@
 #define RC_NWARP (RC_BW + 1)         // + one decision warp
 #define RC_NTHR (RC_NWARP * 32)      // threads per chain
 
+struct RowSum { double cT, c2, L2i; int T; unsigned stamp; };   // row summary of the incremental scan, see rc_sampler.cu
 struct rc_kparams {
   int n, cap, tiles, npad_max;
   int qD, qL;
@@ -51,6 +52,7 @@ struct rc_kparams {
   unsigned* Vv;         // [nchains][n]       change count at which each point's cached entries were last all valid (0: never)
   unsigned* epochs;     // [nchains][cap + 1] change count at which each slot last changed (>= 1), then the chain's change count
   int tw_smem;          // the per-point counts of a chain live in shared memory during a launch
+  RowSum* Rs;           // [nchains][n]       row summaries of the incremental scan (32 B each, see rc_sampler.cu)
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   int ovl_min_thr;      // the scan runs beside the restricted scans when the chain has at least this many threads (0: never)
   int rs_team;          // ... and this many of them run the restricted scans
