@@ -6,6 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include <thread>
+#include <chrono>
 #include "rc_sampler.cuh"
 
 static thread_local char g_err[512] = "";
@@ -287,10 +288,18 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   if (getenv("RCB200_VERBOSE") && stream_ok)
     fprintf(stderr, "[rcb200] n=%lld cap=%d tiles=%d npad=%lld (full %lld) G=%d smem=%zu (max %d) chains=%lld\n", (long long)n, cap, tiles,
             (long long)npad, (long long)npad_full, G, smem, maxsmem, (long long)nchains);
+  const bool vb_ = getenv("RCB200_VERBOSE") != nullptr;
+  auto tnow_ = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tc0_ = tnow_();
   // host-side state: 0-based slots and sizes (MCMCState, src/types.jl:131-137)
   std::vector<uint8_t> lab((size_t)nchains * n);
   std::vector<int> sizes((size_t)nchains * cap, 0);
-  for (int64_t c = 0; c < nchains; ++c)
+  for (int64_t c = 0; c < nchains; ++c) {
+    if (c > 0 && memcmp(init_labels + c * n, init_labels + (c - 1) * n, sizeof(int64_t) * (size_t)n) == 0) {   // same as the chain before: copy
+      memcpy(lab.data() + c * n, lab.data() + (c - 1) * n, (size_t)n);
+      memcpy(sizes.data() + c * cap, sizes.data() + (c - 1) * cap, sizeof(int) * (size_t)cap);
+      continue;
+    }
     for (int64_t j = 0; j < n; ++j) {
       const int64_t l = init_labels[c * n + j];
       if (l < 1 || l > cap) {
@@ -301,10 +310,12 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
       lab[c * n + j] = (uint8_t)(l - 1);
       sizes[c * cap + (l - 1)] += 1;
     }
+  }
   for (int64_t c = 0; c < nchains; ++c)
     if (!(init_r[c] > 0) || !(init_p[c] > 0 && init_p[c] < 1)) {
       rc_set_error("initial r must be > 0 and p in (0, 1) (chain %lld)", (long long)c); return RC_ERR_ARG;
     }
+  const double tc1_ = tnow_();
   rc_sampler* s = new rc_sampler();     // value-initialised: every scalar member starts at zero
   s->shared_init = nchains > 1;
   for (int64_t c = 1; c < nchains && s->shared_init; ++c) s->shared_init = memcmp(lab.data(), lab.data() + c * n, (size_t)n) == 0;
@@ -384,6 +395,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   TRY(dalloc(&s->r_acc, (size_t)nchains * opt->numiters));
   TRY(dalloc(&s->sm_acc, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
   TRY(dalloc(&s->sm_split, (size_t)nchains * opt->numiters * std::max<int64_t>(opt->numMH, 1)));
+  const double tc2_ = tnow_();
 #undef TRY
 #define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc_set_error("sampler setup: CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); rc_sampler_destroy(s); return RC_ERR_CUDA; } } while (0)
   TRYC(cudaMemcpy(s->labels, lab.data(), lab.size(), cudaMemcpyHostToDevice));
@@ -439,6 +451,7 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
   rc_launch_tables(s->par, (int)n, s->LGA, s->LGZ, s->LOGN, s->stream);
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) { rc_set_error("sampler setup failed: %s", cudaGetErrorString(e)); rc_sampler_destroy(s); return RC_ERR_CUDA; }
+  if (vb_) fprintf(stderr, "[rcb200] sampler create: host labels %.1f ms, allocations %.1f ms, uploads / memsets / tables %.1f ms\n", (tc1_ - tc0_) * 1e3, (tc2_ - tc1_) * 1e3, (tnow_() - tc2_) * 1e3);
   *out = s;
   return RC_OK;
 }

@@ -1733,6 +1733,53 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   csync(c);
   if (tid == 0) { c.sc->itmp[1] = 0; c.sc->itmp[2] = 0; }
   if (P.maxK > 0 && ci == cj && K >= P.maxK) { csync(c); return; }          // :384-386
+  if (ci != cj && c.S) {
+    // Merge proposals that cannot be accepted.  The acceptance ratio of a merge (:435-468) is
+    //   prior ratio + likelihood ratio - log proposal ratio,   log proposal ratio = -(sum of the final scan's log transition
+    // probabilities) >= 0,
+    // and neither the prior ratio nor the likelihood ratio depends on the restricted scans: the merged state is known (sizes,
+    // block sums W[ci] + W[cj]).  So x = prior ratio + likelihood ratio bounds the ratio from above (every log transition
+    // probability is <= 0 and floating-point addition is monotone), and when log U >= min(0, x) the proposal is rejected
+    // whatever the restricted scans would have produced -- they are not run.  (A NaN x fails the test and takes the long way.)
+    // The uniforms are counter-based, so skipping the scans' draws changes nothing else.
+    const int szf = c.sizes[ci] + c.sizes[cj];
+    rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);
+    for (int t = tid; t < cap; t += c.nthr) {                               // row cj of the merged state
+      rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
+      rc_add128(bD, c.WD[tri(cj, t, cap)]); rc_add128(bL, c.WL[tri(cj, t, cap)]);
+      rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
+      rc_i128 z; z.lo = 0; z.hi = 0;
+      rows[0 * cap + t] = z; rows[1 * cap + t] = z;
+    }
+    if (tid == 0) {
+      rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
+      rc_add128(bbD, c.WD[tri(cj, cj, cap)]); rc_add128(bbL, c.WL[tri(cj, cj, cap)]);
+      rc_add128(bbD, c.WD[tri(ci, cj, cap)]); rc_add128(bbD, c.WD[tri(ci, cj, cap)]);
+      rc_add128(bbL, c.WL[tri(ci, cj, cap)]); rc_add128(bbL, c.WL[tri(ci, cj, cap)]);
+      rc_i128 z; z.lo = 0; z.hi = 0;
+      c.sc->aaD = z; c.sc->aaL = z; c.sc->abD = z; c.sc->abL = z; c.sc->bbD = bbD; c.sc->bbL = bbL;
+      c.sc->fslotA = ci; c.sc->fslotB = cj;
+    }
+    for (int s = tid; s < cap; s += c.nthr) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
+    csync(c);
+    const double ll_fin = loglik_eval(c, c.szL);
+    if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; }
+    const double ll_cur = loglik_eval(c, c.sizes);
+    if (tid == 0) {
+      const double log_prior_ratio = -(rc_log((double)K) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r)) +
+                                     rc_lgamma((double)(szf - 1) + r) + rc_log((double)szf) +
+                                     -(rc_lgamma((double)(c.sizes[ci] - 1) + r) + rc_lgamma((double)(c.sizes[cj] - 1) + r) +
+                                       rc_log((double)c.sizes[ci]) + rc_log((double)c.sizes[cj]));
+      const double x = log_prior_ratio + (ll_fin - ll_cur);
+      const double lu = rc_log(rc_draw1(c.key, it, RC_SITE_SM_ACCEPT, mh, 0, 0));
+      c.sc->itmp[7] = (lu >= rc_min0(x) + 1e-6) ? 1 : 0;                     // (1e-6: slack for a log transition probability that rounds above 0)
+#ifdef RC_NO_STATS
+      st_add(c, ST_DEC_WAIT, c.sc->itmp[7]);                                 // (default library: merge proposals rejected by the bound)
+#endif
+    }
+    csync(c);
+    if (c.sc->itmp[7]) return;                                               // itmp[1] (accept) and itmp[2] (split) are 0
+  }
   // S = members of ci or cj except i, j, ascending (:389-390): ordered compaction
   {
     const int chunk = (n + c.nthr - 1) / c.nthr;
