@@ -58,6 +58,7 @@ struct Scal {
   int forked;                             // numMH > 1: an accepted proposal replaced the local state this iteration
   int fslotA, fslotB;                     // slots whose W rows come from the scratch rows (-1: none)
   int itmp[8];
+  double llcur; unsigned llclk;           // incremental kernel: loglik of the chain's own state at change count llclk (0: none)
 };
 
 #define RC_MQ 16                     // move queue entries (moves not yet patched into the permutation)
@@ -1122,6 +1123,18 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
   return c.sc->dtmp[0];
 }
 
+// loglik of the chain's own state (fslotA / fslotB must be -1).  Incremental kernel: the value only changes when the state does,
+// so it is kept with the chain's change count -- a stationary chain evaluates it once, not twice per iteration.
+__device__ double loglik_cur(const Ctx& c) {
+  if (c.inc && c.sc->llclk == c.inc->clk) return c.sc->llcur;               // (uniform: both were written before the last barrier)
+  const double v = loglik_eval(c, c.sizes);
+  if (c.inc) {
+    if (c.ctid == 0) { c.sc->llcur = v; c.sc->llclk = c.inc->clk; }
+    csync(c);
+  }
+  return v;
+}
+
 __device__ __forceinline__ double xlogy(double a, double b) { return (a == 0.0 && !rc_isnan(b)) ? 0.0 : a * rc_log(b); }
 __device__ __forceinline__ double xlog1py(double a, double b) { return (a == 0.0 && !rc_isnan(b)) ? 0.0 : a * rc_log1p(b); }
 
@@ -1217,6 +1230,10 @@ __device__ void update_p(const Ctx& c, unsigned it) {
 // Prior term of joining an existing cluster of size s (mcmc.jl:226, 324) for this iteration's (r, p):
 // LPR[s] = log(s+1) + log p + log(s-1+r) - log(s), evaluated in the reference's order.
 // ------------------------------------------------------------------------------------------------
+// ... and the same value on demand (incremental kernel: only a few sizes are ever needed per iteration, so no table is built)
+__device__ __forceinline__ double lpr_at(const Ctx& c, int s) {
+  return c.kp->LOGN[s + 1] + c.sc->logp + rc_log((double)(s - 1) + c.sc->r) - c.kp->LOGN[s];
+}
 __device__ void build_lpr(const Ctx& c) {
   const rc_kparams& kp = *c.kp;
   const double r = c.sc->r, logp = c.sc->logp;
@@ -1551,7 +1568,7 @@ __device__ void restricted_scans_team(const Ctx& c, int nS, int ca, int cb, int 
         for (int u = 0; u < 3; ++u) {
           const int idx = lane + 32 * u, tb = idx >> 4, off = idx & 15;
           const int sz = min(max(((tb & 1) ? loB : loA) + off, 0), c.n);
-          wv[u] = tb < 2 ? kp.LGA[sz] : (tb < 4 ? kp.LGZ[sz] : c.LPR[sz]);
+          wv[u] = tb < 2 ? kp.LGA[sz] : (tb < 4 ? kp.LGZ[sz] : lpr_at(c, sz > 0 ? sz : 1));
         }
         long long sAd = 0, sAl = 0, sBd = 0, sBl = 0;
         int szA = 0, szB = 0, forcedto = 0;
@@ -1764,7 +1781,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     csync(c);
     const double ll_fin = loglik_eval(c, c.szL);
     if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; }
-    const double ll_cur = loglik_eval(c, c.sizes);
+    const double ll_cur = loglik_cur(c);
     if (tid == 0) {
       const double log_prior_ratio = -(rc_log((double)K) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r)) +
                                      rc_lgamma((double)(szf - 1) + r) + rc_log((double)szf) +
@@ -2043,7 +2060,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   }
   const double ll_fin = loglik_eval(c, c.szL);                              // :462-464
   if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; }
-  const double ll_cur = loglik_eval(c, c.sizes);
+  const double ll_cur = loglik_cur(c);
   if (tid == 0) {
     const double log_lik_ratio = ll_fin - ll_cur;
     const double lar = rc_min0(log_prior_ratio + log_lik_ratio - log_proposal_ratio);   // :467-468
@@ -2403,9 +2420,9 @@ __device__ void inc_build_tables(const Ctx& c, int only_a = -1, int only_b = -1)
     base += __popc(m);
     if (e0 < 0 && em) e0 = w * 32 + __ffs(em) - 1;
     if (s < cap && (only_a < 0 || s == only_a || s == only_b)) {
-      c.tabs[s] = kp.LGA[sz]; c.tabs[cap + s] = kp.LGZ[sz]; c.tabs[2 * cap + s] = c.LPR[sz > 0 ? sz : 1];
+      c.tabs[s] = kp.LGA[sz]; c.tabs[cap + s] = kp.LGZ[sz]; c.tabs[2 * cap + s] = lpr_at(c, sz > 0 ? sz : 1);
       c.tabs[3 * cap + s] = kp.LGA[sz > 0 ? sz - 1 : 0]; c.tabs[4 * cap + s] = kp.LGZ[sz > 0 ? sz - 1 : 0];
-      c.tabs[5 * cap + s] = c.LPR[sz > 1 ? sz - 1 : 1];
+      c.tabs[5 * cap + s] = lpr_at(c, sz > 1 ? sz - 1 : 1);
     }
   }
   if (only_a >= 0 && lane == 0) { const unsigned m = ++sh->clk; c.tchg[only_a] = m; c.tchg[only_b] = m; }   // clusters a and b changed: their cached terms are stale
@@ -2690,7 +2707,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
   for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.tchg[s] = kp.epochs[(size_t)chain * (cap + 1) + s]; }
   if (kp.tw_smem) for (int j = tid; j < n; j += nt) c.tw[j] = kp.Vv[(size_t)chain * n + j];
-  if (tid == 0) { c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap]; c.inc->mksum = 1; c.inc->tabs_ok = 0; c.inc->maxtab = 0.0; c.inc->nfast_dry = 0; c.inc->scanfast = 0; }
+  if (tid == 0) { c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap]; c.inc->mksum = 1; c.inc->tabs_ok = 0; c.inc->maxtab = 0.0; c.inc->nfast_dry = 0; c.inc->scanfast = 0; c.sc->llclk = 0u; c.sc->llcur = 0.0; }
   if (tid == 0) {
     Scal& s = *c.sc;
     s.r = kp.r[chain]; s.p = kp.p[chain];
@@ -2718,7 +2735,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
       }
     }
     csync(c);
-    build_lpr(c);
+    // (the size-dependent prior terms are evaluated where they are needed: lpr_at)
     if (tid == 0) st_add(c, ST_RP, RC_CLOCK() - ti0);
     // sample_labels! (:540)
     const bool multi = kp.numMH > 1;
@@ -2766,7 +2783,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
       const long long j = (iter - kp.burnin) / kp.thin - 1;
       if (j < kp.numsamples) {
         record_labels(c, kp.out_labels + ((size_t)chain * kp.numsamples + j) * n);
-        const double ll = loglik_eval(c, c.sizes);
+        const double ll = loglik_cur(c);
         if (c.cwarp == 0) {
           const double lpv = logprior_eval(c);
           if (tid == 0) {
