@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moving", action="store_true")
+    ap.add_argument("--no-noshort", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-post", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -322,6 +323,18 @@ def main():
                       "chains_per_gpu": per, "moves_per_sweep": mv2,
                       "note": "256 chains sharded over the GPUs: a sweep of one chain is sequential in the points, so fewer chains per GPU leave SMs idle"}
 
+    # ---- the same headline run with the exact shortcuts off (RCB200_SHORTCUTS=0): every row evaluated, every merge proposal's
+    #      restricted scans run -- what the kernel costs when nothing can be skipped ----
+    noshort = None
+    if not args.no_noshort:
+        os.environ["RCB200_SHORTCUTS"] = "0"
+        try:
+            d4, w4, mv4, _, _, _ = timed_sampler(pkg, torch, dist, world, data, params, lab, args.chains, chain0, args, W, steps, local_rank)
+        finally:
+            os.environ.pop("RCB200_SHORTCUTS", None)
+        noshort = {"value": world * args.chains * steps / d4, "unit": "chain-sweeps/s", "ms_per_step": d4 / steps * 1e3, "moves_per_sweep": mv4,
+                   "note": "RCB200_SHORTCUTS=0: row summaries and the merge-proposal bound disabled (results are identical either way)"}
+
     # ---- a chain that moves: sigma = 0.25, the reference's own cap maxK (PriorHyperparamsList.maxK, src/types.jl:107) ----
     moving = None
     if not args.no_moving:
@@ -336,8 +349,9 @@ def main():
                                          f"maxK={args.moving_maxK}, {args.chains} chains per GPU, init true labels, {args.moving_warmup} untimed sweeps first",
                              "why_maxK": "at sigma = 0.25 the model opens several hundred clusters at this n; the sampler holds at most 255 live "
                                          "clusters per chain, so the run uses the reference's own cap parameter"},
-                  "note": "per sweep the chain moves ~2 % of the points and its split-merge proposals involve clusters of thousands of points: the "
-                          "restricted Gibbs scans (sequential, O(members) per move) dominate"}
+                  "note": "per sweep the chain moves ~2 % of the points (every move invalidates the row summaries) and its split-merge proposals "
+                          "involve clusters of thousands of points; most merge proposals are rejected by their bound, the splits' restricted "
+                          "Gibbs scans (sequential, O(members) per move) and the full scan's move updates dominate"}
         del data2
 
     # ---- end-to-end through the public API with HOST buffers (upload D, build, run, read results back) ----
@@ -396,10 +410,11 @@ def main():
                 "fp64_pipe_frac": prof.get("fp64_pipe_frac"), "issue_active_frac": prof.get("issue_active_frac"),
                 "note": "algorithmic bytes = chains x 16 n (n-1) per sweep: what a scan that reads every row costs (SURVEY 8d).  This kernel does "
                         "not read the rows: each chain keeps the sums of every row by cluster (exact integers) and a Gibbs step reads one 16-byte "
-                        "entry per live cluster; only a move streams a row.  frac > 1 therefore measures the work avoided, dram_frac is the real "
-                        "DRAM utilisation (ncu bytes / step time / peak); the kernel is bound by latency -- the sequential dependence of the "
-                        "restricted Gibbs scans (one warp) and of the batches of the full scan -- not by a pipe: fp64_pipe_frac and "
-                        "issue_active_frac are ncu's (profiles/r02_kchaininc_summary.md)"}
+                        "entry per live cluster; only a move streams a row; a row whose stored leader margin already proves the outcome is not "
+                        "evaluated at all, and a merge proposal whose prior + likelihood ratio already lies below log U is rejected without its "
+                        "restricted scans (both exact; no_shortcuts gives the rate with them off).  frac > 1 therefore measures the work avoided, "
+                        "dram_frac is the real DRAM utilisation (ncu bytes / step time / peak); the kernel is bound by latency, not by a pipe: "
+                        "fp64_pipe_frac and issue_active_frac are ncu's (profiles/r02_kchaininc_summary.md)"}
     cpu = None
     if not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1
@@ -413,7 +428,7 @@ def main():
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (exact i64 fixed-point cluster sums)", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": 1, "roofline": roofline, "cpu_baseline": cpu,
-            "moves_per_sweep": moves, "strong": strong, "moving": moving, "post": post,
+            "moves_per_sweep": moves, "strong": strong, "no_shortcuts": noshort, "moving": moving, "post": post,
             "wall_ms_per_step": wall_s / steps * 1e3, "K_final_chain0": Kfinal}
     emit(line)
     if world > 1:

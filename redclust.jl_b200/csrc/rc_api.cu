@@ -45,7 +45,7 @@ struct rc_sampler {
   uint8_t* origM; longlong4* AB; double2* L2s; double2* NZ; double* LPR; longlong2* DG; double* terms;
   long long* stats; unsigned* gridbar; bool coresident;
   double2* Cc; unsigned *Vv, *epochs;   // incremental mode: cached per-slot terms, per-point / per-slot change counts that validate them
-  int tw_smem;
+  int tw_smem, shortcuts;
   void* Rs;                    // row summaries of the incremental scan (nchains x n x 32 B)
   longlong2* S;                // incremental mode: [nchains][cap][n] row sums by slot (null: streaming mode)
   bool inc;                    // incremental mode (k_chain_inc) instead of the streaming kernel (k_chain)
@@ -179,7 +179,7 @@ void fill_kparams(const rc_sampler* s, rc_kparams& kp) {
   memset(&kp, 0, sizeof(kp));
   kp.n = (int)s->d->n; kp.cap = s->cap; kp.tiles = s->tiles; kp.npad_max = s->npad_max;
   kp.qD = s->d->qD; kp.qL = s->d->qL; kp.DL = s->DLp ? s->DLp : s->d->DL;
-  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs; kp.tw_smem = s->tw_smem; kp.Rs = (RowSum*)s->Rs;
+  kp.S = s->S; kp.terms_stride = s->terms_stride; kp.inc_mcap = s->inc_mcap; kp.ovl_min_thr = s->ovl_min_thr; kp.rs_team = s->rs_team; kp.Cc = s->Cc; kp.Vv = s->Vv; kp.epochs = s->epochs; kp.tw_smem = s->tw_smem; kp.shortcuts = s->shortcuts; kp.Rs = (RowSum*)s->Rs;
   kp.colpos = s->colpos; kp.colpt = s->colpt;
   kp.P = s->par;
   kp.abratio = s->par.alpha * rc_log(s->par.beta) - rc_lgamma(s->par.alpha);    // mcmc.jl:17,186,293
@@ -349,6 +349,8 @@ static int32_t sampler_create_impl(bool opt_loglik_only, const rc_data* d, const
     int nthr = nchains <= nsm ? 512 : (nchains <= 2 * nsm ? 256 : 256);
     if (const char* e = getenv("RCB200_INC_THREADS")) nthr = std::max(32, std::min(512, atoi(e) / 32 * 32));
     s->inc_nthr = nthr;
+    s->shortcuts = 1;
+    if (const char* e = getenv("RCB200_SHORTCUTS")) s->shortcuts = atoi(e) != 0;
     // The scan runs beside the restricted scans (dry, on a copy of the labels) when there is one proposal per iteration:
     // measured at n = 10^4 / 50 clusters, 256 threads with 64 on the restricted scans +12 % (256 chains), 512 with 128 +11 %.
     s->ovl_min_thr = 256; s->rs_team = nthr >= 512 ? 128 : 64;

@@ -1750,7 +1750,7 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
   csync(c);
   if (tid == 0) { c.sc->itmp[1] = 0; c.sc->itmp[2] = 0; }
   if (P.maxK > 0 && ci == cj && K >= P.maxK) { csync(c); return; }          // :384-386
-  if (ci != cj && c.S) {
+  if (ci != cj && c.S && kp.shortcuts) {
     // Merge proposals that cannot be accepted.  The acceptance ratio of a merge (:435-468) is
     //   prior ratio + likelihood ratio - log proposal ratio,   log proposal ratio = -(sum of the final scan's log transition
     // probabilities) >= 0,
@@ -2612,7 +2612,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
     int K = 0;
     for (int s = lane; s < cap; s += 32) K += c.sizes[s] > 0;
     for (int off = 16; off; off >>= 1) K += __shfl_xor_sync(0xffffffffu, K, off);
-    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); sh->hint = nrows; sh->mksum = sh->nmoves <= 2 ? 1 : 0; }
+    if (lane == 0) { c.sc->K = K; st_add(c, ST_MOVES, sh->nmoves); sh->hint = nrows; sh->mksum = (sh->nmoves <= 2 && c.kp->shortcuts) ? 1 : 0; }
   }
   csync(c);
 }
@@ -2707,7 +2707,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
   for (int j = tid; j < n; j += nt) c.lab[j] = kp.labels[(size_t)chain * n + j];
   for (int s = tid; s < cap; s += nt) { c.sizes[s] = kp.sizes[(size_t)chain * cap + s]; c.tchg[s] = kp.epochs[(size_t)chain * (cap + 1) + s]; }
   if (kp.tw_smem) for (int j = tid; j < n; j += nt) c.tw[j] = kp.Vv[(size_t)chain * n + j];
-  if (tid == 0) { c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap]; c.inc->mksum = 1; c.inc->tabs_ok = 0; c.inc->maxtab = 0.0; c.inc->nfast_dry = 0; c.inc->scanfast = 0; c.sc->llclk = 0u; c.sc->llcur = 0.0; }
+  if (tid == 0) { c.inc->clk = kp.epochs[(size_t)chain * (cap + 1) + cap]; c.inc->mksum = kp.shortcuts ? 1 : 0; c.inc->tabs_ok = 0; c.inc->maxtab = 0.0; c.inc->nfast_dry = 0; c.inc->scanfast = 0; c.sc->llclk = 0u; c.sc->llcur = 0.0; }
   if (tid == 0) {
     Scal& s = *c.sc;
     s.r = kp.r[chain]; s.p = kp.p[chain];

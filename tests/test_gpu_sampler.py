@@ -279,3 +279,40 @@ def test_team_shapes_are_bit_identical(pkg, orc, monkeypatch, env):
         moved += int((np.diff(ref["labels"].astype(np.int64), axis=0) != 0).sum())
     splits = sum(int(r[1]["sm_split"].sum()) for r in res)
     assert moved > 200 and 0 < splits < 75                       # the run moved points and proposed both splits and merges
+
+
+@pytest.mark.parametrize("shortcuts", ["1", "0"])
+def test_shortcuts_fire_and_change_nothing(pkg, orc, monkeypatch, shortcuts):
+    """Row summaries (a row whose stored leader margin proves the Gumbel-max outcome is not evaluated) and the bound that
+    rejects hopeless merge proposals without their restricted scans: on a well separated mixture most rows and most merge
+    proposals take the shortcut, and every output still equals the oracle's -- as it does with RCB200_SHORTCUTS=0."""
+    monkeypatch.setenv("RCB200_SHORTCUTS", shortcuts)
+    monkeypatch.setenv("RCB200_SCAN", "inc")
+    X, lab = mixture(600, 6, 10, 0.12, 4)
+    data = pkg.MCMCData.from_points(X)
+    D = data.D
+    params = pkg.params_from_labels(D, lab)
+    iters, nch = 40, 2
+    res, smp = run_both(pkg, orc, D, lab, params, iters, 0, 1, 5, 1, seed=9, nchains=nch)
+    assert smp.check_sums() == (0, 0)
+    for got, ref, st in res:
+        assert_same(got, ref, st)
+    st = smp.stats()
+    fast_rows, quick_rejects = int(st["bulk_rows"].sum()), int(st["dec_wait"].sum())     # (counts in the default library)
+    merges = sum(int((r[1]["sm_split"] == 0).sum()) for r in res)
+    if shortcuts == "1":
+        assert fast_rows > 0.5 * iters * nch * 600, fast_rows
+        assert quick_rejects > 0.5 * merges, (quick_rejects, merges)
+    else:
+        assert fast_rows == 0 and quick_rejects == 0
+    # a chain that moves (loose mixture, wrong start): summaries are invalidated by every move, proposals are sometimes accepted
+    X2, lab2 = mixture(500, 8, 10, 0.4, 11)
+    g = np.random.default_rng(1)
+    init = g.integers(1, 5, size=500)
+    init = (np.unique(init, return_inverse=True)[1] + 1).astype(np.int64)
+    data2 = pkg.MCMCData.from_points(X2)
+    params2 = pkg.params_from_labels(data2.D, lab2, maxK=30)
+    res2, smp2 = run_both(pkg, orc, data2.D, init, params2, 30, 0, 1, 5, 1, seed=2, nchains=2)
+    assert smp2.check_sums() == (0, 0)
+    for got, ref, st in res2:
+        assert_same(got, ref, st)
