@@ -2492,7 +2492,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
             const double lpT = (T == li ? c.tabs[5 * cap + T] : c.tabs[2 * cap + T]) + rs.cT;
             const double bound = sh->maxtab + rs.c2;
             const double lpnew = (kp.LOGN[Ki + 1] + c.sc->r * c.sc->log1mp) + (0.0 + (P.repulsion ? rs.L2i : copysign(0.0, rs.L2i)));
-            if (lpT - bound > RC_SUM_MARGIN && (!hasnew || lpT - lpnew > RC_SUM_MARGIN) && lpT < RC_INF && lpT > -RC_INF) {
+            if (lpT - bound > RC_SUM_MARGIN && (!hasnew || (lpT - lpnew > RC_SUM_MARGIN && lpnew > -RC_INF)) && lpT < RC_INF && lpT > -RC_INF) {
               const int kk = (int)c.rank[T];                                 // the leader's own uniform must be > 0 (else its noise is -Inf)
               const rc_draw dr = rc_draw2(c.key, it, RC_SITE_SCAN, 0, (uint32_t)i, (uint32_t)(kk >> 1));
               if (((kk & 1) ? dr.u1 : dr.u0) > 0.0) r = T;

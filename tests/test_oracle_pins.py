@@ -247,3 +247,31 @@ def test_psm_against_reference_held_oracle_coclustering(pkg, orc, golden, k):
     off = ~np.eye(100, dtype=bool)
     assert np.abs(psm - cc)[off].mean() < 0.04
     assert np.corrcoef(psm[off], cc[off])[0, 1] > 0.85
+
+
+def test_assumptions_of_the_exact_shortcuts(tmp_path):
+    """The two shortcuts of the incremental kernel rest on properties of the shared math header, pinned here
+    on the CPU: (a) rc_log(x) <= 0 for every x <= 1 tried, and rc_log(1) == 0 -- every log transition probability of a
+    restricted scan is <= 0, so prior + likelihood ratio bounds a merge's acceptance ratio from above; (b) the Gumbel noise
+    -log(-log u) of a 53-bit uniform u in (0, 1) lies in [-3.61, 36.74]: a leader ahead by more than 41 cannot lose."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "pins.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include <cmath>
+#include "%s/redclust.jl_b200/csrc/rc_math.h"
+int main() {
+  double worst = -1.0, x = 1.0;
+  for (int i = 0; i < 100000; ++i) { x = nextafter(x, 0.0); const double v = rc_log(x); if (v > worst) worst = v; }
+  unsigned long long s = 12345;
+  for (int i = 0; i < 5000000; ++i) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; const double u = (double)((s >> 11) + 1) * 0x1p-53; const double v = rc_log(u); if (v > worst) worst = v; }
+  printf("%%.17g %%.17g %%.17g %%.17g\n", rc_log(1.0), worst, -rc_log(-rc_log(0x1p-53)), -rc_log(-rc_log(1.0 - 0x1p-53)));
+  return 0;
+}
+""" % root)
+    exe = tmp_path / "pins"
+    subprocess.run(["g++", "-O2", "-fno-fast-math", "-ffp-contract=off", "-o", str(exe), str(src)], check=True)
+    one, worst, lo, hi = map(float, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    assert one == 0.0 and worst <= 0.0
+    assert -3.61 < lo < -3.60 and 36.73 < hi < 36.74 and hi - lo < 41.0
