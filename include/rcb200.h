@@ -160,7 +160,8 @@ int32_t rc_sampler_copy_acceptances(const rc_sampler* s, int64_t chain, uint8_t*
 int32_t rc_sampler_copy_state(const rc_sampler* s, int64_t chain, int64_t* labels, double* r, double* p);
 /* Profiling aid (no reference equivalent): 16 SM-cycle counters per chain accumulated by the chain kernel.
  * out: nchains x 16 int64.  Only librcb200_stats.so carries the clock reads; the default library returns the
- * move / rebuild counts and zeros for the cycle slots. */
+ * move / rebuild counts, zeros for the cycle slots, and two counts of the incremental kernel's exact shortcuts: slot 4 the
+ * rows decided by their stored summaries, slot 0 the merge proposals rejected by their acceptance bound. */
 int32_t rc_sampler_copy_stats(const rc_sampler* s, int64_t* out);
 /* Per-chain status after a run: 0 ok, RC_ERR_SLOTS if the chain needed more than slot_cap simultaneously live
  * clusters and stopped there (the reference allows up to n, src/types.jl:135, src/mcmc.jl:199).
