@@ -2480,6 +2480,7 @@ __device__ void inc_full_scan(const Ctx& c, unsigned it, int istart, bool dry) {
       const int nbA = min(NT, n - i0);
       if (tid < nbA) {
         const int i = i0 + tid;
+        if (i + NT < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(c.Rs + i + NT));        // the next batch's summary
         const RowSum rs = c.Rs[i];
         int r = -3;                                                         // undecided
         if (rs.stamp == sh->clk) {
