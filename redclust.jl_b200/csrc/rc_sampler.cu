@@ -1089,6 +1089,11 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
   }
   csync(c);
   const int K = c.sc->itmp[0];
+  // The terms are added by one thread in the reference's order (:54), which is a chain of dependent additions: when they fit,
+  // they are staged in shared memory (the split-merge member scratch, dead whenever a log-likelihood is evaluated) in exactly
+  // that order -- K diagonal terms, then the pairs (k, t > k) row by row -- instead of being read back from global memory.
+  const int nT = K + K * (K - 1) / 2;
+  double* st = (c.mAB && (size_t)nT * sizeof(double) <= (size_t)c.mcap * sizeof(longlong4)) ? reinterpret_cast<double*>(c.mAB) : nullptr;
   for (int idx = c.ctid; idx < K * K; idx += c.nthr) {
     const int ki = idx / K, ti = idx - ki * K;
     if (ti < ki) continue;
@@ -1108,15 +1113,20 @@ __device__ double loglik_eval(const Ctx& c, const int* sz) {
       const double g = P.gamma + msD;
       term = (P.delta2 - 1) * msL - pairs * kp.lgd2 + kp.zgratio + rc_lgamma(z) - z * rc_log(g);
     }
-    c.terms[idx] = term;
+    if (st) st[ki == ti ? ki : K + ki * K - ki * (ki + 1) / 2 + (ti - ki - 1)] = term;
+    else c.terms[idx] = term;
   }
   csync(c);
   if (c.ctid == 0) {
-    double L1 = 0;
-    for (int ki = 0; ki < K; ++ki) L1 += c.terms[ki * K + ki];
-    double L2 = 0;
-    for (int ki = 0; ki < K; ++ki)
-      for (int ti = ki + 1; ti < K; ++ti) L2 += c.terms[ki * K + ti];
+    double L1 = 0, L2 = 0;
+    if (st) {
+      for (int q = 0; q < K; ++q) L1 += st[q];
+      for (int q = K; q < nT; ++q) L2 += st[q];
+    } else {
+      for (int ki = 0; ki < K; ++ki) L1 += c.terms[ki * K + ki];
+      for (int ki = 0; ki < K; ++ki)
+        for (int ti = ki + 1; ti < K; ++ti) L2 += c.terms[ki * K + ti];
+    }
     c.sc->dtmp[0] = P.repulsion ? (L1 + L2) : (L1 + copysign(0.0, L2));      // :54
   }
   csync(c);
