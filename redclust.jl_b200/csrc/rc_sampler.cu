@@ -3,33 +3,39 @@
 //
 //   sample_r!  (mcmc.jl:80-136)      -> update_r()
 //   sample_p!  (mcmc.jl:138-155)     -> update_p()
-//   sample_labels! (mcmc.jl:356-479) -> splitmerge_step() x numMH, then full_scan()
-//   sample_labels_Gibbs! (:158-256)  -> full_scan(): bulk_loop() / reduce_tile() + decide_rows()
-//   sample_labels_Gibbs_restricted! (:259-354) -> restricted_scans()
+//   sample_labels! (mcmc.jl:356-479) -> splitmerge_step() x numMH, then inc_full_scan() / full_scan()
+//   sample_labels_Gibbs! (:158-256)  -> inc_full_scan(): inc_eval_row();  full_scan(): bulk_loop() / reduce_tile() + decide_rows()
+//   sample_labels_Gibbs_restricted! (:259-354) -> restricted_scans_team() / restricted_scans()
 //   loglik (:1-56), logprior (:58-78), record step (:546-554), sortlabels (utils.jl:69-74)
 //
-// Organisation (DESIGN.md sections 2-3):
+// Two kernels share the device functions below (DESIGN.md sections 2-3).  Both work on DL[i][j] = {Dq, Lq}, the 64-bit
+// fixed-point images of D and log D: every cluster sum is an exact integer, so results do not depend on tiling, lane count,
+// reduction order -- or on whether a sum is recomputed or maintained -- and are bit-identical to the CPU oracle.
+//
+// k_chain_inc (default): one CTA = one chain, all iterations of a launch inside the kernel.
+//   * S[slot][x] = sum of row x over the members of slot is kept in HBM; a Gibbs step reads one entry per live slot
+//     (inc_eval_row: G lanes per row, the lane's slots in registers), only a move streams a row (inc_update_S).
+//   * Rows are evaluated speculatively in batches and committed up to the first one that moves (inc_full_scan).
+//   * Per-slot terms are cached (Cc) and validated by change counts (tw / tchg); a row whose stored summary (RowSum) proves
+//     the Gumbel-max outcome is decided without being evaluated.
+//   * Split-merge by the whole team: member sums gathered once (member_sums_inc), restricted scans with the moves of eight
+//     steps resolved inside a warp (restricted_scans_team), merge proposals that cannot be accepted rejected by their bound
+//     (splitmerge_step); the scan runs dry beside the restricted scans while it is long.
+//   * W (K x K block sums, 128-bit) is maintained from the row sums of every move, so loglik() never reads D.
+//
+// k_chain<G> (round 1, RCB200_SCAN=stream or when S does not fit): the streaming kernel.
 //   * One CTA runs G chains (G x 160 threads: 4 bulk warps + 1 decision warp per chain) plus two CTA-level helper
 //     warps.  During the full Gibbs scan all chains of a CTA visit rows 0..n-1 together, so every 1024-column tile
 //     of row i of DL is staged ONCE into a 6-stage shared-memory ring by the producer warp (cp.async.bulk -> UBLKCP,
-//     mbarrier full/empty) and reduced by all G chains against their own label vectors.  CTAs on other SMs walk the
-//     same rows at about the same time and hit L2, so HBM traffic per sweep is ~ n^2 x 16 B / (chains sharing a
-//     row load).  The noise warp precomputes the Gumbel noise of the rows ahead of the decisions.
-//   * DL[i][j] = {Dq, Lq}: 64-bit fixed-point images of D and log D.  Every cluster sum is an exact
-//     integer, so results do not depend on tiling, lane count or reduction order: the kernel is
-//     bit-identical to the CPU oracle by construction.  (The COLUMNS of the streamed matrix may be label-sorted,
-//     see cpos().)
+//     mbarrier full/empty) and reduced by all G chains against their own label vectors.  The noise warp precomputes the
+//     Gumbel noise of the rows ahead of the decisions.
 //   * Row reduction: columns are kept in a (tile, label)-sorted permutation whose label runs are padded to
-//     chunks of 8; one warp reduces a tile, a lane walks its contiguous chunks (8 gathers from the staged tile per
-//     chunk) keeping a running sum, a warp-shuffle segmented scan merges runs that span lanes, totals go to per-warp
-//     bins.  No atomics, no label compares in the inner loop.  A move patches the permutation in place (rebuild
-//     when a run is full).
+//     chunks of 8; one warp reduces a tile, a lane walks its contiguous chunks keeping a running sum, a warp-shuffle
+//     segmented scan merges runs that span lanes, totals go to per-warp bins.  A move patches the permutation in place.
 //   * The decision warp does the sequential part: bins of row i -> log-weights (lane = slot) -> Gumbel arg-max ->
 //     move; it runs one row behind the bulk warps.
-//   * The K x K block-sum matrices W (128-bit integers) are maintained incrementally from the row sums
-//     of every move, so loglik() never re-reads D: it is O(K^2) transcendentals.
 //   * Split-merge: row sums of the members of ci u cj are taken once (launch state); the restricted
-//     scans then run on a single warp from running candidate sums, eight steps at a time.
+//     scans then run on a single warp from running candidate sums, eight steps at a time (restricted_scans).
 #include <algorithm>
 #include "rc_sampler.cuh"
 
@@ -2227,7 +2233,7 @@ __device__ __noinline__ int inc_eval_row(const RowCtx c, unsigned it, int i) {
   const bool hasnew = (P.maxK == 0 || Ki < P.maxK) && Ki < n;               // :198
   if (hasnew && e < 0) return -2;
   const double* __restrict__ tabs = c.tabs;
-  // the point's own slot is always evaluated from its row sum: that load starts now, under the epoch round trip
+  // the point's own slot is always evaluated from its row sum: that load starts now
   longlong2 own_s = make_longlong2(0, 0);
   if (!single && (li & (G - 1)) == g) own_s = c.S[(size_t)li * n + i];
   // ---- the lane's slots: liveness (i detached), cached terms or row sums, all loads up front ----
