@@ -1,6 +1,6 @@
 """Randomised parity stress of the sampler against the CPU oracle: many small problems of varying separation, start state and
 options (the exact shortcuts -- row summaries, merge bound -- fire on the separated ones and must not change a bit).
-usage: python tools/stress_parity.py [cases] [seed]"""
+usage: python tools/stress_parity.py [cases] [seed] [max n]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,10 +9,11 @@ import __graft_entry__ as g
 pkg = g.load_package(); orc = g.load_oracle()
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+nmax = int(sys.argv[3]) if len(sys.argv) > 3 else 420
 bad = 0; fast_total = 0; quick_total = 0; moved_total = 0
 t0 = time.time()
 for case in range(cases):
-    n = int(rng.integers(60, 420)); K = int(rng.integers(2, 13)); dim = int(rng.integers(2, 14)); sig = float(rng.choice([0.05, 0.1, 0.15, 0.25, 0.4, 0.6]))
+    n = int(rng.integers(60, nmax)); K = int(rng.integers(2, 13)); dim = int(rng.integers(2, 14)); sig = float(rng.choice([0.05, 0.1, 0.15, 0.25, 0.4, 0.6]))
     w = rng.dirichlet(np.full(K, float(K)))
     lab = np.sort(rng.choice(K, size=n, p=w)) + 1
     lab = (np.unique(lab, return_inverse=True)[1] + 1).astype(np.int64)
