@@ -189,6 +189,7 @@ struct Ctx {
   int* res;               // incremental mode (shared memory): [nthr] slot chosen by each row of a batch
   double2* Cc;            // incremental mode (global): [cap][n] cached per-slot terms, see inc_eval_row
   RowSum* Rs;             // incremental mode (global): [n] row summaries
+  double* LLF; unsigned* LLFs;   // incremental mode (global): [cap][cap] loglik of the state with slot ci merged into cj, and the change count it was computed at (0: never)
   unsigned* tw;           // incremental mode (shared memory when it fits, else global): [n] change count at which point x's cached entries were last made valid
   unsigned* tchg;         // incremental mode (shared memory): [cap] change count at which each slot last gained or lost a point
   unsigned short* Slist;  // members of ci u cj: S ascending, then i, then j
@@ -1776,27 +1777,34 @@ __device__ void splitmerge_step(Ctx& c, unsigned it, unsigned mh, bool commit) {
     // whatever the restricted scans would have produced -- they are not run.  (A NaN x fails the test and takes the long way.)
     // The uniforms are counter-based, so skipping the scans' draws changes nothing else.
     const int szf = c.sizes[ci] + c.sizes[cj];
-    rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);
-    for (int t = tid; t < cap; t += c.nthr) {                               // row cj of the merged state
-      rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
-      rc_add128(bD, c.WD[tri(cj, t, cap)]); rc_add128(bL, c.WL[tri(cj, t, cap)]);
-      rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
-      rc_i128 z; z.lo = 0; z.hi = 0;
-      rows[0 * cap + t] = z; rows[1 * cap + t] = z;
+    // (the merged state's log-likelihood only changes when the chain's state does: kept per ordered pair with the change count)
+    const size_t pidx = (size_t)ci * cap + cj;
+    const bool have = c.LLFs[pidx] == c.inc->clk;                            // (written before the last barrier: uniform)
+    double ll_fin;
+    if (have) ll_fin = c.LLF[pidx];
+    else {
+      rc_i128* rows = reinterpret_cast<rc_i128*>(c.partial);
+      for (int t = tid; t < cap; t += c.nthr) {                             // row cj of the merged state
+        rc_i128 bD = c.WD[tri(ci, t, cap)], bL = c.WL[tri(ci, t, cap)];
+        rc_add128(bD, c.WD[tri(cj, t, cap)]); rc_add128(bL, c.WL[tri(cj, t, cap)]);
+        rows[2 * cap + t] = bD; rows[3 * cap + t] = bL;
+        rc_i128 z; z.lo = 0; z.hi = 0;
+        rows[0 * cap + t] = z; rows[1 * cap + t] = z;
+      }
+      if (tid == 0) {
+        rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
+        rc_add128(bbD, c.WD[tri(cj, cj, cap)]); rc_add128(bbL, c.WL[tri(cj, cj, cap)]);
+        rc_add128(bbD, c.WD[tri(ci, cj, cap)]); rc_add128(bbD, c.WD[tri(ci, cj, cap)]);
+        rc_add128(bbL, c.WL[tri(ci, cj, cap)]); rc_add128(bbL, c.WL[tri(ci, cj, cap)]);
+        rc_i128 z; z.lo = 0; z.hi = 0;
+        c.sc->aaD = z; c.sc->aaL = z; c.sc->abD = z; c.sc->abL = z; c.sc->bbD = bbD; c.sc->bbL = bbL;
+        c.sc->fslotA = ci; c.sc->fslotB = cj;
+      }
+      for (int s = tid; s < cap; s += c.nthr) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
+      csync(c);
+      ll_fin = loglik_eval(c, c.szL);
+      if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; c.LLF[pidx] = ll_fin; c.LLFs[pidx] = c.inc->clk; }
     }
-    if (tid == 0) {
-      rc_i128 bbD = c.WD[tri(ci, ci, cap)], bbL = c.WL[tri(ci, ci, cap)];
-      rc_add128(bbD, c.WD[tri(cj, cj, cap)]); rc_add128(bbL, c.WL[tri(cj, cj, cap)]);
-      rc_add128(bbD, c.WD[tri(ci, cj, cap)]); rc_add128(bbD, c.WD[tri(ci, cj, cap)]);
-      rc_add128(bbL, c.WL[tri(ci, cj, cap)]); rc_add128(bbL, c.WL[tri(ci, cj, cap)]);
-      rc_i128 z; z.lo = 0; z.hi = 0;
-      c.sc->aaD = z; c.sc->aaL = z; c.sc->abD = z; c.sc->abL = z; c.sc->bbD = bbD; c.sc->bbL = bbL;
-      c.sc->fslotA = ci; c.sc->fslotB = cj;
-    }
-    for (int s = tid; s < cap; s += c.nthr) c.szL[s] = (s == ci) ? 0 : (s == cj ? szf : c.sizes[s]);   // sizes of the merged state
-    csync(c);
-    const double ll_fin = loglik_eval(c, c.szL);
-    if (tid == 0) { c.sc->fslotA = -1; c.sc->fslotB = -1; }
     const double ll_cur = loglik_cur(c);
     if (tid == 0) {
       const double log_prior_ratio = -(rc_log((double)K) + r * rc_log(1 - p) - rc_log(p) - rc_lgamma(r)) +
@@ -2688,6 +2696,7 @@ __global__ void __launch_bounds__(512, 1) k_chain_inc(const __grid_constant__ rc
     c.tchg = reinterpret_cast<unsigned*>(smem + L.ep);
     c.tw = kp.tw_smem ? reinterpret_cast<unsigned*>(smem + L.tw) : kp.Vv + (size_t)chain * n;
     c.Rs = kp.Rs + (size_t)chain * n;
+    c.LLF = kp.LLF + (size_t)chain * cap * cap; c.LLFs = kp.LLFs + (size_t)chain * cap * cap;
     c.partial = reinterpret_cast<longlong2*>(smem + L.partial);
     c.sc = reinterpret_cast<Scal*>(smem + L.sc);
     c.inc = reinterpret_cast<IncShared*>(smem + L.inc);
@@ -2940,7 +2949,7 @@ __global__ void __launch_bounds__(RC_NTHR * G + RC_XTHR, 1) k_chain(const __grid
   c.n = n; c.cap = cap; c.tiles = tiles; c.qD = kp.qD; c.qL = kp.qL; c.DL = kp.DL; c.kp = &kp;
   c.colpos = kp.colpos; c.colpt = kp.colpt;
   c.ctid = threadIdx.x % RC_NTHR; c.cwarp = c.ctid >> 5; c.lane = c.ctid & 31; c.barid = 1 + cl; c.bbarid = 1 + G + cl;
-  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.tw = nullptr; c.tchg = nullptr; c.Rs = nullptr;
+  c.nthr = RC_NTHR; c.nwarp = RC_NWARP; c.S = nullptr; c.inc = nullptr; c.mcap = 0; c.mAB = nullptr; c.mDG = nullptr; c.mL2s = nullptr; c.live = nullptr; c.rank = nullptr; c.tabs = nullptr; c.res = nullptr; c.Cc = nullptr; c.tw = nullptr; c.tchg = nullptr; c.Rs = nullptr; c.LLF = nullptr; c.LLFs = nullptr;
   {
     const ChainLayout L = chain_layout(n, cap, tiles, kp.npad_max);
     c.stage_bytes = stage_bytes_for(n);

@@ -53,6 +53,7 @@ struct rc_kparams {
   unsigned* epochs;     // [nchains][cap + 1] change count at which each slot last changed (>= 1), then the chain's change count
   int tw_smem;          // the per-point counts of a chain live in shared memory during a launch
   int shortcuts;        // 1: rows decided by their summaries and merge proposals rejected by their bound skip the work (same results; RCB200_SHORTCUTS=0 turns both off)
+  double* LLF; unsigned* LLFs;   // [nchains][cap][cap] merged-state log-likelihoods per ordered slot pair and their change counts
   RowSum* Rs;           // [nchains][n]       row summaries of the incremental scan (32 B each, see rc_sampler.cu)
   int inc_mcap;         // incremental mode: split-merge members that fit the shared-memory scratch (64 B each)
   int ovl_min_thr;      // the scan runs beside the restricted scans when the chain has at least this many threads (0: never)
